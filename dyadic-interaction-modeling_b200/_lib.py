@@ -1,0 +1,121 @@
+"""Build (nvcc, in-tree) and load libdimb200.so, the C-ABI declared in include/dimb200.h.
+
+The library is the product: there is no Python/CPU fallback.  `load()` raises if the shared object is missing and cannot
+be built, and every entry point returns DIM_ENODEVICE (raised here as RuntimeError) without an sm_100 GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import glob
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+CSRC = os.path.join(_HERE, "csrc")
+SO_PATH = os.path.join(_HERE, "libdimb200.so")
+HEADER = os.path.join(ROOT, "include", "dimb200.h")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+_lock = threading.Lock()
+_lib = None
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def _stale() -> bool:
+    if not os.path.exists(SO_PATH):
+        return True
+    t = os.path.getmtime(SO_PATH)
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + [HEADER]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into libdimb200.so next to this file (cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return SO_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not os.path.exists(nvcc):
+        nvcc = "nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + sources() + ["-o", SO_PATH + ".tmp"]
+    if verbose:
+        print(" ".join(cmd))
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    os.replace(SO_PATH + ".tmp", SO_PATH)
+    return SO_PATH
+
+
+class VQConfigC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("in_dim", "hidden", "layers", "heads", "ffn", "n_embed", "zdim", "pe_max_len")] \
+        + [("neg_slope", C.c_float)]
+
+
+class S2SConfigC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("dim_in", "dim", "dim_audio", "depth", "heads", "dim_head", "max_seq_len",
+                                         "num_tokens", "ff_mult")]
+
+
+P, I, F, SZ, I64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64
+
+# name -> (restype, argtypes); must list every function declared in include/dimb200.h (checked by tests/test_abi.py)
+SIGNATURES = {
+    "dim_last_error": (C.c_char_p, []),
+    "dim_version": (I, []),
+    "dim_launch_count": (C.c_uint64, []),
+    "dim_vq_argmin": (I, [P, P, P, I, I, I, P]),
+    "dim_vq_gather": (I, [P, P, P, I, I, I, P, P]),
+    "dim_linear_f32": (I, [P, I, P, P, P, I, P, I, I, I, I, I, F, P]),
+    "dim_conv5_leaky_f32": (I, [P, P, P, P, P, I, I, I, F, P]),
+    "dim_repack_conv_weight": (I, [P, P, I, I, P]),
+    "dim_instance_norm_f32": (I, [P, P, I, I, I, F, P]),
+    "dim_layer_norm_f32": (I, [P, P, P, P, I, I, F, P]),
+    "dim_attention_f32": (I, [P, I, P, I, P, I, P, I, P, P, I, I, I, I, I, F, I, P]),
+    "dim_create": (I, [C.POINTER(P), I]),
+    "dim_destroy": (I, [P]),
+    "dim_set_tensor": (I, [P, C.c_char_p, P, I, I, C.POINTER(I64)]),
+    "dim_vqvae_build": (I, [P, C.c_char_p, C.POINTER(VQConfigC), I, C.POINTER(I)]),
+    "dim_vqvae_workspace_bytes": (SZ, [P, I, I, I]),
+    "dim_vqvae_encode": (I, [P, I, P, P, P, I, I, P, P, P, P, SZ, P]),
+    "dim_vqvae_decode": (I, [P, I, P, P, P, I, I, P, P, SZ, P]),
+    "dim_slmft_build": (I, [P, C.POINTER(S2SConfigC), I, C.POINTER(I)]),
+    "dim_slmft_workspace_bytes": (SZ, [P, I, I, I, I]),
+    "dim_slmft_context": (I, [P, I, P, P, P, I, I, P, P, SZ, P]),
+    "dim_slmft_generate": (I, [P, I, P, P, P, I, I, I, F, I, P, P, P, P, SZ, P]),
+}
+
+
+def load(build_if_missing: bool = True):
+    """Return the ctypes handle of libdimb200.so (building it first when the sources are newer)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if build_if_missing:
+            try:
+                build()
+            except Exception:
+                if not os.path.exists(SO_PATH):
+                    raise
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(f"{SO_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                               "there is no fallback path")
+        lib = C.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+        return lib
+
+
+def check(code: int, what: str = ""):
+    if code != 0:
+        msg = load().dim_last_error()
+        raise RuntimeError(f"libdimb200 {what} failed (code {code}): {msg.decode() if msg else ''}")

@@ -1,0 +1,55 @@
+"""SLMFT.forward(mode='val') on the engines (/root/reference/code/seq2seq_pretrain.py:496-514).
+
+Same results as the reference call; the work the reference computes and throws away is skipped:
+the speaker VQ encodes (z_speaker is never read) and the duplicated forward_vq call.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+
+def continuous_loss(pred, target, mask):
+    """forward_continuous_loss (seq2seq_pretrain.py:466-478): reporting only, stays in PyTorch."""
+    target, mask = target[:, 1:, :], mask[:, 1:]
+    B = len(target)
+    target = target.reshape(B * target.shape[1], -1)
+    pred = pred.reshape(B * pred.shape[1], -1)
+    mask = mask.reshape(-1)
+    p, t = pred[mask], target[mask]
+    return torch.mean(F.pairwise_distance(p[:, 6:], t[:, 6:])) + torch.mean(F.pairwise_distance(p[:, 0:6], t[:, 0:6]))
+
+
+@torch.no_grad()
+def listener_codes(vq_engine, v_listener, mask):
+    """forward_vq, listener half (:489-491): per-sample encode of the valid prefix == batched encode with
+    lens and batch_index 0 for everyone.  Returns z_l (B,T) int64 with -100 on padding."""
+    B, T, _ = v_listener.shape
+    lens = mask.sum(dim=1).to(torch.int32)
+    zero = torch.zeros(B, dtype=torch.int32, device=v_listener.device)
+    idx, _, _ = vq_engine.encode(v_listener, lens=lens, batch_index=zero)
+    return idx.masked_fill(~mask, -100)
+
+
+@torch.no_grad()
+def slmft_forward_val(s2s_engine, vq_engine, v_speaker, v_listener, v_audio, mask, temperature=1.0, uniforms=None,
+                      batch_index=None, return_codes=False, greedy=None):
+    """-> (total_loss, dict, pred_cont_seq_l (B,T-1,56)) like SLMFT.forward(..., mode='val').
+
+    The reference samples (temperature 1, top-k 52, torch.multinomial).  Here: `uniforms` (B,T-1) given -> inverse-CDF
+    sampling with them; uniforms None and greedy is not False -> argmax decoding (the deterministic parity mode)."""
+    B, T, _ = v_speaker.shape
+    z_l = listener_codes(vq_engine, v_listener, mask)
+    ctx = s2s_engine.context(v_speaker, v_audio, mask)
+    if uniforms is None and greedy is not False:
+        codes = s2s_engine.generate(ctx, mask, z_l[:, 0], T - 1, temperature=0.0)
+    else:
+        if uniforms is None:
+            uniforms = torch.rand(B, T - 1, device=v_speaker.device)
+        codes = s2s_engine.generate(ctx, mask, z_l[:, 0], T - 1, temperature=temperature, uniforms=uniforms)
+    pred = vq_engine.decode(codes=codes, batch_index=batch_index)
+    l_cont = continuous_loss(pred, v_listener, mask)
+    d = {"l_ce_s": 0, "l_ce_l": 0.0, "l_cont_s": 0, "l_cont_l": l_cont, "nce": 0, "c_acc": 0}
+    if return_codes:
+        return l_cont, d, pred, codes
+    return l_cont, d, pred

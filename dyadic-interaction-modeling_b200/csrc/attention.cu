@@ -1,0 +1,308 @@
+// fp32 attention kernels (parity mode).
+//   attn_prefill_f32 : flash-style tiled attention over frames, online softmax, 64x64 score tiles in shared memory.
+//                      VQ-VAE layers (Dh 48, scale hidden^-0.5, no mask; models/lib/base_models.py:136-143) and
+//                      x-transformers encoders (Dh 64, causal + key-padding mask, -FLT_MAX fill).
+//   attn_decode_f32  : one query per (batch, head) against a token-major K/V cache (self-attention with in-kernel
+//                      append of the new key/value, or cross-attention over the projected context); HBM-bound:
+//                      each half-warp streams whole 256-byte head rows with 128-bit loads.
+#include "attention.cuh"
+
+namespace dimb {
+
+namespace {
+
+constexpr int TQ = 64, TKV = 64;
+
+template <int DH>
+__global__ void __launch_bounds__(256) attn_prefill_f32(const AttnArgs p) {
+  constexpr int DP = DH + 4;            // padded row: conflict-free 128-bit reads at stride 16 rows
+  constexpr int DJ = DH / 16;           // output columns per thread
+  extern __shared__ __align__(16) float smem[];
+  float* Qs = smem;                     // [TQ][DP]
+  float* Ks = Qs + TQ * DP;             // [TKV][DP]
+  float* Vs = Ks + TKV * DP;            // [TKV][DH]
+  float* Ps = Vs + TKV * DH;            // [TQ][TKV+4]
+  constexpr int PP = TKV + 4;
+
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TQ;
+  const float* qb = p.q + (size_t)b * p.Tq * p.ldq + h * DH;
+  const float* kb = p.k + (size_t)b * p.Tk * p.ldk + h * DH;
+  const float* vb = p.v + (size_t)b * p.Tk * p.ldv + h * DH;
+  const int klen = p.lens ? min(__ldg(p.lens + b), p.Tk) : p.Tk;     // keys >= klen do not exist
+  const uint8_t* km = p.key_mask ? p.key_mask + (size_t)b * p.Tk : nullptr;
+
+  for (int i = tid; i < TQ * (DH / 4); i += 256) {
+    int r = i / (DH / 4), c = (i % (DH / 4)) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + r < p.Tq) v = *reinterpret_cast<const float4*>(qb + (size_t)(q0 + r) * p.ldq + c);
+    *reinterpret_cast<float4*>(Qs + r * DP + c) = v;
+  }
+
+  float m_run[4], l_run[4], o[4][DJ];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m_run[i] = -INFINITY;
+    l_run[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < DJ; ++j) o[i][j] = 0.f;
+  }
+
+  int nkt = (klen + TKV - 1) / TKV;
+  if (p.causal) nkt = min(nkt, (min(q0 + TQ, p.Tq) - 1) / TKV + 1);   // tiles right of the diagonal contribute exp(-FLT_MAX - m) = 0
+
+  for (int kt = 0; kt < nkt; ++kt) {
+    const int k0 = kt * TKV;
+    __syncthreads();                    // previous tile's Ps / Vs fully consumed (and Qs written, first time)
+    for (int i = tid; i < TKV * (DH / 4); i += 256) {
+      int r = i / (DH / 4), c = (i % (DH / 4)) * 4;
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (k0 + r < klen) {
+        kv = *reinterpret_cast<const float4*>(kb + (size_t)(k0 + r) * p.ldk + c);
+        vv = *reinterpret_cast<const float4*>(vb + (size_t)(k0 + r) * p.ldv + c);
+      }
+      *reinterpret_cast<float4*>(Ks + r * DP + c) = kv;
+      *reinterpret_cast<float4*>(Vs + r * DH + c) = vv;
+    }
+    __syncthreads();
+
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll
+    for (int d = 0; d < DH; d += 4) {
+      float4 qv[4], kv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qv[i] = *reinterpret_cast<const float4*>(Qs + (ty + 16 * i) * DP + d);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) kv[j] = *reinterpret_cast<const float4*>(Ks + (tx + 16 * j) * DP + d);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          s[i][j] = fmaf(qv[i].x, kv[j].x, s[i][j]);
+          s[i][j] = fmaf(qv[i].y, kv[j].y, s[i][j]);
+          s[i][j] = fmaf(qv[i].z, kv[j].z, s[i][j]);
+          s[i][j] = fmaf(qv[i].w, kv[j].w, s[i][j]);
+        }
+    }
+
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int qi = q0 + ty + 16 * i;
+      float tmax = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int kj = k0 + tx + 16 * j;
+        float v = s[i][j] * p.scale;
+        if (kj >= klen) v = -INFINITY;                                  // not a key at all
+        else if ((km && !km[kj]) || (p.causal && kj > qi)) v = -FLT_MAX;   // masked_fill(-finfo.max)
+        s[i][j] = v;
+        tmax = fmaxf(tmax, v);
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, off));
+      const float m_new = fmaxf(m_run[i], tmax);
+      const float alpha = (m_run[i] == -INFINITY) ? 0.f : expf(m_run[i] - m_new);
+      float psum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float pv = (s[i][j] == -INFINITY) ? 0.f : expf(s[i][j] - m_new);
+        Ps[(ty + 16 * i) * PP + tx + 16 * j] = pv;
+        psum += pv;
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, off);
+      l_run[i] = l_run[i] * alpha + psum;
+      m_run[i] = m_new;
+#pragma unroll
+      for (int j = 0; j < DJ; ++j) o[i][j] *= alpha;
+    }
+    __syncthreads();
+
+#pragma unroll 4
+    for (int kk = 0; kk < TKV; kk += 4) {
+      float4 pv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pv[i] = *reinterpret_cast<const float4*>(Ps + (ty + 16 * i) * PP + kk);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float vv[DJ];
+#pragma unroll
+        for (int j = 0; j < DJ; ++j) vv[j] = Vs[(kk + u) * DH + tx + 16 * j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float pe = u == 0 ? pv[i].x : (u == 1 ? pv[i].y : (u == 2 ? pv[i].z : pv[i].w));
+#pragma unroll
+          for (int j = 0; j < DJ; ++j) o[i][j] = fmaf(pe, vv[j], o[i][j]);
+        }
+      }
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int qi = q0 + ty + 16 * i;
+    if (qi >= p.Tq) continue;
+    const float inv = l_run[i] > 0.f ? 1.f / l_run[i] : 0.f;
+    float* orow = p.out + ((size_t)b * p.Tq + qi) * p.ldo + h * DH;
+#pragma unroll
+    for (int j = 0; j < DJ; ++j) orow[tx + 16 * j] = o[i][j] * inv;
+  }
+}
+
+// ---- decode: one query row per (b,h) ----------------------------------------------------------------------------
+// 128 threads = 8 half-warps; a half-warp owns whole keys (16 lanes x float4 = 64 dims).
+__global__ void __launch_bounds__(128) attn_decode_f32(const DecodeAttnArgs p) {
+  constexpr int DH = 64;
+  extern __shared__ __align__(16) float sc[];          // [nkeys_max] scores, then [8][64] partial outputs
+  __shared__ float red[8];
+  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int hw = tid >> 4, l16 = tid & 15;
+  const int pos = p.step ? *p.step : 0;                                   // index of the token being decoded
+  const int nkeys = p.append ? pos + 1 : p.Tk;
+  float* kbase = p.k + (size_t)b * p.kv_batch_stride + h * DH;
+  float* vbase = p.v + (size_t)b * p.kv_batch_stride + h * DH;
+
+  if (p.append) {                                                        // cache[pos] <- this step's k, v
+    if (tid < 16)
+      *reinterpret_cast<float4*>(kbase + (size_t)pos * p.kv_tok_stride + l16 * 4) =
+          *reinterpret_cast<const float4*>(p.k_new + (size_t)b * p.ld_new + h * DH + l16 * 4);
+    else if (tid < 32)
+      *reinterpret_cast<float4*>(vbase + (size_t)pos * p.kv_tok_stride + l16 * 4) =
+          *reinterpret_cast<const float4*>(p.v_new + (size_t)b * p.ld_new + h * DH + l16 * 4);
+    __syncthreads();
+  }
+  const float4 qv = *reinterpret_cast<const float4*>(p.q + (size_t)b * p.ldq + h * DH + l16 * 4);
+  const uint8_t* km = p.key_mask ? p.key_mask + (size_t)b * p.Tk : nullptr;
+
+  // scores
+  for (int base = 0; base < nkeys; base += 32) {       // warp-uniform trip count: the shuffles below need all lanes
+    const int j0 = base + hw;
+    float4 kv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int j = j0 + 8 * u;
+      kv[u] = j < nkeys ? *reinterpret_cast<const float4*>(kbase + (size_t)j * p.kv_tok_stride + l16 * 4)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int j = j0 + 8 * u;
+      float d = qv.x * kv[u].x + qv.y * kv[u].y + qv.z * kv[u].z + qv.w * kv[u].w;
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+      if (l16 == 0 && j < nkeys) sc[j] = (km && !km[j]) ? -FLT_MAX : d * p.scale;
+    }
+  }
+  __syncthreads();
+  // softmax statistics
+  float mx = -INFINITY;
+  for (int j = tid; j < nkeys; j += 128) mx = fmaxf(mx, sc[j]);
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float sum = 0.f;
+  for (int j = tid; j < nkeys; j += 128) {
+    float e = expf(sc[j] - mx);
+    sc[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  const float inv = 1.f / (red[0] + red[1] + red[2] + red[3]);
+
+  // out = P V
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int base = 0; base < nkeys; base += 32) {
+    const int j0 = base + hw;
+    float4 vv[4];
+    float pj[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int j = j0 + 8 * u;
+      bool ok = j < nkeys;
+      vv[u] = ok ? *reinterpret_cast<const float4*>(vbase + (size_t)j * p.kv_tok_stride + l16 * 4)
+                 : make_float4(0.f, 0.f, 0.f, 0.f);
+      pj[u] = ok ? sc[j] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      acc.x = fmaf(pj[u], vv[u].x, acc.x); acc.y = fmaf(pj[u], vv[u].y, acc.y);
+      acc.z = fmaf(pj[u], vv[u].z, acc.z); acc.w = fmaf(pj[u], vv[u].w, acc.w);
+    }
+  }
+  float* part = sc + p.sc_floats;                       // [8][64]
+  *reinterpret_cast<float4*>(part + hw * DH + l16 * 4) = acc;
+  __syncthreads();
+  if (tid < DH) {
+    float r = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) r += part[w * DH + tid];
+    p.out[(size_t)b * p.ldo + h * DH + tid] = r * inv;
+  }
+}
+
+}  // namespace
+
+int launch_attention_prefill(const AttnArgs& a, cudaStream_t s) {
+  DIM_REQUIRE(a.Dh == 48 || a.Dh == 64, "attention: head dim must be 48 or 64");
+  DIM_REQUIRE(a.B > 0 && a.H > 0 && a.Tq > 0 && a.Tk > 0, "attention: empty");
+  DIM_REQUIRE(a.ldq % 4 == 0 && a.ldk % 4 == 0 && a.ldv % 4 == 0, "attention: leading dims must be multiples of 4");
+  dim3 grid(cdiv(a.Tq, TQ), a.H, a.B);
+  if (a.Dh == 48) {
+    constexpr size_t smem = (TQ * 52 + TKV * 52 + TKV * 48 + TQ * (TKV + 4)) * sizeof(float);
+    static bool once = false;
+    if (!once) {
+      DIM_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_f32<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      once = true;
+    }
+    attn_prefill_f32<48><<<grid, 256, smem, s>>>(a);
+  } else {
+    constexpr size_t smem = (TQ * 68 + TKV * 68 + TKV * 64 + TQ * (TKV + 4)) * sizeof(float);
+    static bool once = false;
+    if (!once) {
+      DIM_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_f32<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      once = true;
+    }
+    attn_prefill_f32<64><<<grid, 256, smem, s>>>(a);
+  }
+  DIM_LAUNCHED();
+  return DIM_OK;
+}
+
+int launch_attention_decode(DecodeAttnArgs a, int max_keys, cudaStream_t s) {
+  DIM_REQUIRE(a.B > 0 && a.H > 0, "decode attention: empty");
+  a.sc_floats = (max_keys + 3) / 4 * 4;
+  size_t smem = (size_t)(a.sc_floats + 8 * 64) * sizeof(float);
+  DIM_REQUIRE(smem <= 200 * 1024, "decode attention: too many keys for one CTA");
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    DIM_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  attn_decode_f32<<<a.B * a.H, 128, smem, s>>>(a);
+  DIM_LAUNCHED();
+  return DIM_OK;
+}
+
+}  // namespace dimb
+
+using namespace dimb;
+
+extern "C" int dim_attention_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out,
+                                 int ldo, const uint8_t* key_mask, const int32_t* lens, int B, int H, int Tq, int Tk, int Dh,
+                                 float scale, int causal, void* stream) {
+  if (int e = ensure_device()) return e;
+  AttnArgs a;
+  a.q = q; a.ldq = ldq; a.k = k; a.ldk = ldk; a.v = v; a.ldv = ldv; a.out = out; a.ldo = ldo;
+  a.key_mask = key_mask; a.lens = lens; a.B = B; a.H = H; a.Tq = Tq; a.Tk = Tk; a.Dh = Dh; a.scale = scale;
+  a.causal = causal;
+  return launch_attention_prefill(a, as_stream(stream));
+}

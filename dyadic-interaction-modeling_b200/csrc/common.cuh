@@ -1,0 +1,74 @@
+// Shared device/host helpers for libdimb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <math.h>
+#include <float.h>
+#include <string>
+#include <atomic>
+
+#include "../../include/dimb200.h"
+
+namespace dimb {
+
+// ---- error plumbing ---------------------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+extern std::atomic<uint64_t> g_launches;
+
+#define DIM_CHECK_CUDA(expr)                                                                         \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      return ::dimb::fail(DIM_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));            \
+  } while (0)
+
+#define DIM_REQUIRE(cond, msg)                                                                       \
+  do {                                                                                               \
+    if (!(cond)) return ::dimb::fail(DIM_EINVAL, std::string(msg) + " [" #cond "]");                 \
+  } while (0)
+
+// Call after every kernel launch: counts it and surfaces launch-configuration errors.
+#define DIM_LAUNCHED()                                                                               \
+  do {                                                                                               \
+    ::dimb::g_launches.fetch_add(1, std::memory_order_relaxed);                                      \
+    cudaError_t _e = cudaGetLastError();                                                             \
+    if (_e != cudaSuccess) return ::dimb::fail(DIM_ECUDA, std::string("launch: ") + cudaGetErrorString(_e)); \
+  } while (0)
+
+int ensure_device();   // DIM_OK when the current device is sm_100; DIM_ENODEVICE otherwise
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- device helpers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float act_apply(float x, int act, float slope) {
+  switch (act) {
+    case DIM_ACT_LEAKY:
+      return x > 0.f ? x : x * slope;
+    case DIM_ACT_GELU_TANH: {
+      // x * 0.5 * (1 + tanh(sqrt(2/pi) * (x + 0.044715 x^3)))  -- utils/base_model_util.py:81-94
+      float u = 0.7978845608028654f * (x + 0.044715f * (x * x * x));
+      return x * (0.5f * (1.0f + tanhf(u)));
+    }
+    case DIM_ACT_GELU_ERF:
+      return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f));
+    default:
+      return x;
+  }
+}
+
+}  // namespace dimb

@@ -1,0 +1,680 @@
+// Model-level entry points: a handle owns the weight registry (reference state_dict keys -> borrowed device pointers),
+// re-packed weights, and the launch sequences of
+//   * VQAutoEncoder.encode / decode           (/root/reference/code/models/stage1_BIWI.py:22-37, :307-317, :376-393)
+//   * SLMFT.forward_encoder + context concat   (/root/reference/code/seq2seq_pretrain.py:431-446)
+//   * decoder_joint.generate                   (seq2seq_pretrain.py:450; x-transformers 1.30.16)
+// Everything is enqueued on the caller's stream; no host synchronisation inside.
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemm_f32.cuh"
+#include "rowops.cuh"
+#include "vq.cuh"
+
+using namespace dimb;
+
+namespace {
+
+struct TensorRef {
+  const void* p = nullptr;
+  int dtype = DIM_DTYPE_F32;
+  std::vector<int64_t> shape;
+};
+
+struct VqLayer {
+  const float *ln1_g, *ln1_b, *wqkv, *wo, *bo, *ln2_g, *ln2_b, *w1, *b1, *w2, *b2;
+};
+
+struct VqModel {
+  dim_vq_config cfg{};
+  int precision = DIM_PREC_FP32;
+  const float *map_w, *map_b, *conv_b, *emb_w, *emb_b, *pe, *post_w, *post_b;
+  float* conv_wr = nullptr;
+  std::vector<VqLayer> enc;
+  const float *pre_w, *pre_b, *dconv_b, *demb_w, *demb_b, *dpe, *rev_w;
+  float* dconv_wr = nullptr;
+  std::vector<VqLayer> dec;
+  const float* codebook;
+};
+
+struct XtAttn {
+  const float *norm_g = nullptr, *norm_b = nullptr, *wq = nullptr, *wo = nullptr;
+  float* wqkv = nullptr;   // owned: cat(to_q, to_k, to_v) [3*inner, dim]   (self attention)
+  float* wkv = nullptr;    // owned: cat(to_k, to_v)       [2*inner, dim]   (cross attention)
+};
+struct XtFF {
+  const float *norm_g = nullptr, *norm_b = nullptr, *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
+};
+struct XtEncoder {
+  int dim_in = 0;
+  const float *proj_w = nullptr, *proj_b = nullptr, *pos_emb = nullptr, *final_g = nullptr, *final_b = nullptr;
+  std::vector<XtAttn> attn;
+  std::vector<XtFF> ff;
+};
+struct S2SModel {
+  dim_s2s_config cfg{};
+  int precision = DIM_PREC_FP32;
+  XtEncoder enc_s, enc_joint;
+  const float *patch_s = nullptr, *patch_dec_s = nullptr, *norm_s_g = nullptr, *norm_s_b = nullptr;
+  const float* token_emb = nullptr;
+  std::vector<XtAttn> self_attn, cross_attn;
+  std::vector<XtFF> ff;
+  const float *final_g = nullptr, *final_b = nullptr, *logits_w = nullptr, *logits_b = nullptr;
+};
+
+}  // namespace
+
+struct dim_handle_s {
+  int device = 0;
+  std::unordered_map<std::string, TensorRef> tensors;
+  std::vector<std::unique_ptr<VqModel>> vq;
+  std::vector<std::unique_ptr<S2SModel>> s2s;
+  std::vector<void*> owned;
+};
+
+namespace {
+
+// Look a float tensor up by name and check its shape.  required=false returns nullptr quietly when absent.
+int lookup(dim_handle_s* h, const std::string& name, std::initializer_list<int64_t> shape, bool required,
+           const float** out) {
+  *out = nullptr;
+  auto it = h->tensors.find(name);
+  if (it == h->tensors.end()) {
+    if (!required) return DIM_OK;
+    return fail(DIM_EMISSING, "weight not registered: " + name);
+  }
+  const TensorRef& t = it->second;
+  if (t.dtype != DIM_DTYPE_F32) return fail(DIM_EINVAL, "weight is not fp32: " + name);
+  std::vector<int64_t> want(shape);
+  if (t.shape != want) {
+    std::string got, exp;
+    for (auto v : t.shape) got += std::to_string(v) + ",";
+    for (auto v : want) exp += std::to_string(v) + ",";
+    return fail(DIM_EINVAL, "shape mismatch for " + name + ": got (" + got + ") expected (" + exp + ")");
+  }
+  *out = static_cast<const float*>(t.p);
+  return DIM_OK;
+}
+
+#define LOOKUP(dst, name, req, ...)                                             \
+  do {                                                                          \
+    if (int _e = lookup(h, (name), {__VA_ARGS__}, (req), &(dst))) return _e;     \
+  } while (0)
+
+int owned_alloc(dim_handle_s* h, size_t bytes, float** out) {
+  void* p = nullptr;
+  DIM_CHECK_CUDA(cudaMalloc(&p, bytes));
+  h->owned.push_back(p);
+  *out = static_cast<float*>(p);
+  return DIM_OK;
+}
+
+int build_vq_stack(dim_handle_s* h, const std::string& p, const dim_vq_config& c, std::vector<VqLayer>& out) {
+  const int64_t H = c.hidden, F = c.ffn;
+  out.resize(c.layers);
+  for (int l = 0; l < c.layers; ++l) {
+    VqLayer& L = out[l];
+    std::string a = p + ".net." + std::to_string(2 * l) + ".fn", m = p + ".net." + std::to_string(2 * l + 1) + ".fn";
+    LOOKUP(L.ln1_g, a + ".norm.weight", true, H);
+    LOOKUP(L.ln1_b, a + ".norm.bias", true, H);
+    LOOKUP(L.wqkv, a + ".fn.to_qkv.weight", true, 3 * H, H);
+    LOOKUP(L.wo, a + ".fn.to_out.weight", true, H, H);
+    LOOKUP(L.bo, a + ".fn.to_out.bias", true, H);
+    LOOKUP(L.ln2_g, m + ".norm.weight", true, H);
+    LOOKUP(L.ln2_b, m + ".norm.bias", true, H);
+    LOOKUP(L.w1, m + ".fn.l1.weight", true, F, H);
+    LOOKUP(L.b1, m + ".fn.l1.bias", true, F);
+    LOOKUP(L.w2, m + ".fn.l2.weight", true, H, F);
+    LOOKUP(L.b2, m + ".fn.l2.bias", true, H);
+  }
+  return DIM_OK;
+}
+
+// ---- VQ-VAE workspace layout (floats per frame row) ---------------------------------------------------------------
+struct VqWs {
+  float *h0, *h1, *x, *ln, *qkv, *att, *ff, *z;
+  int64_t* idx;
+  size_t bytes;
+};
+VqWs carve_vq(const dim_vq_config& c, int B, int T, void* base) {
+  size_t R = (size_t)B * T;
+  char* p = static_cast<char*>(base);
+  VqWs w{};
+  auto take = [&](size_t nfloat) {
+    float* r = reinterpret_cast<float*>(p);
+    p += align_up(nfloat * sizeof(float), 256);
+    return r;
+  };
+  w.h0 = take(R * c.hidden); w.h1 = take(R * c.hidden); w.x = take(R * c.hidden); w.ln = take(R * c.hidden);
+  w.qkv = take(R * 3 * c.hidden); w.att = take(R * c.hidden); w.ff = take(R * c.ffn); w.z = take(R * c.zdim);
+  w.idx = reinterpret_cast<int64_t*>(take(R * 2));
+  w.bytes = (size_t)(p - static_cast<char*>(base));
+  return w;
+}
+
+// conv(k5, replicate) + LeakyReLU + InstanceNorm, Linear + pe[batch], transformer stack: shared by encoder and decoder.
+int vq_trunk(const VqModel& m, const std::vector<VqLayer>& layers, const float* conv_wr, const float* conv_b,
+             const float* emb_w, const float* emb_b, const float* pe, VqWs& w, const int32_t* lens,
+             const int32_t* batch_index, int B, int T, cudaStream_t s) {
+  const dim_vq_config& c = m.cfg;
+  const int R = B * T, H = c.hidden;
+  {  // h1 = leaky(conv5(h0) + b)
+    GemmArgs a;
+    a.A = w.h0; a.lda = H; a.W = conv_wr; a.bias = conv_b; a.C = w.h1; a.ldc = H; a.M = R; a.N = H; a.K = 5 * H;
+    a.act = DIM_ACT_LEAKY; a.slope = c.neg_slope; a.conv_T = T; a.conv_C = H; a.lens = lens;
+    if (int e = launch_gemm_f32(a, s)) return e;
+  }
+  if (int e = launch_instance_norm(w.h1, lens, B, T, H, 1e-5f, s)) return e;
+  {  // x = h1 @ emb^T + b + pe[batch_index[b]]
+    GemmArgs a;
+    a.A = w.h1; a.lda = H; a.W = emb_w; a.bias = emb_b; a.C = w.x; a.ldc = H; a.M = R; a.N = H; a.K = H;
+    a.tab = pe; a.ldtab = H; a.tab_mode = 1; a.tab_index = batch_index; a.tab_T = T;
+    if (int e = launch_gemm_f32(a, s)) return e;
+  }
+  const int Dh = H / c.heads;
+  for (const VqLayer& L : layers) {
+    if (int e = launch_layer_norm(w.x, L.ln1_g, L.ln1_b, w.ln, nullptr, R, H, 1e-5f, s)) return e;
+    {
+      GemmArgs a;
+      a.A = w.ln; a.lda = H; a.W = L.wqkv; a.C = w.qkv; a.ldc = 3 * H; a.M = R; a.N = 3 * H; a.K = H;
+      if (int e = launch_gemm_f32(a, s)) return e;
+    }
+    {
+      AttnArgs a;                      // 'b n (qkv h d)': q at col 0, k at H, v at 2H
+      a.q = w.qkv; a.k = w.qkv + H; a.v = w.qkv + 2 * H; a.ldq = a.ldk = a.ldv = 3 * H;
+      a.out = w.att; a.ldo = H; a.lens = lens; a.B = B; a.H = c.heads; a.Tq = T; a.Tk = T; a.Dh = Dh;
+      a.scale = 1.0f / sqrtf((float)H);          // hidden_size**-0.5, not head_dim
+      if (int e = launch_attention_prefill(a, s)) return e;
+    }
+    {
+      GemmArgs a;
+      a.A = w.att; a.lda = H; a.W = L.wo; a.bias = L.bo; a.residual = w.x; a.ldr = H; a.C = w.x; a.ldc = H;
+      a.M = R; a.N = H; a.K = H;
+      if (int e = launch_gemm_f32(a, s)) return e;
+    }
+    if (int e = launch_layer_norm(w.x, L.ln2_g, L.ln2_b, w.ln, nullptr, R, H, 1e-5f, s)) return e;
+    {
+      GemmArgs a;
+      a.A = w.ln; a.lda = H; a.W = L.w1; a.bias = L.b1; a.C = w.ff; a.ldc = c.ffn; a.M = R; a.N = c.ffn; a.K = H;
+      a.act = DIM_ACT_GELU_TANH;
+      if (int e = launch_gemm_f32(a, s)) return e;
+    }
+    {
+      GemmArgs a;
+      a.A = w.ff; a.lda = c.ffn; a.W = L.w2; a.bias = L.b2; a.residual = w.x; a.ldr = H; a.C = w.x; a.ldc = H;
+      a.M = R; a.N = H; a.K = c.ffn;
+      if (int e = launch_gemm_f32(a, s)) return e;
+    }
+  }
+  return DIM_OK;
+}
+
+// ---- x-transformers pieces ----------------------------------------------------------------------------------------
+int build_xt_attn(dim_handle_s* h, const std::string& lp, int dim, int ctx_dim, int inner, bool cross, XtAttn& A) {
+  const float *wk, *wv;
+  LOOKUP(A.norm_g, lp + ".0.0.weight", true, dim);
+  LOOKUP(A.norm_b, lp + ".0.0.bias", false, dim);
+  LOOKUP(A.wq, lp + ".1.to_q.weight", true, inner, dim);
+  LOOKUP(wk, lp + ".1.to_k.weight", true, inner, ctx_dim);
+  LOOKUP(wv, lp + ".1.to_v.weight", true, inner, ctx_dim);
+  LOOKUP(A.wo, lp + ".1.to_out.weight", true, dim, inner);
+  size_t qb = (size_t)inner * dim * sizeof(float), kb = (size_t)inner * ctx_dim * sizeof(float);
+  if (!cross) {
+    if (int e = owned_alloc(h, qb + 2 * kb, &A.wqkv)) return e;
+    DIM_CHECK_CUDA(cudaMemcpy(A.wqkv, A.wq, qb, cudaMemcpyDeviceToDevice));
+    DIM_CHECK_CUDA(cudaMemcpy(A.wqkv + (size_t)inner * dim, wk, kb, cudaMemcpyDeviceToDevice));
+    DIM_CHECK_CUDA(cudaMemcpy(A.wqkv + (size_t)2 * inner * dim, wv, kb, cudaMemcpyDeviceToDevice));
+  } else {
+    if (int e = owned_alloc(h, 2 * kb, &A.wkv)) return e;
+    DIM_CHECK_CUDA(cudaMemcpy(A.wkv, wk, kb, cudaMemcpyDeviceToDevice));
+    DIM_CHECK_CUDA(cudaMemcpy(A.wkv + (size_t)inner * ctx_dim, wv, kb, cudaMemcpyDeviceToDevice));
+  }
+  return DIM_OK;
+}
+
+int build_xt_ff(dim_handle_s* h, const std::string& lp, int dim, int mult, XtFF& F) {
+  LOOKUP(F.norm_g, lp + ".0.0.weight", true, dim);
+  LOOKUP(F.norm_b, lp + ".0.0.bias", false, dim);
+  LOOKUP(F.w1, lp + ".1.ff.0.0.weight", true, (int64_t)mult * dim, dim);
+  LOOKUP(F.b1, lp + ".1.ff.0.0.bias", true, (int64_t)mult * dim);
+  LOOKUP(F.w2, lp + ".1.ff.2.weight", true, dim, (int64_t)mult * dim);
+  LOOKUP(F.b2, lp + ".1.ff.2.bias", true, dim);
+  return DIM_OK;
+}
+
+int build_xt_encoder(dim_handle_s* h, const std::string& name, int dim_in, const dim_s2s_config& c, XtEncoder& E) {
+  const int inner = c.heads * c.dim_head;
+  E.dim_in = dim_in;
+  LOOKUP(E.proj_w, name + ".project_in.weight", true, c.dim, dim_in);
+  LOOKUP(E.proj_b, name + ".project_in.bias", false, c.dim);
+  LOOKUP(E.pos_emb, name + ".pos_emb.emb.weight", true, c.max_seq_len, c.dim);
+  E.attn.resize(c.depth);
+  E.ff.resize(c.depth);
+  for (int l = 0; l < c.depth; ++l) {
+    std::string p = name + ".attn_layers.layers.";
+    if (int e = build_xt_attn(h, p + std::to_string(2 * l), c.dim, c.dim, inner, false, E.attn[l])) return e;
+    if (int e = build_xt_ff(h, p + std::to_string(2 * l + 1), c.dim, c.ff_mult, E.ff[l])) return e;
+  }
+  LOOKUP(E.final_g, name + ".attn_layers.final_norm.weight", true, c.dim);
+  LOOKUP(E.final_b, name + ".attn_layers.final_norm.bias", false, c.dim);
+  return DIM_OK;
+}
+
+struct CtxWs {
+  float *x, *ln, *qkv, *att, *ff;
+  size_t bytes;
+};
+CtxWs carve_ctx(const dim_s2s_config& c, int B, int T, void* base) {
+  size_t R = (size_t)B * T;
+  const int inner = c.heads * c.dim_head;
+  char* p = static_cast<char*>(base);
+  CtxWs w{};
+  auto take = [&](size_t nfloat) {
+    float* r = reinterpret_cast<float*>(p);
+    p += align_up(nfloat * sizeof(float), 256);
+    return r;
+  };
+  w.x = take(R * c.dim); w.ln = take(R * c.dim); w.qkv = take(R * 3 * inner); w.att = take(R * inner);
+  w.ff = take(R * c.ff_mult * c.dim);
+  w.bytes = (size_t)(p - static_cast<char*>(base));
+  return w;
+}
+
+// ContinuousTransformerWrapper(x, mask, attn_mask=causal, return_embeddings=True); result left in w.x
+int xt_encoder_forward(const S2SModel& m, const XtEncoder& E, const float* in, const float* a_add, const uint8_t* mask,
+                       CtxWs& w, int B, int T, cudaStream_t s) {
+  const dim_s2s_config& c = m.cfg;
+  const int R = B * T, D = c.dim, inner = c.heads * c.dim_head, F = c.ff_mult * c.dim;
+  {  // x = project_in(in + a_add) + pos_emb[t] * dim^-0.5
+    GemmArgs a;
+    a.A = in; a.lda = E.dim_in; a.W = E.proj_w; a.bias = E.proj_b; a.C = w.x; a.ldc = D; a.M = R; a.N = D; a.K = E.dim_in;
+    a.a_add = a_add; a.tab = E.pos_emb; a.ldtab = D; a.tab_mode = 2; a.tab_T = T; a.tab_scale = 1.0f / sqrtf((float)D);
+    if (int e = launch_gemm_f32(a, s)) return e;
+  }
+  for (int l = 0; l < c.depth; ++l) {
+    const XtAttn& A = E.attn[l];
+    const XtFF& FF = E.ff[l];
+    if (int e = launch_layer_norm(w.x, A.norm_g, A.norm_b, w.ln, nullptr, R, D, 1e-5f, s)) return e;
+    {
+      GemmArgs a;
+      a.A = w.ln; a.lda = D; a.W = A.wqkv; a.C = w.qkv; a.ldc = 3 * inner; a.M = R; a.N = 3 * inner; a.K = D;
+      if (int e = launch_gemm_f32(a, s)) return e;
+    }
+    {
+      AttnArgs a;
+      a.q = w.qkv; a.k = w.qkv + inner; a.v = w.qkv + 2 * inner; a.ldq = a.ldk = a.ldv = 3 * inner;
+      a.out = w.att; a.ldo = inner; a.key_mask = mask; a.B = B; a.H = c.heads; a.Tq = T; a.Tk = T; a.Dh = c.dim_head;
+      a.scale = 1.0f / sqrtf((float)c.dim_head); a.causal = 1;
+      if (int e = launch_attention_prefill(a, s)) return e;
+    }
+    {
+      GemmArgs a;
+      a.A = w.att; a.lda = inner; a.W = A.wo; a.residual = w.x; a.ldr = D; a.C = w.x; a.ldc = D; a.M = R; a.N = D;
+      a.K = inner;
+      if (int e = launch_gemm_f32(a, s)) return e;
+    }
+    if (int e = launch_layer_norm(w.x, FF.norm_g, FF.norm_b, w.ln, nullptr, R, D, 1e-5f, s)) return e;
+    {
+      GemmArgs a;
+      a.A = w.ln; a.lda = D; a.W = FF.w1; a.bias = FF.b1; a.C = w.ff; a.ldc = F; a.M = R; a.N = F; a.K = D;
+      a.act = DIM_ACT_GELU_ERF;
+      if (int e = launch_gemm_f32(a, s)) return e;
+    }
+    {
+      GemmArgs a;
+      a.A = w.ff; a.lda = F; a.W = FF.w2; a.bias = FF.b2; a.residual = w.x; a.ldr = D; a.C = w.x; a.ldc = D; a.M = R;
+      a.N = D; a.K = F;
+      if (int e = launch_gemm_f32(a, s)) return e;
+    }
+  }
+  return launch_layer_norm(w.x, E.final_g, E.final_b, w.x, nullptr, R, D, 1e-5f, s);
+}
+
+struct GenWs {
+  std::vector<float*> cross_kv;            // per layer [B,T,2*inner]
+  std::vector<float*> self_k, self_v;      // per layer [B,steps+1,inner]
+  float *x, *ln, *qkv, *att, *ff, *logits;
+  int64_t* tokens;                         // [B, steps+1]
+  int* step;
+  size_t bytes;
+};
+GenWs carve_gen(const dim_s2s_config& c, int B, int T, int steps, void* base) {
+  const int inner = c.heads * c.dim_head, D = c.dim + c.dim_audio;
+  char* p = static_cast<char*>(base);
+  GenWs w{};
+  auto take = [&](size_t nfloat) {
+    float* r = reinterpret_cast<float*>(p);
+    p += align_up(nfloat * sizeof(float), 256);
+    return r;
+  };
+  for (int l = 0; l < c.depth; ++l) w.cross_kv.push_back(take((size_t)B * T * 2 * inner));
+  for (int l = 0; l < c.depth; ++l) {
+    w.self_k.push_back(take((size_t)B * (steps + 1) * inner));
+    w.self_v.push_back(take((size_t)B * (steps + 1) * inner));
+  }
+  w.x = take((size_t)B * D); w.ln = take((size_t)B * D); w.qkv = take((size_t)B * 3 * inner);
+  w.att = take((size_t)B * inner); w.ff = take((size_t)B * c.ff_mult * D); w.logits = take((size_t)B * c.num_tokens);
+  w.tokens = reinterpret_cast<int64_t*>(take((size_t)B * (steps + 1) * 2));
+  w.step = reinterpret_cast<int*>(take(64));
+  w.bytes = (size_t)(p - static_cast<char*>(base));
+  return w;
+}
+
+}  // namespace
+
+// ======================================================== C ABI ========================================================
+
+extern "C" int dim_create(dim_handle_t* out, int device) {
+  DIM_REQUIRE(out != nullptr, "dim_create: null out");
+  DIM_CHECK_CUDA(cudaSetDevice(device));
+  if (int e = ensure_device()) return e;
+  auto* h = new dim_handle_s();
+  h->device = device;
+  *out = h;
+  return DIM_OK;
+}
+
+extern "C" int dim_destroy(dim_handle_t h) {
+  if (!h) return DIM_OK;
+  for (void* p : h->owned) cudaFree(p);
+  delete h;
+  return DIM_OK;
+}
+
+extern "C" int dim_set_tensor(dim_handle_t h, const char* name, const void* ptr, int dtype, int ndim, const int64_t* shape) {
+  DIM_REQUIRE(h && name && ptr && ndim >= 0 && ndim <= 8, "dim_set_tensor: bad argument");
+  TensorRef t;
+  t.p = ptr;
+  t.dtype = dtype;
+  t.shape.assign(shape, shape + ndim);
+  h->tensors[name] = t;
+  return DIM_OK;
+}
+
+extern "C" int dim_vqvae_build(dim_handle_t h, const char* prefix_c, const dim_vq_config* cfg, int precision, int* model) {
+  DIM_REQUIRE(h && cfg && model, "dim_vqvae_build: null argument");
+  DIM_REQUIRE(precision == DIM_PREC_FP32, "dim_vqvae_build: only DIM_PREC_FP32 is implemented for the VQ-VAE");
+  const dim_vq_config& c = *cfg;
+  DIM_REQUIRE(c.hidden % 16 == 0 && c.hidden % c.heads == 0, "hidden must be a multiple of 16 and of heads");
+  DIM_REQUIRE(c.hidden / c.heads == 48 || c.hidden / c.heads == 64, "head dim must be 48 or 64");
+  DIM_REQUIRE(c.in_dim % 4 == 0 && c.zdim % 4 == 0 && c.ffn % 4 == 0, "dims must be multiples of 4");
+  std::string p = prefix_c ? prefix_c : "";
+  auto m = std::make_unique<VqModel>();
+  m->cfg = c;
+  m->precision = precision;
+  const int64_t H = c.hidden, Z = c.zdim;
+  const float *conv_w, *dconv_w;
+  LOOKUP(m->map_w, p + "encoder.vertice_mapping.0.weight", true, H, c.in_dim);
+  LOOKUP(m->map_b, p + "encoder.vertice_mapping.0.bias", true, H);
+  LOOKUP(conv_w, p + "encoder.squasher.0.0.weight", true, H, H, 5);
+  LOOKUP(m->conv_b, p + "encoder.squasher.0.0.bias", true, H);
+  LOOKUP(m->emb_w, p + "encoder.encoder_linear_embedding.net.weight", true, H, H);
+  LOOKUP(m->emb_b, p + "encoder.encoder_linear_embedding.net.bias", true, H);
+  LOOKUP(m->pe, p + "encoder.encoder_pos_embedding.pe", true, c.pe_max_len, 1, H);
+  LOOKUP(m->post_w, p + "encoder.encoder_linear_embedding_post.net.weight", true, Z, H);
+  LOOKUP(m->post_b, p + "encoder.encoder_linear_embedding_post.net.bias", true, Z);
+  if (int e = build_vq_stack(h, p + "encoder.encoder_transformer", c, m->enc)) return e;
+  LOOKUP(m->pre_w, p + "decoder.decoder_linear_embedding_pre.net.weight", true, H, Z);
+  LOOKUP(m->pre_b, p + "decoder.decoder_linear_embedding_pre.net.bias", true, H);
+  LOOKUP(dconv_w, p + "decoder.expander.0.0.weight", true, H, H, 5);
+  LOOKUP(m->dconv_b, p + "decoder.expander.0.0.bias", true, H);
+  LOOKUP(m->demb_w, p + "decoder.decoder_linear_embedding.net.weight", true, H, H);
+  LOOKUP(m->demb_b, p + "decoder.decoder_linear_embedding.net.bias", true, H);
+  LOOKUP(m->dpe, p + "decoder.decoder_pos_embedding.pe", true, c.pe_max_len, 1, H);
+  LOOKUP(m->rev_w, p + "decoder.vertice_map_reverse.weight", true, c.in_dim, H);
+  if (int e = build_vq_stack(h, p + "decoder.decoder_transformer", c, m->dec)) return e;
+  LOOKUP(m->codebook, p + "quantize.embedding.weight", true, c.n_embed, Z);
+  size_t cb = (size_t)H * H * 5 * sizeof(float);
+  if (int e = owned_alloc(h, cb, &m->conv_wr)) return e;
+  if (int e = owned_alloc(h, cb, &m->dconv_wr)) return e;
+  if (int e = dim_repack_conv_weight(conv_w, m->conv_wr, c.hidden, c.hidden, nullptr)) return e;
+  if (int e = dim_repack_conv_weight(dconv_w, m->dconv_wr, c.hidden, c.hidden, nullptr)) return e;
+  DIM_CHECK_CUDA(cudaStreamSynchronize(nullptr));
+  h->vq.push_back(std::move(m));
+  *model = (int)h->vq.size() - 1;
+  return DIM_OK;
+}
+
+extern "C" size_t dim_vqvae_workspace_bytes(dim_handle_t h, int model, int B, int T) {
+  if (!h || model < 0 || model >= (int)h->vq.size() || B <= 0 || T <= 0) return 0;
+  return carve_vq(h->vq[model]->cfg, B, T, nullptr).bytes;
+}
+
+extern "C" int dim_vqvae_encode(dim_handle_t h, int model, const float* x, const int32_t* lens, const int32_t* batch_index,
+                                int B, int T, int64_t* idx, float* z, float* quant_bcl, void* ws, size_t ws_bytes,
+                                void* stream) {
+  DIM_REQUIRE(h && model >= 0 && model < (int)h->vq.size(), "dim_vqvae_encode: bad model");
+  DIM_REQUIRE(x && B > 0 && T > 0 && (idx || z), "dim_vqvae_encode: bad argument");
+  const VqModel& m = *h->vq[model];
+  const dim_vq_config& c = m.cfg;
+  DIM_REQUIRE(batch_index != nullptr || B <= c.pe_max_len, "batch larger than the positional table (SURVEY F4/H3)");
+  VqWs w = carve_vq(c, B, T, ws);
+  if (ws == nullptr || ws_bytes < w.bytes) return fail(DIM_EWORKSPACE, "dim_vqvae_encode: workspace too small");
+  cudaStream_t s = as_stream(stream);
+  const int R = B * T, H = c.hidden;
+  {  // h0 = leaky(x @ map^T + b)
+    GemmArgs a;
+    a.A = x; a.lda = c.in_dim; a.W = m.map_w; a.bias = m.map_b; a.C = w.h0; a.ldc = H; a.M = R; a.N = H; a.K = c.in_dim;
+    a.act = DIM_ACT_LEAKY; a.slope = c.neg_slope;
+    if (int e = launch_gemm_f32(a, s)) return e;
+  }
+  if (int e = vq_trunk(m, m.enc, m.conv_wr, m.conv_b, m.emb_w, m.emb_b, m.pe, w, lens, batch_index, B, T, s)) return e;
+  float* zbuf = z ? z : w.z;
+  {
+    GemmArgs a;
+    a.A = w.x; a.lda = H; a.W = m.post_w; a.bias = m.post_b; a.C = zbuf; a.ldc = c.zdim; a.M = R; a.N = c.zdim; a.K = H;
+    if (int e = launch_gemm_f32(a, s)) return e;
+  }
+  int64_t* ibuf = idx ? idx : w.idx;
+  if (idx || quant_bcl)
+    if (int e = launch_vq_argmin(zbuf, m.codebook, ibuf, R, c.zdim, c.n_embed, s)) return e;
+  if (quant_bcl)
+    if (int e = launch_vq_gather_bcl(ibuf, m.codebook, quant_bcl, B, T, c.zdim, c.n_embed, s)) return e;
+  return DIM_OK;
+}
+
+extern "C" int dim_vqvae_decode(dim_handle_t h, int model, const int64_t* codes, const float* quant_bcl,
+                                const int32_t* batch_index, int B, int L, float* out, void* ws, size_t ws_bytes,
+                                void* stream) {
+  DIM_REQUIRE(h && model >= 0 && model < (int)h->vq.size(), "dim_vqvae_decode: bad model");
+  DIM_REQUIRE((codes != nullptr) != (quant_bcl != nullptr), "dim_vqvae_decode: pass exactly one of codes / quant");
+  DIM_REQUIRE(out && B > 0 && L > 0, "dim_vqvae_decode: bad argument");
+  const VqModel& m = *h->vq[model];
+  const dim_vq_config& c = m.cfg;
+  DIM_REQUIRE(batch_index != nullptr || B <= c.pe_max_len, "batch larger than the positional table (SURVEY F4/H3)");
+  VqWs w = carve_vq(c, B, L, ws);
+  if (ws == nullptr || ws_bytes < w.bytes) return fail(DIM_EWORKSPACE, "dim_vqvae_decode: workspace too small");
+  cudaStream_t s = as_stream(stream);
+  const int R = B * L, H = c.hidden;
+  if (codes) {
+    if (int e = launch_vq_gather(codes, m.codebook, w.z, R, c.zdim, c.n_embed, nullptr, s)) return e;
+  } else {
+    if (int e = launch_rows_from_bcl(quant_bcl, w.z, B, L, c.zdim, s)) return e;
+  }
+  {
+    GemmArgs a;
+    a.A = w.z; a.lda = c.zdim; a.W = m.pre_w; a.bias = m.pre_b; a.C = w.h0; a.ldc = H; a.M = R; a.N = H; a.K = c.zdim;
+    if (int e = launch_gemm_f32(a, s)) return e;
+  }
+  if (int e = vq_trunk(m, m.dec, m.dconv_wr, m.dconv_b, m.demb_w, m.demb_b, m.dpe, w, nullptr, batch_index, B, L, s))
+    return e;
+  {
+    GemmArgs a;
+    a.A = w.x; a.lda = H; a.W = m.rev_w; a.C = out; a.ldc = c.in_dim; a.M = R; a.N = c.in_dim; a.K = H;
+    if (int e = launch_gemm_f32(a, s)) return e;
+  }
+  return DIM_OK;
+}
+
+extern "C" int dim_slmft_build(dim_handle_t h, const dim_s2s_config* cfg, int precision, int* model) {
+  DIM_REQUIRE(h && cfg && model, "dim_slmft_build: null argument");
+  DIM_REQUIRE(precision == DIM_PREC_FP32, "dim_slmft_build: only DIM_PREC_FP32 is implemented so far");
+  const dim_s2s_config& c = *cfg;
+  DIM_REQUIRE(c.dim_head == 64, "x-transformers dim_head must be 64");
+  DIM_REQUIRE(c.dim % 4 == 0 && c.dim_in % 4 == 0 && c.dim_audio % 4 == 0, "dims must be multiples of 4");
+  DIM_REQUIRE(c.num_tokens <= 1024, "num_tokens must be <= 1024");
+  auto m = std::make_unique<S2SModel>();
+  m->cfg = c;
+  m->precision = precision;
+  const int inner = c.heads * c.dim_head, D = c.dim + c.dim_audio;
+  if (int e = build_xt_encoder(h, "encoder_s", c.dim_in, c, m->enc_s)) return e;
+  if (int e = build_xt_encoder(h, "encoder_joint", c.dim, c, m->enc_joint)) return e;
+  LOOKUP(m->patch_s, "patch_embed_s", true, 1, 1, c.dim_in);
+  LOOKUP(m->patch_dec_s, "patch_embed_dec_s", true, 1, 1, c.dim);
+  LOOKUP(m->norm_s_g, "norm_s.weight", true, c.dim);
+  LOOKUP(m->norm_s_b, "norm_s.bias", true, c.dim);
+  const std::string dn = "decoder_joint.net";
+  LOOKUP(m->token_emb, dn + ".token_emb.emb.weight", true, c.num_tokens, D);
+  m->self_attn.resize(c.depth);
+  m->cross_attn.resize(c.depth);
+  m->ff.resize(c.depth);
+  for (int l = 0; l < c.depth; ++l) {
+    std::string p = dn + ".attn_layers.layers.";
+    if (int e = build_xt_attn(h, p + std::to_string(3 * l), D, D, inner, false, m->self_attn[l])) return e;
+    if (int e = build_xt_attn(h, p + std::to_string(3 * l + 1), D, D, inner, true, m->cross_attn[l])) return e;
+    if (int e = build_xt_ff(h, p + std::to_string(3 * l + 2), D, c.ff_mult, m->ff[l])) return e;
+  }
+  LOOKUP(m->final_g, dn + ".attn_layers.final_norm.weight", true, D);
+  LOOKUP(m->final_b, dn + ".attn_layers.final_norm.bias", false, D);
+  LOOKUP(m->logits_w, dn + ".to_logits.weight", true, c.num_tokens, D);
+  LOOKUP(m->logits_b, dn + ".to_logits.bias", false, c.num_tokens);
+  h->s2s.push_back(std::move(m));
+  *model = (int)h->s2s.size() - 1;
+  return DIM_OK;
+}
+
+extern "C" size_t dim_slmft_workspace_bytes(dim_handle_t h, int model, int B, int T, int steps) {
+  if (!h || model < 0 || model >= (int)h->s2s.size() || B <= 0 || T <= 0) return 0;
+  const dim_s2s_config& c = h->s2s[model]->cfg;
+  size_t a = carve_ctx(c, B, T, nullptr).bytes;
+  size_t b = steps > 0 ? carve_gen(c, B, T, steps, nullptr).bytes : 0;
+  return a > b ? a : b;
+}
+
+extern "C" int dim_slmft_context(dim_handle_t h, int model, const float* v_speaker, const float* v_audio,
+                                 const uint8_t* mask, int B, int T, float* ctx, void* ws, size_t ws_bytes, void* stream) {
+  DIM_REQUIRE(h && model >= 0 && model < (int)h->s2s.size(), "dim_slmft_context: bad model");
+  DIM_REQUIRE(v_speaker && v_audio && ctx && B > 0 && T > 0, "dim_slmft_context: bad argument");
+  const S2SModel& m = *h->s2s[model];
+  const dim_s2s_config& c = m.cfg;
+  DIM_REQUIRE(T <= c.max_seq_len, "sequence longer than the positional table");
+  CtxWs w = carve_ctx(c, B, T, ws);
+  if (ws == nullptr || ws_bytes < w.bytes) return fail(DIM_EWORKSPACE, "dim_slmft_context: workspace too small");
+  cudaStream_t s = as_stream(stream);
+  if (int e = xt_encoder_forward(m, m.enc_s, v_speaker, m.patch_s, mask, w, B, T, s)) return e;
+  // encoder_joint's project_in writes w.x, so its input (encoder_s's output in w.x) is staged in w.att, which the
+  // first attention of encoder_joint overwrites only after project_in has consumed it (same stream).
+  DIM_CHECK_CUDA(cudaMemcpyAsync(w.att, w.x, (size_t)B * T * c.dim * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (int e = xt_encoder_forward(m, m.enc_joint, w.att, nullptr, mask, w, B, T, s)) return e;
+  if (int e = launch_layer_norm(w.x, m.norm_s_g, m.norm_s_b, w.ln, nullptr, B * T, c.dim, 1e-5f, s)) return e;
+  return launch_build_context(w.ln, m.patch_dec_s, v_audio, ctx, nullptr, (size_t)B * T, c.dim, c.dim_audio, s);
+}
+
+extern "C" int dim_slmft_generate(dim_handle_t h, int model, const float* ctx, const uint8_t* mask, const int64_t* prompt,
+                                  int B, int T, int steps, float temperature, int top_k, const float* uniforms,
+                                  int64_t* out_codes, float* logits_out, void* ws, size_t ws_bytes, void* stream) {
+  DIM_REQUIRE(h && model >= 0 && model < (int)h->s2s.size(), "dim_slmft_generate: bad model");
+  DIM_REQUIRE(ctx && prompt && out_codes && B > 0 && T > 0 && steps > 0, "dim_slmft_generate: bad argument");
+  DIM_REQUIRE(temperature >= 0.f, "temperature must be >= 0");
+  DIM_REQUIRE(temperature == 0.f || (uniforms && top_k > 0), "sampling needs uniforms and top_k");
+  const S2SModel& m = *h->s2s[model];
+  const dim_s2s_config& c = m.cfg;
+  const int inner = c.heads * c.dim_head, D = c.dim + c.dim_audio, F = c.ff_mult * D, V = c.num_tokens;
+  GenWs w = carve_gen(c, B, T, steps, ws);
+  if (ws == nullptr || ws_bytes < w.bytes) return fail(DIM_EWORKSPACE, "dim_slmft_generate: workspace too small");
+  cudaStream_t s = as_stream(stream);
+  const float scale = 1.0f / sqrtf((float)c.dim_head);
+
+  for (int l = 0; l < c.depth; ++l) {  // cross-attention K/V of the whole context, once
+    GemmArgs a;
+    a.A = ctx; a.lda = D; a.W = m.cross_attn[l].wkv; a.C = w.cross_kv[l]; a.ldc = 2 * inner; a.M = B * T; a.N = 2 * inner;
+    a.K = D;
+    if (int e = launch_gemm_f32(a, s)) return e;
+  }
+  DIM_CHECK_CUDA(cudaMemcpy2DAsync(w.tokens, (size_t)(steps + 1) * sizeof(int64_t), prompt, sizeof(int64_t), sizeof(int64_t),
+                                   B, cudaMemcpyDeviceToDevice, s));
+  if (int e = launch_set_step(w.step, 0, s)) return e;
+
+  const int max_keys = std::max(T, steps + 1);
+  for (int st = 0; st < steps; ++st) {
+    if (int e = launch_embed_tokens(w.tokens, steps + 1, w.step, m.token_emb, w.x, B, D, V, s)) return e;
+    for (int l = 0; l < c.depth; ++l) {
+      const XtAttn& SA = m.self_attn[l];
+      const XtAttn& CA = m.cross_attn[l];
+      const XtFF& FF = m.ff[l];
+      // --- causal self attention with KV cache
+      if (int e = launch_layer_norm(w.x, SA.norm_g, SA.norm_b, w.ln, nullptr, B, D, 1e-5f, s)) return e;
+      {
+        GemmArgs a;
+        a.A = w.ln; a.lda = D; a.W = SA.wqkv; a.C = w.qkv; a.ldc = 3 * inner; a.M = B; a.N = 3 * inner; a.K = D;
+        if (int e = launch_gemm_f32(a, s)) return e;
+      }
+      {
+        DecodeAttnArgs a;
+        a.q = w.qkv; a.ldq = 3 * inner; a.k = w.self_k[l]; a.v = w.self_v[l];
+        a.kv_batch_stride = (size_t)(steps + 1) * inner; a.kv_tok_stride = inner;
+        a.k_new = w.qkv + inner; a.v_new = w.qkv + 2 * inner; a.ld_new = 3 * inner; a.append = 1; a.step = w.step;
+        a.out = w.att; a.ldo = inner; a.B = B; a.H = c.heads; a.Tk = 0; a.scale = scale;
+        if (int e = launch_attention_decode(a, max_keys, s)) return e;
+      }
+      {
+        GemmArgs a;
+        a.A = w.att; a.lda = inner; a.W = SA.wo; a.residual = w.x; a.ldr = D; a.C = w.x; a.ldc = D; a.M = B; a.N = D;
+        a.K = inner;
+        if (int e = launch_gemm_f32(a, s)) return e;
+      }
+      // --- cross attention over the cached context K/V
+      if (int e = launch_layer_norm(w.x, CA.norm_g, CA.norm_b, w.ln, nullptr, B, D, 1e-5f, s)) return e;
+      {
+        GemmArgs a;
+        a.A = w.ln; a.lda = D; a.W = CA.wq; a.C = w.qkv; a.ldc = inner; a.M = B; a.N = inner; a.K = D;
+        if (int e = launch_gemm_f32(a, s)) return e;
+      }
+      {
+        DecodeAttnArgs a;
+        a.q = w.qkv; a.ldq = inner; a.k = w.cross_kv[l]; a.v = w.cross_kv[l] + inner;
+        a.kv_batch_stride = (size_t)T * 2 * inner; a.kv_tok_stride = 2 * inner; a.append = 0; a.step = w.step;
+        a.key_mask = mask; a.out = w.att; a.ldo = inner; a.B = B; a.H = c.heads; a.Tk = T; a.scale = scale;
+        if (int e = launch_attention_decode(a, max_keys, s)) return e;
+      }
+      {
+        GemmArgs a;
+        a.A = w.att; a.lda = inner; a.W = CA.wo; a.residual = w.x; a.ldr = D; a.C = w.x; a.ldc = D; a.M = B; a.N = D;
+        a.K = inner;
+        if (int e = launch_gemm_f32(a, s)) return e;
+      }
+      // --- feed forward
+      if (int e = launch_layer_norm(w.x, FF.norm_g, FF.norm_b, w.ln, nullptr, B, D, 1e-5f, s)) return e;
+      {
+        GemmArgs a;
+        a.A = w.ln; a.lda = D; a.W = FF.w1; a.bias = FF.b1; a.C = w.ff; a.ldc = F; a.M = B; a.N = F; a.K = D;
+        a.act = DIM_ACT_GELU_ERF;
+        if (int e = launch_gemm_f32(a, s)) return e;
+      }
+      {
+        GemmArgs a;
+        a.A = w.ff; a.lda = F; a.W = FF.w2; a.bias = FF.b2; a.residual = w.x; a.ldr = D; a.C = w.x; a.ldc = D; a.M = B;
+        a.N = D; a.K = F;
+        if (int e = launch_gemm_f32(a, s)) return e;
+      }
+    }
+    if (int e = launch_layer_norm(w.x, m.final_g, m.final_b, w.ln, nullptr, B, D, 1e-5f, s)) return e;
+    {
+      GemmArgs a;
+      a.A = w.ln; a.lda = D; a.W = m.logits_w; a.bias = m.logits_b; a.C = w.logits; a.ldc = V; a.M = B; a.N = V; a.K = D;
+      if (int e = launch_gemm_f32(a, s)) return e;
+    }
+    if (int e = launch_sample(w.logits, B, V, temperature, top_k, uniforms, steps, w.step, w.tokens, steps + 1, 1,
+                              logits_out, steps * V, s))
+      return e;
+    if (int e = launch_advance_step(w.step, s)) return e;
+  }
+  DIM_CHECK_CUDA(cudaMemcpy2DAsync(out_codes, (size_t)steps * sizeof(int64_t), w.tokens + 1,
+                                   (size_t)(steps + 1) * sizeof(int64_t), (size_t)steps * sizeof(int64_t), B,
+                                   cudaMemcpyDeviceToDevice, s));
+  return DIM_OK;
+}

@@ -1,0 +1,291 @@
+// fp32 FFMA GEMMs with fused prologue/epilogue (see gemm_f32.cuh).  sm_100a.
+#include "gemm_f32.cuh"
+
+namespace dimb {
+
+namespace {
+
+constexpr int BK = 16;
+
+__device__ __forceinline__ float epilogue_elem(const GemmArgs& p, float v, int row, int col) {
+  if (p.bias) v += __ldg(p.bias + col);
+  if (p.tab_mode == 1) {
+    int g = row / p.tab_T;
+    if (p.tab_index) g = __ldg(p.tab_index + g);
+    v = __fadd_rn(v, __ldg(p.tab + (size_t)g * p.ldtab + col));
+  } else if (p.tab_mode == 2) {
+    int g = row % p.tab_T;
+    v = __fadd_rn(v, __fmul_rn(__ldg(p.tab + (size_t)g * p.ldtab + col), p.tab_scale));
+  }
+  v = act_apply(v, p.act, p.slope);
+  if (p.residual) v = __fadd_rn(v, p.residual[(size_t)row * p.ldr + col]);   // plain load: may alias C (in-place residual)
+  return v;
+}
+
+// Source pointer of A(row, k0..k0+3); handles conv-mode gathering.  k0 % 4 == 0.
+__device__ __forceinline__ const float* a_src(const GemmArgs& p, int row, int k0) {
+  if (p.conv_T > 0) {
+    int tap = k0 / p.conv_C, c = k0 - tap * p.conv_C;
+    int b = row / p.conv_T, t = row - b * p.conv_T;
+    int L = p.lens ? __ldg(p.lens + b) : p.conv_T;
+    int ts = min(max(t + tap - 2, 0), L - 1);
+    return p.A + ((size_t)b * p.conv_T + ts) * p.lda + c;
+  }
+  return p.A + (size_t)row * p.lda + k0;
+}
+
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_f32_tiled(const GemmArgs p) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  constexpr int TMG = TM > 4 ? 2 : 1, TMW = TM / TMG;   // row groups / width
+  constexpr int TNG = TN > 4 ? 2 : 1, TNW = TN / TNG;
+  static_assert(TNW == 4, "column micro-tile is one float4 per group");
+  constexpr int LA = (BM * 4 + NT - 1) / NT, LW = (BN * 4 + NT - 1) / NT;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Ws[BK][BN + 4];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  float4 ra[LA], rw[LW];
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < LA; ++i) {
+      int idx = tid + i * NT;
+      int r = idx >> 2, kq = (idx & 3) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < BM * 4 && m0 + r < p.M && k0 + kq < p.K) {
+        v = __ldg(reinterpret_cast<const float4*>(a_src(p, m0 + r, k0 + kq)));
+        if (p.a_add) {
+          float4 e = __ldg(reinterpret_cast<const float4*>(p.a_add + k0 + kq));
+          v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+        }
+      }
+      ra[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < LW; ++i) {
+      int idx = tid + i * NT;
+      int r = idx >> 2, kq = (idx & 3) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < BN * 4 && n0 + r < p.N && k0 + kq < p.K)
+        v = __ldg(reinterpret_cast<const float4*>(p.W + (size_t)(n0 + r) * p.K + k0 + kq));
+      rw[i] = v;
+    }
+  };
+  auto store_tiles = [&]() {
+#pragma unroll
+    for (int i = 0; i < LA; ++i) {
+      int idx = tid + i * NT;
+      if (idx < BM * 4) {
+        int r = idx >> 2, kq = (idx & 3) * 4;
+        As[kq + 0][r] = ra[i].x; As[kq + 1][r] = ra[i].y; As[kq + 2][r] = ra[i].z; As[kq + 3][r] = ra[i].w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < LW; ++i) {
+      int idx = tid + i * NT;
+      if (idx < BN * 4) {
+        int r = idx >> 2, kq = (idx & 3) * 4;
+        Ws[kq + 0][r] = rw[i].x; Ws[kq + 1][r] = rw[i].y; Ws[kq + 2][r] = rw[i].z; Ws[kq + 3][r] = rw[i].w;
+      }
+    }
+  };
+
+  const int nk = (p.K + BK - 1) / BK;
+  load_tiles(0);
+  store_tiles();
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    if (kt + 1 < nk) load_tiles((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[TM], w[TN];
+#pragma unroll
+      for (int g = 0; g < TMG; ++g) {
+        const float* src = &As[k][g * (BM / TMG) + ty * TMW];
+        if (TMW == 4) {
+          float4 v = *reinterpret_cast<const float4*>(src);
+          a[g * TMW + 0] = v.x; a[g * TMW + 1] = v.y; a[g * TMW + 2] = v.z; a[g * TMW + 3] = v.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < TMW; ++i) a[g * TMW + i] = src[i];
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < TNG; ++g) {
+        float4 v = *reinterpret_cast<const float4*>(&Ws[k][g * (BN / TNG) + tx * TNW]);
+        w[g * 4 + 0] = v.x; w[g * 4 + 1] = v.y; w[g * 4 + 2] = v.z; w[g * 4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+    if (kt + 1 < nk) {
+      store_tiles();
+      __syncthreads();
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int row = m0 + (i / TMW) * (BM / TMG) + ty * TMW + (i % TMW);
+    if (row >= p.M) continue;
+#pragma unroll
+    for (int g = 0; g < TNG; ++g) {
+      int col = n0 + g * (BN / TNG) + tx * TNW;
+      if (col >= p.N) continue;
+      float4 o;
+      o.x = epilogue_elem(p, acc[i][g * 4 + 0], row, col + 0);
+      o.y = epilogue_elem(p, acc[i][g * 4 + 1], row, col + 1);
+      o.z = epilogue_elem(p, acc[i][g * 4 + 2], row, col + 2);
+      o.w = epilogue_elem(p, acc[i][g * 4 + 3], row, col + 3);
+      if (p.C) *reinterpret_cast<float4*>(p.C + (size_t)row * p.ldc + col) = o;
+      if (p.Cb) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(p.Cb + (size_t)row * p.ldcb + col) = pk;
+      }
+    }
+  }
+}
+
+// Skinny GEMM: one warp per output column, all MT rows; W streamed once with 128-bit loads, A served by L1.
+template <int MT>
+__global__ void __launch_bounds__(128) gemm_f32_skinny(const GemmArgs p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 4 + warp;
+  if (n >= p.N) return;
+  const int k4n = p.K >> 2;
+  const float4* w = reinterpret_cast<const float4*>(p.W + (size_t)n * p.K);
+  float acc[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) acc[m] = 0.f;
+
+  constexpr int U = 4;
+  for (int k4 = lane; k4 < k4n; k4 += 32 * U) {
+    float4 wv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int kk = k4 + u * 32;
+      wv[u] = kk < k4n ? __ldcs(w + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int kk = k4 + u * 32;
+      if (kk < k4n) {
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.a_add) e = __ldg(reinterpret_cast<const float4*>(p.a_add) + kk);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          if (m < p.M) {
+            float4 av = __ldg(reinterpret_cast<const float4*>(p.A + (size_t)m * p.lda) + kk);
+            acc[m] = fmaf(av.x + e.x, wv[u].x, acc[m]);
+            acc[m] = fmaf(av.y + e.y, wv[u].y, acc[m]);
+            acc[m] = fmaf(av.z + e.z, wv[u].z, acc[m]);
+            acc[m] = fmaf(av.w + e.w, wv[u].w, acc[m]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MT; ++m) acc[m] = warp_sum(acc[m]);
+  if (lane == 0) {
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      if (m < p.M) {
+        float o = epilogue_elem(p, acc[m], m, n);
+        if (p.C) p.C[(size_t)m * p.ldc + n] = o;
+        if (p.Cb) p.Cb[(size_t)m * p.ldcb + n] = __float2bfloat16_rn(o);
+      }
+    }
+  }
+}
+
+__global__ void repack_conv_kernel(const float* __restrict__ w, float* __restrict__ o, int Cout, int Cin) {
+  size_t n = (size_t)Cout * Cin * 5;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int c = i % Cin;
+    int tap = (i / Cin) % 5;
+    int co = i / ((size_t)Cin * 5);
+    o[i] = w[((size_t)co * Cin + c) * 5 + tap];
+  }
+}
+
+template <int BM, int BN, int TM, int TN>
+int launch_tiled(const GemmArgs& a, cudaStream_t s) {
+  dim3 grid(cdiv(a.N, BN), cdiv(a.M, BM));
+  gemm_f32_tiled<BM, BN, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, s>>>(a);
+  DIM_LAUNCHED();
+  return DIM_OK;
+}
+
+}  // namespace
+
+int launch_gemm_f32(const GemmArgs& a, cudaStream_t s) {
+  DIM_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem");
+  DIM_REQUIRE(a.K % 4 == 0 && a.N % 4 == 0, "gemm: K and N must be multiples of 4");
+  DIM_REQUIRE(a.lda % 4 == 0 && (a.C == nullptr || a.ldc % 4 == 0), "gemm: leading dims must be multiples of 4");
+  DIM_REQUIRE(a.C != nullptr || a.Cb != nullptr, "gemm: no output");
+  if (a.conv_T > 0) DIM_REQUIRE(a.conv_C % BK == 0 && a.K == 5 * a.conv_C, "gemm: conv mode needs Cin % 16 == 0");
+  if (a.M <= 8 && a.conv_T == 0) {
+    dim3 grid(cdiv(a.N, 4));
+    if (a.M == 1) gemm_f32_skinny<1><<<grid, 128, 0, s>>>(a);
+    else if (a.M == 2) gemm_f32_skinny<2><<<grid, 128, 0, s>>>(a);
+    else if (a.M <= 4) gemm_f32_skinny<4><<<grid, 128, 0, s>>>(a);
+    else gemm_f32_skinny<8><<<grid, 128, 0, s>>>(a);
+    DIM_LAUNCHED();
+    return DIM_OK;
+  }
+  // Pick the tile so that the grid covers the 148 SMs when it can.
+  long tiles128 = (long)cdiv(a.M, 128) * cdiv(a.N, 128);
+  long tiles64 = (long)cdiv(a.M, 64) * cdiv(a.N, 64);
+  if (tiles128 >= 148) return launch_tiled<128, 128, 8, 8>(a, s);
+  if (tiles64 >= 96 || a.M > 32) return launch_tiled<64, 64, 4, 4>(a, s);
+  return launch_tiled<32, 64, 2, 4>(a, s);
+}
+
+}  // namespace dimb
+
+// ---- C ABI ------------------------------------------------------------------------------------------------------
+using namespace dimb;
+
+extern "C" int dim_linear_f32(const float* A, int lda, const float* W, const float* bias, const float* residual,
+                              int ldr, float* C, int ldc, int M, int N, int K, int act, float slope, void* stream) {
+  if (int e = ensure_device()) return e;
+  GemmArgs a;
+  a.A = A; a.lda = lda; a.W = W; a.bias = bias; a.residual = residual; a.ldr = ldr; a.C = C; a.ldc = ldc;
+  a.M = M; a.N = N; a.K = K; a.act = act; a.slope = slope;
+  return launch_gemm_f32(a, as_stream(stream));
+}
+
+extern "C" int dim_conv5_leaky_f32(const float* x, const float* Wr, const float* bias, const int32_t* lens, float* y,
+                                   int B, int T, int C, float slope, void* stream) {
+  if (int e = ensure_device()) return e;
+  GemmArgs a;
+  a.A = x; a.lda = C; a.W = Wr; a.bias = bias; a.C = y; a.ldc = C;
+  a.M = B * T; a.N = C; a.K = 5 * C; a.act = DIM_ACT_LEAKY; a.slope = slope;
+  a.conv_T = T; a.conv_C = C; a.lens = lens;
+  return launch_gemm_f32(a, as_stream(stream));
+}
+
+
+extern "C" int dim_repack_conv_weight(const float* w_oik, float* w_oki, int Cout, int Cin, void* stream) {
+  if (int e = ensure_device()) return e;
+  DIM_REQUIRE(Cout > 0 && Cin > 0, "repack: bad shape");
+  repack_conv_kernel<<<148 * 4, 256, 0, as_stream(stream)>>>(w_oik, w_oki, Cout, Cin);
+  DIM_LAUNCHED();
+  return DIM_OK;
+}

@@ -1,0 +1,29 @@
+// fp32 GEMM family (parity mode): C = epilogue(A @ W^T), nn.Linear weight layout W[N,K].
+//   * tiled register-blocked FFMA kernel for M > 8 (also serves the 5-tap replicate-padded Conv1d as an implicit GEMM)
+//   * weight-streaming skinny kernel for M <= 8 (the autoregressive decode step at small batch: HBM-bound on W)
+#pragma once
+#include "common.cuh"
+
+namespace dimb {
+
+struct GemmArgs {
+  const float* A = nullptr; int lda = 0;      // [M,K] rows lda apart (conv mode: frames (B,T,Cin), lda = Cin)
+  const float* W = nullptr;                   // [N,K] row-major
+  const float* bias = nullptr;                // [N]
+  const float* residual = nullptr; int ldr = 0;   // [M,N], added after the activation
+  float* C = nullptr; int ldc = 0;            // [M,N]
+  __nv_bfloat16* Cb = nullptr; int ldcb = 0;  // optional bf16 copy of C
+  int M = 0, N = 0, K = 0;
+  int act = DIM_ACT_NONE; float slope = 0.f;
+  const float* a_add = nullptr;               // [K] added to every row of A while loading (patch_embed_s)
+  int conv_T = 0, conv_C = 0;                 // conv mode when conv_T > 0: K = 5*conv_C, row r=(b,t) gathers t-2..t+2 clamped
+  const int32_t* lens = nullptr;              // [B] valid lengths for the conv clamp
+  const float* tab = nullptr; int ldtab = 0;  // table added before the activation:
+  int tab_mode = 0;                           //   1: row tab_index[r / tab_T] (or r / tab_T)  -- pe[batch]  (F4 quirk)
+  const int32_t* tab_index = nullptr;         //   2: row (r % tab_T)                          -- pos_emb[t] * tab_scale
+  int tab_T = 1; float tab_scale = 1.f;
+};
+
+int launch_gemm_f32(const GemmArgs& a, cudaStream_t s);
+
+}  // namespace dimb

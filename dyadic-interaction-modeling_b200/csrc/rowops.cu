@@ -1,0 +1,302 @@
+// Row-wise kernels: LayerNorm, InstanceNorm over time, embedding/context assembly, logits sampling.  All HBM-bound:
+// coalesced 128-bit accesses, warp-shuffle reductions, grids sized from the row count.
+#include "rowops.cuh"
+
+namespace dimb {
+
+namespace {
+
+// One warp per row.  dim % 4 == 0, dim <= 128 * MAXV (MAXV float4 per lane kept in registers: one HBM read per element).
+template <int MAXV>
+__global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ gain,
+                                                         const float* __restrict__ bias, float* __restrict__ y,
+                                                         __nv_bfloat16* __restrict__ yb, int rows, int dim, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int n4 = dim >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * dim);
+  float4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int c = lane + 32 * i;
+    if (c < n4) {
+      v[i] = xr[c];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / (float)dim;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int c = lane + 32 * i;
+    if (c < n4) {
+      float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (cc * cc + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)dim + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int c = lane + 32 * i;
+    if (c < n4) {
+      float4 g = __ldg(reinterpret_cast<const float4*>(gain) + c);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x; o.y = (v[i].y - mean) * rstd * g.y;
+      o.z = (v[i].z - mean) * rstd * g.z; o.w = (v[i].w - mean) * rstd * g.w;
+      if (bias) {
+        float4 b = __ldg(reinterpret_cast<const float4*>(bias) + c);
+        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+      }
+      if (y) reinterpret_cast<float4*>(y + (size_t)warp * dim)[c] = o;
+      if (yb) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(yb + (size_t)warp * dim)[c] = pk;
+      }
+    }
+  }
+}
+
+// InstanceNorm1d over time on frames (B,T,C): block = 32 channels x 8 time lanes of one sample.
+__global__ void __launch_bounds__(256) instance_norm_kernel(float* __restrict__ x, const int32_t* __restrict__ lens, int T,
+                                                            int C, float eps) {
+  __shared__ float red[8][33];
+  __shared__ float stat[2][32];
+  const int b = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), tl = threadIdx.x >> 5;
+  const int L = lens ? min(lens[b], T) : T;
+  float* xb = x + (size_t)b * T * C;
+  const bool ok = c < C;
+  float s = 0.f;
+  if (ok)
+    for (int t = tl; t < L; t += 8) s += xb[(size_t)t * C + c];
+  red[tl][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (tl == 0) {
+    float m = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m += red[i][threadIdx.x];
+    stat[0][threadIdx.x] = m / (float)L;
+  }
+  __syncthreads();
+  const float mean = stat[0][threadIdx.x & 31];
+  float q = 0.f;
+  if (ok)
+    for (int t = tl; t < L; t += 8) {
+      float d = xb[(size_t)t * C + c] - mean;
+      q += d * d;
+    }
+  red[tl][threadIdx.x & 31] = q;
+  __syncthreads();
+  if (tl == 0) {
+    float m = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m += red[i][threadIdx.x];
+    stat[1][threadIdx.x] = rsqrtf(m / (float)L + eps);     // biased variance, like F.instance_norm
+  }
+  __syncthreads();
+  const float rstd = stat[1][threadIdx.x & 31];
+  if (ok)
+    for (int t = tl; t < L; t += 8) {
+      size_t o = (size_t)t * C + c;
+      xb[o] = (xb[o] - mean) * rstd;
+    }
+}
+
+// ctx[b,t,:] = cat(x_s[b,t,:] + pe_dec[:], audio[b,t,:])      seq2seq_pretrain.py:445-446
+__global__ void build_context_kernel(const float* __restrict__ xs, const float* __restrict__ pe_dec,
+                                     const float* __restrict__ audio, float* __restrict__ ctx, __nv_bfloat16* ctxb,
+                                     size_t rows, int d1, int d2) {
+  const int d4 = (d1 + d2) >> 2, a4 = d1 >> 2;
+  size_t total = rows * d4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t r = i / d4;
+    int c = (int)(i - r * d4);
+    float4 v;
+    if (c < a4) {
+      v = reinterpret_cast<const float4*>(xs + r * d1)[c];
+      float4 e = __ldg(reinterpret_cast<const float4*>(pe_dec) + c);
+      v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+    } else {
+      v = reinterpret_cast<const float4*>(audio + r * d2)[c - a4];
+    }
+    if (ctx) reinterpret_cast<float4*>(ctx)[i] = v;
+    if (ctxb) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(ctxb)[i] = pk;
+    }
+  }
+}
+
+// x[b,:] = token_emb[tok[b],:]   (TransformerWrapper token embedding; no positional term for SLMFT)
+__global__ void embed_tokens_kernel(const int64_t* __restrict__ tok, int tok_stride, const int* __restrict__ step,
+                                    const float* __restrict__ emb, float* __restrict__ x, int B, int D, int V) {
+  const int b = blockIdx.x;
+  const int64_t* tp = tok + (size_t)b * tok_stride + (step ? *step : 0);
+  int64_t t = *tp;
+  t = t < 0 ? 0 : (t >= V ? V - 1 : t);
+  const float4* src = reinterpret_cast<const float4*>(emb + (size_t)t * D);
+  float4* dst = reinterpret_cast<float4*>(x + (size_t)b * D);
+  for (int i = threadIdx.x; i < (D >> 2); i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
+// One block (256 threads) per row of logits [V <= 1024].  Greedy: first maximal index (torch.argmax on CPU returns the
+// first occurrence).  Sampling: keep the top_k largest logits (ties broken toward the lower index, like a stable
+// descending sort), softmax(l / temperature) over them in fp32, inverse-CDF draw in index order with the supplied uniform.
+__global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ logits, int V, float temperature, int top_k,
+                                                     const float* __restrict__ uniforms, int u_stride,
+                                                     const int* __restrict__ step, int64_t* __restrict__ out,
+                                                     int out_stride, int out_offset, float* __restrict__ logits_out,
+                                                     int lo_stride) {
+  __shared__ float sl[1024];
+  __shared__ float sp[1024];
+  __shared__ float redf[8];
+  __shared__ int redi[8];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int st = step ? *step : 0;
+  const float* lr = logits + (size_t)b * V;
+  for (int i = tid; i < V; i += 256) {
+    float v = lr[i];
+    sl[i] = v;
+    if (logits_out) logits_out[(size_t)b * lo_stride + (size_t)st * V + i] = v;
+  }
+  __syncthreads();
+  int64_t* dst = out + (size_t)b * out_stride + out_offset + st;
+  if (temperature == 0.f) {
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < V; i += 256) {
+      float v = sl[i];
+      if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) { redf[warp] = best; redi[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < 8; ++w)
+        if (redf[w] > best || (redf[w] == best && redi[w] < bi)) { best = redf[w]; bi = redi[w]; }
+      *dst = bi == 0x7fffffff ? 0 : bi;
+    }
+    return;
+  }
+  // rank of element i = #{j : l_j > l_i or (l_j == l_i and j < i)} ; kept iff rank < top_k
+  float mx = -INFINITY;
+  for (int i = tid; i < V; i += 256) {
+    float v = sl[i];
+    int rank = 0;
+    for (int j = 0; j < V; ++j) {
+      float w = sl[j];
+      rank += (w > v) || (w == v && j < i);
+    }
+    bool keep = rank < top_k;
+    sp[i] = keep ? v / temperature : -INFINITY;
+    if (keep) mx = fmaxf(mx, v / temperature);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) redf[warp] = mx;
+  __syncthreads();
+  mx = redf[0];
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, redf[w]);
+  __syncthreads();
+  for (int i = tid; i < V; i += 256) sp[i] = sp[i] == -INFINITY ? 0.f : expf(sp[i] - mx);
+  __syncthreads();
+  if (tid == 0) {
+    // sequential fp64 CDF in index order: V <= 1024, one thread, ~1 us; deterministic by construction
+    double tot = 0.0;
+    for (int i = 0; i < V; ++i) tot += (double)sp[i];
+    double target = (double)uniforms[(size_t)b * u_stride + st] * tot, c = 0.0;
+    int pick = -1, last = 0;
+    for (int i = 0; i < V; ++i) {
+      if (sp[i] > 0.f) last = i;
+      c += (double)sp[i];
+      if (pick < 0 && c > target) pick = i;
+    }
+    *dst = pick < 0 ? last : pick;
+  }
+}
+
+__global__ void advance_step_kernel(int* step) { *step += 1; }
+__global__ void set_step_kernel(int* step, int v) { *step = v; }
+
+}  // namespace
+
+int launch_layer_norm(const float* x, const float* gain, const float* bias, float* y, __nv_bfloat16* yb, int rows, int dim,
+                      float eps, cudaStream_t s) {
+  DIM_REQUIRE(rows > 0 && dim > 0 && dim % 4 == 0 && dim <= 4096, "layer_norm: dim must be a multiple of 4, <= 4096");
+  if (dim <= 384) layer_norm_kernel<3><<<cdiv(rows, 8), 256, 0, s>>>(x, gain, bias, y, yb, rows, dim, eps);
+  else if (dim <= 1152) layer_norm_kernel<9><<<cdiv(rows, 8), 256, 0, s>>>(x, gain, bias, y, yb, rows, dim, eps);
+  else layer_norm_kernel<32><<<cdiv(rows, 8), 256, 0, s>>>(x, gain, bias, y, yb, rows, dim, eps);
+  DIM_LAUNCHED();
+  return DIM_OK;
+}
+
+int launch_instance_norm(float* x, const int32_t* lens, int B, int T, int C, float eps, cudaStream_t s) {
+  DIM_REQUIRE(B > 0 && T > 0 && C > 0, "instance_norm: empty");
+  instance_norm_kernel<<<dim3(cdiv(C, 32), B), 256, 0, s>>>(x, lens, T, C, eps);
+  DIM_LAUNCHED();
+  return DIM_OK;
+}
+
+int launch_build_context(const float* xs, const float* pe_dec, const float* audio, float* ctx, __nv_bfloat16* ctxb,
+                         size_t rows, int d1, int d2, cudaStream_t s) {
+  DIM_REQUIRE(d1 % 4 == 0 && d2 % 4 == 0, "context dims must be multiples of 4");
+  size_t total = rows * ((d1 + d2) / 4);
+  int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  build_context_kernel<<<blocks, 256, 0, s>>>(xs, pe_dec, audio, ctx, ctxb, rows, d1, d2);
+  DIM_LAUNCHED();
+  return DIM_OK;
+}
+
+int launch_embed_tokens(const int64_t* tok, int tok_stride, const int* step, const float* emb, float* x, int B, int D, int V,
+                        cudaStream_t s) {
+  embed_tokens_kernel<<<B, 128, 0, s>>>(tok, tok_stride, step, emb, x, B, D, V);
+  DIM_LAUNCHED();
+  return DIM_OK;
+}
+
+int launch_sample(const float* logits, int B, int V, float temperature, int top_k, const float* uniforms, int u_stride,
+                  const int* step, int64_t* out, int out_stride, int out_offset, float* logits_out, int lo_stride,
+                  cudaStream_t s) {
+  DIM_REQUIRE(V > 0 && V <= 1024, "sample: vocabulary must be <= 1024");
+  DIM_REQUIRE(temperature == 0.f || (uniforms != nullptr && top_k > 0), "sample: sampling needs uniforms and top_k");
+  sample_kernel<<<B, 256, 0, s>>>(logits, V, temperature, top_k, uniforms, u_stride, step, out, out_stride, out_offset,
+                                  logits_out, lo_stride);
+  DIM_LAUNCHED();
+  return DIM_OK;
+}
+
+int launch_advance_step(int* step, cudaStream_t s) {
+  advance_step_kernel<<<1, 1, 0, s>>>(step);
+  DIM_LAUNCHED();
+  return DIM_OK;
+}
+int launch_set_step(int* step, int v, cudaStream_t s) {
+  set_step_kernel<<<1, 1, 0, s>>>(step, v);
+  DIM_LAUNCHED();
+  return DIM_OK;
+}
+
+}  // namespace dimb
+
+using namespace dimb;
+
+extern "C" int dim_layer_norm_f32(const float* x, const float* gain, const float* bias, float* y, int rows, int dim,
+                                  float eps, void* stream) {
+  if (int e = ensure_device()) return e;
+  return launch_layer_norm(x, gain, bias, y, nullptr, rows, dim, eps, as_stream(stream));
+}
+
+extern "C" int dim_instance_norm_f32(float* x, const int32_t* lens, int B, int T, int C, float eps, void* stream) {
+  if (int e = ensure_device()) return e;
+  return launch_instance_norm(x, lens, B, T, C, eps, as_stream(stream));
+}

@@ -1,0 +1,19 @@
+// Row-wise kernels (LayerNorm, InstanceNorm, context assembly, token embedding, sampling).  See rowops.cu.
+#pragma once
+#include "common.cuh"
+#include <algorithm>
+
+namespace dimb {
+int launch_layer_norm(const float* x, const float* gain, const float* bias, float* y, __nv_bfloat16* yb, int rows, int dim,
+                      float eps, cudaStream_t s);
+int launch_instance_norm(float* x, const int32_t* lens, int B, int T, int C, float eps, cudaStream_t s);
+int launch_build_context(const float* xs, const float* pe_dec, const float* audio, float* ctx, __nv_bfloat16* ctxb,
+                         size_t rows, int d1, int d2, cudaStream_t s);
+int launch_embed_tokens(const int64_t* tok, int tok_stride, const int* step, const float* emb, float* x, int B, int D, int V,
+                        cudaStream_t s);
+int launch_sample(const float* logits, int B, int V, float temperature, int top_k, const float* uniforms, int u_stride,
+                  const int* step, int64_t* out, int out_stride, int out_offset, float* logits_out, int lo_stride,
+                  cudaStream_t s);
+int launch_advance_step(int* step, cudaStream_t s);
+int launch_set_step(int* step, int v, cudaStream_t s);
+}  // namespace dimb

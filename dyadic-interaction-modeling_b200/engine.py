@@ -1,0 +1,172 @@
+"""Model-level engines over the C-ABI handle (include/dimb200.h, "Model level").
+
+VQEngine   : VQAutoEncoder.encode / decode   (/root/reference/code/models/stage1_BIWI.py:22-37)
+SLMFTEngine: SLMFT.forward_encoder + context, decoder_joint.generate (seq2seq_pretrain.py:431-452)
+
+Weights are registered by their reference state_dict keys; the engines keep the CUDA tensors alive (the library
+borrows the pointers).  Workspaces are torch allocations owned here and reused across calls.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from .schema import S2SConfig, VQConfig
+
+PREC_FP32, PREC_BF16 = 0, 1
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class Handle:
+    """dim_handle_t with the registered tensors kept alive."""
+
+    def __init__(self, device=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("dim_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        h = C.c_void_p()
+        _lib.check(self.lib.dim_create(C.byref(h), self.device.index), "dim_create")
+        self.h = h
+        self.keep = {}
+
+    def register(self, state_dict, prefix=""):
+        """Copy (if needed) every fp32 tensor of `state_dict` to the device and register it under prefix+key."""
+        for k, v in state_dict.items():
+            if not torch.is_tensor(v) or not v.is_floating_point():
+                continue
+            t = v.detach().to(device=self.device, dtype=torch.float32).contiguous()
+            name = prefix + k
+            self.keep[name] = t
+            shape = (C.c_int64 * t.dim())(*t.shape)
+            _lib.check(self.lib.dim_set_tensor(self.h, name.encode(), t.data_ptr(), 0, t.dim(), shape), "dim_set_tensor")
+
+    def close(self):
+        if getattr(self, "h", None):
+            torch.cuda.synchronize(self.device)
+            self.lib.dim_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _Workspace:
+    def __init__(self, device):
+        self.device = device
+        self.buf = None
+
+    def get(self, nbytes):
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = None
+            self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self.buf
+
+
+class VQEngine:
+    def __init__(self, handle: Handle, cfg: VQConfig = VQConfig(), prefix: str = "", precision: int = PREC_FP32):
+        self.handle, self.cfg, self.prefix = handle, cfg, prefix
+        cc = _lib.VQConfigC(cfg.in_dim, cfg.hidden_size, cfg.num_hidden_layers, cfg.num_attention_heads,
+                            cfg.intermediate_size, cfg.n_embed, cfg.zquant_dim * cfg.face_quan_num, cfg.pe_max_len, cfg.neg)
+        torch.cuda.synchronize(handle.device)
+        m = C.c_int(-1)
+        _lib.check(handle.lib.dim_vqvae_build(handle.h, prefix.encode(), C.byref(cc), precision, C.byref(m)),
+                   "dim_vqvae_build")
+        self.model = m.value
+        self.ws = _Workspace(handle.device)
+
+    def _workspace(self, B, T):
+        n = self.handle.lib.dim_vqvae_workspace_bytes(self.handle.h, self.model, B, T)
+        return self.ws.get(n), n
+
+    def encode(self, x, lens=None, batch_index=None, want_z=False, want_quant=False):
+        """x (B,T,in_dim) fp32 cuda -> idx (B,T) int64 [, z (B,T,zdim), quant (B,zdim,T)]."""
+        assert x.is_cuda and x.dtype == torch.float32
+        x = x.contiguous()
+        B, T, _ = x.shape
+        dev = x.device
+        idx = torch.empty(B, T, dtype=torch.int64, device=dev)
+        z = torch.empty(B, T, self.cfg.zquant_dim, dtype=torch.float32, device=dev) if want_z else None
+        q = torch.empty(B, self.cfg.zquant_dim, T, dtype=torch.float32, device=dev) if want_quant else None
+        ws, n = self._workspace(B, T)
+        _lib.check(self.handle.lib.dim_vqvae_encode(self.handle.h, self.model, x.data_ptr(), _ptr(lens), _ptr(batch_index),
+                                                    B, T, idx.data_ptr(), _ptr(z), _ptr(q), ws.data_ptr(), n, _stream()),
+                   "dim_vqvae_encode")
+        return idx, z, q
+
+    def decode(self, codes=None, quant=None, batch_index=None):
+        """codes (B,L) int64 or quant (B,zdim,L) fp32 -> frames (B,L,in_dim)."""
+        src = codes if codes is not None else quant
+        assert src.is_cuda
+        if codes is not None:
+            codes = codes.contiguous()
+            B, L = codes.shape
+        else:
+            quant = quant.contiguous()
+            B, _, L = quant.shape
+        out = torch.empty(B, L, self.cfg.in_dim, dtype=torch.float32, device=src.device)
+        ws, n = self._workspace(B, L)
+        _lib.check(self.handle.lib.dim_vqvae_decode(self.handle.h, self.model, _ptr(codes), _ptr(quant), _ptr(batch_index),
+                                                    B, L, out.data_ptr(), ws.data_ptr(), n, _stream()), "dim_vqvae_decode")
+        return out
+
+
+class SLMFTEngine:
+    def __init__(self, handle: Handle, cfg: S2SConfig = S2SConfig(), precision: int = PREC_FP32):
+        self.handle, self.cfg = handle, cfg
+        cc = _lib.S2SConfigC(cfg.dim_in, cfg.dim, cfg.dim_audio, cfg.depth, cfg.heads, cfg.dim_head, cfg.max_seq_len,
+                             cfg.num_tokens, cfg.ff_mult)
+        torch.cuda.synchronize(handle.device)
+        m = C.c_int(-1)
+        _lib.check(handle.lib.dim_slmft_build(handle.h, C.byref(cc), precision, C.byref(m)), "dim_slmft_build")
+        self.model = m.value
+        self.ws = _Workspace(handle.device)
+
+    def _workspace(self, B, T, steps):
+        n = self.handle.lib.dim_slmft_workspace_bytes(self.handle.h, self.model, B, T, steps)
+        return self.ws.get(n), n
+
+    def context(self, v_speaker, v_audio, mask):
+        """-> ctx (B,T,dim+dim_audio) fp32 (seq2seq_pretrain.py:431-446)."""
+        v_speaker, v_audio = v_speaker.contiguous(), v_audio.contiguous()
+        B, T, _ = v_speaker.shape
+        m8 = mask.to(torch.uint8).contiguous()
+        ctx = torch.empty(B, T, self.cfg.dec_dim, dtype=torch.float32, device=v_speaker.device)
+        ws, n = self._workspace(B, T, 0)
+        _lib.check(self.handle.lib.dim_slmft_context(self.handle.h, self.model, v_speaker.data_ptr(), v_audio.data_ptr(),
+                                                     m8.data_ptr(), B, T, ctx.data_ptr(), ws.data_ptr(), n, _stream()),
+                   "dim_slmft_context")
+        return ctx
+
+    def generate(self, ctx, mask, prompt, steps, temperature=0.0, top_k=None, uniforms=None, return_logits=False):
+        """prompt (B,) or (B,1) int64 -> codes (B,steps) int64 (seq2seq_pretrain.py:450)."""
+        B, T, _ = ctx.shape
+        ctx = ctx.contiguous()
+        m8 = mask.to(torch.uint8).contiguous()
+        prompt = prompt.reshape(B).contiguous()
+        if top_k is None:
+            top_k = math.ceil(self.cfg.top_k_frac * self.cfg.num_tokens)
+        out = torch.empty(B, steps, dtype=torch.int64, device=ctx.device)
+        logits = torch.empty(B, steps, self.cfg.num_tokens, dtype=torch.float32, device=ctx.device) if return_logits else None
+        if uniforms is not None:
+            uniforms = uniforms.to(device=ctx.device, dtype=torch.float32).contiguous()
+            assert uniforms.shape == (B, steps)
+        ws, n = self._workspace(B, T, steps)
+        _lib.check(self.handle.lib.dim_slmft_generate(self.handle.h, self.model, ctx.data_ptr(), m8.data_ptr(),
+                                                      prompt.data_ptr(), B, T, steps, float(temperature), int(top_k),
+                                                      _ptr(uniforms), out.data_ptr(), _ptr(logits), ws.data_ptr(), n,
+                                                      _stream()), "dim_slmft_generate")
+        return (out, logits) if return_logits else out

@@ -1,0 +1,150 @@
+/*
+ * dimb200.h -- C ABI of libdimb200.so: the B200 (sm_100a) kernels behind the DIM inference hot path.
+ *
+ * The reference (Boese0601/Dyadic-Interaction-Modeling) is pure PyTorch: it has no FFI, its "operators" are ATen
+ * calls inside Python modules.  Each entry point below therefore cites the reference Python lines whose arithmetic it
+ * replaces; INTEGRATION.md shows the ctypes stub a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with `h_`; plain sizes, no torch types;
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*); the caller owns every buffer,
+ *     including workspaces (query the size first); weights registered with dim_set_tensor are BORROWED and must
+ *     outlive the handle; derived (re-packed) weights are owned by the handle;
+ *   - return value: 0 = OK, otherwise a DIM_E* code; dim_last_error() returns a thread-local message;
+ *   - no CPU fallback: every entry point fails with DIM_ENODEVICE when no sm_100 device is usable;
+ *   - a handle is not thread-safe; one process per GPU.
+ *   - row-major everywhere; "frames" (B,T,C) means C fastest.
+ */
+#ifndef DIMB200_H
+#define DIMB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIM_OK 0
+#define DIM_EINVAL 1      /* bad argument / shape */
+#define DIM_ENODEVICE 2   /* no usable sm_100 GPU */
+#define DIM_ECUDA 3       /* CUDA runtime error (message has the detail) */
+#define DIM_EMISSING 4    /* a required weight was not registered */
+#define DIM_EWORKSPACE 5  /* workspace too small */
+
+/* activation selectors for fused GEMM epilogues */
+#define DIM_ACT_NONE 0
+#define DIM_ACT_LEAKY 1      /* LeakyReLU(slope)             stage1_BIWI.py:262,267 */
+#define DIM_ACT_GELU_TANH 2  /* tanh-approximated GELU       utils/base_model_util.py:81-94 */
+#define DIM_ACT_GELU_ERF 3   /* exact GELU (nn.GELU())       x-transformers FeedForward */
+
+/* arithmetic modes of a built model */
+#define DIM_PREC_FP32 0   /* fp32 storage + fp32 FFMA accumulation: the parity mode (<=1e-4 vs the reference) */
+#define DIM_PREC_BF16 1   /* bf16 weights/activations/KV, fp32 accumulate (tcgen05), fp32 softmax/LayerNorm/residual */
+
+const char* dim_last_error(void);
+int dim_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+uint64_t dim_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Operator level (one kernel each).  These are what the unit parity tests call.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Codebook nearest neighbour.  Replaces models/lib/quantizer.py:38-45 (d = |z|^2 + |e|^2 - 2 z E^T ; argmin, first
+ * minimum wins).  z [N,D] fp32, codebook [K,D] fp32, idx [N] int64.  D % 4 == 0, D <= 256, K <= 4096. */
+int dim_vq_argmin(const float* z, const float* codebook, int64_t* idx, int N, int D, int K, void* stream);
+
+/* Codebook row gather.  Replaces the one-hot (N,K)x(K,D) matmul of quantizer.py:79-90 and
+ * seq2seq_pretrain.py:457-461.  idx [N] int64 -> out [N,D] fp32 (rows).  Returns DIM_EINVAL semantics on the device
+ * are not possible; out-of-range indices are clamped into [0,K) and counted in *bad (nullable, device int32). */
+int dim_vq_gather(const int64_t* idx, const float* codebook, float* out, int N, int D, int K, int32_t* bad,
+                  void* stream);
+
+/* C[M,N] = act(A[M,K] @ W[N,K]^T + bias[N]) + residual[M,N]     (nn.Linear semantics: base_models.py:48-50,118-119)
+ * fp32 in/out, fp32 FFMA accumulation.  bias/residual nullable.  K % 4 == 0, N % 4 == 0, lda/ldc in elements. */
+int dim_linear_f32(const float* A, int lda, const float* W, const float* bias, const float* residual, int ldr,
+                   float* C, int ldc, int M, int N, int K, int act, float slope, void* stream);
+
+/* Conv1d(C,C,k=5,stride 1,padding 2 replicate) + bias + LeakyReLU(slope) on frames (B,T,C) -> (B,T,C).
+ * Replaces stage1_BIWI.py:265-267 / :331-333.  Wr is the weight re-laid out as [Cout][5][Cin] (dim_repack_conv_weight).
+ * lens [B] int32 (nullable): frames >= lens[b] are treated as absent (replicate padding happens at lens[b]-1). */
+int dim_conv5_leaky_f32(const float* x, const float* Wr, const float* bias, const int32_t* lens, float* y, int B, int T,
+                        int C, float slope, void* stream);
+int dim_repack_conv_weight(const float* w_oik /*[Cout][Cin][5]*/, float* w_oki /*[Cout][5][Cin]*/, int Cout, int Cin,
+                           void* stream);
+
+/* InstanceNorm1d(affine=False, eps) over time, in place on frames (B,T,C): per (b,c) mean and biased variance over
+ * t < lens[b] (or T).  Replaces stage1_BIWI.py:268 / :334. */
+int dim_instance_norm_f32(float* x, const int32_t* lens, int B, int T, int C, float eps, void* stream);
+
+/* LayerNorm over the last dim (eps), gain, optional bias.  base_models.py:14 ; x-transformers bias-free LayerNorm. */
+int dim_layer_norm_f32(const float* x, const float* gain, const float* bias, float* y, int rows, int dim, float eps,
+                       void* stream);
+
+/* Multi-head attention over frames, fp32.  q/k/v point at element (b=0,t=0,h=0,d=0) of tensors whose (b,t) rows are
+ * ld* elements apart and whose head h occupies columns [h*Dh, (h+1)*Dh).  out (B,Tq,H*Dh).
+ *   scores = (q.k) * scale ; masked scores are filled with -FLT_MAX (x-transformers) ; softmax fp32 ; out = P v.
+ *   key_mask (B,Tk) uint8 nullable (1 = keep) ; lens (B) nullable (keys >= lens[b] masked) ; causal: key j > query i masked.
+ * Replaces base_models.py:136-143 (VQ-VAE, Dh=48, scale=hidden**-0.5, no mask) and x-transformers Attend (Dh=64). */
+int dim_attention_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo,
+                      const uint8_t* key_mask, const int32_t* lens, int B, int H, int Tq, int Tk, int Dh, float scale,
+                      int causal, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Model level.  A handle holds registered weights (by reference state_dict key) and built models.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct dim_handle_s* dim_handle_t;
+
+int dim_create(dim_handle_t* out, int device);
+int dim_destroy(dim_handle_t h);
+
+#define DIM_DTYPE_F32 0
+#define DIM_DTYPE_I64 1
+/* Register a weight under its reference state_dict key (e.g. "listener_vq.encoder.squasher.0.0.weight"). */
+int dim_set_tensor(dim_handle_t h, const char* name, const void* ptr, int dtype, int ndim, const int64_t* shape);
+
+typedef struct {
+  int32_t in_dim, hidden, layers, heads, ffn, n_embed, zdim, pe_max_len;
+  float neg_slope;
+} dim_vq_config;        /* code/config.yaml:15-30 */
+
+/* Build a VQ-VAE from the tensors registered under `prefix` ("" or "listener_vq.").  Returns a model id >= 0 in *model. */
+int dim_vqvae_build(dim_handle_t h, const char* prefix, const dim_vq_config* cfg, int precision, int* model);
+size_t dim_vqvae_workspace_bytes(dim_handle_t h, int model, int B, int T);
+
+/* VQAutoEncoder.encode (stage1_BIWI.py:22-27): x (B,T,in_dim) -> idx (B*T) int64 [, z (B,T,zdim) pre-quantisation
+ * latents, quant (B,zdim,T) = E[idx] channel-major like the reference's return].  lens/batch_index (B) int32 nullable:
+ * batch_index[b] selects the positional-encoding row (base_models.py:271-273); default b. */
+int dim_vqvae_encode(dim_handle_t h, int model, const float* x, const int32_t* lens, const int32_t* batch_index, int B,
+                     int T, int64_t* idx, float* z, float* quant_bcl, void* ws, size_t ws_bytes, void* stream);
+/* VQAutoEncoder.decode (stage1_BIWI.py:29-37) of either codes (B*L) int64 -- the gather of seq2seq_pretrain.py:454-463
+ * fused in front -- or a (B,zdim,L) fp32 `quant` tensor (exactly one of codes/quant_bcl non-NULL) -> out (B,L,in_dim). */
+int dim_vqvae_decode(dim_handle_t h, int model, const int64_t* codes, const float* quant_bcl, const int32_t* batch_index,
+                     int B, int L, float* out, void* ws, size_t ws_bytes, void* stream);
+
+typedef struct {
+  int32_t dim_in, dim, dim_audio, depth, heads, dim_head, max_seq_len, num_tokens, ff_mult;
+} dim_s2s_config;       /* seq2seq_pretrain.py:369-386,413 */
+
+int dim_slmft_build(dim_handle_t h, const dim_s2s_config* cfg, int precision, int* model);
+size_t dim_slmft_workspace_bytes(dim_handle_t h, int model, int B, int T, int steps);
+
+/* SLMFT.forward_encoder + context assembly (seq2seq_pretrain.py:431-446): v_speaker (B,T,56), v_audio (B,T,768),
+ * mask (B,T) uint8 -> ctx (B,T,dim+dim_audio) = cat(norm_s(encoder_joint(encoder_s(v+patch_embed_s))) + patch_embed_dec_s, audio) */
+int dim_slmft_context(dim_handle_t h, int model, const float* v_speaker, const float* v_audio, const uint8_t* mask, int B,
+                      int T, float* ctx, void* ws, size_t ws_bytes, void* stream);
+
+/* decoder_joint.generate (seq2seq_pretrain.py:450; x-transformers AutoregressiveWrapper.generate): KV-cached
+ * autoregressive decoding of `steps` tokens from prompt (B) int64, cross-attending ctx (B,T,D) under mask (B,T).
+ * temperature == 0 -> argmax.  temperature > 0 -> top-k filter (top_k logits kept), softmax(logits/temperature) and an
+ * inverse-CDF draw with uniforms (B,steps) fp32 supplied by the caller.  out_codes (B,steps) int64.
+ * logits_out (B,steps,num_tokens) fp32 nullable.  Cross-attention K/V are projected once. */
+int dim_slmft_generate(dim_handle_t h, int model, const float* ctx, const uint8_t* mask, const int64_t* prompt, int B,
+                       int T, int steps, float temperature, int top_k, const float* uniforms, int64_t* out_codes,
+                       float* logits_out, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIMB200_H */

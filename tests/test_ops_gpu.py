@@ -1,0 +1,169 @@
+"""Operator-level parity: each C-ABI kernel against a plain PyTorch fp32 CPU evaluation of the same reference op."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import vqvae as OV  # noqa: E402
+from oracle import xt as OX  # noqa: E402
+
+
+def _g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 384, 56), (300, 1152, 384), (1, 2304, 1152), (3, 512, 1152), (8, 1152, 4608),
+                                    (17, 768, 1152), (600, 56, 384), (4096, 1536, 384), (33, 128, 384)])
+@pytest.mark.parametrize("act", [0, 1, 2, 3])
+def test_linear(M, N, K, act):
+    from dim_b200 import ops
+    g = _g(M * 7 + N + K + act)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / math.sqrt(K)
+    b = torch.randn(N, generator=g) * 0.1
+    r = torch.randn(M, N, generator=g)
+    ref = F.linear(a, w, b)
+    ref = [ref, F.leaky_relu(ref, 0.2), OV.gelu_tanh(ref), F.gelu(ref)][act] + r
+    out = ops.linear(a.cuda(), w.cuda(), b.cuda(), r.cuda(), act=act, slope=0.2).cpu()
+    # fp32 accumulation in a different order: tolerance 2e-5 abs on O(1) values (observed ~2e-6)
+    assert torch.allclose(out, ref, atol=2e-5, rtol=1e-5), float((out - ref).abs().max())
+
+
+def test_linear_no_bias_no_residual():
+    from dim_b200 import ops
+    g = _g(3)
+    a, w = torch.randn(70, 384, generator=g), torch.randn(56, 384, generator=g) / 20
+    out = ops.linear(a.cuda(), w.cuda()).cpu()
+    assert torch.allclose(out, F.linear(a, w), atol=2e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("B,T", [(1, 300), (3, 64), (2, 5), (2, 1)])
+def test_conv5_instnorm(B, T, vq_sd):
+    from dim_b200 import ops
+    g = _g(B * 100 + T)
+    x = torch.randn(B, T, 384, generator=g)
+    w, b = vq_sd["encoder.squasher.0.0.weight"], vq_sd["encoder.squasher.0.0.bias"]
+    y_ref = F.leaky_relu(F.conv1d(F.pad(x.permute(0, 2, 1), (2, 2), mode="replicate"), w, b), 0.2)
+    wr = ops.repack_conv_weight(w.cuda())
+    assert torch.equal(wr.cpu(), w.permute(0, 2, 1).contiguous())
+    y = ops.conv5_leaky(x.cuda(), wr, b.cuda(), 0.2)
+    assert torch.allclose(y.cpu(), y_ref.permute(0, 2, 1), atol=3e-5, rtol=1e-5)
+    if T > 1:
+        n_ref = F.instance_norm(y_ref, eps=1e-5).permute(0, 2, 1)
+        n = ops.instance_norm_(y.clone())
+        assert torch.allclose(n.cpu(), n_ref, atol=5e-5, rtol=1e-4), float((n.cpu() - n_ref).abs().max())
+
+
+def test_conv5_ragged_lens(vq_sd):
+    """lens[b] < T must equal running the valid prefix alone (replicate padding at lens-1)."""
+    from dim_b200 import ops
+    g = _g(11)
+    B, T = 3, 40
+    lens = torch.tensor([40, 17, 5], dtype=torch.int32)
+    x = torch.randn(B, T, 384, generator=g)
+    w, b = vq_sd["decoder.expander.0.0.weight"], vq_sd["decoder.expander.0.0.bias"]
+    wr = ops.repack_conv_weight(w.cuda())
+    y = ops.conv5_leaky(x.cuda(), wr, b.cuda(), 0.2, lens=lens.cuda())
+    n = ops.instance_norm_(y.clone(), lens=lens.cuda()).cpu()
+    for i in range(B):
+        L = int(lens[i])
+        yr = F.leaky_relu(F.conv1d(F.pad(x[i:i + 1, :L].permute(0, 2, 1), (2, 2), mode="replicate"), w, b), 0.2)
+        assert torch.allclose(y[i, :L].cpu(), yr[0].t(), atol=3e-5, rtol=1e-5)
+        nr = F.instance_norm(yr, eps=1e-5)[0].t()
+        assert torch.allclose(n[i, :L], nr, atol=5e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("rows,dim,bias", [(300, 384, True), (7, 1152, False), (1, 1152, False), (1000, 384, False)])
+def test_layer_norm(rows, dim, bias):
+    from dim_b200 import ops
+    g = _g(rows + dim)
+    x = torch.randn(rows, dim, generator=g) * 3 + 1
+    gain = 1 + 0.1 * torch.randn(dim, generator=g)
+    b = 0.1 * torch.randn(dim, generator=g) if bias else None
+    ref = F.layer_norm(x, (dim,), gain, b, 1e-5)
+    out = ops.layer_norm(x.cuda(), gain.cuda(), None if b is None else b.cuda()).cpu()
+    assert torch.allclose(out, ref, atol=5e-6, rtol=1e-5), float((out - ref).abs().max())
+
+
+@pytest.mark.parametrize("B,T,H,Dh,causal,masked", [(1, 300, 8, 48, False, False), (2, 64, 8, 48, False, False),
+                                                    (2, 5, 8, 48, False, False), (1, 300, 12, 64, True, True),
+                                                    (3, 130, 12, 64, True, True), (2, 64, 12, 64, False, True),
+                                                    (1, 1, 12, 64, True, False)])
+def test_attention(B, T, H, Dh, causal, masked):
+    from dim_b200 import ops
+    g = _g(B + T + H + Dh)
+    inner = H * Dh
+    qkv = torch.randn(B, T, 3 * inner, generator=g)
+    scale = (inner ** -0.5) if Dh == 48 else Dh ** -0.5
+    q, k, v = [t.view(B, T, H, Dh).permute(0, 2, 1, 3) for t in qkv.split(inner, dim=-1)]
+    mask = None
+    if masked:
+        lens = torch.randint(max(1, T // 2), T + 1, (B,), generator=g)
+        lens[0] = T
+        mask = torch.arange(T)[None] < lens[:, None]
+    am = ~torch.triu(torch.ones(T, T), diagonal=1).bool() if causal else None
+    ref = OX.attend(q * (scale / Dh ** -0.5), k, v, key_mask=mask, attn_mask=am)   # attend() scales by Dh**-0.5
+    out = ops.attention(qkv.cuda(), H, Dh, scale, key_mask=None if mask is None else mask.to(torch.uint8).cuda(),
+                        causal=causal).cpu()
+    assert torch.allclose(out, ref, atol=2e-5, rtol=1e-4), float((out - ref).abs().max())
+
+
+@pytest.mark.parametrize("N", [1, 63, 300, 5000])
+@pytest.mark.parametrize("scale", [0.5, 1.0 / 512])
+def test_vq_argmin(N, scale):
+    """Bit-exact indices vs the reference formula; tokens whose reference top-2 gap is within 4 ulp of d are
+    tie-ambiguous (accumulation order decides) and are only required to pick one of the two."""
+    from dim_b200 import ops
+    g = _g(N)
+    z = torch.randn(N, 128, generator=g) * 0.7
+    E = torch.randn(512, 128, generator=g) * scale if scale > 0.01 else (torch.rand(512, 128, generator=g) * 2 - 1) * scale
+    d = OV.distances(z, E)
+    ref = torch.argmin(d, dim=1)
+    d64 = (z.double()[:, None, :] - E.double()[None]).pow(2).sum(-1) if N <= 300 else None
+    idx = ops.vq_argmin(z.cuda(), E.cuda()).cpu()
+    top2 = torch.topk(d, 2, dim=1, largest=False)
+    gap = top2.values[:, 1] - top2.values[:, 0]
+    ulp = torch.finfo(torch.float32).eps * top2.values[:, 0].abs()
+    ambiguous = gap <= 4 * ulp
+    bad = (idx != ref) & ~ambiguous
+    assert not bad.any(), f"{int(bad.sum())} non-ambiguous mismatches"
+    mism = idx != ref
+    if mism.any():   # ambiguous ones must still be the runner-up
+        assert torch.equal(idx[mism], top2.indices[mism, 1])
+    if d64 is not None and scale == 0.5:
+        assert torch.equal(idx, d64.argmin(1))
+
+
+def test_vq_argmin_ties_first_index():
+    from dim_b200 import ops
+    E = torch.randn(512, 128, generator=_g(5))
+    E[300] = E[17]
+    E[400] = E[17]
+    z = E[[17, 300, 400, 5]].clone()
+    idx = ops.vq_argmin(z.cuda(), E.cuda()).cpu()
+    assert idx.tolist() == [17, 17, 17, 5]
+
+
+@pytest.mark.parametrize("N", [1, 5, 299, 76544])
+def test_vq_gather(N):
+    from dim_b200 import ops
+    g = _g(N)
+    E = torch.randn(512, 128, generator=g)
+    idx = torch.randint(0, 512, (N,), generator=g)
+    out = ops.vq_gather(idx.cuda(), E.cuda()).cpu()
+    assert torch.equal(out, E[idx])                                  # bit-exact rows
+    if N <= 299:
+        sd = {"quantize.embedding.weight": E}
+        assert torch.equal(out, OV.codebook_entry(sd, idx))          # == the reference's one-hot matmul
+
+
+def test_vq_gather_out_of_range_counted():
+    from dim_b200 import ops
+    E = torch.randn(512, 128, generator=_g(1))
+    idx = torch.tensor([0, 511, 512, -100, 7])
+    out, bad = ops.vq_gather(idx.cuda(), E.cuda(), count_bad=True)
+    assert int(bad.item()) == 2
+    assert torch.equal(out.cpu()[[0, 1, 4]], E[[0, 511, 7]])

@@ -1,0 +1,101 @@
+"""SLMFT (seq2seq_pretrain.py:431-514) on the GPU vs the restated oracle (x-transformers half: parity UNPINNED, see
+oracle/xt.py).  Greedy decoding is compared token by token; at the first divergence, if any, the oracle's top-2 logit
+margin must be below 1e-4 (tie-ambiguous), otherwise the test fails."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import dim_b200  # noqa: E402
+from dim_b200.schema import S2SConfig, VQConfig  # noqa: E402
+from oracle import slmft as OS  # noqa: E402
+from oracle import xt as OX  # noqa: E402
+
+S2S, VQ = S2SConfig(), VQConfig()
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def engines(slmft_sd):
+    from dim_b200.engine import Handle, SLMFTEngine, VQEngine
+    h = Handle()
+    h.register(slmft_sd)
+    return SLMFTEngine(h, S2S), VQEngine(h, VQ, prefix="listener_vq.")
+
+
+@pytest.mark.parametrize("B,T,ragged", [(1, 40, False), (3, 70, True), (2, 130, True)])
+def test_context(engines, slmft_sd, B, T, ragged):
+    s2s, _ = engines
+    c = dim_b200.synth.make_clips(B, T, seed=B + T, ragged=ragged)
+    ctx = s2s.context(c["v_speaker"].cuda(), c["v_audio"].cuda(), c["mask"].cuda()).cpu()
+    x_s = OS.forward_encoder(slmft_sd, c["v_speaker"], c["mask"], S2S)
+    ref = OS.decoder_context(slmft_sd, x_s, c["v_audio"])
+    m = c["mask"]
+    # padded query rows are "discarded downstream" (masked as cross-attention keys); compare valid rows
+    assert torch.allclose(ctx[m], ref[m], atol=TOL), float((ctx[m] - ref[m]).abs().max())
+
+
+def _compare_codes(codes, logits, ref_codes, ref_logits):
+    B, S = ref_codes.shape
+    for b in range(B):
+        neq = (codes[b] != ref_codes[b]).nonzero()
+        if len(neq) == 0:
+            assert torch.allclose(logits[b], ref_logits[b], atol=5e-4), float((logits[b] - ref_logits[b]).abs().max())
+            continue
+        t = int(neq[0])
+        assert torch.allclose(logits[b, :t + 1], ref_logits[b, :t + 1], atol=5e-4)
+        top2 = torch.topk(ref_logits[b, t], 2).values
+        assert float(top2[0] - top2[1]) < 1e-4, f"sample {b} diverged at step {t} with margin {float(top2[0]-top2[1])}"
+
+
+@pytest.mark.parametrize("B,T,ragged", [(1, 48, False), (3, 40, True), (9, 24, False)])
+def test_generate_greedy(engines, slmft_sd, B, T, ragged):
+    s2s, _ = engines
+    c = dim_b200.synth.make_clips(B, T, seed=100 + B, ragged=ragged)
+    x_s = OS.forward_encoder(slmft_sd, c["v_speaker"], c["mask"], S2S)
+    ctx = OS.decoder_context(slmft_sd, x_s, c["v_audio"])
+    prompt = torch.randint(0, 512, (B, 1), generator=torch.Generator().manual_seed(B))
+    ref_codes, ref_logits = OX.generate(slmft_sd, "decoder_joint.net", prompt, T - 1, S2S.depth, ctx, c["mask"],
+                                        return_logits=True)
+    codes, logits = s2s.generate(ctx.cuda(), c["mask"].cuda(), prompt.cuda(), T - 1, return_logits=True)
+    _compare_codes(codes.cpu(), logits.cpu(), ref_codes, ref_logits)
+
+
+def test_generate_sampled_with_uniforms(engines, slmft_sd):
+    """temperature 1, top-k 52 (ceil(0.1*512)), draws from supplied uniforms."""
+    s2s, _ = engines
+    B, T = 2, 36
+    c = dim_b200.synth.make_clips(B, T, seed=5)
+    x_s = OS.forward_encoder(slmft_sd, c["v_speaker"], c["mask"], S2S)
+    ctx = OS.decoder_context(slmft_sd, x_s, c["v_audio"])
+    prompt = torch.tensor([[3], [400]])
+    u = torch.rand(B, T - 1, generator=torch.Generator().manual_seed(77))
+    ref = OX.generate(slmft_sd, "decoder_joint.net", prompt, T - 1, S2S.depth, ctx, c["mask"], temperature=1.0, uniforms=u)
+    out = s2s.generate(ctx.cuda(), c["mask"].cuda(), prompt.cuda(), T - 1, temperature=1.0, uniforms=u.cuda(),
+                       top_k=math.ceil(0.1 * 512)).cpu()
+    agree = (out == ref).float().mean()
+    # a draw within ~1e-6 of a CDF boundary may legitimately flip and then the sequences diverge; demand the
+    # common prefix be long and the first difference (if any) be explainable
+    if not torch.equal(out, ref):
+        for b in range(B):
+            neq = (out[b] != ref[b]).nonzero()
+            if len(neq):
+                assert int(neq[0]) > 5, f"early divergence at {int(neq[0])} (agreement {float(agree):.2f})"
+    assert len(out.unique()) > 8                                    # sampling really explores the codebook
+
+
+def test_forward_val_end_to_end(engines, slmft_sd):
+    """SLMFT.forward(mode='val') = listener VQ encode -> encoders -> generate -> gather -> VQ decode."""
+    from dim_b200.compat_api import slmft_forward_val
+    s2s, vq = engines
+    B, T = 2, 32
+    c = dim_b200.synth.make_clips(B, T, seed=8, ragged=True)
+    ref_loss, _, ref_pred, inter = OS.forward_val(slmft_sd, c["v_speaker"], c["v_listener"], c["v_audio"], c["mask"], S2S, VQ,
+                                                  return_intermediates=True)
+    loss, d, pred, codes = slmft_forward_val(s2s, vq, c["v_speaker"].cuda(), c["v_listener"].cuda(), c["v_audio"].cuda(),
+                                             c["mask"].cuda(), return_codes=True)
+    assert torch.equal(codes.cpu(), inter["codes"])
+    assert torch.allclose(pred.cpu(), ref_pred, atol=TOL), float((pred.cpu() - ref_pred).abs().max())
+    assert abs(float(loss) - float(ref_loss)) < 1e-4
