@@ -63,6 +63,11 @@ class S2SConfigC(C.Structure):
                                          "num_tokens", "ff_mult")]
 
 
+class ProfEntryC(C.Structure):
+    _fields_ = [("category", C.c_int32), ("launches", C.c_int32), ("ms", C.c_double), ("bytes", C.c_double),
+                ("flops", C.c_double)]
+
+
 P, I, F, SZ, I64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64
 
 # name -> (restype, argtypes); must list every function declared in include/dimb200.h (checked by tests/test_abi.py)
@@ -70,6 +75,9 @@ SIGNATURES = {
     "dim_last_error": (C.c_char_p, []),
     "dim_version": (I, []),
     "dim_launch_count": (C.c_uint64, []),
+    "dim_profile_enable": (I, [I]),
+    "dim_profile_collect": (I, [C.POINTER(ProfEntryC), I, C.POINTER(I)]),
+    "dim_profile_category_name": (C.c_char_p, [I]),
     "dim_vq_argmin": (I, [P, P, P, I, I, I, P]),
     "dim_vq_gather": (I, [P, P, P, I, I, I, P, P]),
     "dim_linear_f32": (I, [P, I, P, P, P, I, P, I, I, I, I, I, F, P]),
@@ -119,3 +127,17 @@ def check(code: int, what: str = ""):
     if code != 0:
         msg = load().dim_last_error()
         raise RuntimeError(f"libdimb200 {what} failed (code {code}): {msg.decode() if msg else ''}")
+
+
+def profile_enable(on: bool):
+    check(load().dim_profile_enable(int(on)), "dim_profile_enable")
+
+
+def profile_collect():
+    """-> list of dict(category, launches, ms, bytes, flops) since the last collect (synchronises the device)."""
+    lib = load()
+    arr = (ProfEntryC * 32)()
+    n = C.c_int(0)
+    check(lib.dim_profile_collect(arr, 32, C.byref(n)), "dim_profile_collect")
+    return [dict(category=lib.dim_profile_category_name(arr[i].category).decode(), launches=arr[i].launches,
+                 ms=arr[i].ms, bytes=arr[i].bytes, flops=arr[i].flops) for i in range(n.value)]

@@ -256,6 +256,9 @@ int launch_attention_prefill(const AttnArgs& a, cudaStream_t s) {
   DIM_REQUIRE(a.B > 0 && a.H > 0 && a.Tq > 0 && a.Tk > 0, "attention: empty");
   DIM_REQUIRE(a.ldq % 4 == 0 && a.ldk % 4 == 0 && a.ldv % 4 == 0, "attention: leading dims must be multiples of 4");
   dim3 grid(cdiv(a.Tq, TQ), a.H, a.B);
+  // algorithmic: read q,k,v once, write out once; QK^T and PV (causal: half)
+  ProfScope ps(CAT_ATTN_PREFILL, s, 4.0 * a.B * a.H * a.Dh * (2.0 * a.Tq + 2.0 * a.Tk),
+               4.0 * a.B * a.H * (double)a.Tq * a.Tk * a.Dh * (a.causal ? 0.5 : 1.0));
   if (a.Dh == 48) {
     constexpr size_t smem = (TQ * 52 + TKV * 52 + TKV * 48 + TQ * (TKV + 4)) * sizeof(float);
     static bool once = false;
@@ -287,7 +290,11 @@ int launch_attention_decode(DecodeAttnArgs a, int max_keys, cudaStream_t s) {
     DIM_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  attn_decode_f32<<<a.B * a.H, 128, smem, s>>>(a);
+  {
+    const double keys = a.append ? (double)(a.prof_pos + 1) : (double)a.Tk;   // K and V rows actually read
+    ProfScope ps(CAT_ATTN_DECODE, s, 4.0 * a.B * a.H * 64.0 * (2.0 * keys + 2.0), 4.0 * a.B * a.H * 64.0 * keys);
+    attn_decode_f32<<<a.B * a.H, 128, smem, s>>>(a);
+  }
   DIM_LAUNCHED();
   return DIM_OK;
 }

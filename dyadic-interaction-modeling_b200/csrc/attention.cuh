@@ -28,6 +28,7 @@ struct DecodeAttnArgs {
   int B = 0, H = 0, Tk = 0;                               // Tk: number of keys when append == 0
   float scale = 1.f;
   int sc_floats = 0;                                      // set by the launcher
+  int prof_pos = 0;                                       // host copy of *step, for profiling byte counts only
 };
 int launch_attention_decode(DecodeAttnArgs a, int max_keys, cudaStream_t s);
 

@@ -39,6 +39,25 @@ extern std::atomic<uint64_t> g_launches;
 
 int ensure_device();   // DIM_OK when the current device is sm_100; DIM_ENODEVICE otherwise
 
+// ---- optional per-kernel-category timing (dim_profile_*): CUDA events around each launch on the launching stream ----
+enum ProfCat {
+  CAT_GEMM_TILED = 0, CAT_GEMM_SKINNY, CAT_CONV, CAT_LAYERNORM, CAT_INSTNORM, CAT_ATTN_PREFILL, CAT_ATTN_DECODE,
+  CAT_VQ_ARGMIN, CAT_VQ_GATHER, CAT_SAMPLE, CAT_MISC, CAT_GEMM_TC, CAT_COUNT
+};
+extern bool g_prof_on;
+void prof_begin(int cat, cudaStream_t s, double bytes, double flops);
+void prof_end(cudaStream_t s);
+struct ProfScope {
+  cudaStream_t s;
+  bool on;
+  ProfScope(int cat, cudaStream_t st, double bytes, double flops) : s(st), on(g_prof_on) {
+    if (on) prof_begin(cat, s, bytes, flops);
+  }
+  ~ProfScope() {
+    if (on) prof_end(s);
+  }
+};
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

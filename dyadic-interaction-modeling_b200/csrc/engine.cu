@@ -618,7 +618,7 @@ extern "C" int dim_slmft_generate(dim_handle_t h, int model, const float* ctx, c
         a.q = w.qkv; a.ldq = 3 * inner; a.k = w.self_k[l]; a.v = w.self_v[l];
         a.kv_batch_stride = (size_t)(steps + 1) * inner; a.kv_tok_stride = inner;
         a.k_new = w.qkv + inner; a.v_new = w.qkv + 2 * inner; a.ld_new = 3 * inner; a.append = 1; a.step = w.step;
-        a.out = w.att; a.ldo = inner; a.B = B; a.H = c.heads; a.Tk = 0; a.scale = scale;
+        a.out = w.att; a.ldo = inner; a.B = B; a.H = c.heads; a.Tk = 0; a.scale = scale; a.prof_pos = st;
         if (int e = launch_attention_decode(a, max_keys, s)) return e;
       }
       {

@@ -227,6 +227,8 @@ __global__ void repack_conv_kernel(const float* __restrict__ w, float* __restric
 template <int BM, int BN, int TM, int TN>
 int launch_tiled(const GemmArgs& a, cudaStream_t s) {
   dim3 grid(cdiv(a.N, BN), cdiv(a.M, BM));
+  ProfScope ps(a.conv_T > 0 ? CAT_CONV : CAT_GEMM_TILED, s, 4.0 * ((double)a.M * (a.conv_T > 0 ? a.conv_C : a.K) + (double)a.N * a.K + (double)a.M * a.N),
+               2.0 * a.M * (double)a.N * a.K);
   gemm_f32_tiled<BM, BN, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, s>>>(a);
   DIM_LAUNCHED();
   return DIM_OK;
@@ -242,6 +244,8 @@ int launch_gemm_f32(const GemmArgs& a, cudaStream_t s) {
   if (a.conv_T > 0) DIM_REQUIRE(a.conv_C % BK == 0 && a.K == 5 * a.conv_C, "gemm: conv mode needs Cin % 16 == 0");
   if (a.M <= 8 && a.conv_T == 0) {
     dim3 grid(cdiv(a.N, 4));
+    ProfScope ps(CAT_GEMM_SKINNY, s, 4.0 * ((double)a.M * a.K + (double)a.N * a.K + (double)a.M * a.N),
+                 2.0 * a.M * (double)a.N * a.K);
     if (a.M == 1) gemm_f32_skinny<1><<<grid, 128, 0, s>>>(a);
     else if (a.M == 2) gemm_f32_skinny<2><<<grid, 128, 0, s>>>(a);
     else if (a.M <= 4) gemm_f32_skinny<4><<<grid, 128, 0, s>>>(a);
@@ -285,6 +289,7 @@ extern "C" int dim_conv5_leaky_f32(const float* x, const float* Wr, const float*
 extern "C" int dim_repack_conv_weight(const float* w_oik, float* w_oki, int Cout, int Cin, void* stream) {
   if (int e = ensure_device()) return e;
   DIM_REQUIRE(Cout > 0 && Cin > 0, "repack: bad shape");
+  ProfScope ps(CAT_MISC, as_stream(stream), 8.0 * Cout * Cin * 5, 0);
   repack_conv_kernel<<<148 * 4, 256, 0, as_stream(stream)>>>(w_oik, w_oki, Cout, Cin);
   DIM_LAUNCHED();
   return DIM_OK;

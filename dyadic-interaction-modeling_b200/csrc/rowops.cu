@@ -233,6 +233,7 @@ __global__ void set_step_kernel(int* step, int v) { *step = v; }
 int launch_layer_norm(const float* x, const float* gain, const float* bias, float* y, __nv_bfloat16* yb, int rows, int dim,
                       float eps, cudaStream_t s) {
   DIM_REQUIRE(rows > 0 && dim > 0 && dim % 4 == 0 && dim <= 4096, "layer_norm: dim must be a multiple of 4, <= 4096");
+  ProfScope ps(CAT_LAYERNORM, s, (y ? 8.0 : 4.0) * rows * dim + (yb ? 2.0 * rows * dim : 0.0), 8.0 * rows * dim);
   if (dim <= 384) layer_norm_kernel<3><<<cdiv(rows, 8), 256, 0, s>>>(x, gain, bias, y, yb, rows, dim, eps);
   else if (dim <= 1152) layer_norm_kernel<9><<<cdiv(rows, 8), 256, 0, s>>>(x, gain, bias, y, yb, rows, dim, eps);
   else layer_norm_kernel<32><<<cdiv(rows, 8), 256, 0, s>>>(x, gain, bias, y, yb, rows, dim, eps);
@@ -242,6 +243,7 @@ int launch_layer_norm(const float* x, const float* gain, const float* bias, floa
 
 int launch_instance_norm(float* x, const int32_t* lens, int B, int T, int C, float eps, cudaStream_t s) {
   DIM_REQUIRE(B > 0 && T > 0 && C > 0, "instance_norm: empty");
+  ProfScope ps(CAT_INSTNORM, s, 8.0 * B * T * C, 6.0 * B * T * C);
   instance_norm_kernel<<<dim3(cdiv(C, 32), B), 256, 0, s>>>(x, lens, T, C, eps);
   DIM_LAUNCHED();
   return DIM_OK;
@@ -252,6 +254,7 @@ int launch_build_context(const float* xs, const float* pe_dec, const float* audi
   DIM_REQUIRE(d1 % 4 == 0 && d2 % 4 == 0, "context dims must be multiples of 4");
   size_t total = rows * ((d1 + d2) / 4);
   int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  ProfScope ps(CAT_MISC, s, 8.0 * rows * (d1 + d2), 0);
   build_context_kernel<<<blocks, 256, 0, s>>>(xs, pe_dec, audio, ctx, ctxb, rows, d1, d2);
   DIM_LAUNCHED();
   return DIM_OK;
@@ -259,6 +262,7 @@ int launch_build_context(const float* xs, const float* pe_dec, const float* audi
 
 int launch_embed_tokens(const int64_t* tok, int tok_stride, const int* step, const float* emb, float* x, int B, int D, int V,
                         cudaStream_t s) {
+  ProfScope ps(CAT_MISC, s, 8.0 * B * D, 0);
   embed_tokens_kernel<<<B, 128, 0, s>>>(tok, tok_stride, step, emb, x, B, D, V);
   DIM_LAUNCHED();
   return DIM_OK;
@@ -269,6 +273,7 @@ int launch_sample(const float* logits, int B, int V, float temperature, int top_
                   cudaStream_t s) {
   DIM_REQUIRE(V > 0 && V <= 1024, "sample: vocabulary must be <= 1024");
   DIM_REQUIRE(temperature == 0.f || (uniforms != nullptr && top_k > 0), "sample: sampling needs uniforms and top_k");
+  ProfScope ps(CAT_SAMPLE, s, 4.0 * B * V + 8.0 * B, 0);
   sample_kernel<<<B, 256, 0, s>>>(logits, V, temperature, top_k, uniforms, u_stride, step, out, out_stride, out_offset,
                                   logits_out, lo_stride);
   DIM_LAUNCHED();
@@ -276,11 +281,13 @@ int launch_sample(const float* logits, int B, int V, float temperature, int top_
 }
 
 int launch_advance_step(int* step, cudaStream_t s) {
+  ProfScope ps(CAT_MISC, s, 4, 0);
   advance_step_kernel<<<1, 1, 0, s>>>(step);
   DIM_LAUNCHED();
   return DIM_OK;
 }
 int launch_set_step(int* step, int v, cudaStream_t s) {
+  ProfScope ps(CAT_MISC, s, 4, 0);
   set_step_kernel<<<1, 1, 0, s>>>(step, v);
   DIM_LAUNCHED();
   return DIM_OK;

@@ -185,6 +185,7 @@ int launch_vq_argmin(const float* z, const float* E, int64_t* idx, int N, int D,
   DIM_REQUIRE(D == 128 || D == 64 || D == 256, "vq_argmin: D must be 64, 128 or 256");
   dim3 grid(cdiv(N, TT));
   size_t smem = ((size_t)(TT + TC) * (D + 4) + TT + TC) * sizeof(float);
+  ProfScope ps(CAT_VQ_ARGMIN, s, (double)N * (4.0 * D + 8.0), 2.0 * N * (double)D * K);     // 520 B / token
 #define DIM_ARGMIN_CASE(DD)                                                                                      \
   {                                                                                                              \
     static bool once = false;                                                                                    \
@@ -204,18 +205,21 @@ int launch_vq_gather(const int64_t* idx, const float* E, float* out, int N, int 
   DIM_REQUIRE(N > 0 && D % 4 == 0 && K > 0, "vq_gather: bad sizes");
   int warps_needed = cdiv(N, 4);
   int blocks = std::min(cdiv(warps_needed, 8), 148 * 8);
+  ProfScope ps(CAT_VQ_GATHER, s, (double)N * (4.0 * D + 8.0), 0);                          // 520 B / code
   vq_gather_kernel<<<blocks, 256, 0, s>>>(idx, E, out, N, D / 4, K, bad);
   DIM_LAUNCHED();
   return DIM_OK;
 }
 
 int launch_vq_gather_bcl(const int64_t* idx, const float* E, float* out, int B, int L, int D, int K, cudaStream_t s) {
+  ProfScope ps(CAT_VQ_GATHER, s, (double)B * L * (4.0 * D + 8.0), 0);
   vq_gather_bcl_kernel<<<dim3(cdiv(L, 32), cdiv(D, 32), B), 256, 0, s>>>(idx, E, out, L, D, K);
   DIM_LAUNCHED();
   return DIM_OK;
 }
 
 int launch_rows_from_bcl(const float* q, float* rows, int B, int L, int D, cudaStream_t s) {
+  ProfScope ps(CAT_MISC, s, 8.0 * B * L * D, 0);
   rows_from_bcl_kernel<<<dim3(cdiv(L, 32), cdiv(D, 32), B), 256, 0, s>>>(q, rows, L, D);
   DIM_LAUNCHED();
   return DIM_OK;

@@ -47,6 +47,19 @@ int dim_version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 uint64_t dim_launch_count(void);
 
+/* Per-kernel-category timing for bench.py's roofline: when enabled, every launch is bracketed by CUDA events on its own
+ * stream; dim_profile_collect synchronises the device, sums (launches, ms, algorithmic bytes, algorithmic flops) per
+ * category since the last collect and clears the log.  Enabling it serialises nothing but adds event overhead: never
+ * leave it on inside a throughput measurement. */
+typedef struct {
+  int32_t category;
+  int32_t launches;
+  double ms, bytes, flops;
+} dim_prof_entry;
+int dim_profile_enable(int on);
+int dim_profile_collect(dim_prof_entry* out, int max_entries, int* n_out);
+const char* dim_profile_category_name(int category);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Operator level (one kernel each).  These are what the unit parity tests call.
  * ---------------------------------------------------------------------------------------------------------- */
