@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the DIM inference hot path on B200.
+
+One "step" = one SLMFT.forward(mode='val')-equivalent pass over a batch of synthetic ViCo-shape clips
+(/root/reference/code/seq2seq_pretrain.py:496-514 driven as in x_engine_pt.py:258): listener VQ encode -> speaker
+encoders -> (T-1)-step KV-cached autoregressive decode with top-k(52) sampling from pre-drawn uniforms -> codebook gather
+-> VQ decode.  Metric (BASELINE.json): generated listener-motion frames per second, frames = B * (T-1).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload NAME] [--precision fp32|bf16]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...        (N > 1: one rank per GPU)
+
+Prints ONE JSON line on rank 0 (contract in the task statement): value = whole-job frames/s with inputs resident in HBM;
+e2e = same metric through the public API with pinned-host inputs (H2D + D2H inside the timed region); roofline = the
+kernel category that dominates the step, timed with CUDA events on the launching stream in one extra profiled step;
+cpu_baseline = the CPU oracle (restated reference, oracle/) on a bounded sample on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (clips per GPU, frames per clip, note)
+    "vico_b256": (256, 300, "BASELINE.json configs[2]: batch=256 ViCo-shape clips (T=300: 30 fps x 10 s) per GPU"),
+    "vico_b1": (1, 300, "BASELINE.json configs[1]: single ViCo-shape clip, KV-cache on"),
+    "candor_b256": (256, 250, "BASELINE.json configs[3]: CANDOR-shape clips (T=250), 256 per GPU (2048 over 8 GPUs)"),
+    "lm_listener_b32": (32, 1024, "BASELINE.json configs[4]: LM-Listener-shape chunks (T=1024), B=32"),
+    "tiny": (4, 32, "smoke-sized"),
+}
+METRIC = "listener motion frames/sec (ViCo-shape clips, SLMFT val forward: VQ encode + encoders + AR generate + VQ decode)"
+UNIT = "frames/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"], tensor_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            top = sorted(sm)[len(sm) // 2:]                       # upper half = samples under load
+            out.update(sm_mhz=statistics.median(top), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_oracle_sample(frames, threads=None, repeats=1, warm=True):
+    """Time the CPU oracle (oracle/slmft.py, PyTorch fp32, all host threads) on ONE clip of `frames` frames.
+    Variant timed: cross-attention K/V projected once and none of the work the reference discards (the FASTEST
+    restatement of the reference; its real code path does strictly more work: SURVEY F9/F10)."""
+    import dim_b200
+    from dim_b200.schema import S2SConfig, VQConfig
+    from oracle import slmft as OS
+    if threads:
+        torch.set_num_threads(threads)
+    sd = dim_b200.synth.make_slmft_state_dict(131)
+    c = dim_b200.synth.make_clips(1, frames, seed=0)
+    u = torch.rand(1, frames - 1, generator=torch.Generator().manual_seed(1))
+    run = lambda cc, uu: OS.forward_val(sd, cc["v_speaker"], cc["v_listener"], cc["v_audio"], cc["mask"], S2SConfig(),
+                                        VQConfig(), temperature=1.0, uniforms=uu)
+    if warm:
+        w = dim_b200.synth.make_clips(1, 16, seed=1)
+        run(w, torch.rand(1, 15))
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        run(c, u)
+        best = min(best, time.perf_counter() - t0)
+    return (frames - 1) / best, best
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (restated oracle: x-transformers is not installable offline and
+    seq2seq_pretrain.py hard-codes .cuda()) on this box's host cores.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    B, T, note = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # calibrate so that the whole run stays within a few minutes
+    t0 = time.perf_counter()
+    cpu_oracle_sample(24, warm=True)
+    per_frame = (time.perf_counter() - t0) / (23 + 15)
+    budget = 240.0
+    frames = T
+    while frames > 32 and per_frame * frames * (args.steps + args.warmup) > budget:
+        frames //= 2
+    import dim_b200
+    from dim_b200.schema import S2SConfig, VQConfig
+    from oracle import slmft as OS
+    sd = dim_b200.synth.make_slmft_state_dict(131)
+    clip = dim_b200.synth.make_clips(1, frames, seed=0)
+    u = torch.rand(1, frames - 1, generator=torch.Generator().manual_seed(1))
+    step = lambda: OS.forward_val(sd, clip["v_speaker"], clip["v_listener"], clip["v_audio"], clip["mask"], S2SConfig(),
+                                  VQConfig(), temperature=1.0, uniforms=u)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = args.steps * (frames - 1) / dt
+    sample = (f"1 clip x {frames} frames per step (of the {B}x{T} workload), PyTorch {torch.__version__} CPU fp32, "
+              f"{torch.get_num_threads()} threads; restated reference with cross-KV projected once and discarded work skipped")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "clips_per_gpu": B, "frames_per_clip": T, "note": note},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_native(args):
+    import dim_b200
+    from dim_b200 import _lib
+    from dim_b200 import dist as D
+    from dim_b200.compat_api import slmft_forward_val
+    from dim_b200.engine import PREC_BF16, PREC_FP32, PREC_FP32_TC, Handle, SLMFTEngine, VQEngine
+    from dim_b200.schema import S2SConfig, VQConfig
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (native) needs a B200: the CUDA path has no CPU fallback")
+    rank, world, local = D.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B, T, note = WORKLOADS[args.workload]
+    steps_ar = T - 1
+    prec = {"bf16": PREC_BF16, "fp32": PREC_FP32, "fp32_tc": PREC_FP32_TC}[args.precision]
+    vq_prec = PREC_FP32 if prec == PREC_FP32 else PREC_FP32_TC      # the VQ-VAE keeps fp32-grade maths: code indices are bit-exact
+
+    h = Handle()
+    h.register(dim_b200.synth.make_slmft_state_dict(131))
+    s2s = SLMFTEngine(h, S2SConfig(), precision=prec)
+    vq = VQEngine(h, VQConfig(), prefix="listener_vq.", precision=vq_prec)
+
+    # this rank's shard of the global batch (weak scaling: B clips per GPU), global batch positions for the F4 quirk
+    clips = dim_b200.synth.make_clips(B, T, seed=1000 + rank, speaker="ones" if args.speaker_ones else "randn")
+    batch_index = torch.arange(rank * B, (rank + 1) * B, dtype=torch.int32, device=dev)
+    host = {k: clips[k].pin_memory() for k in ("v_speaker", "v_listener", "v_audio", "mask")}
+    u = torch.rand(B, steps_ar, generator=torch.Generator().manual_seed(7 + rank)).to(dev)
+    res = {k: v.to(dev) for k, v in host.items()}
+    pred_host = torch.empty(B, steps_ar, 56).pin_memory()
+
+    def step_resident():
+        loss, d, pred, codes = slmft_forward_val(s2s, vq, res["v_speaker"], res["v_listener"], res["v_audio"], res["mask"],
+                                                 temperature=1.0, uniforms=u, batch_index=batch_index, return_codes=True)
+        all_codes = D.all_gather_codes(codes, world * B) if world > 1 else codes     # the one collective of the path
+        return pred, all_codes
+
+    def step_e2e():
+        dv = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        loss, d, pred, codes = slmft_forward_val(s2s, vq, dv["v_speaker"], dv["v_listener"], dv["v_audio"], dv["mask"],
+                                                 temperature=1.0, uniforms=u, batch_index=batch_index, return_codes=True)
+        if world > 1:
+            D.all_gather_codes(codes, world * B)
+        pred_host.copy_(pred, non_blocking=True)
+        return pred
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.load().dim_launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = _lib.load().dim_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # one extra profiled step: CUDA events around every launch, on the launching stream (rank 0 reports)
+    prof = []
+    if rank == 0 or world > 1:
+        _lib.profile_enable(True)
+        step_resident()
+        prof = _lib.profile_collect()
+        _lib.profile_enable(False)
+    barrier()
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    frames_total = world * B * steps_ar
+    value = frames_total * args.steps / (ms / 1e3)
+    e2e_value = frames_total * args.steps / (ms_e2e / 1e3)
+    peaks = load_peaks()
+    tot_ms = sum(p["ms"] for p in prof) or 1.0
+    prof.sort(key=lambda p: -p["ms"])
+    top = prof[0]
+    hbm_cats = {"attn_decode", "vq_gather", "layer_norm", "instance_norm", "gemm_f32_skinny", "misc", "sample"}
+    per_launch_ms = top["ms"] / top["launches"]
+    tensor_peak = peaks["tensor_sustained"]
+    if top["category"] in hbm_cats:
+        ach = top["bytes"] / top["launches"] / (per_launch_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"]}
+    else:
+        ach = top["flops"] / top["launches"] / (per_launch_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": peaks["tensor_sustained"], "unit": "TFLOP/s",
+                "frac": ach / peaks["tensor_sustained"]}
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(top["category"])
+    roof.update(traffic=traffic, kernel=top["category"], launches_per_step=top["launches"], avg_launch_us=1e3 * per_launch_ms,
+                share_of_step=top["ms"] / tot_ms, peak_source=peaks["source"],
+                how="CUDA events around every launch of one extra (untimed-for-value) step, on the launching stream")
+    kernels = [{"kernel": p["category"], "launches": p["launches"], "ms": round(p["ms"], 3), "share": round(p["ms"] / tot_ms, 4),
+                "GB/s": round(p["bytes"] / (p["ms"] * 1e-3) / 1e9, 1), "TFLOP/s": round(p["flops"] / (p["ms"] * 1e-3) / 1e12, 2)}
+               for p in prof]
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        fps, secs = cpu_oracle_sample(T if T <= 300 else 300, threads=cores, repeats=2)
+        cpu = {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"1 clip x {min(T, 300)} frames, best of 2 ({secs:.1f} s), oracle/slmft.py forward_val (restated reference, "
+                         f"cross-KV once, discarded work skipped), PyTorch CPU fp32"}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"bf16": "bf16", "fp32": "f32", "fp32_tc": "f32 (bf16x3 split on tcgen05, fp32 accumulate)"}[args.precision], "data": "synthetic",
+            "config": {"workload": args.workload, "clips_per_gpu": B, "frames_per_clip": T, "generated_frames_per_clip": steps_ar,
+                       "global_batch": world * B, "decode": "top-k 52 sampling, temperature 1, pre-drawn uniforms, KV cache on",
+                       "parallelism": f"dp{world} (clips sharded, one all-gather of codes)" if world > 1 else "single GPU",
+                       "l2": "inputs+workspace per step >> 126 MB L2 (no explicit flush needed)", "note": note},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": pred_host.numel() * 4,
+                    "ms_per_step": ms_e2e / args.steps, "api": "dim_b200.compat_api.slmft_forward_val (SLMFT.forward mode='val')"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernels}
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="vico_b256", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="fp32_tc", choices=["fp32", "fp32_tc", "bf16"],
+                    help="fp32: FFMA kernels; fp32_tc: fp32-accurate GEMMs on tcgen05 (3-plane bf16 split); bf16: bf16 GEMM operands")
+    ap.add_argument("--speaker-ones", action="store_true", help="ViCo loader behaviour: speaker motion replaced by ones")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -81,6 +81,8 @@ SIGNATURES = {
     "dim_vq_argmin": (I, [P, P, P, I, I, I, P]),
     "dim_vq_gather": (I, [P, P, P, I, I, I, P, P]),
     "dim_linear_f32": (I, [P, I, P, P, P, I, P, I, I, I, I, I, F, P]),
+    "dim_split_bf16_planes": (I, [P, I, I, I, I, P, P]),
+    "dim_linear_bf16_planes": (I, [P, P, I, I, P, P, I, P, I, I, I, I, F, P]),
     "dim_conv5_leaky_f32": (I, [P, P, P, P, P, I, I, I, F, P]),
     "dim_repack_conv_weight": (I, [P, P, I, I, P]),
     "dim_instance_norm_f32": (I, [P, P, I, I, I, F, P]),

@@ -12,6 +12,7 @@
 #include "attention.cuh"
 #include "common.cuh"
 #include "gemm_f32.cuh"
+#include "gemm_tc.cuh"
 #include "rowops.cuh"
 #include "vq.cuh"
 
@@ -25,6 +26,13 @@ struct TensorRef {
   std::vector<int64_t> shape;
 };
 
+// Tensor-core dispatch state of one built model: planes == 0 -> fp32 FFMA kernels; 1 -> plain bf16 operands;
+// 3 -> exact 3-way bf16 split of fp32 operands (6 products, fp32-grade results).  wmap: fp32 weight -> its plane matrix.
+struct TcCtx {
+  int planes = 0;
+  std::unordered_map<const float*, const __nv_bfloat16*> wmap;
+};
+
 struct VqLayer {
   const float *ln1_g, *ln1_b, *wqkv, *wo, *bo, *ln2_g, *ln2_b, *w1, *b1, *w2, *b2;
 };
@@ -32,6 +40,7 @@ struct VqLayer {
 struct VqModel {
   dim_vq_config cfg{};
   int precision = DIM_PREC_FP32;
+  TcCtx tc;
   const float *map_w, *map_b, *conv_b, *emb_w, *emb_b, *pe, *post_w, *post_b;
   float* conv_wr = nullptr;
   std::vector<VqLayer> enc;
@@ -58,6 +67,7 @@ struct XtEncoder {
 struct S2SModel {
   dim_s2s_config cfg{};
   int precision = DIM_PREC_FP32;
+  TcCtx tc;
   XtEncoder enc_s, enc_joint;
   const float *patch_s = nullptr, *patch_dec_s = nullptr, *norm_s_g = nullptr, *norm_s_b = nullptr;
   const float* token_emb = nullptr;
@@ -113,6 +123,34 @@ int owned_alloc(dim_handle_s* h, size_t bytes, float** out) {
   return DIM_OK;
 }
 
+int planes_of(int precision) {
+  return precision == DIM_PREC_BF16 ? 1 : (precision == DIM_PREC_FP32_TC ? 3 : 0);
+}
+
+// Split an fp32 weight [N,K] into its bf16 plane matrix (owned by the handle) and remember it.
+int tc_add_weight(dim_handle_s* h, TcCtx& tc, const float* W, int N, int K) {
+  if (tc.planes == 0 || W == nullptr || tc.wmap.count(W)) return DIM_OK;
+  const int kp = tc_round_k(K);
+  float* buf = nullptr;
+  if (int e = owned_alloc(h, (size_t)N * tc.planes * kp * sizeof(__nv_bfloat16), &buf)) return e;
+  GemmArgs a;
+  a.A = W; a.lda = K; a.M = N; a.K = K;
+  if (int e = launch_split_planes(a, reinterpret_cast<__nv_bfloat16*>(buf), kp, tc.planes, nullptr)) return e;
+  tc.wmap[W] = reinterpret_cast<const __nv_bfloat16*>(buf);
+  return DIM_OK;
+}
+
+// One Linear: tensor cores (operand split + tcgen05 GEMM) when the model is built for them and the problem is tall enough
+// to fill 128-row MMA tiles, otherwise the fp32 FFMA kernels.
+int run_gemm(const TcCtx& tc, const GemmArgs& a, __nv_bfloat16* scratch, cudaStream_t s) {
+  if (tc.planes == 0 || a.M < 64 || scratch == nullptr) return launch_gemm_f32(a, s);
+  auto it = tc.wmap.find(a.W);
+  if (it == tc.wmap.end()) return launch_gemm_f32(a, s);
+  const int kp = tc_round_k(a.K);
+  if (int e = launch_split_planes(a, scratch, kp, tc.planes, s)) return e;
+  return launch_gemm_tc(a, scratch, it->second, kp, tc.planes, s);
+}
+
 int build_vq_stack(dim_handle_s* h, const std::string& p, const dim_vq_config& c, std::vector<VqLayer>& out) {
   const int64_t H = c.hidden, F = c.ffn;
   out.resize(c.layers);
@@ -137,10 +175,11 @@ int build_vq_stack(dim_handle_s* h, const std::string& p, const dim_vq_config& c
 // ---- VQ-VAE workspace layout (floats per frame row) ---------------------------------------------------------------
 struct VqWs {
   float *h0, *h1, *x, *ln, *qkv, *att, *ff, *z;
+  __nv_bfloat16* ap;
   int64_t* idx;
   size_t bytes;
 };
-VqWs carve_vq(const dim_vq_config& c, int B, int T, void* base) {
+VqWs carve_vq(const dim_vq_config& c, int planes, int B, int T, void* base) {
   size_t R = (size_t)B * T;
   char* p = static_cast<char*>(base);
   VqWs w{};
@@ -152,6 +191,8 @@ VqWs carve_vq(const dim_vq_config& c, int B, int T, void* base) {
   w.h0 = take(R * c.hidden); w.h1 = take(R * c.hidden); w.x = take(R * c.hidden); w.ln = take(R * c.hidden);
   w.qkv = take(R * 3 * c.hidden); w.att = take(R * c.hidden); w.ff = take(R * c.ffn); w.z = take(R * c.zdim);
   w.idx = reinterpret_cast<int64_t*>(take(R * 2));
+  const size_t kmax = (size_t)tc_round_k(std::max(5 * c.hidden, c.ffn));        // widest A operand: the conv's im2col rows
+  w.ap = planes ? reinterpret_cast<__nv_bfloat16*>(take(R * planes * kmax / 2 + 64)) : nullptr;
   w.bytes = (size_t)(p - static_cast<char*>(base));
   return w;
 }
@@ -166,14 +207,14 @@ int vq_trunk(const VqModel& m, const std::vector<VqLayer>& layers, const float* 
     GemmArgs a;
     a.A = w.h0; a.lda = H; a.W = conv_wr; a.bias = conv_b; a.C = w.h1; a.ldc = H; a.M = R; a.N = H; a.K = 5 * H;
     a.act = DIM_ACT_LEAKY; a.slope = c.neg_slope; a.conv_T = T; a.conv_C = H; a.lens = lens;
-    if (int e = launch_gemm_f32(a, s)) return e;
+    if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
   }
   if (int e = launch_instance_norm(w.h1, lens, B, T, H, 1e-5f, s)) return e;
   {  // x = h1 @ emb^T + b + pe[batch_index[b]]
     GemmArgs a;
     a.A = w.h1; a.lda = H; a.W = emb_w; a.bias = emb_b; a.C = w.x; a.ldc = H; a.M = R; a.N = H; a.K = H;
     a.tab = pe; a.ldtab = H; a.tab_mode = 1; a.tab_index = batch_index; a.tab_T = T;
-    if (int e = launch_gemm_f32(a, s)) return e;
+    if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
   }
   const int Dh = H / c.heads;
   for (const VqLayer& L : layers) {
@@ -181,7 +222,7 @@ int vq_trunk(const VqModel& m, const std::vector<VqLayer>& layers, const float* 
     {
       GemmArgs a;
       a.A = w.ln; a.lda = H; a.W = L.wqkv; a.C = w.qkv; a.ldc = 3 * H; a.M = R; a.N = 3 * H; a.K = H;
-      if (int e = launch_gemm_f32(a, s)) return e;
+      if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
     }
     {
       AttnArgs a;                      // 'b n (qkv h d)': q at col 0, k at H, v at 2H
@@ -194,20 +235,20 @@ int vq_trunk(const VqModel& m, const std::vector<VqLayer>& layers, const float* 
       GemmArgs a;
       a.A = w.att; a.lda = H; a.W = L.wo; a.bias = L.bo; a.residual = w.x; a.ldr = H; a.C = w.x; a.ldc = H;
       a.M = R; a.N = H; a.K = H;
-      if (int e = launch_gemm_f32(a, s)) return e;
+      if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
     }
     if (int e = launch_layer_norm(w.x, L.ln2_g, L.ln2_b, w.ln, nullptr, R, H, 1e-5f, s)) return e;
     {
       GemmArgs a;
       a.A = w.ln; a.lda = H; a.W = L.w1; a.bias = L.b1; a.C = w.ff; a.ldc = c.ffn; a.M = R; a.N = c.ffn; a.K = H;
       a.act = DIM_ACT_GELU_TANH;
-      if (int e = launch_gemm_f32(a, s)) return e;
+      if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
     }
     {
       GemmArgs a;
       a.A = w.ff; a.lda = c.ffn; a.W = L.w2; a.bias = L.b2; a.residual = w.x; a.ldr = H; a.C = w.x; a.ldc = H;
       a.M = R; a.N = H; a.K = c.ffn;
-      if (int e = launch_gemm_f32(a, s)) return e;
+      if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
     }
   }
   return DIM_OK;
@@ -266,9 +307,10 @@ int build_xt_encoder(dim_handle_s* h, const std::string& name, int dim_in, const
 
 struct CtxWs {
   float *x, *ln, *qkv, *att, *ff;
+  __nv_bfloat16* ap;
   size_t bytes;
 };
-CtxWs carve_ctx(const dim_s2s_config& c, int B, int T, void* base) {
+CtxWs carve_ctx(const dim_s2s_config& c, int planes, int B, int T, void* base) {
   size_t R = (size_t)B * T;
   const int inner = c.heads * c.dim_head;
   char* p = static_cast<char*>(base);
@@ -280,6 +322,7 @@ CtxWs carve_ctx(const dim_s2s_config& c, int B, int T, void* base) {
   };
   w.x = take(R * c.dim); w.ln = take(R * c.dim); w.qkv = take(R * 3 * inner); w.att = take(R * inner);
   w.ff = take(R * c.ff_mult * c.dim);
+  w.ap = planes ? reinterpret_cast<__nv_bfloat16*>(take(R * planes * (size_t)tc_round_k(c.ff_mult * c.dim) / 2 + 64)) : nullptr;
   w.bytes = (size_t)(p - static_cast<char*>(base));
   return w;
 }
@@ -293,7 +336,7 @@ int xt_encoder_forward(const S2SModel& m, const XtEncoder& E, const float* in, c
     GemmArgs a;
     a.A = in; a.lda = E.dim_in; a.W = E.proj_w; a.bias = E.proj_b; a.C = w.x; a.ldc = D; a.M = R; a.N = D; a.K = E.dim_in;
     a.a_add = a_add; a.tab = E.pos_emb; a.ldtab = D; a.tab_mode = 2; a.tab_T = T; a.tab_scale = 1.0f / sqrtf((float)D);
-    if (int e = launch_gemm_f32(a, s)) return e;
+    if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
   }
   for (int l = 0; l < c.depth; ++l) {
     const XtAttn& A = E.attn[l];
@@ -302,7 +345,7 @@ int xt_encoder_forward(const S2SModel& m, const XtEncoder& E, const float* in, c
     {
       GemmArgs a;
       a.A = w.ln; a.lda = D; a.W = A.wqkv; a.C = w.qkv; a.ldc = 3 * inner; a.M = R; a.N = 3 * inner; a.K = D;
-      if (int e = launch_gemm_f32(a, s)) return e;
+      if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
     }
     {
       AttnArgs a;
@@ -315,20 +358,20 @@ int xt_encoder_forward(const S2SModel& m, const XtEncoder& E, const float* in, c
       GemmArgs a;
       a.A = w.att; a.lda = inner; a.W = A.wo; a.residual = w.x; a.ldr = D; a.C = w.x; a.ldc = D; a.M = R; a.N = D;
       a.K = inner;
-      if (int e = launch_gemm_f32(a, s)) return e;
+      if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
     }
     if (int e = launch_layer_norm(w.x, FF.norm_g, FF.norm_b, w.ln, nullptr, R, D, 1e-5f, s)) return e;
     {
       GemmArgs a;
       a.A = w.ln; a.lda = D; a.W = FF.w1; a.bias = FF.b1; a.C = w.ff; a.ldc = F; a.M = R; a.N = F; a.K = D;
       a.act = DIM_ACT_GELU_ERF;
-      if (int e = launch_gemm_f32(a, s)) return e;
+      if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
     }
     {
       GemmArgs a;
       a.A = w.ff; a.lda = F; a.W = FF.w2; a.bias = FF.b2; a.residual = w.x; a.ldr = D; a.C = w.x; a.ldc = D; a.M = R;
       a.N = D; a.K = F;
-      if (int e = launch_gemm_f32(a, s)) return e;
+      if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
     }
   }
   return launch_layer_norm(w.x, E.final_g, E.final_b, w.x, nullptr, R, D, 1e-5f, s);
@@ -340,9 +383,10 @@ struct GenWs {
   float *x, *ln, *qkv, *att, *ff, *logits;
   int64_t* tokens;                         // [B, steps+1]
   int* step;
+  __nv_bfloat16* ap;                       // A-operand plane scratch for the tensor-core GEMMs
   size_t bytes;
 };
-GenWs carve_gen(const dim_s2s_config& c, int B, int T, int steps, void* base) {
+GenWs carve_gen(const dim_s2s_config& c, int planes, int B, int T, int steps, void* base) {
   const int inner = c.heads * c.dim_head, D = c.dim + c.dim_audio;
   char* p = static_cast<char*>(base);
   GenWs w{};
@@ -360,6 +404,11 @@ GenWs carve_gen(const dim_s2s_config& c, int B, int T, int steps, void* base) {
   w.att = take((size_t)B * inner); w.ff = take((size_t)B * c.ff_mult * D); w.logits = take((size_t)B * c.num_tokens);
   w.tokens = reinterpret_cast<int64_t*>(take((size_t)B * (steps + 1) * 2));
   w.step = reinterpret_cast<int*>(take(64));
+  {
+    const size_t rows_ctx = (size_t)B * T, rows_step = (size_t)B;
+    const size_t need = std::max(rows_ctx * tc_round_k(D), rows_step * tc_round_k(c.ff_mult * D)) * planes;
+    w.ap = planes ? reinterpret_cast<__nv_bfloat16*>(take(need / 2 + 64)) : nullptr;
+  }
   w.bytes = (size_t)(p - static_cast<char*>(base));
   return w;
 }
@@ -397,7 +446,8 @@ extern "C" int dim_set_tensor(dim_handle_t h, const char* name, const void* ptr,
 
 extern "C" int dim_vqvae_build(dim_handle_t h, const char* prefix_c, const dim_vq_config* cfg, int precision, int* model) {
   DIM_REQUIRE(h && cfg && model, "dim_vqvae_build: null argument");
-  DIM_REQUIRE(precision == DIM_PREC_FP32, "dim_vqvae_build: only DIM_PREC_FP32 is implemented for the VQ-VAE");
+  DIM_REQUIRE(precision == DIM_PREC_FP32 || precision == DIM_PREC_FP32_TC || precision == DIM_PREC_BF16,
+              "dim_vqvae_build: unknown precision");
   const dim_vq_config& c = *cfg;
   DIM_REQUIRE(c.hidden % 16 == 0 && c.hidden % c.heads == 0, "hidden must be a multiple of 16 and of heads");
   DIM_REQUIRE(c.hidden / c.heads == 48 || c.hidden / c.heads == 64, "head dim must be 48 or 64");
@@ -406,6 +456,7 @@ extern "C" int dim_vqvae_build(dim_handle_t h, const char* prefix_c, const dim_v
   auto m = std::make_unique<VqModel>();
   m->cfg = c;
   m->precision = precision;
+  m->tc.planes = planes_of(precision);
   const int64_t H = c.hidden, Z = c.zdim;
   const float *conv_w, *dconv_w;
   LOOKUP(m->map_w, p + "encoder.vertice_mapping.0.weight", true, H, c.in_dim);
@@ -433,6 +484,25 @@ extern "C" int dim_vqvae_build(dim_handle_t h, const char* prefix_c, const dim_v
   if (int e = owned_alloc(h, cb, &m->dconv_wr)) return e;
   if (int e = dim_repack_conv_weight(conv_w, m->conv_wr, c.hidden, c.hidden, nullptr)) return e;
   if (int e = dim_repack_conv_weight(dconv_w, m->dconv_wr, c.hidden, c.hidden, nullptr)) return e;
+  {
+    TcCtx& tc = m->tc;
+    const int Hh = c.hidden;
+    if (int e = tc_add_weight(h, tc, m->map_w, Hh, c.in_dim)) return e;
+    if (int e = tc_add_weight(h, tc, m->conv_wr, Hh, 5 * Hh)) return e;
+    if (int e = tc_add_weight(h, tc, m->emb_w, Hh, Hh)) return e;
+    if (int e = tc_add_weight(h, tc, m->post_w, c.zdim, Hh)) return e;
+    if (int e = tc_add_weight(h, tc, m->pre_w, Hh, c.zdim)) return e;
+    if (int e = tc_add_weight(h, tc, m->dconv_wr, Hh, 5 * Hh)) return e;
+    if (int e = tc_add_weight(h, tc, m->demb_w, Hh, Hh)) return e;
+    if (int e = tc_add_weight(h, tc, m->rev_w, c.in_dim, Hh)) return e;
+    for (auto* stack : {&m->enc, &m->dec})
+      for (const VqLayer& L : *stack) {
+        if (int e = tc_add_weight(h, tc, L.wqkv, 3 * Hh, Hh)) return e;
+        if (int e = tc_add_weight(h, tc, L.wo, Hh, Hh)) return e;
+        if (int e = tc_add_weight(h, tc, L.w1, c.ffn, Hh)) return e;
+        if (int e = tc_add_weight(h, tc, L.w2, Hh, c.ffn)) return e;
+      }
+  }
   DIM_CHECK_CUDA(cudaStreamSynchronize(nullptr));
   h->vq.push_back(std::move(m));
   *model = (int)h->vq.size() - 1;
@@ -441,7 +511,7 @@ extern "C" int dim_vqvae_build(dim_handle_t h, const char* prefix_c, const dim_v
 
 extern "C" size_t dim_vqvae_workspace_bytes(dim_handle_t h, int model, int B, int T) {
   if (!h || model < 0 || model >= (int)h->vq.size() || B <= 0 || T <= 0) return 0;
-  return carve_vq(h->vq[model]->cfg, B, T, nullptr).bytes;
+  return carve_vq(h->vq[model]->cfg, h->vq[model]->tc.planes, B, T, nullptr).bytes;
 }
 
 extern "C" int dim_vqvae_encode(dim_handle_t h, int model, const float* x, const int32_t* lens, const int32_t* batch_index,
@@ -452,7 +522,7 @@ extern "C" int dim_vqvae_encode(dim_handle_t h, int model, const float* x, const
   const VqModel& m = *h->vq[model];
   const dim_vq_config& c = m.cfg;
   DIM_REQUIRE(batch_index != nullptr || B <= c.pe_max_len, "batch larger than the positional table (SURVEY F4/H3)");
-  VqWs w = carve_vq(c, B, T, ws);
+  VqWs w = carve_vq(c, m.tc.planes, B, T, ws);
   if (ws == nullptr || ws_bytes < w.bytes) return fail(DIM_EWORKSPACE, "dim_vqvae_encode: workspace too small");
   cudaStream_t s = as_stream(stream);
   const int R = B * T, H = c.hidden;
@@ -460,14 +530,14 @@ extern "C" int dim_vqvae_encode(dim_handle_t h, int model, const float* x, const
     GemmArgs a;
     a.A = x; a.lda = c.in_dim; a.W = m.map_w; a.bias = m.map_b; a.C = w.h0; a.ldc = H; a.M = R; a.N = H; a.K = c.in_dim;
     a.act = DIM_ACT_LEAKY; a.slope = c.neg_slope;
-    if (int e = launch_gemm_f32(a, s)) return e;
+    if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
   }
   if (int e = vq_trunk(m, m.enc, m.conv_wr, m.conv_b, m.emb_w, m.emb_b, m.pe, w, lens, batch_index, B, T, s)) return e;
   float* zbuf = z ? z : w.z;
   {
     GemmArgs a;
     a.A = w.x; a.lda = H; a.W = m.post_w; a.bias = m.post_b; a.C = zbuf; a.ldc = c.zdim; a.M = R; a.N = c.zdim; a.K = H;
-    if (int e = launch_gemm_f32(a, s)) return e;
+    if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
   }
   int64_t* ibuf = idx ? idx : w.idx;
   if (idx || quant_bcl)
@@ -486,7 +556,7 @@ extern "C" int dim_vqvae_decode(dim_handle_t h, int model, const int64_t* codes,
   const VqModel& m = *h->vq[model];
   const dim_vq_config& c = m.cfg;
   DIM_REQUIRE(batch_index != nullptr || B <= c.pe_max_len, "batch larger than the positional table (SURVEY F4/H3)");
-  VqWs w = carve_vq(c, B, L, ws);
+  VqWs w = carve_vq(c, m.tc.planes, B, L, ws);
   if (ws == nullptr || ws_bytes < w.bytes) return fail(DIM_EWORKSPACE, "dim_vqvae_decode: workspace too small");
   cudaStream_t s = as_stream(stream);
   const int R = B * L, H = c.hidden;
@@ -498,21 +568,22 @@ extern "C" int dim_vqvae_decode(dim_handle_t h, int model, const int64_t* codes,
   {
     GemmArgs a;
     a.A = w.z; a.lda = c.zdim; a.W = m.pre_w; a.bias = m.pre_b; a.C = w.h0; a.ldc = H; a.M = R; a.N = H; a.K = c.zdim;
-    if (int e = launch_gemm_f32(a, s)) return e;
+    if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
   }
   if (int e = vq_trunk(m, m.dec, m.dconv_wr, m.dconv_b, m.demb_w, m.demb_b, m.dpe, w, nullptr, batch_index, B, L, s))
     return e;
   {
     GemmArgs a;
     a.A = w.x; a.lda = H; a.W = m.rev_w; a.C = out; a.ldc = c.in_dim; a.M = R; a.N = c.in_dim; a.K = H;
-    if (int e = launch_gemm_f32(a, s)) return e;
+    if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
   }
   return DIM_OK;
 }
 
 extern "C" int dim_slmft_build(dim_handle_t h, const dim_s2s_config* cfg, int precision, int* model) {
   DIM_REQUIRE(h && cfg && model, "dim_slmft_build: null argument");
-  DIM_REQUIRE(precision == DIM_PREC_FP32, "dim_slmft_build: only DIM_PREC_FP32 is implemented so far");
+  DIM_REQUIRE(precision == DIM_PREC_FP32 || precision == DIM_PREC_FP32_TC || precision == DIM_PREC_BF16,
+              "dim_slmft_build: unknown precision");
   const dim_s2s_config& c = *cfg;
   DIM_REQUIRE(c.dim_head == 64, "x-transformers dim_head must be 64");
   DIM_REQUIRE(c.dim % 4 == 0 && c.dim_in % 4 == 0 && c.dim_audio % 4 == 0, "dims must be multiples of 4");
@@ -520,6 +591,7 @@ extern "C" int dim_slmft_build(dim_handle_t h, const dim_s2s_config* cfg, int pr
   auto m = std::make_unique<S2SModel>();
   m->cfg = c;
   m->precision = precision;
+  m->tc.planes = planes_of(precision);
   const int inner = c.heads * c.dim_head, D = c.dim + c.dim_audio;
   if (int e = build_xt_encoder(h, "encoder_s", c.dim_in, c, m->enc_s)) return e;
   if (int e = build_xt_encoder(h, "encoder_joint", c.dim, c, m->enc_joint)) return e;
@@ -542,6 +614,29 @@ extern "C" int dim_slmft_build(dim_handle_t h, const dim_s2s_config* cfg, int pr
   LOOKUP(m->final_b, dn + ".attn_layers.final_norm.bias", false, D);
   LOOKUP(m->logits_w, dn + ".to_logits.weight", true, c.num_tokens, D);
   LOOKUP(m->logits_b, dn + ".to_logits.bias", false, c.num_tokens);
+  {
+    TcCtx& tc = m->tc;
+    for (XtEncoder* E : {&m->enc_s, &m->enc_joint}) {
+      if (int e = tc_add_weight(h, tc, E->proj_w, c.dim, E->dim_in)) return e;
+      for (int l = 0; l < c.depth; ++l) {
+        if (int e = tc_add_weight(h, tc, E->attn[l].wqkv, 3 * inner, c.dim)) return e;
+        if (int e = tc_add_weight(h, tc, E->attn[l].wo, c.dim, inner)) return e;
+        if (int e = tc_add_weight(h, tc, E->ff[l].w1, c.ff_mult * c.dim, c.dim)) return e;
+        if (int e = tc_add_weight(h, tc, E->ff[l].w2, c.dim, c.ff_mult * c.dim)) return e;
+      }
+    }
+    for (int l = 0; l < c.depth; ++l) {
+      if (int e = tc_add_weight(h, tc, m->self_attn[l].wqkv, 3 * inner, D)) return e;
+      if (int e = tc_add_weight(h, tc, m->self_attn[l].wo, D, inner)) return e;
+      if (int e = tc_add_weight(h, tc, m->cross_attn[l].wq, inner, D)) return e;
+      if (int e = tc_add_weight(h, tc, m->cross_attn[l].wkv, 2 * inner, D)) return e;
+      if (int e = tc_add_weight(h, tc, m->cross_attn[l].wo, D, inner)) return e;
+      if (int e = tc_add_weight(h, tc, m->ff[l].w1, c.ff_mult * D, D)) return e;
+      if (int e = tc_add_weight(h, tc, m->ff[l].w2, D, c.ff_mult * D)) return e;
+    }
+    if (int e = tc_add_weight(h, tc, m->logits_w, c.num_tokens, D)) return e;
+    DIM_CHECK_CUDA(cudaStreamSynchronize(nullptr));
+  }
   h->s2s.push_back(std::move(m));
   *model = (int)h->s2s.size() - 1;
   return DIM_OK;
@@ -550,8 +645,9 @@ extern "C" int dim_slmft_build(dim_handle_t h, const dim_s2s_config* cfg, int pr
 extern "C" size_t dim_slmft_workspace_bytes(dim_handle_t h, int model, int B, int T, int steps) {
   if (!h || model < 0 || model >= (int)h->s2s.size() || B <= 0 || T <= 0) return 0;
   const dim_s2s_config& c = h->s2s[model]->cfg;
-  size_t a = carve_ctx(c, B, T, nullptr).bytes;
-  size_t b = steps > 0 ? carve_gen(c, B, T, steps, nullptr).bytes : 0;
+  const int planes = h->s2s[model]->tc.planes;
+  size_t a = carve_ctx(c, planes, B, T, nullptr).bytes;
+  size_t b = steps > 0 ? carve_gen(c, planes, B, T, steps, nullptr).bytes : 0;
   return a > b ? a : b;
 }
 
@@ -562,7 +658,7 @@ extern "C" int dim_slmft_context(dim_handle_t h, int model, const float* v_speak
   const S2SModel& m = *h->s2s[model];
   const dim_s2s_config& c = m.cfg;
   DIM_REQUIRE(T <= c.max_seq_len, "sequence longer than the positional table");
-  CtxWs w = carve_ctx(c, B, T, ws);
+  CtxWs w = carve_ctx(c, m.tc.planes, B, T, ws);
   if (ws == nullptr || ws_bytes < w.bytes) return fail(DIM_EWORKSPACE, "dim_slmft_context: workspace too small");
   cudaStream_t s = as_stream(stream);
   if (int e = xt_encoder_forward(m, m.enc_s, v_speaker, m.patch_s, mask, w, B, T, s)) return e;
@@ -584,7 +680,7 @@ extern "C" int dim_slmft_generate(dim_handle_t h, int model, const float* ctx, c
   const S2SModel& m = *h->s2s[model];
   const dim_s2s_config& c = m.cfg;
   const int inner = c.heads * c.dim_head, D = c.dim + c.dim_audio, F = c.ff_mult * D, V = c.num_tokens;
-  GenWs w = carve_gen(c, B, T, steps, ws);
+  GenWs w = carve_gen(c, m.tc.planes, B, T, steps, ws);
   if (ws == nullptr || ws_bytes < w.bytes) return fail(DIM_EWORKSPACE, "dim_slmft_generate: workspace too small");
   cudaStream_t s = as_stream(stream);
   const float scale = 1.0f / sqrtf((float)c.dim_head);
@@ -593,7 +689,7 @@ extern "C" int dim_slmft_generate(dim_handle_t h, int model, const float* ctx, c
     GemmArgs a;
     a.A = ctx; a.lda = D; a.W = m.cross_attn[l].wkv; a.C = w.cross_kv[l]; a.ldc = 2 * inner; a.M = B * T; a.N = 2 * inner;
     a.K = D;
-    if (int e = launch_gemm_f32(a, s)) return e;
+    if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
   }
   DIM_CHECK_CUDA(cudaMemcpy2DAsync(w.tokens, (size_t)(steps + 1) * sizeof(int64_t), prompt, sizeof(int64_t), sizeof(int64_t),
                                    B, cudaMemcpyDeviceToDevice, s));
@@ -611,7 +707,7 @@ extern "C" int dim_slmft_generate(dim_handle_t h, int model, const float* ctx, c
       {
         GemmArgs a;
         a.A = w.ln; a.lda = D; a.W = SA.wqkv; a.C = w.qkv; a.ldc = 3 * inner; a.M = B; a.N = 3 * inner; a.K = D;
-        if (int e = launch_gemm_f32(a, s)) return e;
+        if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
       }
       {
         DecodeAttnArgs a;
@@ -625,14 +721,14 @@ extern "C" int dim_slmft_generate(dim_handle_t h, int model, const float* ctx, c
         GemmArgs a;
         a.A = w.att; a.lda = inner; a.W = SA.wo; a.residual = w.x; a.ldr = D; a.C = w.x; a.ldc = D; a.M = B; a.N = D;
         a.K = inner;
-        if (int e = launch_gemm_f32(a, s)) return e;
+        if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
       }
       // --- cross attention over the cached context K/V
       if (int e = launch_layer_norm(w.x, CA.norm_g, CA.norm_b, w.ln, nullptr, B, D, 1e-5f, s)) return e;
       {
         GemmArgs a;
         a.A = w.ln; a.lda = D; a.W = CA.wq; a.C = w.qkv; a.ldc = inner; a.M = B; a.N = inner; a.K = D;
-        if (int e = launch_gemm_f32(a, s)) return e;
+        if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
       }
       {
         DecodeAttnArgs a;
@@ -645,7 +741,7 @@ extern "C" int dim_slmft_generate(dim_handle_t h, int model, const float* ctx, c
         GemmArgs a;
         a.A = w.att; a.lda = inner; a.W = CA.wo; a.residual = w.x; a.ldr = D; a.C = w.x; a.ldc = D; a.M = B; a.N = D;
         a.K = inner;
-        if (int e = launch_gemm_f32(a, s)) return e;
+        if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
       }
       // --- feed forward
       if (int e = launch_layer_norm(w.x, FF.norm_g, FF.norm_b, w.ln, nullptr, B, D, 1e-5f, s)) return e;
@@ -653,20 +749,20 @@ extern "C" int dim_slmft_generate(dim_handle_t h, int model, const float* ctx, c
         GemmArgs a;
         a.A = w.ln; a.lda = D; a.W = FF.w1; a.bias = FF.b1; a.C = w.ff; a.ldc = F; a.M = B; a.N = F; a.K = D;
         a.act = DIM_ACT_GELU_ERF;
-        if (int e = launch_gemm_f32(a, s)) return e;
+        if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
       }
       {
         GemmArgs a;
         a.A = w.ff; a.lda = F; a.W = FF.w2; a.bias = FF.b2; a.residual = w.x; a.ldr = D; a.C = w.x; a.ldc = D; a.M = B;
         a.N = D; a.K = F;
-        if (int e = launch_gemm_f32(a, s)) return e;
+        if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
       }
     }
     if (int e = launch_layer_norm(w.x, m.final_g, m.final_b, w.ln, nullptr, B, D, 1e-5f, s)) return e;
     {
       GemmArgs a;
       a.A = w.ln; a.lda = D; a.W = m.logits_w; a.bias = m.logits_b; a.C = w.logits; a.ldc = V; a.M = B; a.N = V; a.K = D;
-      if (int e = launch_gemm_f32(a, s)) return e;
+      if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
     }
     if (int e = launch_sample(w.logits, B, V, temperature, top_k, uniforms, steps, w.step, w.tokens, steps + 1, 1,
                               logits_out, steps * V, s))

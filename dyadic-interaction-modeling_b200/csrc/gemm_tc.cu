@@ -1,0 +1,404 @@
+// tcgen05 GEMM for sm_100a:  C[M,N] = epilogue( sum_pairs A_pa[M,Kp] @ W_pw[N,Kp]^T )   bf16 operands, fp32 accumulation in TMEM.
+//
+//   * operands are K-major bf16 "plane" matrices: Ap = [M, planes*Kp], Wp = [N, planes*Kp] (Kp = K rounded up to 64, zero
+//     padded).  planes == 1 is a plain bf16 GEMM.  planes == 2/3 hold the bf16 split of fp32 values (x = h + m + l, 8 mantissa
+//     bits each): summing the products of the listed plane pairs on the tensor cores reproduces an fp32 GEMM to ~2^-16
+//     (3 pairs) or ~2^-23 (6 pairs) relative error per product -- this is how the fp32-parity mode reaches tensor-core speed.
+//   * one 128 x BN output tile per CTA; 192 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one
+//     elected lane issues tcgen05.mma, accumulator 128 lanes x BN columns of TMEM), warps 2-5 = epilogue
+//     (tcgen05.ld 32x32b -> registers -> fused bias / table add / activation / residual -> 128-bit global stores).
+//   * A and W tiles (128 x 64 and BN x 64 bf16) are staged by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) into a
+//     STAGES-deep shared-memory ring guarded by full/empty mbarriers; tcgen05.commit releases slots and signals the epilogue.
+//   * smem is sized so that two CTAs fit per SM: one tile's epilogue overlaps the other's MMA main loop.
+#include <cuda.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "gemm_tc.cuh"
+
+namespace dimb {
+
+namespace {
+
+constexpr int BM = 128, BKE = 64;            // tile rows, K elements per stage (64 bf16 = 128 B = one swizzle row)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(x), "r"(y), "r"(bar)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
+//   start address >> 4 | LBO (=1, unused for swizzled K-major) << 16 | SBO (1024 B between 8-row groups) >> 4 << 32 |
+//   version 1 << 46 | layout SWIZZLE_128B (2) << 61
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_c),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+struct TcParams {
+  GemmArgs e;                 // epilogue fields + M, N (A/W/K of `e` are unused here)
+  int kblocks;                // Kp / 64
+  int npairs;
+  int pa[6], pw[6];           // plane index of A / W for each accumulated pair
+  int kp;                     // padded K (elements) = plane stride
+};
+
+__device__ __forceinline__ float tc_epilogue_elem(const GemmArgs& p, float v, int row, int col) {
+  if (p.bias) v += __ldg(p.bias + col);
+  if (p.tab_mode == 1) {
+    int g = row / p.tab_T;
+    if (p.tab_index) g = __ldg(p.tab_index + g);
+    v = __fadd_rn(v, __ldg(p.tab + (size_t)g * p.ldtab + col));
+  } else if (p.tab_mode == 2) {
+    int g = row % p.tab_T;
+    v = __fadd_rn(v, __fmul_rn(__ldg(p.tab + (size_t)g * p.ldtab + col), p.tab_scale));
+  }
+  v = act_apply(v, p.act, p.slope);
+  if (p.residual) v = __fadd_rn(v, p.residual[(size_t)row * p.ldr + col]);
+  return v;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192) gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA,
+                                                         const __grid_constant__ CUtensorMap tmW, const TcParams p) {
+  constexpr uint32_t A_BYTES = BM * BKE * 2, W_BYTES = BN * BKE * 2, STAGE_BYTES = A_BYTES + W_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B tiles need 1024-byte alignment
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int total_kb = p.kblocks * p.npairs;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&accum_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {                                   // whole warp allocates BN TMEM columns (power of two >= 32)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < total_kb; ++it) {
+        const int pair = it / p.kblocks, kb = it - pair * p.kblocks;
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+        const uint32_t fb = smem_u32(&full_bar[stage]);
+        mbar_expect_tx(fb, STAGE_BYTES);
+        const uint32_t sa = smem_base + stage * STAGE_BYTES;
+        tma_load_2d(sa, &tmA, p.pa[pair] * p.kp + kb * BKE, m0, fb);
+        tma_load_2d(sa + A_BYTES, &tmW, p.pw[pair] * p.kp + kb * BKE, n0, fb);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      // instruction descriptor: D fp32 (1<<4), A bf16 (1<<7), B bf16 (1<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < total_kb; ++it) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_base + stage * STAGE_BYTES;
+        const uint64_t adesc = make_sdesc(sa), bdesc = make_sdesc(sa + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BKE / 16; ++k)            // UMMA_K = 16 bf16 = 32 bytes: +2 in the (addr >> 4) field
+          umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it | k) != 0 ? 1u : 0u);
+        umma_commit(smem_u32(&empty_bar[stage]));     // slot reusable once these MMAs have read it
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(smem_u32(&accum_bar));              // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5; warp w may only touch TMEM lanes 32*(w%4) .. +31 =====
+    const int q = warp & 3;
+    mbar_wait(smem_u32(&accum_bar), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = m0 + q * 32 + lane;
+    const GemmArgs& e = p.e;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t r[16];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < e.M) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int col = n0 + c0 + g * 4;
+          if (col < e.N) {                             // N % 4 == 0: a float4 is entirely inside or outside
+            float4 o;
+            o.x = tc_epilogue_elem(e, __uint_as_float(r[g * 4 + 0]), row, col + 0);
+            o.y = tc_epilogue_elem(e, __uint_as_float(r[g * 4 + 1]), row, col + 1);
+            o.z = tc_epilogue_elem(e, __uint_as_float(r[g * 4 + 2]), row, col + 2);
+            o.w = tc_epilogue_elem(e, __uint_as_float(r[g * 4 + 3]), row, col + 3);
+            if (e.C) *reinterpret_cast<float4*>(e.C + (size_t)row * e.ldc + col) = o;
+            if (e.Cb) {
+              __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+              uint2 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&lo);
+              pk.y = *reinterpret_cast<uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(e.Cb + (size_t)row * e.ldcb + col) = pk;
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+  }
+}
+
+// ---- host: tensor maps ----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// bf16 matrix [rows, cols] with row pitch ld (elements); box = 64 columns x box_rows rows, 128-byte swizzle.
+int make_map(const __nv_bfloat16* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+  using Key = std::tuple<const void*, int, int, int, int>;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  Key key{ptr, rows, cols, ld, box_rows};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return DIM_OK; }
+  }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(DIM_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2] = {(cuuint32_t)BKE, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DIM_ECUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = *out;
+  return DIM_OK;
+}
+
+template <int BN, int STAGES>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcParams& p, cudaStream_t s) {
+  constexpr size_t smem = (size_t)STAGES * (BM * BKE * 2 + BN * BKE * 2) + 1024;
+  static bool once = false;
+  if (!once) {
+    DIM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    once = true;
+  }
+  dim3 grid(cdiv(p.e.N, BN), cdiv(p.e.M, BM));
+  ProfScope ps(CAT_GEMM_TC, s, 2.0 * ((double)p.e.M + p.e.N) * p.kp * p.npairs + 4.0 * p.e.M * p.e.N,
+               2.0 * p.e.M * (double)p.e.N * p.kp * p.npairs);
+  gemm_bf16_tcgen05<BN, STAGES><<<grid, 192, smem, s>>>(tmA, tmW, p);
+  DIM_LAUNCHED();
+  return DIM_OK;
+}
+
+
+// fp32 -> bf16 planes.  One thread per 4 consecutive k of one row.
+__global__ void __launch_bounds__(256) split_planes_kernel(const GemmArgs a, __nv_bfloat16* __restrict__ out, int kp,
+                                                           int planes) {
+  const int k4n = kp >> 2;
+  const size_t total = (size_t)a.M * k4n;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / k4n), k0 = (int)(i - (size_t)row * k4n) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (k0 < a.K) {
+      const float* src;
+      if (a.conv_T > 0) {
+        int tap = k0 / a.conv_C, c = k0 - tap * a.conv_C;
+        int b = row / a.conv_T, t = row - b * a.conv_T;
+        int L = a.lens ? __ldg(a.lens + b) : a.conv_T;
+        int ts = min(max(t + tap - 2, 0), L - 1);
+        src = a.A + ((size_t)b * a.conv_T + ts) * a.lda + c;
+      } else {
+        src = a.A + (size_t)row * a.lda + k0;
+      }
+      float4 x = *reinterpret_cast<const float4*>(src);
+      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+      if (a.a_add) {
+        float4 e = __ldg(reinterpret_cast<const float4*>(a.a_add + k0));
+        v[0] += e.x; v[1] += e.y; v[2] += e.z; v[3] += e.w;
+      }
+    }
+    __nv_bfloat16* dst = out + (size_t)row * planes * kp + k0;
+    for (int pl = 0; pl < planes; ++pl) {
+      __nv_bfloat16 h[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        h[j] = __float2bfloat16_rn(v[j]);
+        v[j] = v[j] - __bfloat162float(h[j]);          // exact: the remainder of an RN split is representable
+      }
+      uint2 pk;
+      pk.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+      pk.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+      *reinterpret_cast<uint2*>(dst + (size_t)pl * kp) = pk;
+    }
+  }
+}
+
+}  // namespace
+
+int launch_split_planes(const GemmArgs& a, __nv_bfloat16* out, int kp, int planes, cudaStream_t s) {
+  DIM_REQUIRE(a.M > 0 && a.K > 0 && a.K % 4 == 0 && kp % 64 == 0 && kp >= a.K, "split: bad K");
+  DIM_REQUIRE(planes >= 1 && planes <= 3, "split: planes must be 1..3");
+  if (a.conv_T > 0) DIM_REQUIRE(a.conv_C % 4 == 0 && a.K == 5 * a.conv_C, "split: conv mode needs K = 5*C");
+  size_t total = (size_t)a.M * (kp / 4);
+  int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 32);
+  ProfScope ps(CAT_MISC, s, (double)a.M * a.K * 4.0 + (double)a.M * kp * planes * 2.0, 0);
+  split_planes_kernel<<<blocks, 256, 0, s>>>(a, out, kp, planes);
+  DIM_LAUNCHED();
+  return DIM_OK;
+}
+
+int tc_pairs(int planes, int* pa, int* pw) {
+  // plane 0 = high, 1 = middle, 2 = low part of the bf16 split.  Products kept: all with (index sum) < planes.
+  int n = 0;
+  for (int s = planes - 1; s >= 0; --s)        // smallest contributions first
+    for (int i = 0; i <= s; ++i) {
+      pa[n] = i;
+      pw[n] = s - i;
+      ++n;
+    }
+  return n;
+}
+
+int launch_gemm_tc(const GemmArgs& e, const __nv_bfloat16* Ap, const __nv_bfloat16* Wp, int kp, int planes, cudaStream_t s) {
+  DIM_REQUIRE(e.M > 0 && e.N > 0 && kp > 0 && kp % BKE == 0, "gemm_tc: Kp must be a positive multiple of 64");
+  DIM_REQUIRE(e.N % 4 == 0 && (e.C == nullptr || e.ldc % 4 == 0) && (e.Cb == nullptr || e.ldcb % 4 == 0),
+              "gemm_tc: N and output pitches must be multiples of 4");
+  DIM_REQUIRE(planes >= 1 && planes <= 3, "gemm_tc: planes must be 1..3");
+  DIM_REQUIRE(e.C != nullptr || e.Cb != nullptr, "gemm_tc: no output");
+  DIM_REQUIRE(((uintptr_t)Ap & 15) == 0 && ((uintptr_t)Wp & 15) == 0, "gemm_tc: operands must be 16-byte aligned");
+  TcParams p;
+  p.e = e;
+  p.kblocks = kp / BKE;
+  p.kp = kp;
+  p.npairs = tc_pairs(planes, p.pa, p.pw);
+  // Narrow tiles when the grid would not cover the SMs (skinny decode-step GEMMs stream weights: more CTAs = more
+  // memory parallelism); wide tiles otherwise.
+  const long tiles128 = (long)cdiv(e.M, BM) * cdiv(e.N, 128);
+  const long tiles64 = (long)cdiv(e.M, BM) * cdiv(e.N, 64);
+  CUtensorMap tmA, tmW;
+  if (int err = make_map(Ap, e.M, planes * kp, planes * kp, BM, &tmA)) return err;
+  if (tiles128 >= 120) {
+    if (int err = make_map(Wp, e.N, planes * kp, planes * kp, 128, &tmW)) return err;
+    return launch_tc<128, 3>(tmA, tmW, p, s);
+  }
+  if (tiles64 >= 120) {
+    if (int err = make_map(Wp, e.N, planes * kp, planes * kp, 64, &tmW)) return err;
+    return launch_tc<64, 4>(tmA, tmW, p, s);
+  }
+  if (int err = make_map(Wp, e.N, planes * kp, planes * kp, 32, &tmW)) return err;
+  return launch_tc<32, 4>(tmA, tmW, p, s);
+}
+
+}  // namespace dimb
+
+using namespace dimb;
+
+extern "C" int dim_split_bf16_planes(const float* X, int ldx, int rows, int K, int planes, void* out, void* stream) {
+  if (int e = ensure_device()) return e;
+  GemmArgs a;
+  a.A = X; a.lda = ldx; a.M = rows; a.K = K;
+  return launch_split_planes(a, static_cast<__nv_bfloat16*>(out), tc_round_k(K), planes, as_stream(stream));
+}
+
+extern "C" int dim_linear_bf16_planes(const void* Ap, const void* Wp, int K, int planes, const float* bias,
+                                      const float* residual, int ldr, float* C, int ldc, int M, int N, int act, float slope,
+                                      void* stream) {
+  if (int e = ensure_device()) return e;
+  GemmArgs a;
+  a.bias = bias; a.residual = residual; a.ldr = ldr; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K; a.act = act;
+  a.slope = slope;
+  return launch_gemm_tc(a, static_cast<const __nv_bfloat16*>(Ap), static_cast<const __nv_bfloat16*>(Wp), tc_round_k(K), planes,
+                        as_stream(stream));
+}

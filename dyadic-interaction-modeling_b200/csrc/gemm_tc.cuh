@@ -1,0 +1,19 @@
+// tcgen05 (5th-gen tensor core) GEMM on bf16 plane operands + the fp32 -> bf16-plane split.  See gemm_tc.cu.
+#pragma once
+#include "common.cuh"
+#include "gemm_f32.cuh"
+
+namespace dimb {
+
+inline int tc_round_k(int K) { return (K + 63) / 64 * 64; }
+
+// out[row, p*kp + k] = p-th bf16 part of A'(row,k) for k < K (0 for K <= k < kp), where A' is A with the GemmArgs
+// prologue applied (a_add, conv-mode gather with replicate clamp / lens).  Uses a.A, a.lda, a.M, a.K, a.a_add, a.conv_*.
+int launch_split_planes(const GemmArgs& a, __nv_bfloat16* out, int kp, int planes, cudaStream_t s);
+
+// C = epilogue(sum over plane pairs of Ap_i @ Wp_j^T); epilogue fields, M and N are taken from `e`.
+int launch_gemm_tc(const GemmArgs& e, const __nv_bfloat16* Ap, const __nv_bfloat16* Wp, int kp, int planes, cudaStream_t s);
+
+int tc_pairs(int planes, int* pa, int* pw);
+
+}  // namespace dimb

@@ -16,7 +16,7 @@ import torch
 from . import _lib
 from .schema import S2SConfig, VQConfig
 
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_FP32_TC = 0, 1, 2
 
 
 def _stream():

@@ -59,6 +59,27 @@ def linear(a, w, bias=None, residual=None, act=0, slope=0.0):
     return out
 
 
+def split_planes(x, planes):
+    """fp32 (rows,K) -> bf16 plane matrix (rows, planes*Kp), Kp = K rounded up to 64 (zero padded)."""
+    _req(x, torch.float32, "x")
+    rows, K = x.shape
+    kp = (K + 63) // 64 * 64
+    out = torch.empty(rows, planes * kp, dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.load().dim_split_bf16_planes(_ptr(x), K, rows, K, planes, _ptr(out), _stream()), "dim_split_bf16_planes")
+    return out
+
+
+def linear_tc(a, w, bias=None, residual=None, act=0, slope=0.0, planes=3):
+    """Same contract as linear() but on the tcgen05 tensor cores via the bf16 plane split (planes=1: plain bf16)."""
+    M, K = a.shape
+    N = w.shape[0]
+    ap, wp = split_planes(a, planes), split_planes(w, planes)
+    out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    _lib.check(_lib.load().dim_linear_bf16_planes(_ptr(ap), _ptr(wp), K, planes, _ptr(bias), _ptr(residual), N, _ptr(out), N,
+                                                  M, N, act, float(slope), _stream()), "dim_linear_bf16_planes")
+    return out
+
+
 def repack_conv_weight(w_oik):
     _req(w_oik, torch.float32, "w")
     co, ci, k = w_oik.shape

@@ -40,7 +40,9 @@ extern "C" {
 
 /* arithmetic modes of a built model */
 #define DIM_PREC_FP32 0   /* fp32 storage + fp32 FFMA accumulation: the parity mode (<=1e-4 vs the reference) */
-#define DIM_PREC_BF16 1   /* bf16 weights/activations/KV, fp32 accumulate (tcgen05), fp32 softmax/LayerNorm/residual */
+#define DIM_PREC_BF16 1   /* GEMM operands rounded to bf16, fp32 accumulate on tcgen05; fp32 softmax/LayerNorm/residual */
+#define DIM_PREC_FP32_TC 2 /* fp32-accurate GEMMs on tcgen05: operands split exactly into 3 bf16 planes, 6 products summed in
+                              fp32 (TMEM).  Same parity bar as DIM_PREC_FP32 at tensor-core speed. */
 
 const char* dim_last_error(void);
 int dim_version(void);
@@ -78,6 +80,15 @@ int dim_vq_gather(const int64_t* idx, const float* codebook, float* out, int N, 
  * fp32 in/out, fp32 FFMA accumulation.  bias/residual nullable.  K % 4 == 0, N % 4 == 0, lda/ldc in elements. */
 int dim_linear_f32(const float* A, int lda, const float* W, const float* bias, const float* residual, int ldr,
                    float* C, int ldc, int M, int N, int K, int act, float slope, void* stream);
+
+/* Tensor-core (tcgen05) path of the same Linear.  Operands are bf16 "plane" matrices [rows, planes*Kp], Kp = K rounded up
+ * to 64 and zero padded: planes == 1 is plain bf16; planes == 2 / 3 hold the exact bf16 split x = h + m (+ l) of fp32
+ * values, and the GEMM accumulates the 3 / 6 significant plane-pair products in fp32 (TMEM), i.e. an fp32-accurate
+ * Linear at tensor-core speed.  dim_split_bf16_planes produces a plane matrix from fp32 rows. */
+int dim_split_bf16_planes(const float* X, int ldx, int rows, int K, int planes, void* out_bf16, void* stream);
+int dim_linear_bf16_planes(const void* A_planes, const void* W_planes, int K, int planes, const float* bias,
+                           const float* residual, int ldr, float* C, int ldc, int M, int N, int act, float slope,
+                           void* stream);
 
 /* Conv1d(C,C,k=5,stride 1,padding 2 replicate) + bias + LeakyReLU(slope) on frames (B,T,C) -> (B,T,C).
  * Replaces stage1_BIWI.py:265-267 / :331-333.  Wr is the weight re-laid out as [Cout][5][Cin] (dim_repack_conv_weight).

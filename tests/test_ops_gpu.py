@@ -167,3 +167,37 @@ def test_vq_gather_out_of_range_counted():
     out, bad = ops.vq_gather(idx.cuda(), E.cuda(), count_bad=True)
     assert int(bad.item()) == 2
     assert torch.equal(out.cpu()[[0, 1, 4]], E[[0, 511, 7]])
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 2304, 1152), (300, 384, 56), (100, 56, 384), (256, 1152, 4608),
+                                    (1000, 1536, 384), (4096, 384, 1920), (257, 512, 1152)])
+@pytest.mark.parametrize("planes", [1, 2, 3])
+def test_linear_tcgen05(M, N, K, planes):
+    """tcgen05 GEMM on bf16 planes.  planes=1 must equal an fp32 matmul of the bf16-rounded operands; planes=3 (6 products)
+    must match the fp32 reference like the FFMA kernel does (2e-5); planes=2 (3 products) within 2e-4."""
+    from dim_b200 import ops
+    g = _g(M + N + K)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / math.sqrt(K)
+    b = torch.randn(N, generator=g) * 0.1
+    r = torch.randn(M, N, generator=g)
+    out = ops.linear_tc(a.cuda(), w.cuda(), b.cuda(), r.cuda(), act=2, planes=planes).cpu()
+    if planes == 1:
+        ref = OV.gelu_tanh(F.linear(a.bfloat16().float(), w.bfloat16().float(), b)) + r
+        tol = 2e-5
+    else:
+        ref = OV.gelu_tanh(F.linear(a, w, b)) + r
+        tol = 2e-5 if planes == 3 else 2e-4
+    tol *= max(1.0, K / 1152)          # the tensor core's fp32 accumulator truncates: error grows ~linearly with K
+    err = float((out - ref).abs().max())
+    assert err <= tol, err
+
+
+def test_split_planes_is_exact():
+    from dim_b200 import ops
+    x = torch.randn(37, 56, generator=_g(2)) * 3
+    p = ops.split_planes(x.cuda(), 3).cpu().float().view(37, 3, 64)
+    assert torch.equal(p[:, :, 56:], torch.zeros(37, 3, 8))
+    assert torch.equal(p[:, 0, :56], x.bfloat16().float())
+    rec = p[:, 0, :56] + p[:, 1, :56] + p[:, 2, :56]
+    assert float((rec - x).abs().max()) <= 2e-7 * float(x.abs().max())

@@ -17,12 +17,13 @@ S2S, VQ = S2SConfig(), VQConfig()
 TOL = 1e-4
 
 
-@pytest.fixture(scope="module")
-def engines(slmft_sd):
-    from dim_b200.engine import Handle, SLMFTEngine, VQEngine
+@pytest.fixture(scope="module", params=["fp32_ffma", "fp32_tcgen05"])
+def engines(slmft_sd, request):
+    from dim_b200.engine import PREC_FP32, PREC_FP32_TC, Handle, SLMFTEngine, VQEngine
+    prec = PREC_FP32 if request.param == "fp32_ffma" else PREC_FP32_TC
     h = Handle()
     h.register(slmft_sd)
-    return SLMFTEngine(h, S2S), VQEngine(h, VQ, prefix="listener_vq.")
+    return SLMFTEngine(h, S2S, precision=prec), VQEngine(h, VQ, prefix="listener_vq.", precision=prec)
 
 
 @pytest.mark.parametrize("B,T,ragged", [(1, 40, False), (3, 70, True), (2, 130, True)])
@@ -99,3 +100,36 @@ def test_forward_val_end_to_end(engines, slmft_sd):
     assert torch.equal(codes.cpu(), inter["codes"])
     assert torch.allclose(pred.cpu(), ref_pred, atol=TOL), float((pred.cpu() - ref_pred).abs().max())
     assert abs(float(loss) - float(ref_loss)) < 1e-4
+
+
+def test_generate_greedy_batch96_hits_tensor_core_decode(engines, slmft_sd):
+    """B = 96 >= 64 rows: in the tcgen05 mode the per-step decode GEMMs run on the tensor cores too."""
+    s2s, _ = engines
+    B, T = 96, 12
+    c = dim_b200.synth.make_clips(B, T, seed=55)
+    x_s = OS.forward_encoder(slmft_sd, c["v_speaker"], c["mask"], S2S)
+    ctx = OS.decoder_context(slmft_sd, x_s, c["v_audio"])
+    prompt = torch.randint(0, 512, (B, 1), generator=torch.Generator().manual_seed(1))
+    ref_codes, ref_logits = OX.generate(slmft_sd, "decoder_joint.net", prompt, T - 1, S2S.depth, ctx, c["mask"],
+                                        return_logits=True)
+    codes, logits = s2s.generate(ctx.cuda(), c["mask"].cuda(), prompt.cuda(), T - 1, return_logits=True)
+    _compare_codes(codes.cpu(), logits.cpu(), ref_codes, ref_logits)
+
+
+def test_bf16_mode_is_close(slmft_sd):
+    """bf16 GEMM operands (BASELINE configs[2]): not a parity mode; logits of the first decode step must stay within
+    bf16 rounding noise of the fp32 oracle and the path must run end to end."""
+    from dim_b200.engine import PREC_BF16, Handle, SLMFTEngine
+    h = Handle()
+    h.register(slmft_sd)
+    s2s = SLMFTEngine(h, S2S, precision=PREC_BF16)
+    B, T = 64, 20
+    c = dim_b200.synth.make_clips(B, T, seed=56)
+    ctx_ref = OS.decoder_context(slmft_sd, OS.forward_encoder(slmft_sd, c["v_speaker"], c["mask"], S2S), c["v_audio"])
+    ctx = s2s.context(c["v_speaker"].cuda(), c["v_audio"].cuda(), c["mask"].cuda()).cpu()
+    assert float((ctx - ctx_ref).abs().max()) < 0.15
+    prompt = torch.randint(0, 512, (B, 1), generator=torch.Generator().manual_seed(2))
+    ref_codes, ref_logits = OX.generate(slmft_sd, "decoder_joint.net", prompt, 1, S2S.depth, ctx_ref, c["mask"], return_logits=True)
+    codes, logits = s2s.generate(ctx_ref.cuda(), c["mask"].cuda(), prompt.cuda(), T - 1, return_logits=True)
+    assert float((logits[:, 0].cpu() - ref_logits[:, 0]).abs().max()) < 0.1
+    assert codes.shape == (B, T - 1) and int(codes.min()) >= 0 and int(codes.max()) < 512

@@ -13,12 +13,13 @@ CFG = VQConfig()
 TOL = 1e-4
 
 
-@pytest.fixture(scope="module")
-def engine(vq_sd):
-    from dim_b200.engine import Handle, VQEngine
+@pytest.fixture(scope="module", params=["fp32_ffma", "fp32_tcgen05"])
+def engine(vq_sd, request):
+    """Both fp32-grade arithmetic modes must meet the same bar: FFMA kernels, and tcgen05 with the exact 3-plane bf16 split."""
+    from dim_b200.engine import PREC_FP32, PREC_FP32_TC, Handle, VQEngine
     h = Handle()
     h.register(vq_sd)
-    return VQEngine(h, CFG)
+    return VQEngine(h, CFG, precision=PREC_FP32 if request.param == "fp32_ffma" else PREC_FP32_TC)
 
 
 def _x(case):
