@@ -2,7 +2,7 @@
 //   attn_prefill_f32 : flash-style tiled attention over frames, online softmax, 64x64 score tiles in shared memory.
 //                      VQ-VAE layers (Dh 48, scale hidden^-0.5, no mask; models/lib/base_models.py:136-143) and
 //                      x-transformers encoders (Dh 64, causal + key-padding mask, -FLT_MAX fill).
-//   attn_decode_f32  : one query per (batch, head) against a token-major K/V cache (self-attention with in-kernel
+//   attn_decode      : one query per (batch, head) against a token-major K/V cache (self-attention with in-kernel
 //                      append of the new key/value, or cross-attention over the projected context); HBM-bound:
 //                      each half-warp streams whole 256-byte head rows with 128-bit loads.
 #include "attention.cuh"
@@ -147,15 +147,50 @@ __global__ void __launch_bounds__(256) attn_prefill_f32(const AttnArgs p) {
     const int qi = q0 + ty + 16 * i;
     if (qi >= p.Tq) continue;
     const float inv = l_run[i] > 0.f ? 1.f / l_run[i] : 0.f;
-    float* orow = p.out + ((size_t)b * p.Tq + qi) * p.ldo + h * DH;
+    if (p.out) {
+      float* orow = p.out + ((size_t)b * p.Tq + qi) * p.ldo + h * DH;
 #pragma unroll
-    for (int j = 0; j < DJ; ++j) orow[tx + 16 * j] = o[i][j] * inv;
+      for (int j = 0; j < DJ; ++j) orow[tx + 16 * j] = o[i][j] * inv;
+    }
+    if (p.out_p) {
+      __nv_bfloat16* prow = p.out_p + ((size_t)b * p.Tq + qi) * p.planes * p.kp + h * DH;
+#pragma unroll
+      for (int j = 0; j < DJ; ++j) store_planes1(prow + tx + 16 * j, o[i][j] * inv, p.planes, p.kp);
+    }
   }
 }
 
 // ---- decode: one query row per (b,h) ----------------------------------------------------------------------------
-// 128 threads = 8 half-warps; a half-warp owns whole keys (16 lanes x float4 = 64 dims).
-__global__ void __launch_bounds__(128) attn_decode_f32(const DecodeAttnArgs p) {
+// 128 threads = 8 half-warps; a half-warp owns whole keys (16 lanes x 4 elements = 64 dims: 256 B fp32 / 128 B bf16 rows).
+template <bool BF16>
+struct KvIo;
+template <>
+struct KvIo<false> {
+  typedef float T;
+  static __device__ __forceinline__ float4 ld(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void st(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <>
+struct KvIo<true> {
+  typedef __nv_bfloat16 T;
+  static __device__ __forceinline__ float4 ld(const __nv_bfloat16* p) {
+    uint2 u = *reinterpret_cast<const uint2*>(p);
+    float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.x));
+    float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, float4 v) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&lo);
+    u.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+
+template <bool BF16>
+__global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeAttnArgs p) {
+  typedef typename KvIo<BF16>::T KT;
   constexpr int DH = 64;
   extern __shared__ __align__(16) float sc[];          // [nkeys_max] scores, then [8][64] partial outputs
   __shared__ float red[8];
@@ -164,16 +199,16 @@ __global__ void __launch_bounds__(128) attn_decode_f32(const DecodeAttnArgs p) {
   const int hw = tid >> 4, l16 = tid & 15;
   const int pos = p.step ? *p.step : 0;                                   // index of the token being decoded
   const int nkeys = p.append ? pos + 1 : p.Tk;
-  float* kbase = p.k + (size_t)b * p.kv_batch_stride + h * DH;
-  float* vbase = p.v + (size_t)b * p.kv_batch_stride + h * DH;
+  KT* kbase = static_cast<KT*>(p.k) + (size_t)b * p.kv_batch_stride + h * DH;
+  KT* vbase = static_cast<KT*>(p.v) + (size_t)b * p.kv_batch_stride + h * DH;
 
   if (p.append) {                                                        // cache[pos] <- this step's k, v
     if (tid < 16)
-      *reinterpret_cast<float4*>(kbase + (size_t)pos * p.kv_tok_stride + l16 * 4) =
-          *reinterpret_cast<const float4*>(p.k_new + (size_t)b * p.ld_new + h * DH + l16 * 4);
+      KvIo<BF16>::st(kbase + (size_t)pos * p.kv_tok_stride + l16 * 4,
+                     *reinterpret_cast<const float4*>(p.k_new + (size_t)b * p.ld_new + h * DH + l16 * 4));
     else if (tid < 32)
-      *reinterpret_cast<float4*>(vbase + (size_t)pos * p.kv_tok_stride + l16 * 4) =
-          *reinterpret_cast<const float4*>(p.v_new + (size_t)b * p.ld_new + h * DH + l16 * 4);
+      KvIo<BF16>::st(vbase + (size_t)pos * p.kv_tok_stride + l16 * 4,
+                     *reinterpret_cast<const float4*>(p.v_new + (size_t)b * p.ld_new + h * DH + l16 * 4));
     __syncthreads();
   }
   const float4 qv = *reinterpret_cast<const float4*>(p.q + (size_t)b * p.ldq + h * DH + l16 * 4);
@@ -186,8 +221,7 @@ __global__ void __launch_bounds__(128) attn_decode_f32(const DecodeAttnArgs p) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       int j = j0 + 8 * u;
-      kv[u] = j < nkeys ? *reinterpret_cast<const float4*>(kbase + (size_t)j * p.kv_tok_stride + l16 * 4)
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
+      kv[u] = j < nkeys ? KvIo<BF16>::ld(kbase + (size_t)j * p.kv_tok_stride + l16 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -228,8 +262,7 @@ __global__ void __launch_bounds__(128) attn_decode_f32(const DecodeAttnArgs p) {
     for (int u = 0; u < 4; ++u) {
       int j = j0 + 8 * u;
       bool ok = j < nkeys;
-      vv[u] = ok ? *reinterpret_cast<const float4*>(vbase + (size_t)j * p.kv_tok_stride + l16 * 4)
-                 : make_float4(0.f, 0.f, 0.f, 0.f);
+      vv[u] = ok ? KvIo<BF16>::ld(vbase + (size_t)j * p.kv_tok_stride + l16 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       pj[u] = ok ? sc[j] : 0.f;
     }
 #pragma unroll
@@ -245,7 +278,8 @@ __global__ void __launch_bounds__(128) attn_decode_f32(const DecodeAttnArgs p) {
     float r = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) r += part[w * DH + tid];
-    p.out[(size_t)b * p.ldo + h * DH + tid] = r * inv;
+    if (p.out) p.out[(size_t)b * p.ldo + h * DH + tid] = r * inv;
+    if (p.out_p) store_planes1(p.out_p + (size_t)b * p.planes * p.kp + h * DH + tid, r * inv, p.planes, p.kp);
   }
 }
 
@@ -285,15 +319,19 @@ int launch_attention_decode(DecodeAttnArgs a, int max_keys, cudaStream_t s) {
   a.sc_floats = (max_keys + 3) / 4 * 4;
   size_t smem = (size_t)(a.sc_floats + 8 * 64) * sizeof(float);
   DIM_REQUIRE(smem <= 200 * 1024, "decode attention: too many keys for one CTA");
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    DIM_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+  static size_t configured[2] = {48 * 1024, 48 * 1024};
+  const int bf = a.kv_bf16 ? 1 : 0;
+  if (smem > configured[bf]) {
+    if (bf) DIM_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else DIM_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[bf] = smem;
   }
   {
     const double keys = a.append ? (double)(a.prof_pos + 1) : (double)a.Tk;   // K and V rows actually read
-    ProfScope ps(CAT_ATTN_DECODE, s, 4.0 * a.B * a.H * 64.0 * (2.0 * keys + 2.0), 4.0 * a.B * a.H * 64.0 * keys);
-    attn_decode_f32<<<a.B * a.H, 128, smem, s>>>(a);
+    const double esz = bf ? 2.0 : 4.0;
+    ProfScope ps(CAT_ATTN_DECODE, s, a.B * (double)a.H * 64.0 * (2.0 * keys * esz + 8.0), 4.0 * a.B * a.H * 64.0 * keys);
+    if (bf) attn_decode_kernel<true><<<a.B * a.H, 128, smem, s>>>(a);
+    else attn_decode_kernel<false><<<a.B * a.H, 128, smem, s>>>(a);
   }
   DIM_LAUNCHED();
   return DIM_OK;

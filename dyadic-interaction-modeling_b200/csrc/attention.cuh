@@ -7,7 +7,8 @@ namespace dimb {
 struct AttnArgs {
   const float *q = nullptr, *k = nullptr, *v = nullptr;   // element (b=0,t=0,h=0,d=0); rows ld* apart; head h at h*Dh
   int ldq = 0, ldk = 0, ldv = 0;
-  float* out = nullptr; int ldo = 0;                      // (B,Tq,H*Dh)
+  float* out = nullptr; int ldo = 0;                      // (B,Tq,H*Dh)  (nullable when out_p is given)
+  __nv_bfloat16* out_p = nullptr; int planes = 0, kp = 0; // optional bf16-plane copy [B*Tq, planes*kp] for the next GEMM
   const uint8_t* key_mask = nullptr;                      // (B,Tk) 1 = keep  (masked -> -FLT_MAX)
   const int32_t* lens = nullptr;                          // (B) keys >= lens[b] do not exist
   int B = 0, H = 0, Tq = 0, Tk = 0, Dh = 0;
@@ -18,13 +19,16 @@ int launch_attention_prefill(const AttnArgs& a, cudaStream_t s);
 
 struct DecodeAttnArgs {
   const float* q = nullptr; int ldq = 0;                  // (B, H*64) this step's queries
-  float *k = nullptr, *v = nullptr;                       // cache bases: element (b,t,h,d) at b*kv_batch_stride + t*kv_tok_stride + h*64 + d
+  void *k = nullptr, *v = nullptr;                        // cache bases (fp32, or bf16 when kv_bf16): element (b,t,h,d) at
+                                                          //   b*kv_batch_stride + t*kv_tok_stride + h*64 + d   (in elements)
+  int kv_bf16 = 0;
   size_t kv_batch_stride = 0; int kv_tok_stride = 0;
   const float *k_new = nullptr, *v_new = nullptr; int ld_new = 0;   // rows appended at position *step when append != 0
   int append = 0;
   const int* step = nullptr;                              // device scalar: index of the token being decoded
   const uint8_t* key_mask = nullptr;                      // (B,Tk), cross attention only
-  float* out = nullptr; int ldo = 0;                      // (B, H*64)
+  float* out = nullptr; int ldo = 0;                      // (B, H*64)  (nullable when out_p is given)
+  __nv_bfloat16* out_p = nullptr; int planes = 0, kp = 0; // optional bf16-plane copy [B, planes*kp]
   int B = 0, H = 0, Tk = 0;                               // Tk: number of keys when append == 0
   float scale = 1.f;
   int sc_floats = 0;                                      // set by the launcher

@@ -90,4 +90,30 @@ __device__ __forceinline__ float act_apply(float x, int act, float slope) {
   }
 }
 
+// Exact bf16 split of fp32 values into `planes` parts (x = h + m + l, round-to-nearest at each step; the remainders are
+// exactly representable), written to plane p at dst + p*kp.  4 consecutive elements per call (8-byte stores).
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* dst, float4 x, int planes, int kp) {
+  float v[4] = {x.x, x.y, x.z, x.w};
+  for (int pl = 0; pl < planes; ++pl) {
+    unsigned short h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat16 b = __float2bfloat16_rn(v[j]);
+      h[j] = __bfloat16_as_ushort(b);
+      v[j] -= __bfloat162float(b);
+    }
+    uint2 pk;
+    pk.x = (uint32_t)h[0] | ((uint32_t)h[1] << 16);
+    pk.y = (uint32_t)h[2] | ((uint32_t)h[3] << 16);
+    *reinterpret_cast<uint2*>(dst + (size_t)pl * kp) = pk;
+  }
+}
+__device__ __forceinline__ void store_planes1(__nv_bfloat16* dst, float x, int planes, int kp) {
+  for (int pl = 0; pl < planes; ++pl) {
+    __nv_bfloat16 b = __float2bfloat16_rn(x);
+    dst[(size_t)pl * kp] = b;
+    x -= __bfloat162float(b);
+  }
+}
+
 }  // namespace dimb

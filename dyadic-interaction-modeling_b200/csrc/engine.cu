@@ -142,11 +142,17 @@ int tc_add_weight(dim_handle_s* h, TcCtx& tc, const float* W, int N, int K) {
 
 // One Linear: tensor cores (operand split + tcgen05 GEMM) when the model is built for them and the problem is tall enough
 // to fill 128-row MMA tiles, otherwise the fp32 FFMA kernels.
+inline bool tc_on(const TcCtx& tc, int M) { return tc.planes > 0 && M >= 64; }
+
 int run_gemm(const TcCtx& tc, const GemmArgs& a, __nv_bfloat16* scratch, cudaStream_t s) {
-  if (tc.planes == 0 || a.M < 64 || scratch == nullptr) return launch_gemm_f32(a, s);
   auto it = tc.wmap.find(a.W);
-  if (it == tc.wmap.end()) return launch_gemm_f32(a, s);
+  const bool tc_ok = tc_on(tc, a.M) && it != tc.wmap.end() && (scratch != nullptr || a.Ap != nullptr);
+  if (!tc_ok) {
+    if (a.Ap != nullptr || a.Cp != nullptr) return fail(DIM_EINVAL, "run_gemm: plane operands without a tensor-core path");
+    return launch_gemm_f32(a, s);
+  }
   const int kp = tc_round_k(a.K);
+  if (a.Ap != nullptr) return launch_gemm_tc(a, a.Ap, it->second, kp, tc.planes, s);
   if (int e = launch_split_planes(a, scratch, kp, tc.planes, s)) return e;
   return launch_gemm_tc(a, scratch, it->second, kp, tc.planes, s);
 }
@@ -175,7 +181,7 @@ int build_vq_stack(dim_handle_s* h, const std::string& p, const dim_vq_config& c
 // ---- VQ-VAE workspace layout (floats per frame row) ---------------------------------------------------------------
 struct VqWs {
   float *h0, *h1, *x, *ln, *qkv, *att, *ff, *z;
-  __nv_bfloat16* ap;
+  __nv_bfloat16 *ap, *ap2;
   int64_t* idx;
   size_t bytes;
 };
@@ -193,6 +199,7 @@ VqWs carve_vq(const dim_vq_config& c, int planes, int B, int T, void* base) {
   w.idx = reinterpret_cast<int64_t*>(take(R * 2));
   const size_t kmax = (size_t)tc_round_k(std::max(5 * c.hidden, c.ffn));        // widest A operand: the conv's im2col rows
   w.ap = planes ? reinterpret_cast<__nv_bfloat16*>(take(R * planes * kmax / 2 + 64)) : nullptr;
+  w.ap2 = planes ? reinterpret_cast<__nv_bfloat16*>(take(R * planes * (size_t)tc_round_k(c.ffn) / 2 + 64)) : nullptr;
   w.bytes = (size_t)(p - static_cast<char*>(base));
   return w;
 }
@@ -217,37 +224,43 @@ int vq_trunk(const VqModel& m, const std::vector<VqLayer>& layers, const float* 
     if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
   }
   const int Dh = H / c.heads;
+  const bool tcp = tc_on(m.tc, R);                      // plane-fused path: LN / attention / FF1 emit bf16 planes directly
+  const int P = m.tc.planes;
   for (const VqLayer& L : layers) {
-    if (int e = launch_layer_norm(w.x, L.ln1_g, L.ln1_b, w.ln, nullptr, R, H, 1e-5f, s)) return e;
+    if (int e = launch_layer_norm(w.x, L.ln1_g, L.ln1_b, tcp ? nullptr : w.ln, nullptr, R, H, 1e-5f, s, tcp ? w.ap : nullptr, P, H))
+      return e;
     {
       GemmArgs a;
-      a.A = w.ln; a.lda = H; a.W = L.wqkv; a.C = w.qkv; a.ldc = 3 * H; a.M = R; a.N = 3 * H; a.K = H;
+      a.A = w.ln; a.lda = H; a.Ap = tcp ? w.ap : nullptr; a.W = L.wqkv; a.C = w.qkv; a.ldc = 3 * H; a.M = R; a.N = 3 * H; a.K = H;
       if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
     }
     {
       AttnArgs a;                      // 'b n (qkv h d)': q at col 0, k at H, v at 2H
       a.q = w.qkv; a.k = w.qkv + H; a.v = w.qkv + 2 * H; a.ldq = a.ldk = a.ldv = 3 * H;
-      a.out = w.att; a.ldo = H; a.lens = lens; a.B = B; a.H = c.heads; a.Tq = T; a.Tk = T; a.Dh = Dh;
+      a.out = tcp ? nullptr : w.att; a.ldo = H; a.out_p = tcp ? w.ap : nullptr; a.planes = P; a.kp = H;
+      a.lens = lens; a.B = B; a.H = c.heads; a.Tq = T; a.Tk = T; a.Dh = Dh;
       a.scale = 1.0f / sqrtf((float)H);          // hidden_size**-0.5, not head_dim
       if (int e = launch_attention_prefill(a, s)) return e;
     }
     {
       GemmArgs a;
-      a.A = w.att; a.lda = H; a.W = L.wo; a.bias = L.bo; a.residual = w.x; a.ldr = H; a.C = w.x; a.ldc = H;
-      a.M = R; a.N = H; a.K = H;
+      a.A = w.att; a.lda = H; a.Ap = tcp ? w.ap : nullptr; a.W = L.wo; a.bias = L.bo; a.residual = w.x; a.ldr = H; a.C = w.x;
+      a.ldc = H; a.M = R; a.N = H; a.K = H;
       if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
     }
-    if (int e = launch_layer_norm(w.x, L.ln2_g, L.ln2_b, w.ln, nullptr, R, H, 1e-5f, s)) return e;
+    if (int e = launch_layer_norm(w.x, L.ln2_g, L.ln2_b, tcp ? nullptr : w.ln, nullptr, R, H, 1e-5f, s, tcp ? w.ap : nullptr, P, H))
+      return e;
     {
       GemmArgs a;
-      a.A = w.ln; a.lda = H; a.W = L.w1; a.bias = L.b1; a.C = w.ff; a.ldc = c.ffn; a.M = R; a.N = c.ffn; a.K = H;
+      a.A = w.ln; a.lda = H; a.Ap = tcp ? w.ap : nullptr; a.W = L.w1; a.bias = L.b1; a.M = R; a.N = c.ffn; a.K = H;
       a.act = DIM_ACT_GELU_TANH;
+      if (tcp) { a.Cp = w.ap2; a.cp_planes = P; a.cp_kp = c.ffn; } else { a.C = w.ff; a.ldc = c.ffn; }
       if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
     }
     {
       GemmArgs a;
-      a.A = w.ff; a.lda = c.ffn; a.W = L.w2; a.bias = L.b2; a.residual = w.x; a.ldr = H; a.C = w.x; a.ldc = H;
-      a.M = R; a.N = H; a.K = c.ffn;
+      a.A = w.ff; a.lda = c.ffn; a.Ap = tcp ? w.ap2 : nullptr; a.W = L.w2; a.bias = L.b2; a.residual = w.x; a.ldr = H; a.C = w.x;
+      a.ldc = H; a.M = R; a.N = H; a.K = c.ffn;
       if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
     }
   }
@@ -307,7 +320,7 @@ int build_xt_encoder(dim_handle_s* h, const std::string& name, int dim_in, const
 
 struct CtxWs {
   float *x, *ln, *qkv, *att, *ff;
-  __nv_bfloat16* ap;
+  __nv_bfloat16 *ap, *ap2;
   size_t bytes;
 };
 CtxWs carve_ctx(const dim_s2s_config& c, int planes, int B, int T, void* base) {
@@ -323,6 +336,7 @@ CtxWs carve_ctx(const dim_s2s_config& c, int planes, int B, int T, void* base) {
   w.x = take(R * c.dim); w.ln = take(R * c.dim); w.qkv = take(R * 3 * inner); w.att = take(R * inner);
   w.ff = take(R * c.ff_mult * c.dim);
   w.ap = planes ? reinterpret_cast<__nv_bfloat16*>(take(R * planes * (size_t)tc_round_k(c.ff_mult * c.dim) / 2 + 64)) : nullptr;
+  w.ap2 = planes ? reinterpret_cast<__nv_bfloat16*>(take(R * planes * (size_t)tc_round_k(c.ff_mult * c.dim) / 2 + 64)) : nullptr;
   w.bytes = (size_t)(p - static_cast<char*>(base));
   return w;
 }
@@ -338,39 +352,46 @@ int xt_encoder_forward(const S2SModel& m, const XtEncoder& E, const float* in, c
     a.a_add = a_add; a.tab = E.pos_emb; a.ldtab = D; a.tab_mode = 2; a.tab_T = T; a.tab_scale = 1.0f / sqrtf((float)D);
     if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
   }
+  const bool tcp = tc_on(m.tc, R);
+  const int P = m.tc.planes;
   for (int l = 0; l < c.depth; ++l) {
     const XtAttn& A = E.attn[l];
     const XtFF& FF = E.ff[l];
-    if (int e = launch_layer_norm(w.x, A.norm_g, A.norm_b, w.ln, nullptr, R, D, 1e-5f, s)) return e;
+    if (int e = launch_layer_norm(w.x, A.norm_g, A.norm_b, tcp ? nullptr : w.ln, nullptr, R, D, 1e-5f, s, tcp ? w.ap : nullptr, P, D))
+      return e;
     {
       GemmArgs a;
-      a.A = w.ln; a.lda = D; a.W = A.wqkv; a.C = w.qkv; a.ldc = 3 * inner; a.M = R; a.N = 3 * inner; a.K = D;
+      a.A = w.ln; a.lda = D; a.Ap = tcp ? w.ap : nullptr; a.W = A.wqkv; a.C = w.qkv; a.ldc = 3 * inner; a.M = R; a.N = 3 * inner;
+      a.K = D;
       if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
     }
     {
       AttnArgs a;
       a.q = w.qkv; a.k = w.qkv + inner; a.v = w.qkv + 2 * inner; a.ldq = a.ldk = a.ldv = 3 * inner;
-      a.out = w.att; a.ldo = inner; a.key_mask = mask; a.B = B; a.H = c.heads; a.Tq = T; a.Tk = T; a.Dh = c.dim_head;
+      a.out = tcp ? nullptr : w.att; a.ldo = inner; a.out_p = tcp ? w.ap : nullptr; a.planes = P; a.kp = inner;
+      a.key_mask = mask; a.B = B; a.H = c.heads; a.Tq = T; a.Tk = T; a.Dh = c.dim_head;
       a.scale = 1.0f / sqrtf((float)c.dim_head); a.causal = 1;
       if (int e = launch_attention_prefill(a, s)) return e;
     }
     {
       GemmArgs a;
-      a.A = w.att; a.lda = inner; a.W = A.wo; a.residual = w.x; a.ldr = D; a.C = w.x; a.ldc = D; a.M = R; a.N = D;
-      a.K = inner;
+      a.A = w.att; a.lda = inner; a.Ap = tcp ? w.ap : nullptr; a.W = A.wo; a.residual = w.x; a.ldr = D; a.C = w.x; a.ldc = D;
+      a.M = R; a.N = D; a.K = inner;
       if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
     }
-    if (int e = launch_layer_norm(w.x, FF.norm_g, FF.norm_b, w.ln, nullptr, R, D, 1e-5f, s)) return e;
+    if (int e = launch_layer_norm(w.x, FF.norm_g, FF.norm_b, tcp ? nullptr : w.ln, nullptr, R, D, 1e-5f, s, tcp ? w.ap : nullptr, P, D))
+      return e;
     {
       GemmArgs a;
-      a.A = w.ln; a.lda = D; a.W = FF.w1; a.bias = FF.b1; a.C = w.ff; a.ldc = F; a.M = R; a.N = F; a.K = D;
+      a.A = w.ln; a.lda = D; a.Ap = tcp ? w.ap : nullptr; a.W = FF.w1; a.bias = FF.b1; a.M = R; a.N = F; a.K = D;
       a.act = DIM_ACT_GELU_ERF;
+      if (tcp) { a.Cp = w.ap2; a.cp_planes = P; a.cp_kp = F; } else { a.C = w.ff; a.ldc = F; }
       if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
     }
     {
       GemmArgs a;
-      a.A = w.ff; a.lda = F; a.W = FF.w2; a.bias = FF.b2; a.residual = w.x; a.ldr = D; a.C = w.x; a.ldc = D; a.M = R;
-      a.N = D; a.K = F;
+      a.A = w.ff; a.lda = F; a.Ap = tcp ? w.ap2 : nullptr; a.W = FF.w2; a.bias = FF.b2; a.residual = w.x; a.ldr = D; a.C = w.x;
+      a.ldc = D; a.M = R; a.N = D; a.K = F;
       if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
     }
   }
@@ -383,10 +404,10 @@ struct GenWs {
   float *x, *ln, *qkv, *att, *ff, *logits;
   int64_t* tokens;                         // [B, steps+1]
   int* step;
-  __nv_bfloat16* ap;                       // A-operand plane scratch for the tensor-core GEMMs
+  __nv_bfloat16 *ap, *ap2;                 // A-operand plane scratch for the tensor-core GEMMs
   size_t bytes;
 };
-GenWs carve_gen(const dim_s2s_config& c, int planes, int B, int T, int steps, void* base) {
+GenWs carve_gen(const dim_s2s_config& c, int planes, bool kv_bf16, int B, int T, int steps, void* base) {
   const int inner = c.heads * c.dim_head, D = c.dim + c.dim_audio;
   char* p = static_cast<char*>(base);
   GenWs w{};
@@ -395,10 +416,11 @@ GenWs carve_gen(const dim_s2s_config& c, int planes, int B, int T, int steps, vo
     p += align_up(nfloat * sizeof(float), 256);
     return r;
   };
-  for (int l = 0; l < c.depth; ++l) w.cross_kv.push_back(take((size_t)B * T * 2 * inner));
+  const size_t kvdiv = kv_bf16 ? 2 : 1;                 // bf16 caches take half the floats
+  for (int l = 0; l < c.depth; ++l) w.cross_kv.push_back(take((size_t)B * T * 2 * inner / kvdiv));
   for (int l = 0; l < c.depth; ++l) {
-    w.self_k.push_back(take((size_t)B * (steps + 1) * inner));
-    w.self_v.push_back(take((size_t)B * (steps + 1) * inner));
+    w.self_k.push_back(take((size_t)B * (steps + 1) * inner / kvdiv));
+    w.self_v.push_back(take((size_t)B * (steps + 1) * inner / kvdiv));
   }
   w.x = take((size_t)B * D); w.ln = take((size_t)B * D); w.qkv = take((size_t)B * 3 * inner);
   w.att = take((size_t)B * inner); w.ff = take((size_t)B * c.ff_mult * D); w.logits = take((size_t)B * c.num_tokens);
@@ -408,6 +430,7 @@ GenWs carve_gen(const dim_s2s_config& c, int planes, int B, int T, int steps, vo
     const size_t rows_ctx = (size_t)B * T, rows_step = (size_t)B;
     const size_t need = std::max(rows_ctx * tc_round_k(D), rows_step * tc_round_k(c.ff_mult * D)) * planes;
     w.ap = planes ? reinterpret_cast<__nv_bfloat16*>(take(need / 2 + 64)) : nullptr;
+    w.ap2 = planes ? reinterpret_cast<__nv_bfloat16*>(take(rows_step * tc_round_k(c.ff_mult * D) * planes / 2 + 64)) : nullptr;
   }
   w.bytes = (size_t)(p - static_cast<char*>(base));
   return w;
@@ -647,7 +670,7 @@ extern "C" size_t dim_slmft_workspace_bytes(dim_handle_t h, int model, int B, in
   const dim_s2s_config& c = h->s2s[model]->cfg;
   const int planes = h->s2s[model]->tc.planes;
   size_t a = carve_ctx(c, planes, B, T, nullptr).bytes;
-  size_t b = steps > 0 ? carve_gen(c, planes, B, T, steps, nullptr).bytes : 0;
+  size_t b = steps > 0 ? carve_gen(c, planes, h->s2s[model]->precision == DIM_PREC_BF16, B, T, steps, nullptr).bytes : 0;
   return a > b ? a : b;
 }
 
@@ -680,15 +703,17 @@ extern "C" int dim_slmft_generate(dim_handle_t h, int model, const float* ctx, c
   const S2SModel& m = *h->s2s[model];
   const dim_s2s_config& c = m.cfg;
   const int inner = c.heads * c.dim_head, D = c.dim + c.dim_audio, F = c.ff_mult * D, V = c.num_tokens;
-  GenWs w = carve_gen(c, m.tc.planes, B, T, steps, ws);
+  const bool kv16 = m.precision == DIM_PREC_BF16;   // bf16 mode keeps both KV caches in bf16 (half the decode-attention bytes)
+  GenWs w = carve_gen(c, m.tc.planes, kv16, B, T, steps, ws);
   if (ws == nullptr || ws_bytes < w.bytes) return fail(DIM_EWORKSPACE, "dim_slmft_generate: workspace too small");
   cudaStream_t s = as_stream(stream);
   const float scale = 1.0f / sqrtf((float)c.dim_head);
 
   for (int l = 0; l < c.depth; ++l) {  // cross-attention K/V of the whole context, once
     GemmArgs a;
-    a.A = ctx; a.lda = D; a.W = m.cross_attn[l].wkv; a.C = w.cross_kv[l]; a.ldc = 2 * inner; a.M = B * T; a.N = 2 * inner;
-    a.K = D;
+    a.A = ctx; a.lda = D; a.W = m.cross_attn[l].wkv; a.M = B * T; a.N = 2 * inner; a.K = D;
+    if (kv16) { a.Cb = reinterpret_cast<__nv_bfloat16*>(w.cross_kv[l]); a.ldcb = 2 * inner; }
+    else { a.C = w.cross_kv[l]; a.ldc = 2 * inner; }
     if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
   }
   DIM_CHECK_CUDA(cudaMemcpy2DAsync(w.tokens, (size_t)(steps + 1) * sizeof(int64_t), prompt, sizeof(int64_t), sizeof(int64_t),
@@ -696,6 +721,8 @@ extern "C" int dim_slmft_generate(dim_handle_t h, int model, const float* ctx, c
   if (int e = launch_set_step(w.step, 0, s)) return e;
 
   const int max_keys = std::max(T, steps + 1);
+  const bool tcp = tc_on(m.tc, B);
+  const int P = m.tc.planes;
   for (int st = 0; st < steps; ++st) {
     if (int e = launch_embed_tokens(w.tokens, steps + 1, w.step, m.token_emb, w.x, B, D, V, s)) return e;
     for (int l = 0; l < c.depth; ++l) {
@@ -703,65 +730,74 @@ extern "C" int dim_slmft_generate(dim_handle_t h, int model, const float* ctx, c
       const XtAttn& CA = m.cross_attn[l];
       const XtFF& FF = m.ff[l];
       // --- causal self attention with KV cache
-      if (int e = launch_layer_norm(w.x, SA.norm_g, SA.norm_b, w.ln, nullptr, B, D, 1e-5f, s)) return e;
+      if (int e = launch_layer_norm(w.x, SA.norm_g, SA.norm_b, tcp ? nullptr : w.ln, nullptr, B, D, 1e-5f, s, tcp ? w.ap : nullptr, P, D))
+        return e;
       {
         GemmArgs a;
-        a.A = w.ln; a.lda = D; a.W = SA.wqkv; a.C = w.qkv; a.ldc = 3 * inner; a.M = B; a.N = 3 * inner; a.K = D;
+        a.A = w.ln; a.lda = D; a.Ap = tcp ? w.ap : nullptr; a.W = SA.wqkv; a.C = w.qkv; a.ldc = 3 * inner; a.M = B; a.N = 3 * inner;
+        a.K = D;
         if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
       }
       {
         DecodeAttnArgs a;
-        a.q = w.qkv; a.ldq = 3 * inner; a.k = w.self_k[l]; a.v = w.self_v[l];
+        a.q = w.qkv; a.ldq = 3 * inner; a.k = w.self_k[l]; a.v = w.self_v[l]; a.kv_bf16 = kv16;
         a.kv_batch_stride = (size_t)(steps + 1) * inner; a.kv_tok_stride = inner;
         a.k_new = w.qkv + inner; a.v_new = w.qkv + 2 * inner; a.ld_new = 3 * inner; a.append = 1; a.step = w.step;
-        a.out = w.att; a.ldo = inner; a.B = B; a.H = c.heads; a.Tk = 0; a.scale = scale; a.prof_pos = st;
+        a.out = tcp ? nullptr : w.att; a.ldo = inner; a.out_p = tcp ? w.ap : nullptr; a.planes = P; a.kp = inner;
+        a.B = B; a.H = c.heads; a.Tk = 0; a.scale = scale; a.prof_pos = st;
         if (int e = launch_attention_decode(a, max_keys, s)) return e;
       }
       {
         GemmArgs a;
-        a.A = w.att; a.lda = inner; a.W = SA.wo; a.residual = w.x; a.ldr = D; a.C = w.x; a.ldc = D; a.M = B; a.N = D;
-        a.K = inner;
+        a.A = w.att; a.lda = inner; a.Ap = tcp ? w.ap : nullptr; a.W = SA.wo; a.residual = w.x; a.ldr = D; a.C = w.x; a.ldc = D;
+        a.M = B; a.N = D; a.K = inner;
         if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
       }
       // --- cross attention over the cached context K/V
-      if (int e = launch_layer_norm(w.x, CA.norm_g, CA.norm_b, w.ln, nullptr, B, D, 1e-5f, s)) return e;
+      if (int e = launch_layer_norm(w.x, CA.norm_g, CA.norm_b, tcp ? nullptr : w.ln, nullptr, B, D, 1e-5f, s, tcp ? w.ap : nullptr, P, D))
+        return e;
       {
         GemmArgs a;
-        a.A = w.ln; a.lda = D; a.W = CA.wq; a.C = w.qkv; a.ldc = inner; a.M = B; a.N = inner; a.K = D;
+        a.A = w.ln; a.lda = D; a.Ap = tcp ? w.ap : nullptr; a.W = CA.wq; a.C = w.qkv; a.ldc = inner; a.M = B; a.N = inner; a.K = D;
         if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
       }
       {
         DecodeAttnArgs a;
-        a.q = w.qkv; a.ldq = inner; a.k = w.cross_kv[l]; a.v = w.cross_kv[l] + inner;
+        a.q = w.qkv; a.ldq = inner; a.kv_bf16 = kv16; a.k = w.cross_kv[l];
+        a.v = kv16 ? static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(w.cross_kv[l]) + inner) : static_cast<void*>(w.cross_kv[l] + inner);
         a.kv_batch_stride = (size_t)T * 2 * inner; a.kv_tok_stride = 2 * inner; a.append = 0; a.step = w.step;
-        a.key_mask = mask; a.out = w.att; a.ldo = inner; a.B = B; a.H = c.heads; a.Tk = T; a.scale = scale;
+        a.key_mask = mask; a.out = tcp ? nullptr : w.att; a.ldo = inner; a.out_p = tcp ? w.ap : nullptr; a.planes = P;
+        a.kp = inner; a.B = B; a.H = c.heads; a.Tk = T; a.scale = scale;
         if (int e = launch_attention_decode(a, max_keys, s)) return e;
       }
       {
         GemmArgs a;
-        a.A = w.att; a.lda = inner; a.W = CA.wo; a.residual = w.x; a.ldr = D; a.C = w.x; a.ldc = D; a.M = B; a.N = D;
-        a.K = inner;
+        a.A = w.att; a.lda = inner; a.Ap = tcp ? w.ap : nullptr; a.W = CA.wo; a.residual = w.x; a.ldr = D; a.C = w.x; a.ldc = D;
+        a.M = B; a.N = D; a.K = inner;
         if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
       }
       // --- feed forward
-      if (int e = launch_layer_norm(w.x, FF.norm_g, FF.norm_b, w.ln, nullptr, B, D, 1e-5f, s)) return e;
+      if (int e = launch_layer_norm(w.x, FF.norm_g, FF.norm_b, tcp ? nullptr : w.ln, nullptr, B, D, 1e-5f, s, tcp ? w.ap : nullptr, P, D))
+        return e;
       {
         GemmArgs a;
-        a.A = w.ln; a.lda = D; a.W = FF.w1; a.bias = FF.b1; a.C = w.ff; a.ldc = F; a.M = B; a.N = F; a.K = D;
+        a.A = w.ln; a.lda = D; a.Ap = tcp ? w.ap : nullptr; a.W = FF.w1; a.bias = FF.b1; a.M = B; a.N = F; a.K = D;
         a.act = DIM_ACT_GELU_ERF;
+        if (tcp) { a.Cp = w.ap2; a.cp_planes = P; a.cp_kp = F; } else { a.C = w.ff; a.ldc = F; }
         if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
       }
       {
         GemmArgs a;
-        a.A = w.ff; a.lda = F; a.W = FF.w2; a.bias = FF.b2; a.residual = w.x; a.ldr = D; a.C = w.x; a.ldc = D; a.M = B;
-        a.N = D; a.K = F;
+        a.A = w.ff; a.lda = F; a.Ap = tcp ? w.ap2 : nullptr; a.W = FF.w2; a.bias = FF.b2; a.residual = w.x; a.ldr = D; a.C = w.x;
+        a.ldc = D; a.M = B; a.N = D; a.K = F;
         if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
       }
     }
-    if (int e = launch_layer_norm(w.x, m.final_g, m.final_b, w.ln, nullptr, B, D, 1e-5f, s)) return e;
+    if (int e = launch_layer_norm(w.x, m.final_g, m.final_b, tcp ? nullptr : w.ln, nullptr, B, D, 1e-5f, s, tcp ? w.ap : nullptr, P, D))
+      return e;
     {
       GemmArgs a;
-      a.A = w.ln; a.lda = D; a.W = m.logits_w; a.bias = m.logits_b; a.C = w.logits; a.ldc = V; a.M = B; a.N = V; a.K = D;
+      a.A = w.ln; a.lda = D; a.Ap = tcp ? w.ap : nullptr; a.W = m.logits_w; a.bias = m.logits_b; a.C = w.logits; a.ldc = V; a.M = B; a.N = V; a.K = D;
       if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
     }
     if (int e = launch_sample(w.logits, B, V, temperature, top_k, uniforms, steps, w.step, w.tokens, steps + 1, 1,

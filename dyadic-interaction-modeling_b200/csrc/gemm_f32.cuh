@@ -13,6 +13,9 @@ struct GemmArgs {
   const float* residual = nullptr; int ldr = 0;   // [M,N], added after the activation
   float* C = nullptr; int ldc = 0;            // [M,N]
   __nv_bfloat16* Cb = nullptr; int ldcb = 0;  // optional bf16 copy of C
+  const __nv_bfloat16* Ap = nullptr;          // tensor-core path: A already split into bf16 planes [M, planes*Kp] (skips the split pass)
+  __nv_bfloat16* Cp = nullptr;                // tensor-core path: also emit C as bf16 planes [M, cp_planes*cp_kp] for the next GEMM
+  int cp_planes = 0, cp_kp = 0;
   int M = 0, N = 0, K = 0;
   int act = DIM_ACT_NONE; float slope = 0.f;
   const float* a_add = nullptr;               // [K] added to every row of A while loading (patch_embed_s)

@@ -4,11 +4,19 @@
 //     padded).  planes == 1 is a plain bf16 GEMM.  planes == 2/3 hold the bf16 split of fp32 values (x = h + m + l, 8 mantissa
 //     bits each): summing the products of the listed plane pairs on the tensor cores reproduces an fp32 GEMM to ~2^-16
 //     (3 pairs) or ~2^-23 (6 pairs) relative error per product -- this is how the fp32-parity mode reaches tensor-core speed.
-//   * one 128 x BN output tile per CTA; 192 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one
-//     elected lane issues tcgen05.mma, accumulator 128 lanes x BN columns of TMEM), warps 2-5 = epilogue
-//     (tcgen05.ld 32x32b -> registers -> fused bias / table add / activation / residual -> 128-bit global stores).
+//   * one 128 x BN output tile per CTA (or per CLUSTER when K is split); 192 threads: warp 0 = TMA producer, warp 1 = TMEM
+//     allocator + MMA issuer (one elected lane issues tcgen05.mma; accumulator = 128 lanes x BN columns of TMEM),
+//     warps 2-5 = epilogue.
 //   * A and W tiles (128 x 64 and BN x 64 bf16) are staged by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) into a
 //     STAGES-deep shared-memory ring guarded by full/empty mbarriers; tcgen05.commit releases slots and signals the epilogue.
+//   * epilogue: tcgen05.ld 32x32b -> registers -> the CTA's (now idle) pipeline smem as an fp32 [128][BN+4] tile ->
+//     whole rows are re-read by the warps so that bias / table / residual loads and the C stores are fully coalesced
+//     128-bit accesses; bias, positional table, activation, residual and bf16 / bf16-plane outputs are fused here.
+//   * split-K for short-M problems (the per-step decode GEMMs, M = batch, which cannot fill 148 SMs with output tiles):
+//     the S CTAs of a thread-block cluster (1,1,S) each accumulate a K-slice of the same output tile, park their partial
+//     tile in their own shared memory, and after a cluster barrier CTA r reduces rows [r*128/S, (r+1)*128/S) by reading
+//     all S partial tiles over distributed shared memory in rank order (deterministic), then runs the fused epilogue.
+//     No global workspace, no atomics.  S depends on K only, never on M: a row's bits do not depend on the batch it is in.
 //   * smem is sized so that two CTAs fit per SM: one tile's epilogue overlaps the other's MMA main loop.
 #include <cuda.h>
 
@@ -83,27 +91,91 @@ struct TcParams {
   int npairs;
   int pa[6], pw[6];           // plane index of A / W for each accumulated pair
   int kp;                     // padded K (elements) = plane stride
+  int splits;                 // split-K factor = cluster size along z (1, 2, 4 or 8)
+  long long* dbg;             // optional timeline of CTA (0,0,0): clock64 stamps (debug / tuning only)
 };
 
-__device__ __forceinline__ float tc_epilogue_elem(const GemmArgs& p, float v, int row, int col) {
-  if (p.bias) v += __ldg(p.bias + col);
-  if (p.tab_mode == 1) {
-    int g = row / p.tab_T;
-    if (p.tab_index) g = __ldg(p.tab_index + g);
-    v = __fadd_rn(v, __ldg(p.tab + (size_t)g * p.ldtab + col));
-  } else if (p.tab_mode == 2) {
-    int g = row % p.tab_T;
-    v = __fadd_rn(v, __fmul_rn(__ldg(p.tab + (size_t)g * p.ldtab + col), p.tab_scale));
+template <int ACT>
+__device__ __forceinline__ float act_fixed(float x, float slope) {
+  if (ACT == DIM_ACT_LEAKY) return x > 0.f ? x : x * slope;
+  if (ACT == DIM_ACT_GELU_TANH) {
+    float u = 0.7978845608028654f * (x + 0.044715f * (x * x * x));
+    return x * (0.5f * (1.0f + tanhf(u)));
   }
-  v = act_apply(v, p.act, p.slope);
-  if (p.residual) v = __fadd_rn(v, p.residual[(size_t)row * p.ldr + col]);
+  if (ACT == DIM_ACT_GELU_ERF) return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f));
+  return x;
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+// Rare epilogue features live out of line: the main loop has ONE warp per scheduler, so its code must stay small enough
+// to sit in the instruction cache (a 45 KB epilogue ran at instruction-fetch speed).
+__device__ __noinline__ float4 tc_tab_add(const GemmArgs& e, float4 o, int row, int col) {
+  int g = e.tab_mode == 1 ? row / e.tab_T : row % e.tab_T;
+  if (e.tab_mode == 1 && e.tab_index) g = __ldg(e.tab_index + g);
+  const float4 t = __ldg(reinterpret_cast<const float4*>(e.tab + (size_t)g * e.ldtab + col));
+  const float sc = e.tab_mode == 1 ? 1.0f : e.tab_scale;
+  o.x = __fadd_rn(o.x, __fmul_rn(t.x, sc)); o.y = __fadd_rn(o.y, __fmul_rn(t.y, sc));
+  o.z = __fadd_rn(o.z, __fmul_rn(t.z, sc)); o.w = __fadd_rn(o.w, __fmul_rn(t.w, sc));
+  return o;
+}
+__device__ __noinline__ void tc_emit_narrow(const GemmArgs& e, float4 o, int row, int col) {
+  if (e.Cb) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(e.Cb + (size_t)row * e.ldcb + col) = pk;
+  }
+  if (e.Cp) {
+    __nv_bfloat16* dst = e.Cp + (size_t)row * e.cp_planes * e.cp_kp + col;
+    float v[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll 1
+    for (int pl = 0; pl < e.cp_planes; ++pl) {
+      unsigned short h[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat16 b = __float2bfloat16_rn(v[j]);
+        h[j] = __bfloat16_as_ushort(b);
+        v[j] -= __bfloat162float(b);
+      }
+      uint2 pk;
+      pk.x = (uint32_t)h[0] | ((uint32_t)h[1] << 16);
+      pk.y = (uint32_t)h[2] | ((uint32_t)h[3] << 16);
+      *reinterpret_cast<uint2*>(dst + (size_t)pl * e.cp_kp) = pk;
+    }
+  }
+}
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t rank) {
+  uint32_t remote;
+  float4 v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote) : "memory");
   return v;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int ACT>
 __global__ void __launch_bounds__(192) gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA,
                                                          const __grid_constant__ CUtensorMap tmW, const TcParams p) {
   constexpr uint32_t A_BYTES = BM * BKE * 2, W_BYTES = BN * BKE * 2, STAGE_BYTES = A_BYTES + W_BYTES;
+  constexpr int CP = BN + 4;                           // fp32 staging-tile pitch (floats): conflict-free 128-bit accesses
+  static_assert((size_t)BM * CP * 4 <= (size_t)STAGES * STAGE_BYTES, "staging tile must fit in the pipeline buffers");
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
@@ -111,9 +183,15 @@ __global__ void __launch_bounds__(192) gemm_bf16_tcgen05(const __grid_constant__
   __shared__ uint32_t tmem_slot;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B tiles need 1024-byte alignment
+  const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  if (dbg && threadIdx.x == 0) p.dbg[0] = clock64();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int total_kb = p.kblocks * p.npairs;
+  const int S = p.splits;                              // == cluster size along z; blockIdx.z is the rank in the cluster
+  // split-K: this CTA accumulates flattened (pair, k-block) iterations [it_begin, it_end)
+  const int it_begin = (int)(((long)blockIdx.z * total_kb) / S);
+  const int it_end = (int)(((long)(blockIdx.z + 1) * total_kb) / S);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -135,13 +213,14 @@ __global__ void __launch_bounds__(192) gemm_bf16_tcgen05(const __grid_constant__
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_slot;
+  if (dbg && threadIdx.x == 0) p.dbg[1] = clock64();
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < total_kb; ++it) {
+      for (int it = it_begin; it < it_end; ++it) {
         const int pair = it / p.kblocks, kb = it - pair * p.kblocks;
         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
         const uint32_t fb = smem_u32(&full_bar[stage]);
@@ -149,6 +228,7 @@ __global__ void __launch_bounds__(192) gemm_bf16_tcgen05(const __grid_constant__
         const uint32_t sa = smem_base + stage * STAGE_BYTES;
         tma_load_2d(sa, &tmA, p.pa[pair] * p.kp + kb * BKE, m0, fb);
         tma_load_2d(sa + A_BYTES, &tmW, p.pw[pair] * p.kp + kb * BKE, n0, fb);
+        if (dbg && it - it_begin < 16) p.dbg[8 + (it - it_begin)] = clock64();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
@@ -159,62 +239,119 @@ __global__ void __launch_bounds__(192) gemm_bf16_tcgen05(const __grid_constant__
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < total_kb; ++it) {
+      for (int it = it_begin; it < it_end; ++it) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (dbg && it - it_begin < 16) p.dbg[24 + (it - it_begin)] = clock64();
         const uint32_t sa = smem_base + stage * STAGE_BYTES;
         const uint64_t adesc = make_sdesc(sa), bdesc = make_sdesc(sa + A_BYTES);
 #pragma unroll
         for (int k = 0; k < BKE / 16; ++k)            // UMMA_K = 16 bf16 = 32 bytes: +2 in the (addr >> 4) field
-          umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it | k) != 0 ? 1u : 0u);
+          umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it > it_begin || k > 0) ? 1u : 0u);
         umma_commit(smem_u32(&empty_bar[stage]));     // slot reusable once these MMAs have read it
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(smem_u32(&accum_bar));              // accumulator complete
+      umma_commit(smem_u32(&accum_bar));              // accumulator complete (covers every MMA issued above)
     }
   } else {
-    // ===== epilogue: warps 2..5; warp w may only touch TMEM lanes 32*(w%4) .. +31 =====
+    // ===== epilogue, phase 1 (warps 2..5; warp w may only touch TMEM lanes 32*(w%4) .. +31) =====
+    // All MMAs are complete when accum_bar fires, hence every TMA write has been consumed: the pipeline buffers are free
+    // and become the fp32 staging tile  stage_tile[row][col], pitch CP.
     const int q = warp & 3;
     mbar_wait(smem_u32(&accum_bar), 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int row = m0 + q * 32 + lane;
-    const GemmArgs& e = p.e;
+    if (dbg && threadIdx.x == 64) p.dbg[2] = clock64();
+    float* stage_tile = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)));
+    float* my_row = stage_tile + (size_t)(q * 32 + lane) * CP;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t r[16];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-          : "r"(taddr)
-          : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < e.M) {
+      float v[16];
+      tmem_ld16(tlane + (uint32_t)c0, v);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int col = n0 + c0 + g * 4;
-          if (col < e.N) {                             // N % 4 == 0: a float4 is entirely inside or outside
-            float4 o;
-            o.x = tc_epilogue_elem(e, __uint_as_float(r[g * 4 + 0]), row, col + 0);
-            o.y = tc_epilogue_elem(e, __uint_as_float(r[g * 4 + 1]), row, col + 1);
-            o.z = tc_epilogue_elem(e, __uint_as_float(r[g * 4 + 2]), row, col + 2);
-            o.w = tc_epilogue_elem(e, __uint_as_float(r[g * 4 + 3]), row, col + 3);
-            if (e.C) *reinterpret_cast<float4*>(e.C + (size_t)row * e.ldc + col) = o;
-            if (e.Cb) {
-              __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
-              uint2 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&lo);
-              pk.y = *reinterpret_cast<uint32_t*>(&hi);
-              *reinterpret_cast<uint2*>(e.Cb + (size_t)row * e.ldcb + col) = pk;
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<float4*>(my_row + c0 + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+      if (dbg && threadIdx.x == 64 && c0 == 0) p.dbg[40] = clock64();
+    }
+    if (dbg && threadIdx.x == 64) p.dbg[5] = clock64();
+  }
+  // every partial tile of the cluster is now in its CTA's shared memory
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncwarp();                                        // re-converge warps 0/1 (single-lane roles) for the .aligned barrier
+  if (S > 1) cluster_sync_all(); else __syncthreads();
+
+  if (dbg && threadIdx.x == 64) p.dbg[6] = clock64();
+  {
+    // ===== epilogue, phase 2 (all 6 warps): this CTA finishes rows [rank*BM/S, (rank+1)*BM/S) of the tile =====
+    // A lane owns 4 fixed columns (its bias is loaded once) and walks down the rows, RB independent rows per iteration so
+    // that the smem/DSMEM reads, residual loads and stores of different rows overlap (one warp per scheduler: ILP matters).
+    constexpr int LPR = BN / 4;                        // lanes per row (one float4 each)
+    constexpr int RPI = 32 / LPR;                      // rows per warp instruction
+    constexpr int RB = 4;                              // rows in flight per lane
+    const GemmArgs& e = p.e;
+    const int rows_here = BM / S, row_begin = (int)blockIdx.z * rows_here, row_end = row_begin + rows_here;
+    const float* stage_tile = reinterpret_cast<const float*>(smem_raw + (smem_base - smem_u32(smem_raw)));
+    const int c = (lane % LPR) * 4;
+    const int col = n0 + c;
+    if (col < e.N) {                                   // N % 4 == 0: a float4 is entirely inside or outside
+      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+      const int stride = 6 * RPI;
+      const bool narrow = e.Cb != nullptr || e.Cp != nullptr;
+#pragma unroll 1
+      for (int r0 = row_begin + warp * RPI + lane / LPR; r0 < row_end; r0 += stride * RB) {
+        float4 acc[RB], res[RB];
+        bool ok[RB];
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          const int r = r0 + u * stride;
+          ok[u] = r < row_end && (m0 + r) < e.M;
+          acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          res[u] = acc[u];
+        }
+        if (S == 1) {
+#pragma unroll
+          for (int u = 0; u < RB; ++u)
+            if (ok[u]) acc[u] = *reinterpret_cast<const float4*>(stage_tile + (size_t)(r0 + u * stride) * CP + c);
+        } else {
+#pragma unroll 1
+          for (int z = 0; z < S; ++z) {                // fixed rank order: deterministic sum; RB remote loads in flight
+#pragma unroll
+            for (int u = 0; u < RB; ++u) {
+              if (ok[u]) {
+                const float4 v = ld_dsmem_f4(smem_base + (uint32_t)(((r0 + u * stride) * CP + c) * 4), (uint32_t)z);
+                acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
+              }
             }
           }
         }
+        if (e.residual) {
+#pragma unroll
+          for (int u = 0; u < RB; ++u)
+            if (ok[u]) res[u] = *reinterpret_cast<const float4*>(e.residual + (size_t)(m0 + r0 + u * stride) * e.ldr + col);
+        }
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          if (!ok[u]) continue;
+          const int row = m0 + r0 + u * stride;
+          float4 o = acc[u];
+          o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w;
+          if (e.tab_mode != 0) o = tc_tab_add(e, o, row, col);
+          o.x = act_fixed<ACT>(o.x, e.slope); o.y = act_fixed<ACT>(o.y, e.slope);
+          o.z = act_fixed<ACT>(o.z, e.slope); o.w = act_fixed<ACT>(o.w, e.slope);
+          o.x = __fadd_rn(o.x, res[u].x); o.y = __fadd_rn(o.y, res[u].y);
+          o.z = __fadd_rn(o.z, res[u].z); o.w = __fadd_rn(o.w, res[u].w);
+          if (e.C) *reinterpret_cast<float4*>(e.C + (size_t)row * e.ldc + col) = o;
+          if (narrow) tc_emit_narrow(e, o, row, col);
+        }
       }
     }
+    if (dbg && threadIdx.x == 64) p.dbg[3] = clock64();
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  // peers may still be reading this CTA's staging tile over DSMEM: leave together
+  __syncwarp();
+  if (S > 1) cluster_sync_all(); else __syncthreads();
+  if (dbg && threadIdx.x == 0) p.dbg[4] = clock64();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
@@ -266,22 +403,42 @@ int make_map(const __nv_bfloat16* ptr, int rows, int cols, int ld, int box_rows,
   return DIM_OK;
 }
 
-template <int BN, int STAGES>
-int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcParams& p, cudaStream_t s) {
+template <int BN, int STAGES, int ACT>
+int launch_tc_act(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcParams& p, cudaStream_t s) {
   constexpr size_t smem = (size_t)STAGES * (BM * BKE * 2 + BN * BKE * 2) + 1024;
   static bool once = false;
   if (!once) {
-    DIM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DIM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, STAGES, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     once = true;
   }
-  dim3 grid(cdiv(p.e.N, BN), cdiv(p.e.M, BM));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(cdiv(p.e.N, BN), cdiv(p.e.M, BM), p.splits);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;     // the S K-slices of one output tile form a cluster
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = p.splits;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   ProfScope ps(CAT_GEMM_TC, s, 2.0 * ((double)p.e.M + p.e.N) * p.kp * p.npairs + 4.0 * p.e.M * p.e.N,
                2.0 * p.e.M * (double)p.e.N * p.kp * p.npairs);
-  gemm_bf16_tcgen05<BN, STAGES><<<grid, 192, smem, s>>>(tmA, tmW, p);
+  DIM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05<BN, STAGES, ACT>, tmA, tmW, p));
   DIM_LAUNCHED();
   return DIM_OK;
 }
 
+template <int BN, int STAGES>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcParams& p, cudaStream_t s) {
+  switch (p.e.act) {
+    case DIM_ACT_LEAKY: return launch_tc_act<BN, STAGES, DIM_ACT_LEAKY>(tmA, tmW, p, s);
+    case DIM_ACT_GELU_TANH: return launch_tc_act<BN, STAGES, DIM_ACT_GELU_TANH>(tmA, tmW, p, s);
+    case DIM_ACT_GELU_ERF: return launch_tc_act<BN, STAGES, DIM_ACT_GELU_ERF>(tmA, tmW, p, s);
+    default: return launch_tc_act<BN, STAGES, DIM_ACT_NONE>(tmA, tmW, p, s);
+  }
+}
 
 // fp32 -> bf16 planes.  One thread per 4 consecutive k of one row.
 __global__ void __launch_bounds__(256) split_planes_kernel(const GemmArgs a, __nv_bfloat16* __restrict__ out, int kp,
@@ -339,6 +496,9 @@ int launch_split_planes(const GemmArgs& a, __nv_bfloat16* out, int kp, int plane
   return DIM_OK;
 }
 
+long long* g_tc_dbg = nullptr;
+int g_tc_force_splits = 0;
+
 int tc_pairs(int planes, int* pa, int* pw) {
   // plane 0 = high, 1 = middle, 2 = low part of the bf16 split.  Products kept: all with (index sum) < planes.
   int n = 0;
@@ -356,28 +516,30 @@ int launch_gemm_tc(const GemmArgs& e, const __nv_bfloat16* Ap, const __nv_bfloat
   DIM_REQUIRE(e.N % 4 == 0 && (e.C == nullptr || e.ldc % 4 == 0) && (e.Cb == nullptr || e.ldcb % 4 == 0),
               "gemm_tc: N and output pitches must be multiples of 4");
   DIM_REQUIRE(planes >= 1 && planes <= 3, "gemm_tc: planes must be 1..3");
-  DIM_REQUIRE(e.C != nullptr || e.Cb != nullptr, "gemm_tc: no output");
+  DIM_REQUIRE(e.C != nullptr || e.Cb != nullptr || e.Cp != nullptr, "gemm_tc: no output");
+  DIM_REQUIRE(e.Cp == nullptr || (e.cp_planes >= 1 && e.cp_planes <= 3 && e.cp_kp >= e.N), "gemm_tc: bad plane output");
   DIM_REQUIRE(((uintptr_t)Ap & 15) == 0 && ((uintptr_t)Wp & 15) == 0, "gemm_tc: operands must be 16-byte aligned");
   TcParams p;
   p.e = e;
   p.kblocks = kp / BKE;
   p.kp = kp;
   p.npairs = tc_pairs(planes, p.pa, p.pw);
-  // Narrow tiles when the grid would not cover the SMs (skinny decode-step GEMMs stream weights: more CTAs = more
-  // memory parallelism); wide tiles otherwise.
-  const long tiles128 = (long)cdiv(e.M, BM) * cdiv(e.N, 128);
-  const long tiles64 = (long)cdiv(e.M, BM) * cdiv(e.N, 64);
+  p.splits = 1;
+  p.dbg = g_tc_dbg;
+  const int total_kb = p.kblocks * p.npairs;
+  const int bn = e.N >= 128 ? 128 : (e.N > 32 ? 64 : 32);
   CUtensorMap tmA, tmW;
   if (int err = make_map(Ap, e.M, planes * kp, planes * kp, BM, &tmA)) return err;
-  if (tiles128 >= 120) {
-    if (int err = make_map(Wp, e.N, planes * kp, planes * kp, 128, &tmW)) return err;
-    return launch_tc<128, 3>(tmA, tmW, p, s);
+  if (int err = make_map(Wp, e.N, planes * kp, planes * kp, bn, &tmW)) return err;
+  if (e.M < 2048) {
+    // Short-M GEMMs: split K over a cluster so that every CTA owns >= ~4 k-blocks.  S depends on (K, planes) only.
+    const int want = total_kb / 4;
+    p.splits = want >= 8 ? 8 : (want >= 4 ? 4 : (want >= 2 ? 2 : 1));
   }
-  if (tiles64 >= 120) {
-    if (int err = make_map(Wp, e.N, planes * kp, planes * kp, 64, &tmW)) return err;
-    return launch_tc<64, 4>(tmA, tmW, p, s);
-  }
-  if (int err = make_map(Wp, e.N, planes * kp, planes * kp, 32, &tmW)) return err;
+  if (g_tc_force_splits > 0) p.splits = g_tc_force_splits;
+  while (p.splits > 1 && p.splits > total_kb) p.splits >>= 1;
+  if (bn == 128) return launch_tc<128, 3>(tmA, tmW, p, s);
+  if (bn == 64) return launch_tc<64, 4>(tmA, tmW, p, s);
   return launch_tc<32, 4>(tmA, tmW, p, s);
 }
 
@@ -401,4 +563,11 @@ extern "C" int dim_linear_bf16_planes(const void* Ap, const void* Wp, int K, int
   a.slope = slope;
   return launch_gemm_tc(a, static_cast<const __nv_bfloat16*>(Ap), static_cast<const __nv_bfloat16*>(Wp), tc_round_k(K), planes,
                         as_stream(stream));
+}
+
+// tuning hooks (not part of the stable ABI): timeline buffer for CTA (0,0,0) and a split-K override
+extern "C" int dim_debug_tc(void* dbg_buffer_64x8B, int force_splits) {
+  dimb::g_tc_dbg = static_cast<long long*>(dbg_buffer_64x8B);
+  dimb::g_tc_force_splits = force_splits;
+  return DIM_OK;
 }

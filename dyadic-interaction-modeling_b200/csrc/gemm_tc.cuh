@@ -15,5 +15,7 @@ int launch_split_planes(const GemmArgs& a, __nv_bfloat16* out, int kp, int plane
 int launch_gemm_tc(const GemmArgs& e, const __nv_bfloat16* Ap, const __nv_bfloat16* Wp, int kp, int planes, cudaStream_t s);
 
 int tc_pairs(int planes, int* pa, int* pw);
+extern long long* g_tc_dbg;
+extern int g_tc_force_splits;
 
 }  // namespace dimb

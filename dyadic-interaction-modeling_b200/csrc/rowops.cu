@@ -10,7 +10,8 @@ namespace {
 template <int MAXV>
 __global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ gain,
                                                          const float* __restrict__ bias, float* __restrict__ y,
-                                                         __nv_bfloat16* __restrict__ yb, int rows, int dim, float eps) {
+                                                         __nv_bfloat16* __restrict__ yb, int rows, int dim, float eps,
+                                                         __nv_bfloat16* __restrict__ yp, int planes, int kp) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const int n4 = dim >> 2;
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict
         pk.y = *reinterpret_cast<uint32_t*>(&hi);
         reinterpret_cast<uint2*>(yb + (size_t)warp * dim)[c] = pk;
       }
+      if (yp) store_planes4(yp + (size_t)warp * planes * kp + c * 4, o, planes, kp);
     }
   }
 }
@@ -231,12 +233,14 @@ __global__ void set_step_kernel(int* step, int v) { *step = v; }
 }  // namespace
 
 int launch_layer_norm(const float* x, const float* gain, const float* bias, float* y, __nv_bfloat16* yb, int rows, int dim,
-                      float eps, cudaStream_t s) {
+                      float eps, cudaStream_t s, __nv_bfloat16* yp, int planes, int kp) {
+  DIM_REQUIRE(yp == nullptr || (planes >= 1 && planes <= 3 && kp == dim), "layer_norm: plane output needs kp == dim");
   DIM_REQUIRE(rows > 0 && dim > 0 && dim % 4 == 0 && dim <= 4096, "layer_norm: dim must be a multiple of 4, <= 4096");
-  ProfScope ps(CAT_LAYERNORM, s, (y ? 8.0 : 4.0) * rows * dim + (yb ? 2.0 * rows * dim : 0.0), 8.0 * rows * dim);
-  if (dim <= 384) layer_norm_kernel<3><<<cdiv(rows, 8), 256, 0, s>>>(x, gain, bias, y, yb, rows, dim, eps);
-  else if (dim <= 1152) layer_norm_kernel<9><<<cdiv(rows, 8), 256, 0, s>>>(x, gain, bias, y, yb, rows, dim, eps);
-  else layer_norm_kernel<32><<<cdiv(rows, 8), 256, 0, s>>>(x, gain, bias, y, yb, rows, dim, eps);
+  ProfScope ps(CAT_LAYERNORM, s, (y ? 8.0 : 4.0) * rows * dim + (yb ? 2.0 * rows * dim : 0.0) + (yp ? 2.0 * planes * rows * dim : 0.0),
+               8.0 * rows * dim);
+  if (dim <= 384) layer_norm_kernel<3><<<cdiv(rows, 8), 256, 0, s>>>(x, gain, bias, y, yb, rows, dim, eps, yp, planes, kp);
+  else if (dim <= 1152) layer_norm_kernel<9><<<cdiv(rows, 8), 256, 0, s>>>(x, gain, bias, y, yb, rows, dim, eps, yp, planes, kp);
+  else layer_norm_kernel<32><<<cdiv(rows, 8), 256, 0, s>>>(x, gain, bias, y, yb, rows, dim, eps, yp, planes, kp);
   DIM_LAUNCHED();
   return DIM_OK;
 }
@@ -300,7 +304,7 @@ using namespace dimb;
 extern "C" int dim_layer_norm_f32(const float* x, const float* gain, const float* bias, float* y, int rows, int dim,
                                   float eps, void* stream) {
   if (int e = ensure_device()) return e;
-  return launch_layer_norm(x, gain, bias, y, nullptr, rows, dim, eps, as_stream(stream));
+  return launch_layer_norm(x, gain, bias, y, nullptr, rows, dim, eps, as_stream(stream), nullptr, 0, 0);
 }
 
 extern "C" int dim_instance_norm_f32(float* x, const int32_t* lens, int B, int T, int C, float eps, void* stream) {

@@ -4,8 +4,9 @@
 #include <algorithm>
 
 namespace dimb {
+// y (fp32), yb (bf16 copy) and yp (bf16 planes [rows, planes*kp], kp == dim) are each optional outputs.
 int launch_layer_norm(const float* x, const float* gain, const float* bias, float* y, __nv_bfloat16* yb, int rows, int dim,
-                      float eps, cudaStream_t s);
+                      float eps, cudaStream_t s, __nv_bfloat16* yp = nullptr, int planes = 0, int kp = 0);
 int launch_instance_norm(float* x, const int32_t* lens, int B, int T, int C, float eps, cudaStream_t s);
 int launch_build_context(const float* xs, const float* pe_dec, const float* audio, float* ctx, __nv_bfloat16* ctxb,
                          size_t rows, int d1, int d2, cudaStream_t s);

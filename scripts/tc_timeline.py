@@ -1,0 +1,41 @@
+"""Tuning aid: per-phase clock64 timeline of one CTA of the tcgen05 GEMM + event timings over shapes (GPU box only)."""
+import ctypes as C
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import dim_b200
+from dim_b200 import _lib, ops
+
+lib = _lib.load()
+lib.dim_debug_tc.argtypes = [C.c_void_p, C.c_int]
+dbg = torch.zeros(64, dtype=torch.int64, device="cuda")
+
+
+def run(M, N, K, planes=1, splits=0, iters=50):
+    a = torch.randn(M, K, device="cuda"); w = torch.randn(N, K, device="cuda") / K ** 0.5
+    ap, wp = ops.split_planes(a, planes), ops.split_planes(w, planes)
+    out = torch.empty(M, N, device="cuda")
+    def call():
+        _lib.check(lib.dim_linear_bf16_planes(ap.data_ptr(), wp.data_ptr(), K, planes, None, None, N, out.data_ptr(), N, M, N, 0, 0.0,
+                                              torch.cuda.current_stream().cuda_stream))
+    lib.dim_debug_tc(dbg.data_ptr(), splits)
+    dbg.zero_(); call(); torch.cuda.synchronize()
+    d = dbg.cpu().tolist()
+    lib.dim_debug_tc(None, splits)
+    for _ in range(5): call()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(iters): call()
+    e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / iters
+    t0 = d[0]
+    tma = [x - t0 for x in d[8:24] if x]
+    mma = [x - t0 for x in d[24:40] if x]
+    print(f"M={M} N={N} K={K} planes={planes} splits={splits}: {us:.1f} us/launch | cycles: setup={d[1]-t0} accum_ready={d[2]-t0} first_chunk={d[40]-t0} staged={d[5]-t0} synced={d[6]-t0} epi_done={d[3]-t0} end={d[4]-t0}")
+    print("   tma issue:", tma)
+    print("   mma start:", mma)
+
+
+if __name__ == "__main__":
+    run(256, 2304, 1152); run(256, 2304, 1152, splits=1); run(128, 128, 384, splits=1); run(128, 32, 384, splits=1)
+    run(8192, 1152, 1152, splits=1)
