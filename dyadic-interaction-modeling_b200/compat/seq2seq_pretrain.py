@@ -1,0 +1,146 @@
+"""seq2seq_pretrain.SLMFT on the B200 kernels (reference: code/seq2seq_pretrain.py:325-514).
+
+Same zero-argument constructor (reads ./config.yaml and the two VQ checkpoints from the working directory), same
+sub-module names and state_dict keys, same `forward(v_speaker, v_listener, v_audio, mask, mode, ...)` contract returning
+`(total_loss, dict, pred_cont_seq_l)`.  mode='val' is the inference hot path and runs entirely in libdimb200:
+
+    forward_vq           listener VQ encode of each sample's valid prefix (batched, lens + batch slot 0)   :480-494
+    forward_encoder      encoder_s -> encoder_joint -> norm_s  (+ context concat)                          :431-446
+    forward_decoder      decoder_joint.generate: KV-cached AR decoding, top-k(52) sampling, T-1 steps      :444-452
+    forward_vq_decoder   codebook gather fused into listener_vq.decode (batched: sample b gets pe[b], F4)  :454-464
+
+Differences in WORK, not in results: the speaker VQ encodes and the duplicated forward_vq call, whose outputs the reference
+discards, are skipped; cross-attention K/V are projected once (F9).  Sampling draws come from torch.rand on
+the device (one uniform per step and clip) instead of torch.multinomial's stream: same distribution, different stream;
+set `self.decode_uniforms` (B,T-1) or `self.greedy = True` for reproducible decoding.
+mode='train' (teacher forcing + loss for fine-tuning) is outside the hot path and raises NotImplementedError.
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from base import config
+from base.baseTrainer import load_state_dict
+from models import get_model
+from x_transformers import (AutoregressiveWrapper, ContinuousAutoregressiveWrapper, ContinuousTransformerWrapper,  # noqa: F401
+                            Decoder, Encoder, TransformerWrapper)
+from x_utils import *  # noqa: F401,F403
+
+from dim_b200 import compat_api
+from dim_b200.engine import PREC_BF16, PREC_FP32, PREC_FP32_TC, Handle, SLMFTEngine, VQEngine  # noqa: F401
+from dim_b200.paramtree import fingerprint
+from dim_b200.schema import S2SConfig, VQConfig
+
+
+class SLMFT(nn.Module):
+    precision = PREC_FP32_TC          # class-level switch: PREC_FP32 (FFMA), PREC_FP32_TC (parity, tensor cores), PREC_BF16
+
+    def __init__(self, config_path="./config.yaml", model_speaker_pth="./runs_speaker_new/_RANK0/model/model.pth.tar",
+                 model_listener_pth="./runs/listener_exp/model/model.pth.tar", load_vq_checkpoints=True):
+        super().__init__()
+        config_speaker = config.load_cfg_from_cfg_file(config_path)
+        config_listener = config.load_cfg_from_cfg_file(config_path)
+        model_speaker, model_listener = get_model(config_speaker), get_model(config_listener)
+        if load_vq_checkpoints:
+            to_cpu = lambda storage, loc: storage.cpu()
+            load_state_dict(model_speaker, torch.load(model_speaker_pth, map_location=to_cpu)["state_dict"])
+            load_state_dict(model_listener, torch.load(model_listener_pth, map_location=to_cpu)["state_dict"])
+            print("Load models successfully")
+        self.speaker_face_quan_num = config_speaker.face_quan_num
+        self.speaker_zquant_dim = config_speaker.zquant_dim
+        self.speaker_vq, self.listener_vq = model_speaker.eval(), model_listener.eval()
+        for p in list(self.speaker_vq.parameters()) + list(self.listener_vq.parameters()):
+            p.requires_grad = False
+
+        dim_in, dim, enc_max_seq_len, dim_a = 56, 384, 2048, 768
+        enc_kwargs = {"depth": 4, "heads": 12, "max_seq_len": 2048}
+        dec_kwargs = {"depth": 4, "heads": 12, "max_seq_len": 2048, "num_tokens": 512}
+        dec_transformer_kwargs = pick_and_pop(["num_tokens", "max_seq_len"], dec_kwargs)  # noqa: F405
+        dec_transformer_kwargs["emb_dropout"] = dec_kwargs.pop("emb_dropout", 0)
+        dec_transformer_kwargs["scaled_sinu_pos_emb"] = dec_kwargs.pop("scaled_sinu_pos_emb", False)
+        dec_transformer_kwargs["use_abs_pos_emb"] = dec_kwargs.pop("use_abs_pos_emb", False)
+        mk_enc = lambda d_in: ContinuousTransformerWrapper(dim_in=d_in, dim_out=dim, max_seq_len=enc_max_seq_len,
+                                                           attn_layers=Encoder(dim=dim, **enc_kwargs))
+        self.encoder_s, self.encoder_l, self.encoder_joint = mk_enc(dim_in), mk_enc(dim_in), mk_enc(dim)
+        self.patch_embed_s = nn.Parameter(torch.zeros(1, 1, dim_in))
+        self.patch_embed_l = nn.Parameter(torch.zeros(1, 1, dim_in))
+        self.patch_embed_dec_s = nn.Parameter(torch.zeros(1, 1, dim))
+        self.patch_embed_dec_l = nn.Parameter(torch.zeros(1, 1, dim))
+        self.norm_s, self.norm_l, self.norm = nn.LayerNorm(dim), nn.LayerNorm(dim), nn.LayerNorm(dim)
+        self.decoder_joint = TransformerWrapper(**dec_transformer_kwargs,
+                                                attn_layers=Decoder(dim=dim + dim_a, cross_attend=True, **dec_kwargs))
+        self.decoder_joint = AutoregressiveWrapper(self.decoder_joint, ignore_index=-100, pad_value=0, mask_prob=0.15)
+        self.decoder_joint.bind(self._generate)
+
+        self._cfg, self._vq_cfg = S2SConfig(), VQConfig.from_cfg(config_listener)
+        self._engines, self._fp = None, None
+        self.greedy = False             # True: argmax decoding (deterministic parity mode)
+        self.decode_uniforms = None     # optional (B, T-1) uniforms for reproducible sampling
+        self.last_codes = None          # generated code sequences of the last val forward (B, T-1) int64
+
+    # ---- engine binding ----
+    def engines(self):
+        fp = fingerprint(self)
+        if self._engines is None or fp != self._fp:
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("SLMFT runs on CUDA only (sm_100a kernels, no CPU fallback): call .to('cuda') first")
+            h = Handle(dev.index)
+            h.register(self.state_dict())
+            vq_prec = PREC_FP32 if self.precision == PREC_FP32 else PREC_FP32_TC
+            self._engines = (SLMFTEngine(h, self._cfg, precision=self.precision),
+                             VQEngine(h, self._vq_cfg, prefix="listener_vq.", precision=vq_prec))
+            self._fp = fp
+        return self._engines
+
+    def _generate(self, prompts, seq_len, temperature=1.0, context=None, context_mask=None, uniforms=None):
+        s2s, _ = self.engines()
+        if self.greedy or temperature == 0.0:
+            return s2s.generate(context, context_mask, prompts, seq_len, temperature=0.0)
+        if uniforms is None:
+            uniforms = self.decode_uniforms if self.decode_uniforms is not None else \
+                torch.rand(prompts.shape[0], seq_len, device=context.device)
+        return s2s.generate(context, context_mask, prompts, seq_len, temperature=temperature, uniforms=uniforms)
+
+    # ---- reference methods ----
+    def forward_encoder(self, v_speaker, mask):
+        """-> x_s (B,T,384) = norm_s(encoder_joint(encoder_s(v + patch_embed_s)))."""
+        s2s, _ = self.engines()
+        return s2s.context(v_speaker.float(), None, mask, want="x_s")
+
+    def forward_decoder(self, x_s, z_l, x_a, mask, mode):
+        if mode == "train":
+            raise NotImplementedError("teacher-forced decoding (mode='train') is outside the inference hot path")
+        x_s = torch.cat([x_s + self.patch_embed_dec_s, x_a], dim=-1)
+        px_l = self.decoder_joint.generate(z_l[:, 0].unsqueeze(1), seq_len=z_l.shape[1] - 1, context=x_s, context_mask=mask)
+        return 0.0, px_l
+
+    def forward_vq_decoder(self, logits_l, mode="train", batch_index=None):
+        pred_seq_l = torch.argmax(logits_l, dim=-1) if mode == "train" else logits_l
+        _, vq = self.engines()
+        return vq.decode(codes=pred_seq_l.contiguous(), batch_index=batch_index)
+
+    def forward_continuous_loss(self, pred, target, mask):
+        return compat_api.continuous_loss(pred, target, mask)
+
+    def forward_vq(self, v_speaker, v_listener, mask):
+        """-> (z_speaker, z_listener) (B,T) int64.  z_speaker is a zero placeholder: the reference computes and never
+        reads it in either mode; z_listener is padded with -100 like :490."""
+        _, vq = self.engines()
+        z_l = compat_api.listener_codes(vq, v_listener.float(), mask)
+        return torch.zeros_like(z_l), z_l
+
+    def forward(self, v_speaker, v_listener, v_audio, mask, mode="train", speaker_ids=None, listener_ids=None,
+                batch_index=None):
+        if mode == "train":
+            raise NotImplementedError("SLMFT.forward(mode='train') (teacher forcing + CE loss) is outside the inference "
+                                      "hot path built here (SURVEY.md 8(f).2); use mode='val'")
+        s2s, vq = self.engines()
+        uniforms = None if self.greedy else (self.decode_uniforms if self.decode_uniforms is not None else
+                                             torch.rand(v_speaker.shape[0], v_speaker.shape[1] - 1, device=v_speaker.device))
+        loss, d, pred, codes = compat_api.slmft_forward_val(s2s, vq, v_speaker.float(), v_listener.float(), v_audio.float(),
+                                                            mask, temperature=1.0, uniforms=uniforms, batch_index=batch_index,
+                                                            return_codes=True, greedy=self.greedy)
+        self.last_codes = codes
+        return loss, d, pred

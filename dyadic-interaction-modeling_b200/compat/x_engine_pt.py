@@ -1,0 +1,49 @@
+"""x_engine_pt.evaluate_test_epoch on the B200 model (reference: code/x_engine_pt.py:232-277).
+
+Same loop contract: for every batch draw `beam_size` = 10 stochastic generations, and per clip keep the sample whose
+Frechet distance to the ground truth is smallest.  Returns (y_trues, y_preds, x_all, data_ids) as lists of numpy arrays
+of shape (src_len-1, 56).  The FD selection stays on the host (numpy/scipy) like the reference; predictions are copied to
+the host once per sample instead of twice per clip."""
+import numpy as np
+import torch
+
+from metrics.eval_utils import calculate_activation_statistics, calculate_frechet_distance
+
+try:  # tqdm is optional
+    from tqdm import tqdm
+except Exception:  # pragma: no cover
+    tqdm = lambda x: x
+
+
+def evaluate_test_epoch(model, loader, device, beam_size=10):
+    y_trues_all, y_preds_all, x_all, data_ids_all = [], [], [], []
+    model.eval()
+    with torch.no_grad():
+        for batch in tqdm(loader):
+            src, tgt, src_len, _, data_ids = batch
+            src, tgt = src.to(device), tgt.to(device)
+            src_s_v, src_s_a = torch.split(src, [56, 768], dim=2)
+            lens = torch.as_tensor(list(src_len), device=device)
+            mask = torch.arange(src.shape[1], device=device)[None, :] < lens[:, None]
+            y_true = tgt[:, 1:, :].cpu().numpy()
+            x_np = src_s_v.cpu().numpy()
+            B = src.shape[0]
+            truth_stats = []
+            for j in range(B):
+                n = int(src_len[j]) - 1
+                y_trues_all.append(y_true[j][:n])
+                data_ids_all.append(data_ids[j])
+                x_all.append(x_np[j, :n])
+                truth_stats.append(calculate_activation_statistics(y_true[j][:n]))
+            best, keep = [float("inf")] * B, [None] * B
+            for _ in range(beam_size):
+                _, _, y_preds = model(src_s_v.contiguous(), tgt, src_s_a.contiguous(), mask, mode="val")
+                yp = y_preds.cpu().numpy()
+                for j in range(B):
+                    n = int(src_len[j]) - 1
+                    mu2, sigma2 = calculate_activation_statistics(yp[j][:n])
+                    fd = calculate_frechet_distance(truth_stats[j][0], truth_stats[j][1], mu2, sigma2)
+                    if fd < best[j]:
+                        best[j], keep[j] = fd, yp[j][:n].copy()
+            y_preds_all.extend(keep)
+    return y_trues_all, y_preds_all, x_all, data_ids_all

@@ -675,9 +675,10 @@ extern "C" size_t dim_slmft_workspace_bytes(dim_handle_t h, int model, int B, in
 }
 
 extern "C" int dim_slmft_context(dim_handle_t h, int model, const float* v_speaker, const float* v_audio,
-                                 const uint8_t* mask, int B, int T, float* ctx, void* ws, size_t ws_bytes, void* stream) {
+                                 const uint8_t* mask, int B, int T, float* ctx, float* x_s, void* ws, size_t ws_bytes,
+                                 void* stream) {
   DIM_REQUIRE(h && model >= 0 && model < (int)h->s2s.size(), "dim_slmft_context: bad model");
-  DIM_REQUIRE(v_speaker && v_audio && ctx && B > 0 && T > 0, "dim_slmft_context: bad argument");
+  DIM_REQUIRE(v_speaker && (ctx || x_s) && (v_audio || !ctx) && B > 0 && T > 0, "dim_slmft_context: bad argument");
   const S2SModel& m = *h->s2s[model];
   const dim_s2s_config& c = m.cfg;
   DIM_REQUIRE(T <= c.max_seq_len, "sequence longer than the positional table");
@@ -690,6 +691,8 @@ extern "C" int dim_slmft_context(dim_handle_t h, int model, const float* v_speak
   DIM_CHECK_CUDA(cudaMemcpyAsync(w.att, w.x, (size_t)B * T * c.dim * sizeof(float), cudaMemcpyDeviceToDevice, s));
   if (int e = xt_encoder_forward(m, m.enc_joint, w.att, nullptr, mask, w, B, T, s)) return e;
   if (int e = launch_layer_norm(w.x, m.norm_s_g, m.norm_s_b, w.ln, nullptr, B * T, c.dim, 1e-5f, s)) return e;
+  if (x_s) DIM_CHECK_CUDA(cudaMemcpyAsync(x_s, w.ln, (size_t)B * T * c.dim * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (!ctx) return DIM_OK;
   return launch_build_context(w.ln, m.patch_dec_s, v_audio, ctx, nullptr, (size_t)B * T, c.dim, c.dim_audio, s);
 }
 

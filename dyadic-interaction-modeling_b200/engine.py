@@ -139,17 +139,24 @@ class SLMFTEngine:
         n = self.handle.lib.dim_slmft_workspace_bytes(self.handle.h, self.model, B, T, steps)
         return self.ws.get(n), n
 
-    def context(self, v_speaker, v_audio, mask):
-        """-> ctx (B,T,dim+dim_audio) fp32 (seq2seq_pretrain.py:431-446)."""
-        v_speaker, v_audio = v_speaker.contiguous(), v_audio.contiguous()
+    def context(self, v_speaker, v_audio, mask, want="ctx"):
+        """want="ctx": generate's context (B,T,dim+dim_audio); want="x_s": forward_encoder's output (B,T,dim)
+        (seq2seq_pretrain.py:431-446)."""
+        v_speaker = v_speaker.contiguous()
         B, T, _ = v_speaker.shape
         m8 = mask.to(torch.uint8).contiguous()
-        ctx = torch.empty(B, T, self.cfg.dec_dim, dtype=torch.float32, device=v_speaker.device)
+        dev = v_speaker.device
+        ctx = xs = None
+        if want == "ctx":
+            v_audio = v_audio.contiguous()
+            ctx = torch.empty(B, T, self.cfg.dec_dim, dtype=torch.float32, device=dev)
+        else:
+            xs = torch.empty(B, T, self.cfg.dim, dtype=torch.float32, device=dev)
         ws, n = self._workspace(B, T, 0)
-        _lib.check(self.handle.lib.dim_slmft_context(self.handle.h, self.model, v_speaker.data_ptr(), v_audio.data_ptr(),
-                                                     m8.data_ptr(), B, T, ctx.data_ptr(), ws.data_ptr(), n, _stream()),
+        _lib.check(self.handle.lib.dim_slmft_context(self.handle.h, self.model, v_speaker.data_ptr(), _ptr(v_audio) if ctx is not None else None,
+                                                     m8.data_ptr(), B, T, _ptr(ctx), _ptr(xs), ws.data_ptr(), n, _stream()),
                    "dim_slmft_context")
-        return ctx
+        return ctx if want == "ctx" else xs
 
     def generate(self, ctx, mask, prompt, steps, temperature=0.0, top_k=None, uniforms=None, return_logits=False):
         """prompt (B,) or (B,1) int64 -> codes (B,steps) int64 (seq2seq_pretrain.py:450)."""

@@ -155,9 +155,11 @@ int dim_slmft_build(dim_handle_t h, const dim_s2s_config* cfg, int precision, in
 size_t dim_slmft_workspace_bytes(dim_handle_t h, int model, int B, int T, int steps);
 
 /* SLMFT.forward_encoder + context assembly (seq2seq_pretrain.py:431-446): v_speaker (B,T,56), v_audio (B,T,768),
- * mask (B,T) uint8 -> ctx (B,T,dim+dim_audio) = cat(norm_s(encoder_joint(encoder_s(v+patch_embed_s))) + patch_embed_dec_s, audio) */
+ * mask (B,T) uint8 -> x_s (B,T,dim) = norm_s(encoder_joint(encoder_s(v+patch_embed_s)))            [forward_encoder's return]
+ *                  -> ctx (B,T,dim+dim_audio) = cat(x_s + patch_embed_dec_s, audio)                 [generate's context]
+ * Either output may be NULL (v_audio may be NULL when ctx is). */
 int dim_slmft_context(dim_handle_t h, int model, const float* v_speaker, const float* v_audio, const uint8_t* mask, int B,
-                      int T, float* ctx, void* ws, size_t ws_bytes, void* stream);
+                      int T, float* ctx, float* x_s, void* ws, size_t ws_bytes, void* stream);
 
 /* decoder_joint.generate (seq2seq_pretrain.py:450; x-transformers AutoregressiveWrapper.generate): KV-cached
  * autoregressive decoding of `steps` tokens from prompt (B) int64, cross-attending ctx (B,T,D) under mask (B,T).

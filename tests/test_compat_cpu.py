@@ -1,0 +1,97 @@
+"""The drop-in module surface (dyadic-interaction-modeling_b200/compat): names, constructor contracts and state_dict keys
+match the reference, checkpoints load strictly, and nothing computes without the CUDA library."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import dim_b200
+from dim_b200.schema import slmft_schema, vqvae_schema
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+COMPAT = os.path.join(ROOT, "dyadic-interaction-modeling_b200", "compat")
+CFG = os.path.join(COMPAT, "config.yaml")
+
+
+@pytest.fixture(scope="module")
+def compat():
+    sys.path.insert(0, COMPAT)
+    import base.config as config
+    import models
+    import seq2seq_pretrain
+    import x_engine_pt
+    yield dict(config=config, models=models, s2s=seq2seq_pretrain, engine=x_engine_pt)
+    sys.path.remove(COMPAT)
+
+
+def test_config_loader_flattens_and_coerces(compat):
+    cfg = compat["config"].load_cfg_from_cfg_file(CFG)
+    assert cfg.arch == "stage1_BIWI" and cfg.hidden_size == 384 and cfg.n_embed == 512 and cfg.neg == 0.2
+    cfg2 = compat["config"].merge_cfg_from_list(cfg, ["batch_size", "4", "TRAIN.base_lr", "0.5", "neg", "1"])
+    assert cfg2.batch_size == 4 and cfg2.base_lr == 0.5 and cfg2.neg == 1.0 and isinstance(cfg2.neg, float)
+    with pytest.raises(AssertionError):
+        compat["config"].merge_cfg_from_list(cfg, ["no_such_key", "1"])
+
+
+def test_vq_state_dict_matches_schema_and_loads_strict(compat, vq_sd):
+    cfg = compat["config"].load_cfg_from_cfg_file(CFG)
+    m = compat["models"].get_model(cfg)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(vqvae_schema().keys()) or set(sd.keys()) == set(vqvae_schema().keys())
+    assert {k: tuple(v.shape) for k, v in sd.items()} == dict(vqvae_schema())
+    m.load_state_dict(vq_sd, strict=True)
+    assert torch.equal(m.quantize.embedding.weight, vq_sd["quantize.embedding.weight"])
+    assert abs(float(m.__class__(cfg).quantize.embedding.weight.abs().max())) <= 1.0 / 512 + 1e-9     # reference init U(+-1/n_e)
+    with pytest.raises(Exception):
+        cfg_bad = compat["config"].merge_cfg_from_list(cfg, ["arch", "stage2"])
+        compat["models"].get_model(cfg_bad)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/code"), reason="reference tree not present on this box")
+def test_vq_keys_equal_the_real_reference():
+    code = ("import sys, json; sys.path.insert(0, '/root/reference/code');"
+            "from base import config; from models import get_model;"
+            "m = get_model(config.load_cfg_from_cfg_file('/root/reference/code/config.yaml'));"
+            "print(json.dumps({k: list(v.shape) for k, v in m.state_dict().items()}))")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True).stdout
+    ref = {k: tuple(v) for k, v in json.loads(out.strip().splitlines()[-1]).items()}
+    assert ref == dict(vqvae_schema())
+
+
+def test_slmft_state_dict_matches_schema_and_loads_strict(compat, slmft_sd):
+    m = compat["s2s"].SLMFT(config_path=CFG, load_vq_checkpoints=False)
+    sd = m.state_dict()
+    want = dict(slmft_schema())
+    assert {k: tuple(v.shape) for k, v in sd.items()} == want
+    m.load_state_dict(slmft_sd, strict=True)
+    for name in ("speaker_vq", "listener_vq", "encoder_s", "encoder_l", "encoder_joint", "decoder_joint", "patch_embed_s",
+                 "patch_embed_l", "patch_embed_dec_s", "patch_embed_dec_l", "norm_s", "norm_l", "norm"):
+        assert hasattr(m, name), name
+    assert hasattr(m.decoder_joint, "net") and hasattr(m.decoder_joint, "generate")
+    assert not any(p.requires_grad for p in m.listener_vq.parameters())            # frozen like the reference (:351-364)
+    assert 149e6 < sum(p.numel() for p in m.parameters()) < 151e6          # SLMFT ~ 150 M parameters
+
+
+def test_no_cpu_fallback(compat, slmft_sd):
+    m = compat["s2s"].SLMFT(config_path=CFG, load_vq_checkpoints=False)
+    c = dim_b200.synth.make_clips(1, 8)
+    with pytest.raises(RuntimeError):
+        m(c["v_speaker"], c["v_listener"], c["v_audio"], c["mask"], mode="val")
+    with pytest.raises(NotImplementedError):
+        m(c["v_speaker"], c["v_listener"], c["v_audio"], c["mask"], mode="train")
+    cfg = compat["config"].load_cfg_from_cfg_file(CFG)
+    with pytest.raises(RuntimeError):
+        compat["models"].get_model(cfg).encode(c["v_listener"])
+
+
+def test_pos_embed_and_x_utils_importable(compat):
+    import pos_embed
+    import x_utils
+    e = pos_embed.get_1d_sincos_pos_embed_from_grid(8, [0, 1, 2])
+    assert e.shape == (3, 8) and abs(e[0, 4] - 1.0) < 1e-12
+    d = {"num_tokens": 512, "max_seq_len": 2048, "depth": 4}
+    assert x_utils.pick_and_pop(["num_tokens", "max_seq_len"], d) == {"num_tokens": 512, "max_seq_len": 2048} and d == {"depth": 4}
+    assert x_utils.groupby_prefix_and_trim("attn_", {"attn_heads": 2, "depth": 1}) == ({"heads": 2}, {"depth": 1})
