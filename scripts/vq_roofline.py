@@ -1,0 +1,54 @@
+"""VQ-lookup roofline (BASELINE metric "VQ-lookup HBM GB/s vs peak"): times dim_vq_gather and dim_vq_argmin alone with CUDA
+events on sizes larger than L2, algorithmic bytes = 520 B per code/token.  Prints one JSON line per kernel."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import dim_b200  # noqa: F401
+from dim_b200 import ops
+
+PEAK = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] \
+    if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) else 6650.0
+
+
+def timeit(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def main():
+    g = torch.Generator().manual_seed(0)
+    E = (torch.randn(512, 128, generator=g) * 0.5).cuda()
+    for N in (76544, 1 << 20, 1 << 22):                       # B=256 x 299 codes; 0.5 GB; 2 GB of rows (> 126 MB L2)
+        idx = torch.randint(0, 512, (N,), generator=g).cuda()
+        out = torch.empty(N, 128, device="cuda")
+        lib = dim_b200._lib.load()
+        s = torch.cuda.current_stream().cuda_stream
+        t = timeit(lambda: lib.dim_vq_gather(idx.data_ptr(), E.data_ptr(), out.data_ptr(), N, 128, 512, None, s))
+        gbs = N * 520 / t / 1e9
+        print(json.dumps({"kernel": "vq_gather", "codes": N, "us": t * 1e6, "GB/s": gbs, "frac_of_hbm_peak": gbs / PEAK, "peak": PEAK,
+                          "algorithmic_bytes_per_code": 520}))
+    for N in (76800, 1 << 20):
+        z = (torch.randn(N, 128, generator=g) * 0.7).cuda()
+        o = torch.empty(N, dtype=torch.int64, device="cuda")
+        lib = dim_b200._lib.load()
+        s = torch.cuda.current_stream().cuda_stream
+        t = timeit(lambda: lib.dim_vq_argmin(z.data_ptr(), E.data_ptr(), o.data_ptr(), N, 128, 512, s))
+        gbs = N * 520 / t / 1e9
+        print(json.dumps({"kernel": "vq_argmin_f32", "tokens": N, "us": t * 1e6, "GB/s": gbs, "frac_of_hbm_peak": gbs / PEAK,
+                          "TFLOP/s": N * 131072 / t / 1e12, "algorithmic_bytes_per_token": 520}))
+
+
+if __name__ == "__main__":
+    main()
