@@ -264,7 +264,8 @@ def run_native(args):
     tot_ms = sum(p["ms"] for p in prof) or 1.0
     prof.sort(key=lambda p: -p["ms"])
     top = prof[0]
-    hbm_cats = {"attn_decode", "vq_gather", "layer_norm", "instance_norm", "gemm_f32_skinny", "misc", "sample"}
+    hbm_cats = {"attn_decode", "vq_gather", "layer_norm", "instance_norm", "gemm_f32_skinny", "gemm_bf16_tcgen05_skinny", "misc",
+                "sample"}
     per_launch_ms = top["ms"] / top["launches"]
     tensor_peak = peaks["tensor_sustained"]
     if top["category"] in hbm_cats:

@@ -161,88 +161,118 @@ __global__ void __launch_bounds__(256) attn_prefill_f32(const AttnArgs p) {
 }
 
 // ---- decode: one query row per (b,h) ----------------------------------------------------------------------------
-// 128 threads = 8 half-warps; a half-warp owns whole keys (16 lanes x 4 elements = 64 dims: 256 B fp32 / 128 B bf16 rows).
+// 128 threads; a group of LPK lanes owns whole keys: every lane moves one 128-bit vector per key (4 fp32 or 8 bf16), so a
+// (b,h) head row -- 256 B fp32 / 128 B bf16, contiguous in the token-major cache -- is one fully used request.
 template <bool BF16>
 struct KvIo;
 template <>
 struct KvIo<false> {
   typedef float T;
-  static __device__ __forceinline__ float4 ld(const float* p) { return *reinterpret_cast<const float4*>(p); }
-  static __device__ __forceinline__ void st(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+  static constexpr int EPL = 4;                       // elements per lane
+  static __device__ __forceinline__ void ld(const float* p, float* v) {
+    const float4 x = *reinterpret_cast<const float4*>(p);
+    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
 };
 template <>
 struct KvIo<true> {
   typedef __nv_bfloat16 T;
-  static __device__ __forceinline__ float4 ld(const __nv_bfloat16* p) {
-    uint2 u = *reinterpret_cast<const uint2*>(p);
-    float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.x));
-    float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.y));
-    return make_float4(a.x, a.y, b.x, b.y);
+  static constexpr int EPL = 8;
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float* v) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
   }
-  static __device__ __forceinline__ void st(__nv_bfloat16* p, float4 v) {
-    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-    uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&lo);
-    u.y = *reinterpret_cast<uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(p) = u;
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float* v) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&b);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 };
 
-template <bool BF16>
-__global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeAttnArgs p) {
+template <bool BF16, int NT>
+__global__ void __launch_bounds__(NT) attn_decode_kernel(const DecodeAttnArgs p) {
   typedef typename KvIo<BF16>::T KT;
-  constexpr int DH = 64;
-  extern __shared__ __align__(16) float sc[];          // [nkeys_max] scores, then [8][64] partial outputs
+  constexpr int DH = 64, EPL = KvIo<BF16>::EPL, LPK = DH / EPL, NG = NT / LPK, U = 4, NW = NT / 32;
+  extern __shared__ __align__(16) float sc[];          // [nkeys_max] scores, then [NG][64] partial outputs
   __shared__ float red[8];
+  pdl_prologue();
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int hw = tid >> 4, l16 = tid & 15;
+  const int grp = tid / LPK, lk = tid % LPK;           // key group of this lane, position inside the head row
   const int pos = p.step ? *p.step : 0;                                   // index of the token being decoded
   const int nkeys = p.append ? pos + 1 : p.Tk;
-  KT* kbase = static_cast<KT*>(p.k) + (size_t)b * p.kv_batch_stride + h * DH;
-  KT* vbase = static_cast<KT*>(p.v) + (size_t)b * p.kv_batch_stride + h * DH;
+  KT* kbase = static_cast<KT*>(p.k) + (size_t)b * p.kv_batch_stride + h * DH + lk * EPL;
+  KT* vbase = static_cast<KT*>(p.v) + (size_t)b * p.kv_batch_stride + h * DH + lk * EPL;
 
+  float q[EPL];
+#pragma unroll
+  for (int i = 0; i < EPL; i += 4) {
+    const float4 x = *reinterpret_cast<const float4*>(p.q + (size_t)b * p.ldq + h * DH + lk * EPL + i);
+    q[i] = x.x; q[i + 1] = x.y; q[i + 2] = x.z; q[i + 3] = x.w;
+  }
   if (p.append) {                                                        // cache[pos] <- this step's k, v
-    if (tid < 16)
-      KvIo<BF16>::st(kbase + (size_t)pos * p.kv_tok_stride + l16 * 4,
-                     *reinterpret_cast<const float4*>(p.k_new + (size_t)b * p.ld_new + h * DH + l16 * 4));
-    else if (tid < 32)
-      KvIo<BF16>::st(vbase + (size_t)pos * p.kv_tok_stride + l16 * 4,
-                     *reinterpret_cast<const float4*>(p.v_new + (size_t)b * p.ld_new + h * DH + l16 * 4));
+    if (grp < 2) {
+      const float* src = (grp == 0 ? p.k_new : p.v_new) + (size_t)b * p.ld_new + h * DH + lk * EPL;
+      float v[EPL];
+#pragma unroll
+      for (int i = 0; i < EPL; i += 4) {
+        const float4 x = *reinterpret_cast<const float4*>(src + i);
+        v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
+      }
+      KvIo<BF16>::st((grp == 0 ? kbase : vbase) + (size_t)pos * p.kv_tok_stride, v);
+    }
     __syncthreads();
   }
-  const float4 qv = *reinterpret_cast<const float4*>(p.q + (size_t)b * p.ldq + h * DH + l16 * 4);
   const uint8_t* km = p.key_mask ? p.key_mask + (size_t)b * p.Tk : nullptr;
 
-  // scores
-  for (int base = 0; base < nkeys; base += 32) {       // warp-uniform trip count: the shuffles below need all lanes
-    const int j0 = base + hw;
-    float4 kv[4];
+  // scores: U keys in flight per group
+  for (int base = 0; base < nkeys; base += NG * U) {   // warp-uniform trip count: the shuffles below need all lanes
+    float kv[U][EPL];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      int j = j0 + 8 * u;
-      kv[u] = j < nkeys ? KvIo<BF16>::ld(kbase + (size_t)j * p.kv_tok_stride + l16 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int u = 0; u < U; ++u) {
+      const int j = base + grp + NG * u;
+      if (j < nkeys) KvIo<BF16>::ld(kbase + (size_t)j * p.kv_tok_stride, kv[u]);
+      else {
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) kv[u][i] = 0.f;
+      }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      int j = j0 + 8 * u;
-      float d = qv.x * kv[u].x + qv.y * kv[u].y + qv.z * kv[u].z + qv.w * kv[u].w;
+    for (int u = 0; u < U; ++u) {
+      const int j = base + grp + NG * u;
+      float d = 0.f;
 #pragma unroll
-      for (int off = 8; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
-      if (l16 == 0 && j < nkeys) sc[j] = (km && !km[j]) ? -FLT_MAX : d * p.scale;
+      for (int i = 0; i < EPL; ++i) d = fmaf(q[i], kv[u][i], d);
+#pragma unroll
+      for (int off = LPK / 2; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+      if (lk == 0 && j < nkeys) sc[j] = (km && !km[j]) ? -FLT_MAX : d * p.scale;
     }
   }
   __syncthreads();
   // softmax statistics
   float mx = -INFINITY;
-  for (int j = tid; j < nkeys; j += 128) mx = fmaxf(mx, sc[j]);
+  for (int j = tid; j < nkeys; j += NT) mx = fmaxf(mx, sc[j]);
   mx = warp_max(mx);
   if (lane == 0) red[warp] = mx;
   __syncthreads();
-  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) mx = fmaxf(mx, red[w]);
   __syncthreads();
   float sum = 0.f;
-  for (int j = tid; j < nkeys; j += 128) {
+  for (int j = tid; j < nkeys; j += NT) {
     float e = expf(sc[j] - mx);
     sc[j] = e;
     sum += e;
@@ -250,34 +280,42 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeAttnArgs p
   sum = warp_sum(sum);
   if (lane == 0) red[warp] = sum;
   __syncthreads();
-  const float inv = 1.f / (red[0] + red[1] + red[2] + red[3]);
+  float tot = red[0];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) tot += red[w];
+  const float inv = 1.f / tot;
 
   // out = P V
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int base = 0; base < nkeys; base += 32) {
-    const int j0 = base + hw;
-    float4 vv[4];
-    float pj[4];
+  float acc[EPL];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      int j = j0 + 8 * u;
-      bool ok = j < nkeys;
-      vv[u] = ok ? KvIo<BF16>::ld(vbase + (size_t)j * p.kv_tok_stride + l16 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      pj[u] = ok ? sc[j] : 0.f;
+  for (int i = 0; i < EPL; ++i) acc[i] = 0.f;
+  for (int base = 0; base < nkeys; base += NG * U) {
+    float vv[U][EPL], pj[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = base + grp + NG * u;
+      pj[u] = 0.f;
+      if (j < nkeys) {
+        KvIo<BF16>::ld(vbase + (size_t)j * p.kv_tok_stride, vv[u]);
+        pj[u] = sc[j];
+      } else {
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) vv[u][i] = 0.f;
+      }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      acc.x = fmaf(pj[u], vv[u].x, acc.x); acc.y = fmaf(pj[u], vv[u].y, acc.y);
-      acc.z = fmaf(pj[u], vv[u].z, acc.z); acc.w = fmaf(pj[u], vv[u].w, acc.w);
-    }
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) acc[i] = fmaf(pj[u], vv[u][i], acc[i]);
   }
-  float* part = sc + p.sc_floats;                       // [8][64]
-  *reinterpret_cast<float4*>(part + hw * DH + l16 * 4) = acc;
+  float* part = sc + p.sc_floats;                       // [NG][64]
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) part[grp * DH + lk * EPL + i] = acc[i];
   __syncthreads();
   if (tid < DH) {
     float r = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) r += part[w * DH + tid];
+    for (int w = 0; w < NG; ++w) r += part[w * DH + tid];
     if (p.out) p.out[(size_t)b * p.ldo + h * DH + tid] = r * inv;
     if (p.out_p) store_planes1(p.out_p + (size_t)b * p.planes * p.kp + h * DH + tid, r * inv, p.planes, p.kp);
   }
@@ -317,21 +355,26 @@ int launch_attention_prefill(const AttnArgs& a, cudaStream_t s) {
 int launch_attention_decode(DecodeAttnArgs a, int max_keys, cudaStream_t s) {
   DIM_REQUIRE(a.B > 0 && a.H > 0, "decode attention: empty");
   a.sc_floats = (max_keys + 3) / 4 * 4;
-  size_t smem = (size_t)(a.sc_floats + 8 * 64) * sizeof(float);
+  size_t smem = (size_t)(a.sc_floats + 16 * 64) * sizeof(float);
   DIM_REQUIRE(smem <= 200 * 1024, "decode attention: too many keys for one CTA");
-  static size_t configured[2] = {48 * 1024, 48 * 1024};
-  const int bf = a.kv_bf16 ? 1 : 0;
-  if (smem > configured[bf]) {
-    if (bf) DIM_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else DIM_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[bf] = smem;
+  // 64-thread CTAs when the whole (batch x heads) grid then fits in one resident wave (32 CTAs / SM): every head streams
+  // concurrently and there is no half-empty tail wave; 128-thread CTAs for larger grids.
+  const bool bf = a.kv_bf16 != 0;
+  const bool small = bf && (long)a.B * a.H <= 148L * 32;   // (fp32 rows are twice as long: 128-thread CTAs measured faster)
+  typedef void (*Kern)(const DecodeAttnArgs);
+  Kern kern = bf ? (small ? (Kern)attn_decode_kernel<true, 64> : (Kern)attn_decode_kernel<true, 128>)
+                 : (small ? (Kern)attn_decode_kernel<false, 64> : (Kern)attn_decode_kernel<false, 128>);
+  static size_t configured[4] = {48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024};
+  const int slot = (bf ? 2 : 0) + (small ? 1 : 0);
+  if (smem > configured[slot]) {
+    DIM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[slot] = smem;
   }
   {
     const double keys = a.append ? (double)(a.prof_pos + 1) : (double)a.Tk;   // K and V rows actually read
     const double esz = bf ? 2.0 : 4.0;
     ProfScope ps(CAT_ATTN_DECODE, s, a.B * (double)a.H * 64.0 * (2.0 * keys * esz + 8.0), 4.0 * a.B * a.H * 64.0 * keys);
-    if (bf) attn_decode_kernel<true><<<a.B * a.H, 128, smem, s>>>(a);
-    else attn_decode_kernel<false><<<a.B * a.H, 128, smem, s>>>(a);
+    DIM_CHECK_CUDA(launch_k(kern, dim3(a.B * a.H), dim3(small ? 64 : 128), smem, s, a));
   }
   DIM_LAUNCHED();
   return DIM_OK;

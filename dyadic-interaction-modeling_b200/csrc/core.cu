@@ -1,5 +1,6 @@
 // Error plumbing, device check, launch counter.
 #include "common.cuh"
+#include <cstdlib>
 #include <vector>
 
 namespace dimb {
@@ -34,6 +35,7 @@ int ensure_device() {
 }
 
 bool g_prof_on = false;
+bool g_pdl_on = getenv("DIM_PDL") != nullptr;   // opt-in: measured slower on this workload (early-resident dependents hold SM slots)
 namespace {
 struct ProfRec { int cat; cudaEvent_t a, b; double bytes, flops; };
 std::vector<ProfRec> g_recs;
@@ -44,7 +46,7 @@ cudaEvent_t get_event() {
 }
 const char* kCatNames[CAT_COUNT] = {"gemm_f32_tiled", "gemm_f32_skinny", "conv5_implicit_gemm", "layer_norm",
                                     "instance_norm", "attn_prefill_f32", "attn_decode", "vq_argmin", "vq_gather",
-                                    "sample", "misc", "gemm_bf16_tcgen05"};
+                                    "sample", "misc", "gemm_bf16_tcgen05", "gemm_bf16_tcgen05_skinny"};
 }  // namespace
 void prof_begin(int cat, cudaStream_t s, double bytes, double flops) {
   ProfRec r{cat, get_event(), get_event(), bytes, flops};

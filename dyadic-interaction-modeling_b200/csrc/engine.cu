@@ -4,6 +4,7 @@
 //   * SLMFT.forward_encoder + context concat   (/root/reference/code/seq2seq_pretrain.py:431-446)
 //   * decoder_joint.generate                   (seq2seq_pretrain.py:450; x-transformers 1.30.16)
 // Everything is enqueued on the caller's stream; no host synchronisation inside.
+#include <cstdlib>
 #include <memory>
 #include <string>
 #include <unordered_map>
@@ -74,6 +75,15 @@ struct S2SModel {
   std::vector<XtAttn> self_attn, cross_attn;
   std::vector<XtFF> ff;
   const float *final_g = nullptr, *final_b = nullptr, *logits_w = nullptr, *logits_b = nullptr;
+  // CUDA graph of ONE decode step (the step index lives in device memory, so every step replays the same graph)
+  struct StepGraph {
+    cudaGraphExec_t exec = nullptr;
+    std::vector<uintptr_t> key;
+    cudaStream_t stream = nullptr;       // side stream the graph runs on (capture is not allowed on the legacy stream)
+    cudaEvent_t fork = nullptr, join = nullptr;
+  };
+  mutable std::vector<StepGraph> graphs;
+  mutable cudaEvent_t fork_ev = nullptr;
 };
 
 }  // namespace
@@ -665,12 +675,34 @@ extern "C" int dim_slmft_build(dim_handle_t h, const dim_s2s_config* cfg, int pr
   return DIM_OK;
 }
 
+// Decoding is a chain of ~49 short, strictly dependent kernels per generated frame: one chain cannot fill the GPU.
+// Clips are independent, so a batch is decoded as up to 4 concurrent groups of >= 128 clips (one 128-row MMA tile each) on
+// side streams: their chains interleave on the SMs and hide each other's launch/pipeline-fill/epilogue latencies.
+// Per-row results do not depend on the grouping (no cross-row arithmetic; split-K depends on K only).
+constexpr int kGroupRows = 128, kMaxGroups = 4;
+int plan_groups(const S2SModel& m, int B, int* begin /*[kMaxGroups+1]*/) {
+  int ng = 1;
+  if (tc_on(m.tc, B) && B >= 2 * kGroupRows) ng = std::min(kMaxGroups, B / kGroupRows);
+  static const bool no_groups = getenv("DIM_NO_GROUPS") != nullptr;
+  if (no_groups) ng = 1;
+  const int per = (B / ng + kGroupRows - 1) / kGroupRows * kGroupRows;      // multiples of 128 rows, remainder in the last
+  for (int g = 0; g <= ng; ++g) begin[g] = std::min(B, g * per);
+  begin[ng] = B;
+  return ng;
+}
+
 extern "C" size_t dim_slmft_workspace_bytes(dim_handle_t h, int model, int B, int T, int steps) {
   if (!h || model < 0 || model >= (int)h->s2s.size() || B <= 0 || T <= 0) return 0;
   const dim_s2s_config& c = h->s2s[model]->cfg;
   const int planes = h->s2s[model]->tc.planes;
   size_t a = carve_ctx(c, planes, B, T, nullptr).bytes;
-  size_t b = steps > 0 ? carve_gen(c, planes, h->s2s[model]->precision == DIM_PREC_BF16, B, T, steps, nullptr).bytes : 0;
+  size_t b = 0;
+  if (steps > 0) {
+    int begin[kMaxGroups + 1];
+    const int ng = plan_groups(*h->s2s[model], B, begin);
+    for (int g = 0; g < ng; ++g)
+      b += carve_gen(c, planes, h->s2s[model]->precision == DIM_PREC_BF16, begin[g + 1] - begin[g], T, steps, nullptr).bytes;
+  }
   return a > b ? a : b;
 }
 
@@ -696,20 +728,16 @@ extern "C" int dim_slmft_context(dim_handle_t h, int model, const float* v_speak
   return launch_build_context(w.ln, m.patch_dec_s, v_audio, ctx, nullptr, (size_t)B * T, c.dim, c.dim_audio, s);
 }
 
-extern "C" int dim_slmft_generate(dim_handle_t h, int model, const float* ctx, const uint8_t* mask, const int64_t* prompt,
-                                  int B, int T, int steps, float temperature, int top_k, const float* uniforms,
-                                  int64_t* out_codes, float* logits_out, void* ws, size_t ws_bytes, void* stream) {
-  DIM_REQUIRE(h && model >= 0 && model < (int)h->s2s.size(), "dim_slmft_generate: bad model");
-  DIM_REQUIRE(ctx && prompt && out_codes && B > 0 && T > 0 && steps > 0, "dim_slmft_generate: bad argument");
-  DIM_REQUIRE(temperature >= 0.f, "temperature must be >= 0");
-  DIM_REQUIRE(temperature == 0.f || (uniforms && top_k > 0), "sampling needs uniforms and top_k");
-  const S2SModel& m = *h->s2s[model];
+namespace {
+// Decode `B` clips on stream `s` (one group).  G: this group's cached step graph.
+int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, const uint8_t* mask, const int64_t* prompt,
+                   int B, int T, int steps, float temperature, int top_k, const float* uniforms, int64_t* out_codes,
+                   float* logits_out, void* ws, size_t ws_bytes, cudaStream_t s) {
   const dim_s2s_config& c = m.cfg;
   const int inner = c.heads * c.dim_head, D = c.dim + c.dim_audio, F = c.ff_mult * D, V = c.num_tokens;
   const bool kv16 = m.precision == DIM_PREC_BF16;   // bf16 mode keeps both KV caches in bf16 (half the decode-attention bytes)
   GenWs w = carve_gen(c, m.tc.planes, kv16, B, T, steps, ws);
   if (ws == nullptr || ws_bytes < w.bytes) return fail(DIM_EWORKSPACE, "dim_slmft_generate: workspace too small");
-  cudaStream_t s = as_stream(stream);
   const float scale = 1.0f / sqrtf((float)c.dim_head);
 
   for (int l = 0; l < c.depth; ++l) {  // cross-attention K/V of the whole context, once
@@ -726,7 +754,7 @@ extern "C" int dim_slmft_generate(dim_handle_t h, int model, const float* ctx, c
   const int max_keys = std::max(T, steps + 1);
   const bool tcp = tc_on(m.tc, B);
   const int P = m.tc.planes;
-  for (int st = 0; st < steps; ++st) {
+  auto enqueue_step = [&](int st, cudaStream_t s) -> int {
     if (int e = launch_embed_tokens(w.tokens, steps + 1, w.step, m.token_emb, w.x, B, D, V, s)) return e;
     for (int l = 0; l < c.depth; ++l) {
       const XtAttn& SA = m.self_attn[l];
@@ -807,9 +835,109 @@ extern "C" int dim_slmft_generate(dim_handle_t h, int model, const float* ctx, c
                               logits_out, steps * V, s))
       return e;
     if (int e = launch_advance_step(w.step, s)) return e;
+    return DIM_OK;
+  };
+
+  // One decode step = 49 short, strictly dependent launches: replay it as a CUDA graph (captured once per distinct call
+  // signature) to remove the per-launch submission cost; DIM_NO_GRAPH=1 or profiling falls back to plain launches.
+  static const bool no_graph = getenv("DIM_NO_GRAPH") != nullptr;
+  if (no_graph || g_prof_on) {
+    for (int st = 0; st < steps; ++st)
+      if (int e = enqueue_step(st, s)) return e;
+  } else {
+    std::vector<uintptr_t> key = {(uintptr_t)ctx, (uintptr_t)mask, (uintptr_t)uniforms, (uintptr_t)logits_out, (uintptr_t)ws,
+                                  (uintptr_t)B, (uintptr_t)T, (uintptr_t)steps, (uintptr_t)top_k,
+                                  (uintptr_t)(temperature * 65536.0f)};
+    if (!G.stream) {
+      DIM_CHECK_CUDA(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+      DIM_CHECK_CUDA(cudaEventCreateWithFlags(&G.fork, cudaEventDisableTiming));
+      DIM_CHECK_CUDA(cudaEventCreateWithFlags(&G.join, cudaEventDisableTiming));
+    }
+    if (G.exec == nullptr || G.key != key) {
+      if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+      if (int e = enqueue_step(0, s)) return e;                       // warm (lazy attribute setup, tensor maps) outside capture
+      if (int e = launch_set_step(w.step, 0, s)) return e;            // ... and rewind the step counter it advanced
+      DIM_CHECK_CUDA(cudaStreamSynchronize(s));
+      cudaGraph_t graph = nullptr;
+      DIM_CHECK_CUDA(cudaStreamBeginCapture(G.stream, cudaStreamCaptureModeThreadLocal));
+      int rc = enqueue_step(0, G.stream);
+      cudaError_t ce = cudaStreamEndCapture(G.stream, &graph);
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      DIM_CHECK_CUDA(ce);
+      DIM_CHECK_CUDA(cudaGraphInstantiate(&G.exec, graph, 0));
+      cudaGraphDestroy(graph);
+      G.key = key;
+    }
+    DIM_CHECK_CUDA(cudaEventRecord(G.fork, s));
+    DIM_CHECK_CUDA(cudaStreamWaitEvent(G.stream, G.fork, 0));
+    for (int st = 0; st < steps; ++st) DIM_CHECK_CUDA(cudaGraphLaunch(G.exec, G.stream));
+    g_launches.fetch_add((uint64_t)steps * (uint64_t)(5 + c.depth * 11), std::memory_order_relaxed);
+    DIM_CHECK_CUDA(cudaEventRecord(G.join, G.stream));
+    DIM_CHECK_CUDA(cudaStreamWaitEvent(s, G.join, 0));
   }
   DIM_CHECK_CUDA(cudaMemcpy2DAsync(out_codes, (size_t)steps * sizeof(int64_t), w.tokens + 1,
                                    (size_t)(steps + 1) * sizeof(int64_t), (size_t)steps * sizeof(int64_t), B,
                                    cudaMemcpyDeviceToDevice, s));
+  return DIM_OK;
+}
+}  // namespace
+
+extern "C" int dim_slmft_generate(dim_handle_t h, int model, const float* ctx, const uint8_t* mask, const int64_t* prompt,
+                                  int B, int T, int steps, float temperature, int top_k, const float* uniforms,
+                                  int64_t* out_codes, float* logits_out, void* ws, size_t ws_bytes, void* stream) {
+  DIM_REQUIRE(h && model >= 0 && model < (int)h->s2s.size(), "dim_slmft_generate: bad model");
+  DIM_REQUIRE(ctx && prompt && out_codes && B > 0 && T > 0 && steps > 0, "dim_slmft_generate: bad argument");
+  DIM_REQUIRE(temperature >= 0.f, "temperature must be >= 0");
+  DIM_REQUIRE(temperature == 0.f || (uniforms && top_k > 0), "sampling needs uniforms and top_k");
+  const S2SModel& m = *h->s2s[model];
+  const dim_s2s_config& c = m.cfg;
+  const int D = c.dim + c.dim_audio, V = c.num_tokens;
+  cudaStream_t s = as_stream(stream);
+  int begin[kMaxGroups + 1];
+  const int ng = plan_groups(m, B, begin);
+  if ((int)m.graphs.size() < kMaxGroups) m.graphs.resize(kMaxGroups);
+  if (ng == 1 || g_prof_on) {
+    if (ng > 1) {   // profiling: same groups, sequentially on the caller's stream (events need one stream)
+      char* wsp = static_cast<char*>(ws);
+      for (int g = 0; g < ng; ++g) {
+        const int b0 = begin[g], bg = begin[g + 1] - b0;
+        const size_t need = carve_gen(c, m.tc.planes, m.precision == DIM_PREC_BF16, bg, T, steps, nullptr).bytes;
+        if ((size_t)(wsp - static_cast<char*>(ws)) + need > ws_bytes) return fail(DIM_EWORKSPACE, "dim_slmft_generate: workspace too small");
+        if (int e = generate_group(m, m.graphs[g], ctx + (size_t)b0 * T * D, mask ? mask + (size_t)b0 * T : nullptr, prompt + b0, bg, T,
+                                   steps, temperature, top_k, uniforms ? uniforms + (size_t)b0 * steps : nullptr,
+                                   out_codes + (size_t)b0 * steps, logits_out ? logits_out + (size_t)b0 * steps * V : nullptr, wsp,
+                                   need, s))
+          return e;
+        wsp += need;
+      }
+      return DIM_OK;
+    }
+    return generate_group(m, m.graphs[0], ctx, mask, prompt, B, T, steps, temperature, top_k, uniforms, out_codes, logits_out, ws,
+                          ws_bytes, s);
+  }
+  // fork: every group decodes on its own side stream, ordered after the caller's stream; join at the end
+  if (!m.fork_ev) DIM_CHECK_CUDA(cudaEventCreateWithFlags(&m.fork_ev, cudaEventDisableTiming));
+  DIM_CHECK_CUDA(cudaEventRecord(m.fork_ev, s));
+  char* wsp = static_cast<char*>(ws);
+  for (int g = 0; g < ng; ++g) {
+    S2SModel::StepGraph& G = m.graphs[g];
+    if (!G.stream) {
+      DIM_CHECK_CUDA(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+      DIM_CHECK_CUDA(cudaEventCreateWithFlags(&G.fork, cudaEventDisableTiming));
+      DIM_CHECK_CUDA(cudaEventCreateWithFlags(&G.join, cudaEventDisableTiming));
+    }
+    const int b0 = begin[g], bg = begin[g + 1] - b0;
+    const size_t need = carve_gen(c, m.tc.planes, m.precision == DIM_PREC_BF16, bg, T, steps, nullptr).bytes;
+    if ((size_t)(wsp - static_cast<char*>(ws)) + need > ws_bytes) return fail(DIM_EWORKSPACE, "dim_slmft_generate: workspace too small");
+    DIM_CHECK_CUDA(cudaStreamWaitEvent(G.stream, m.fork_ev, 0));
+    if (int e = generate_group(m, G, ctx + (size_t)b0 * T * D, mask ? mask + (size_t)b0 * T : nullptr, prompt + b0, bg, T, steps,
+                               temperature, top_k, uniforms ? uniforms + (size_t)b0 * steps : nullptr,
+                               out_codes + (size_t)b0 * steps, logits_out ? logits_out + (size_t)b0 * steps * V : nullptr, wsp, need,
+                               G.stream))
+      return e;
+    DIM_CHECK_CUDA(cudaEventRecord(G.join, G.stream));
+    DIM_CHECK_CUDA(cudaStreamWaitEvent(s, G.join, 0));
+    wsp += need;
+  }
   return DIM_OK;
 }

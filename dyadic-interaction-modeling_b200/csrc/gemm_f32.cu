@@ -44,6 +44,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_f32_tiled(const Ge
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Ws[BK][BN + 4];
 
+  pdl_prologue();
   const int tid = threadIdx.x;
   const int tx = tid % (BN / TN), ty = tid / (BN / TN);
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -164,6 +165,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_f32_tiled(const Ge
 // Skinny GEMM: one warp per output column, all MT rows; W streamed once with 128-bit loads, A served by L1.
 template <int MT>
 __global__ void __launch_bounds__(128) gemm_f32_skinny(const GemmArgs p) {
+  pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * 4 + warp;
   if (n >= p.N) return;
@@ -229,7 +231,7 @@ int launch_tiled(const GemmArgs& a, cudaStream_t s) {
   dim3 grid(cdiv(a.N, BN), cdiv(a.M, BM));
   ProfScope ps(a.conv_T > 0 ? CAT_CONV : CAT_GEMM_TILED, s, 4.0 * ((double)a.M * (a.conv_T > 0 ? a.conv_C : a.K) + (double)a.N * a.K + (double)a.M * a.N),
                2.0 * a.M * (double)a.N * a.K);
-  gemm_f32_tiled<BM, BN, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, s>>>(a);
+  DIM_CHECK_CUDA(launch_k(gemm_f32_tiled<BM, BN, TM, TN>, grid, dim3((BM / TM) * (BN / TN)), 0, s, a));
   DIM_LAUNCHED();
   return DIM_OK;
 }
@@ -246,10 +248,10 @@ int launch_gemm_f32(const GemmArgs& a, cudaStream_t s) {
     dim3 grid(cdiv(a.N, 4));
     ProfScope ps(CAT_GEMM_SKINNY, s, 4.0 * ((double)a.M * a.K + (double)a.N * a.K + (double)a.M * a.N),
                  2.0 * a.M * (double)a.N * a.K);
-    if (a.M == 1) gemm_f32_skinny<1><<<grid, 128, 0, s>>>(a);
-    else if (a.M == 2) gemm_f32_skinny<2><<<grid, 128, 0, s>>>(a);
-    else if (a.M <= 4) gemm_f32_skinny<4><<<grid, 128, 0, s>>>(a);
-    else gemm_f32_skinny<8><<<grid, 128, 0, s>>>(a);
+    if (a.M == 1) DIM_CHECK_CUDA(launch_k(gemm_f32_skinny<1>, grid, dim3(128), 0, s, a));
+    else if (a.M == 2) DIM_CHECK_CUDA(launch_k(gemm_f32_skinny<2>, grid, dim3(128), 0, s, a));
+    else if (a.M <= 4) DIM_CHECK_CUDA(launch_k(gemm_f32_skinny<4>, grid, dim3(128), 0, s, a));
+    else DIM_CHECK_CUDA(launch_k(gemm_f32_skinny<8>, grid, dim3(128), 0, s, a));
     DIM_LAUNCHED();
     return DIM_OK;
   }

@@ -213,6 +213,9 @@ __global__ void __launch_bounds__(192) gemm_bf16_tcgen05(const __grid_constant__
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_slot;
+  // Everything above (barrier init, TMEM allocation, descriptor prefetch) touched no global data: with programmatic
+  // dependent launch it overlapped the previous kernel's tail.  From here on operands written by that kernel are read.
+  pdl_prologue();
   if (dbg && threadIdx.x == 0) p.dbg[1] = clock64();
 
   if (warp == 0) {
@@ -416,14 +419,20 @@ int launch_tc_act(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcParams
   cfg.blockDim = dim3(192);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;     // the S K-slices of one output tile form a cluster
   attr[0].val.clusterDim.x = 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = p.splits;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  ProfScope ps(CAT_GEMM_TC, s, 2.0 * ((double)p.e.M + p.e.N) * p.kp * p.npairs + 4.0 * p.e.M * p.e.N,
+  cfg.numAttrs = g_pdl_on ? 2 : 1;
+  // algorithmic traffic: every operand plane once + the fp32 result; skinny (M < 2048: decode-step) launches are reported
+  // separately because their roofline is HBM (weights streamed once per step), not the tensor pipe
+  const int planes_n = p.npairs == 1 ? 1 : (p.npairs == 3 ? 2 : 3);
+  ProfScope ps(p.e.M < 2048 ? CAT_GEMM_TC_SKINNY : CAT_GEMM_TC, s,
+               2.0 * ((double)p.e.M + p.e.N) * p.kp * planes_n + 4.0 * p.e.M * p.e.N,
                2.0 * p.e.M * (double)p.e.N * p.kp * p.npairs);
   DIM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05<BN, STAGES, ACT>, tmA, tmW, p));
   DIM_LAUNCHED();

@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict
                                                          const float* __restrict__ bias, float* __restrict__ y,
                                                          __nv_bfloat16* __restrict__ yb, int rows, int dim, float eps,
                                                          __nv_bfloat16* __restrict__ yp, int planes, int kp) {
+  pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const int n4 = dim >> 2;
@@ -138,6 +139,7 @@ __global__ void build_context_kernel(const float* __restrict__ xs, const float* 
 // x[b,:] = token_emb[tok[b],:]   (TransformerWrapper token embedding; no positional term for SLMFT)
 __global__ void embed_tokens_kernel(const int64_t* __restrict__ tok, int tok_stride, const int* __restrict__ step,
                                     const float* __restrict__ emb, float* __restrict__ x, int B, int D, int V) {
+  pdl_prologue();
   const int b = blockIdx.x;
   const int64_t* tp = tok + (size_t)b * tok_stride + (step ? *step : 0);
   int64_t t = *tp;
@@ -155,10 +157,11 @@ __global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ l
                                                      const int* __restrict__ step, int64_t* __restrict__ out,
                                                      int out_stride, int out_offset, float* __restrict__ logits_out,
                                                      int lo_stride) {
-  __shared__ float sl[1024];
-  __shared__ float sp[1024];
+  __shared__ __align__(16) float sl[1024];
+  __shared__ __align__(16) float sp[1024];
   __shared__ float redf[8];
   __shared__ int redi[8];
+  pdl_prologue();
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int st = step ? *step : 0;
   const float* lr = logits + (size_t)b * V;
@@ -191,16 +194,26 @@ __global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ l
     }
     return;
   }
-  // rank of element i = #{j : l_j > l_i or (l_j == l_i and j < i)} ; kept iff rank < top_k
+  // rank of element i = #{j : l_j > l_i or (l_j == l_i and j < i)} ; kept iff rank < top_k.
+  // Each thread ranks its elements against the row held in shared memory, 4 comparisons per 128-bit read.
   float mx = -INFINITY;
+  const float4* sl4 = reinterpret_cast<const float4*>(sl);
   for (int i = tid; i < V; i += 256) {
-    float v = sl[i];
+    const float v = sl[i];
     int rank = 0;
-    for (int j = 0; j < V; ++j) {
-      float w = sl[j];
+    for (int j4 = 0; j4 < (V >> 2); ++j4) {
+      const float4 w = sl4[j4];
+      const int j = j4 << 2;
+      rank += (w.x > v) || (w.x == v && j < i);
+      rank += (w.y > v) || (w.y == v && j + 1 < i);
+      rank += (w.z > v) || (w.z == v && j + 2 < i);
+      rank += (w.w > v) || (w.w == v && j + 3 < i);
+    }
+    for (int j = V & ~3; j < V; ++j) {
+      const float w = sl[j];
       rank += (w > v) || (w == v && j < i);
     }
-    bool keep = rank < top_k;
+    const bool keep = rank < top_k;
     sp[i] = keep ? v / temperature : -INFINITY;
     if (keep) mx = fmaxf(mx, v / temperature);
   }
@@ -212,22 +225,57 @@ __global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ l
   __syncthreads();
   for (int i = tid; i < V; i += 256) sp[i] = sp[i] == -INFINITY ? 0.f : expf(sp[i] - mx);
   __syncthreads();
-  if (tid == 0) {
-    // sequential fp64 CDF in index order: V <= 1024, one thread, ~1 us; deterministic by construction
-    double tot = 0.0;
-    for (int i = 0; i < V; ++i) tot += (double)sp[i];
-    double target = (double)uniforms[(size_t)b * u_stride + st] * tot, c = 0.0;
-    int pick = -1, last = 0;
-    for (int i = 0; i < V; ++i) {
-      if (sp[i] > 0.f) last = i;
-      c += (double)sp[i];
-      if (pick < 0 && c > target) pick = i;
-    }
-    *dst = pick < 0 ? last : pick;
+  // Inverse CDF in index order (fp64, deterministic): thread t owns entries [t*per, (t+1)*per); warp 0 turns the 256 chunk
+  // sums into exclusive prefixes; each thread then tests its own entries against target = u * total.
+  __shared__ double chunk[256];
+  __shared__ double total_s;
+  __shared__ int pick_s, last_s;
+  const int per = (V + 255) / 256;                                 // <= 4 for V <= 1024
+  double mine = 0.0;
+  for (int k = 0; k < per; ++k) {
+    const int i = tid * per + k;
+    if (i < V) mine += (double)sp[i];
   }
+  chunk[tid] = mine;
+  if (tid == 0) { pick_s = 0x7fffffff; last_s = 0; }
+  __syncthreads();
+  if (warp == 0) {                                                   // lane l scans chunks 8l .. 8l+7, then a warp scan
+    double loc[8], run = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { loc[k] = run; run += chunk[lane * 8 + k]; }
+    double incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    const double excl = incl - run;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) chunk[lane * 8 + k] = excl + loc[k];
+    if (lane == 31) total_s = incl;
+  }
+  __syncthreads();
+  const double target = (double)uniforms[(size_t)b * u_stride + st] * total_s;
+  double c = chunk[tid];
+  for (int k = 0; k < per; ++k) {
+    const int i = tid * per + k;
+    if (i < V) {
+      const float pv = sp[i];
+      if (pv > 0.f) {
+        atomicMax(&last_s, i);
+        c += (double)pv;
+        if (c > target) atomicMin(&pick_s, i);
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) *dst = pick_s == 0x7fffffff ? last_s : pick_s;
 }
 
-__global__ void advance_step_kernel(int* step) { *step += 1; }
+__global__ void advance_step_kernel(int* step) {
+  pdl_prologue();
+  *step += 1;
+}
 __global__ void set_step_kernel(int* step, int v) { *step = v; }
 
 }  // namespace
@@ -238,9 +286,9 @@ int launch_layer_norm(const float* x, const float* gain, const float* bias, floa
   DIM_REQUIRE(rows > 0 && dim > 0 && dim % 4 == 0 && dim <= 4096, "layer_norm: dim must be a multiple of 4, <= 4096");
   ProfScope ps(CAT_LAYERNORM, s, (y ? 8.0 : 4.0) * rows * dim + (yb ? 2.0 * rows * dim : 0.0) + (yp ? 2.0 * planes * rows * dim : 0.0),
                8.0 * rows * dim);
-  if (dim <= 384) layer_norm_kernel<3><<<cdiv(rows, 8), 256, 0, s>>>(x, gain, bias, y, yb, rows, dim, eps, yp, planes, kp);
-  else if (dim <= 1152) layer_norm_kernel<9><<<cdiv(rows, 8), 256, 0, s>>>(x, gain, bias, y, yb, rows, dim, eps, yp, planes, kp);
-  else layer_norm_kernel<32><<<cdiv(rows, 8), 256, 0, s>>>(x, gain, bias, y, yb, rows, dim, eps, yp, planes, kp);
+  if (dim <= 384) DIM_CHECK_CUDA(launch_k(layer_norm_kernel<3>, dim3(cdiv(rows, 8)), dim3(256), 0, s, x, gain, bias, y, yb, rows, dim, eps, yp, planes, kp));
+  else if (dim <= 1152) DIM_CHECK_CUDA(launch_k(layer_norm_kernel<9>, dim3(cdiv(rows, 8)), dim3(256), 0, s, x, gain, bias, y, yb, rows, dim, eps, yp, planes, kp));
+  else DIM_CHECK_CUDA(launch_k(layer_norm_kernel<32>, dim3(cdiv(rows, 8)), dim3(256), 0, s, x, gain, bias, y, yb, rows, dim, eps, yp, planes, kp));
   DIM_LAUNCHED();
   return DIM_OK;
 }
@@ -267,7 +315,7 @@ int launch_build_context(const float* xs, const float* pe_dec, const float* audi
 int launch_embed_tokens(const int64_t* tok, int tok_stride, const int* step, const float* emb, float* x, int B, int D, int V,
                         cudaStream_t s) {
   ProfScope ps(CAT_MISC, s, 8.0 * B * D, 0);
-  embed_tokens_kernel<<<B, 128, 0, s>>>(tok, tok_stride, step, emb, x, B, D, V);
+  DIM_CHECK_CUDA(launch_k(embed_tokens_kernel, dim3(B), dim3(128), 0, s, tok, tok_stride, step, emb, x, B, D, V));
   DIM_LAUNCHED();
   return DIM_OK;
 }
@@ -278,15 +326,15 @@ int launch_sample(const float* logits, int B, int V, float temperature, int top_
   DIM_REQUIRE(V > 0 && V <= 1024, "sample: vocabulary must be <= 1024");
   DIM_REQUIRE(temperature == 0.f || (uniforms != nullptr && top_k > 0), "sample: sampling needs uniforms and top_k");
   ProfScope ps(CAT_SAMPLE, s, 4.0 * B * V + 8.0 * B, 0);
-  sample_kernel<<<B, 256, 0, s>>>(logits, V, temperature, top_k, uniforms, u_stride, step, out, out_stride, out_offset,
-                                  logits_out, lo_stride);
+  DIM_CHECK_CUDA(launch_k(sample_kernel, dim3(B), dim3(256), 0, s, logits, V, temperature, top_k, uniforms, u_stride, step, out,
+                          out_stride, out_offset, logits_out, lo_stride));
   DIM_LAUNCHED();
   return DIM_OK;
 }
 
 int launch_advance_step(int* step, cudaStream_t s) {
   ProfScope ps(CAT_MISC, s, 4, 0);
-  advance_step_kernel<<<1, 1, 0, s>>>(step);
+  DIM_CHECK_CUDA(launch_k(advance_step_kernel, dim3(1), dim3(1), 0, s, step));
   DIM_LAUNCHED();
   return DIM_OK;
 }

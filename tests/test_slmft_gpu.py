@@ -133,3 +133,26 @@ def test_bf16_mode_is_close(slmft_sd):
     codes, logits = s2s.generate(ctx_ref.cuda(), c["mask"].cuda(), prompt.cuda(), T - 1, return_logits=True)
     assert float((logits[:, 0].cpu() - ref_logits[:, 0]).abs().max()) < 0.1
     assert codes.shape == (B, T - 1) and int(codes.min()) >= 0 and int(codes.max()) < 512
+
+
+def test_concurrent_group_decoding_is_bit_identical(slmft_sd):
+    """B = 256 is decoded as two concurrent 128-clip groups on side streams (CUDA graphs); every clip's codes and logits
+    must equal those of the same clip decoded in a small batch (no cross-row arithmetic; split-K depends on K only)."""
+    from dim_b200.engine import PREC_FP32_TC, Handle, SLMFTEngine
+    h = Handle()
+    h.register(slmft_sd)
+    s2s = SLMFTEngine(h, S2S, precision=PREC_FP32_TC)
+    B, T = 256, 10
+    c = dim_b200.synth.make_clips(B, T, seed=77, ragged=True)
+    ctx = s2s.context(c["v_speaker"].cuda(), c["v_audio"].cuda(), c["mask"].cuda())
+    prompt = torch.randint(0, 512, (B,), generator=torch.Generator().manual_seed(3)).cuda()
+    u = torch.rand(B, T - 1, generator=torch.Generator().manual_seed(4)).cuda()
+    m = c["mask"].cuda()
+    full, full_logits = s2s.generate(ctx, m, prompt, T - 1, temperature=1.0, uniforms=u, return_logits=True)
+    again = s2s.generate(ctx, m, prompt, T - 1, temperature=1.0, uniforms=u)          # graph replay path
+    assert torch.equal(full, again)
+    sl = slice(120, 200)                                                               # straddles the group boundary
+    part, part_logits = s2s.generate(ctx[sl].contiguous(), m[sl].contiguous(), prompt[sl].contiguous(), T - 1, temperature=1.0,
+                                     uniforms=u[sl].contiguous(), return_logits=True)
+    assert torch.equal(part, full[sl]) and torch.equal(part_logits, full_logits[sl])
+    assert len(full.unique()) > 8
