@@ -7,6 +7,9 @@
 //                      each half-warp streams whole 256-byte head rows with 128-bit loads.
 #include "attention.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace dimb {
 
 namespace {
@@ -213,8 +216,8 @@ __global__ void __launch_bounds__(NT) attn_decode_kernel(const DecodeAttnArgs p)
   const int grp = tid / LPK, lk = tid % LPK;           // key group of this lane, position inside the head row
   const int pos = p.step ? *p.step : 0;                                   // index of the token being decoded
   const int nkeys = p.append ? pos + 1 : p.Tk;
-  KT* kbase = static_cast<KT*>(p.k) + (size_t)b * p.kv_batch_stride + h * DH + lk * EPL;
-  KT* vbase = static_cast<KT*>(p.v) + (size_t)b * p.kv_batch_stride + h * DH + lk * EPL;
+  KT* kbase = static_cast<KT*>(p.k) + (size_t)b * p.kv_batch_stride + (size_t)h * p.kv_head_stride + lk * EPL;
+  KT* vbase = static_cast<KT*>(p.v) + (size_t)b * p.kv_batch_stride + (size_t)h * p.kv_head_stride + lk * EPL;
 
   float q[EPL];
 #pragma unroll
@@ -321,7 +324,33 @@ __global__ void __launch_bounds__(NT) attn_decode_kernel(const DecodeAttnArgs p)
   }
 }
 
+// 16-byte vectors: read token-major rows fully coalesced, write 64-element head rows (128 B bf16 / 256 B fp32 chunks).
+template <int VE>
+__global__ void __launch_bounds__(256) kv_head_major_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B, int T,
+                                                            int H) {
+  const int vpr = 2 * H * 64 / VE;                      // vectors per source row
+  const size_t total = (size_t)B * T * vpr, plane = (size_t)B * H * T * 64 / VE;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / vpr;
+    const int cv = (int)(i - row * vpr), col = cv * VE;
+    const int kv = col / (H * 64), hc = col - kv * H * 64, h = hc >> 6, d = hc & 63;
+    const int b = (int)(row / T), t = (int)(row - (size_t)b * T);
+    dst[kv * plane + ((((size_t)b * H + h) * T + t) * 64 + d) / VE] = __ldcs(src + i);
+  }
+}
+
 }  // namespace
+
+int launch_kv_head_major(const void* src, void* dst, int B, int T, int H, int bf16, cudaStream_t s) {
+  DIM_REQUIRE(src && dst && B > 0 && T > 0 && H > 0, "kv_head_major: bad argument");
+  const size_t total = (size_t)B * T * 2 * H * 64 / (bf16 ? 8 : 4);
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 16);
+  ProfScope ps(CAT_MISC, s, (double)total * 32.0, 0);
+  if (bf16) kv_head_major_kernel<8><<<blocks, 256, 0, s>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), B, T, H);
+  else kv_head_major_kernel<4><<<blocks, 256, 0, s>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), B, T, H);
+  DIM_LAUNCHED();
+  return DIM_OK;
+}
 
 int launch_attention_prefill(const AttnArgs& a, cudaStream_t s) {
   DIM_REQUIRE(a.Dh == 48 || a.Dh == 64, "attention: head dim must be 48 or 64");
@@ -360,7 +389,9 @@ int launch_attention_decode(DecodeAttnArgs a, int max_keys, cudaStream_t s) {
   // 64-thread CTAs when the whole (batch x heads) grid then fits in one resident wave (32 CTAs / SM): every head streams
   // concurrently and there is no half-empty tail wave; 128-thread CTAs for larger grids.
   const bool bf = a.kv_bf16 != 0;
-  const bool small = bf && (long)a.B * a.H <= 148L * 32;   // (fp32 rows are twice as long: 128-thread CTAs measured faster)
+  static const int force_nt = getenv("DIM_ATTN_NT") ? atoi(getenv("DIM_ATTN_NT")) : 0;      // tuning hook: 64 or 128
+  const bool small = force_nt ? force_nt == 64
+                              : bf && (long)a.B * a.H <= 148L * 32;   // (fp32 rows are twice as long: 128-thread CTAs measured faster)
   typedef void (*Kern)(const DecodeAttnArgs);
   Kern kern = bf ? (small ? (Kern)attn_decode_kernel<true, 64> : (Kern)attn_decode_kernel<true, 128>)
                  : (small ? (Kern)attn_decode_kernel<false, 64> : (Kern)attn_decode_kernel<false, 128>);

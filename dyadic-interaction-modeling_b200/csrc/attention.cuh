@@ -20,9 +20,9 @@ int launch_attention_prefill(const AttnArgs& a, cudaStream_t s);
 struct DecodeAttnArgs {
   const float* q = nullptr; int ldq = 0;                  // (B, H*64) this step's queries
   void *k = nullptr, *v = nullptr;                        // cache bases (fp32, or bf16 when kv_bf16): element (b,t,h,d) at
-                                                          //   b*kv_batch_stride + t*kv_tok_stride + h*64 + d   (in elements)
-  int kv_bf16 = 0;
-  size_t kv_batch_stride = 0; int kv_tok_stride = 0;
+                                                          //   b*kv_batch_stride + h*kv_head_stride + t*kv_tok_stride + d (elements)
+  int kv_bf16 = 0;                                        // head-major caches [B,H,tokens,64]: head_stride = tokens*64, tok_stride = 64
+  size_t kv_batch_stride = 0, kv_head_stride = 64; int kv_tok_stride = 0;   // (token-major [B,tokens,H*64]: 64 / H*64)
   const float *k_new = nullptr, *v_new = nullptr; int ld_new = 0;   // rows appended at position *step when append != 0
   int append = 0;
   const int* step = nullptr;                              // device scalar: index of the token being decoded
@@ -35,5 +35,9 @@ struct DecodeAttnArgs {
   int prof_pos = 0;                                       // host copy of *step, for profiling byte counts only
 };
 int launch_attention_decode(DecodeAttnArgs a, int max_keys, cudaStream_t s);
+
+// Token-major projected K|V rows [B*T, 2*H*64] (K at column 0, V at H*64; fp32 or bf16) -> head-major caches
+// dst = K[B,H,T,64] followed by V[B,H,T,64]: every (b,h) head is then one contiguous stream for the decode kernel.
+int launch_kv_head_major(const void* src, void* dst, int B, int T, int H, int bf16, cudaStream_t s);
 
 }  // namespace dimb

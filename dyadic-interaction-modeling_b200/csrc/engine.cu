@@ -409,8 +409,9 @@ int xt_encoder_forward(const S2SModel& m, const XtEncoder& E, const float* in, c
 }
 
 struct GenWs {
-  std::vector<float*> cross_kv;            // per layer [B,T,2*inner]
-  std::vector<float*> self_k, self_v;      // per layer [B,steps+1,inner]
+  std::vector<float*> cross_kv;            // per layer, head-major: K[B,H,T,64] then V[B,H,T,64]
+  std::vector<float*> self_k, self_v;      // per layer, head-major [B,H,steps+1,64]
+  float* kv_tmp;                           // token-major [B*T, 2*inner] projection output, re-laid out into cross_kv[l]
   float *x, *ln, *qkv, *att, *ff, *logits;
   int64_t* tokens;                         // [B, steps+1]
   int* step;
@@ -428,6 +429,7 @@ GenWs carve_gen(const dim_s2s_config& c, int planes, bool kv_bf16, int B, int T,
   };
   const size_t kvdiv = kv_bf16 ? 2 : 1;                 // bf16 caches take half the floats
   for (int l = 0; l < c.depth; ++l) w.cross_kv.push_back(take((size_t)B * T * 2 * inner / kvdiv));
+  w.kv_tmp = take((size_t)B * T * 2 * inner / kvdiv);
   for (int l = 0; l < c.depth; ++l) {
     w.self_k.push_back(take((size_t)B * (steps + 1) * inner / kvdiv));
     w.self_v.push_back(take((size_t)B * (steps + 1) * inner / kvdiv));
@@ -743,9 +745,11 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
   for (int l = 0; l < c.depth; ++l) {  // cross-attention K/V of the whole context, once
     GemmArgs a;
     a.A = ctx; a.lda = D; a.W = m.cross_attn[l].wkv; a.M = B * T; a.N = 2 * inner; a.K = D;
-    if (kv16) { a.Cb = reinterpret_cast<__nv_bfloat16*>(w.cross_kv[l]); a.ldcb = 2 * inner; }
-    else { a.C = w.cross_kv[l]; a.ldc = 2 * inner; }
+    if (kv16) { a.Cb = reinterpret_cast<__nv_bfloat16*>(w.kv_tmp); a.ldcb = 2 * inner; }
+    else { a.C = w.kv_tmp; a.ldc = 2 * inner; }
     if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
+    // head-major: each (clip, head) K / V block is one contiguous stream for the per-step attention (DRAM page locality)
+    if (int e = launch_kv_head_major(w.kv_tmp, w.cross_kv[l], B, T, c.heads, kv16, s)) return e;
   }
   DIM_CHECK_CUDA(cudaMemcpy2DAsync(w.tokens, (size_t)(steps + 1) * sizeof(int64_t), prompt, sizeof(int64_t), sizeof(int64_t),
                                    B, cudaMemcpyDeviceToDevice, s));
@@ -772,7 +776,8 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
       {
         DecodeAttnArgs a;
         a.q = w.qkv; a.ldq = 3 * inner; a.k = w.self_k[l]; a.v = w.self_v[l]; a.kv_bf16 = kv16;
-        a.kv_batch_stride = (size_t)(steps + 1) * inner; a.kv_tok_stride = inner;
+        a.kv_batch_stride = (size_t)(steps + 1) * inner; a.kv_head_stride = (size_t)(steps + 1) * c.dim_head;
+        a.kv_tok_stride = c.dim_head;
         a.k_new = w.qkv + inner; a.v_new = w.qkv + 2 * inner; a.ld_new = 3 * inner; a.append = 1; a.step = w.step;
         a.out = tcp ? nullptr : w.att; a.ldo = inner; a.out_p = tcp ? w.ap : nullptr; a.planes = P; a.kp = inner;
         a.B = B; a.H = c.heads; a.Tk = 0; a.scale = scale; a.prof_pos = st;
@@ -795,8 +800,10 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
       {
         DecodeAttnArgs a;
         a.q = w.qkv; a.ldq = inner; a.kv_bf16 = kv16; a.k = w.cross_kv[l];
-        a.v = kv16 ? static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(w.cross_kv[l]) + inner) : static_cast<void*>(w.cross_kv[l] + inner);
-        a.kv_batch_stride = (size_t)T * 2 * inner; a.kv_tok_stride = 2 * inner; a.append = 0; a.step = w.step;
+        const size_t vplane = (size_t)B * T * inner;     // V block follows the K block
+        a.v = kv16 ? static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(w.cross_kv[l]) + vplane) : static_cast<void*>(w.cross_kv[l] + vplane);
+        a.kv_batch_stride = (size_t)T * inner; a.kv_head_stride = (size_t)T * c.dim_head; a.kv_tok_stride = c.dim_head;
+        a.append = 0; a.step = w.step;
         a.key_mask = mask; a.out = tcp ? nullptr : w.att; a.ldo = inner; a.out_p = tcp ? w.ap : nullptr; a.planes = P;
         a.kp = inner; a.B = B; a.H = c.heads; a.Tk = T; a.scale = scale;
         if (int e = launch_attention_decode(a, max_keys, s)) return e;

@@ -138,6 +138,47 @@ __global__ void __launch_bounds__(256) vq_gather_kernel(const int64_t* __restric
   }
 }
 
+// Same contract, staged through shared memory: a CTA assembles TR consecutive output rows (codebook rows come from L2) and
+// hands each finished tile to the TMA engine as ONE contiguous bulk store (cp.async.bulk global <- shared, TR*D*4 bytes),
+// NBUF tiles in flight per CTA.  The SM issues no per-row store instructions and HBM sees long full-line write bursts.
+template <int TR, int NBUF>
+__global__ void __launch_bounds__(256) vq_gather_bulk_kernel(const int64_t* __restrict__ idx, const float* __restrict__ E,
+                                                             float* __restrict__ out, int N, int D4, int K,
+                                                             int32_t* __restrict__ bad) {
+  extern __shared__ __align__(128) float4 gtile[];       // [NBUF][TR * D4]
+  const int tid = threadIdx.x;
+  const int ntiles = (N + TR - 1) / TR;
+  const int per_tile = TR * D4;
+  int buf = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    // the bulk store issued NBUF tiles ago has finished READING this buffer once <= NBUF-1 newer groups are pending
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NBUF - 1) : "memory");
+    __syncthreads();
+    float4* dst = gtile + (size_t)buf * per_tile;
+    const int r0 = t * TR, rows = min(TR, N - r0), n4 = rows * D4;
+#pragma unroll 4
+    for (int i = tid; i < n4; i += 256) {
+      const int r = i / D4, c = i - r * D4;
+      int64_t code = __ldg(idx + r0 + r);
+      if (code < 0 || code >= K) {
+        if (bad && c == 0) atomicAdd(bad, 1);
+        code = code < 0 ? 0 : K - 1;
+      }
+      dst[i] = __ldg(reinterpret_cast<const float4*>(E) + (size_t)code * D4 + c);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> visible to the TMA engine
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t src = (uint32_t)__cvta_generic_to_shared(dst);
+      float* g = out + (size_t)r0 * D4 * 4;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(src), "r"(n4 * 16) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    buf = buf + 1 == NBUF ? 0 : buf + 1;
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // smem must outlive the reads; writes complete
+}
+
 // out[b][d][l] = E[idx[b,l]][d]   (32 codes x 32 dims per tile, transposed through shared memory)
 __global__ void __launch_bounds__(256) vq_gather_bcl_kernel(const int64_t* __restrict__ idx, const float* __restrict__ E,
                                                             float* __restrict__ out, int L, int D, int K) {
@@ -201,12 +242,29 @@ int launch_vq_argmin(const float* z, const float* E, int64_t* idx, int N, int D,
   return DIM_OK;
 }
 
+int g_vq_gather_mode = -1;     // -1: automatic; 0: warp-per-row streaming stores; 1: smem-staged TMA bulk stores (tuning hook)
+
 int launch_vq_gather(const int64_t* idx, const float* E, float* out, int N, int D, int K, int32_t* bad, cudaStream_t s) {
   DIM_REQUIRE(N > 0 && D % 4 == 0 && K > 0, "vq_gather: bad sizes");
-  int warps_needed = cdiv(N, 4);
-  int blocks = std::min(cdiv(warps_needed, 8), 148 * 8);
   ProfScope ps(CAT_VQ_GATHER, s, (double)N * (4.0 * D + 8.0), 0);                          // 520 B / code
-  vq_gather_kernel<<<blocks, 256, 0, s>>>(idx, E, out, N, D / 4, K, bad);
+  constexpr int TR = 32, NBUF = 4;
+  const size_t smem = (size_t)NBUF * TR * D * sizeof(float);
+  const bool bulk_ok = ((uintptr_t)out & 15) == 0 && smem <= 96 * 1024;
+  const int mode = g_vq_gather_mode >= 0 ? g_vq_gather_mode : (N >= 8 * TR ? 1 : 0);
+  if (mode == 1 && bulk_ok) {
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+      DIM_CHECK_CUDA(cudaFuncSetAttribute(vq_gather_bulk_kernel<TR, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    const int per_sm = std::max(1, (int)(200 * 1024 / smem));
+    const int blocks = std::min(cdiv(N, TR), 148 * per_sm);
+    vq_gather_bulk_kernel<TR, NBUF><<<blocks, 256, smem, s>>>(idx, E, out, N, D / 4, K, bad);
+  } else {
+    int warps_needed = cdiv(N, 4);
+    int blocks = std::min(cdiv(warps_needed, 8), 148 * 8);
+    vq_gather_kernel<<<blocks, 256, 0, s>>>(idx, E, out, N, D / 4, K, bad);
+  }
   DIM_LAUNCHED();
   return DIM_OK;
 }
@@ -232,6 +290,12 @@ using namespace dimb;
 extern "C" int dim_vq_argmin(const float* z, const float* codebook, int64_t* idx, int N, int D, int K, void* stream) {
   if (int e = ensure_device()) return e;
   return launch_vq_argmin(z, codebook, idx, N, D, K, as_stream(stream));
+}
+
+// tuning hook (not part of the stable ABI): force a gather implementation (-1 = automatic)
+extern "C" int dim_debug_vq_gather_mode(int mode) {
+  dimb::g_vq_gather_mode = mode;
+  return DIM_OK;
 }
 
 extern "C" int dim_vq_gather(const int64_t* idx, const float* codebook, float* out, int N, int D, int K, int32_t* bad,

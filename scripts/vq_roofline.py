@@ -14,7 +14,12 @@ PEAK = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspa
     if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) else 6650.0
 
 
+NCU = os.environ.get("VQ_NCU") == "1"        # under ncu: largest size only, one launch per implementation
+
+
 def timeit(fn, iters=20, warm=3):
+    if NCU:
+        iters, warm = 1, 0
     for _ in range(warm):
         fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -30,20 +35,28 @@ def timeit(fn, iters=20, warm=3):
 def main():
     g = torch.Generator().manual_seed(0)
     E = (torch.randn(512, 128, generator=g) * 0.5).cuda()
-    for N in (76544, 1 << 20, 1 << 22):                       # B=256 x 299 codes; 0.5 GB; 2 GB of rows (> 126 MB L2)
+    lib = dim_b200._lib.load()
+    s = torch.cuda.current_stream().cuda_stream
+    for N in ((1 << 22,) if NCU else (76544, 1 << 20, 1 << 22)):                     # B=256 x 299 codes; 0.5 GB; 2 GB of rows (> 126 MB L2)
         idx = torch.randint(0, 512, (N,), generator=g).cuda()
         out = torch.empty(N, 128, device="cuda")
-        lib = dim_b200._lib.load()
-        s = torch.cuda.current_stream().cuda_stream
-        t = timeit(lambda: lib.dim_vq_gather(idx.data_ptr(), E.data_ptr(), out.data_ptr(), N, 128, 512, None, s))
-        gbs = N * 520 / t / 1e9
-        print(json.dumps({"kernel": "vq_gather", "codes": N, "us": t * 1e6, "GB/s": gbs, "frac_of_hbm_peak": gbs / PEAK, "peak": PEAK,
-                          "algorithmic_bytes_per_code": 520}))
-    for N in (76800, 1 << 20):
+        ref = E[idx]
+        t = timeit(lambda: out.zero_())                       # write-only ceiling of the same footprint (cudaMemset-class)
+        print(json.dumps({"kernel": "write_only_ceiling(torch zero_)", "codes": N, "us": t * 1e6, "GB/s": N * 512 / t / 1e9,
+                          "frac_of_hbm_peak": N * 512 / t / 1e9 / PEAK}))
+        for mode, name in ((0, "warp-per-row st.cs"), (1, "smem-staged TMA bulk store"), (-1, "default")):
+            lib.dim_debug_vq_gather_mode(mode)
+            out.zero_()
+            t = timeit(lambda: lib.dim_vq_gather(idx.data_ptr(), E.data_ptr(), out.data_ptr(), N, 128, 512, None, s))
+            gbs = N * 520 / t / 1e9
+            print(json.dumps({"kernel": "vq_gather", "impl": name, "codes": N, "us": t * 1e6, "GB/s": gbs,
+                              "frac_of_hbm_peak": gbs / PEAK, "peak": PEAK, "algorithmic_bytes_per_code": 520,
+                              "bit_exact_vs_index_select": bool(torch.equal(out, ref))}))
+        lib.dim_debug_vq_gather_mode(-1)
+        del out, ref
+    for N in ((1 << 20,) if NCU else (76800, 1 << 20)):
         z = (torch.randn(N, 128, generator=g) * 0.7).cuda()
         o = torch.empty(N, dtype=torch.int64, device="cuda")
-        lib = dim_b200._lib.load()
-        s = torch.cuda.current_stream().cuda_stream
         t = timeit(lambda: lib.dim_vq_argmin(z.data_ptr(), E.data_ptr(), o.data_ptr(), N, 128, 512, s))
         gbs = N * 520 / t / 1e9
         print(json.dumps({"kernel": "vq_argmin_f32", "tokens": N, "us": t * 1e6, "GB/s": gbs, "frac_of_hbm_peak": gbs / PEAK,
