@@ -187,6 +187,8 @@ def run_native(args):
     h.register(dim_b200.synth.make_slmft_state_dict(131))
     s2s = SLMFTEngine(h, S2SConfig(), precision=prec)
     vq = VQEngine(h, VQConfig(), prefix="listener_vq.", precision=vq_prec)
+    # bf16 mode ("bf16 fused transformer + VQ decode"): the codes -> frames VQ decoder also runs plain bf16 GEMM operands
+    vq_dec = VQEngine(h, VQConfig(), prefix="listener_vq.", precision=PREC_BF16) if prec == PREC_BF16 else None
 
     # this rank's shard of the global batch (weak scaling: B clips per GPU), global batch positions for the F4 quirk
     clips = dim_b200.synth.make_clips(B, T, seed=1000 + rank, speaker="ones" if args.speaker_ones else "randn")
@@ -198,14 +200,16 @@ def run_native(args):
 
     def step_resident():
         loss, d, pred, codes = slmft_forward_val(s2s, vq, res["v_speaker"], res["v_listener"], res["v_audio"], res["mask"],
-                                                 temperature=1.0, uniforms=u, batch_index=batch_index, return_codes=True)
+                                                 temperature=1.0, uniforms=u, batch_index=batch_index, return_codes=True,
+                                                 vq_decode_engine=vq_dec)
         all_codes = D.all_gather_codes(codes, world * B) if world > 1 else codes     # the one collective of the path
         return pred, all_codes
 
     def step_e2e():
         dv = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
         loss, d, pred, codes = slmft_forward_val(s2s, vq, dv["v_speaker"], dv["v_listener"], dv["v_audio"], dv["mask"],
-                                                 temperature=1.0, uniforms=u, batch_index=batch_index, return_codes=True)
+                                                 temperature=1.0, uniforms=u, batch_index=batch_index, return_codes=True,
+                                                 vq_decode_engine=vq_dec)
         if world > 1:
             D.all_gather_codes(codes, world * B)
         pred_host.copy_(pred, non_blocking=True)

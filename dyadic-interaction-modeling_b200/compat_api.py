@@ -33,11 +33,13 @@ def listener_codes(vq_engine, v_listener, mask):
 
 @torch.no_grad()
 def slmft_forward_val(s2s_engine, vq_engine, v_speaker, v_listener, v_audio, mask, temperature=1.0, uniforms=None,
-                      batch_index=None, return_codes=False, greedy=None):
+                      batch_index=None, return_codes=False, greedy=None, vq_decode_engine=None):
     """-> (total_loss, dict, pred_cont_seq_l (B,T-1,56)) like SLMFT.forward(..., mode='val').
 
     The reference samples (temperature 1, top-k 52, torch.multinomial).  Here: `uniforms` (B,T-1) given -> inverse-CDF
-    sampling with them; uniforms None and greedy is not False -> argmax decoding (the deterministic parity mode)."""
+    sampling with them; uniforms None and greedy is not False -> argmax decoding (the deterministic parity mode).
+    vq_decode_engine: optional second VQEngine over the same weights used for the codes -> frames decode only (the bf16
+    mode decodes with bf16 GEMM operands; the ENCODE side always stays fp32-grade so code indices are exact)."""
     B, T, _ = v_speaker.shape
     z_l = listener_codes(vq_engine, v_listener, mask)
     ctx = s2s_engine.context(v_speaker, v_audio, mask)
@@ -47,7 +49,7 @@ def slmft_forward_val(s2s_engine, vq_engine, v_speaker, v_listener, v_audio, mas
         if uniforms is None:
             uniforms = torch.rand(B, T - 1, device=v_speaker.device)
         codes = s2s_engine.generate(ctx, mask, z_l[:, 0], T - 1, temperature=temperature, uniforms=uniforms)
-    pred = vq_engine.decode(codes=codes, batch_index=batch_index)
+    pred = (vq_decode_engine or vq_engine).decode(codes=codes, batch_index=batch_index)
     l_cont = continuous_loss(pred, v_listener, mask)
     d = {"l_ce_s": 0, "l_ce_l": 0.0, "l_cont_s": 0, "l_cont_l": l_cont, "nce": 0, "c_acc": 0}
     if return_codes:

@@ -163,6 +163,245 @@ __global__ void __launch_bounds__(256) attn_prefill_f32(const AttnArgs p) {
   }
 }
 
+
+// ---- prefill on the tensor cores -------------------------------------------------------------------------------------
+// Same contract as attn_prefill_f32, arithmetic on mma.sync.m16n8k16 (bf16 operands, fp32 accumulate).  Q, K, V and the
+// probabilities P are split EXACTLY into NP bf16 planes (x = h + m + l, round-to-nearest at each step); the plane products
+// with index sum < NP are accumulated: NP = 3 keeps 24 mantissa bits per operand (fp32-grade scores and outputs, the parity
+// mode of the tcgen05 GEMMs), NP = 1 is plain bf16.  64 queries x 64 keys per CTA tile, 4 warps x 16 query rows, online
+// softmax in registers (the m16n8 accumulator layout of S is re-used as the A-operand layout of P), the next K/V tile is
+// prefetched into registers while the current one is multiplied.
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// fp32 pair -> NP packed bf16x2 plane words (low half = first element)
+template <int NP>
+__device__ __forceinline__ void split2(float x, float y, uint32_t* w) {
+#pragma unroll
+  for (int pl = 0; pl < NP; ++pl) {
+    const __nv_bfloat16 bx = __float2bfloat16_rn(x), by = __float2bfloat16_rn(y);
+    w[pl] = (uint32_t)__bfloat16_as_ushort(bx) | ((uint32_t)__bfloat16_as_ushort(by) << 16);
+    x -= __bfloat162float(bx);
+    y -= __bfloat162float(by);
+  }
+}
+template <int NP, int PITCH>
+__device__ __forceinline__ void split_store4(__nv_bfloat16* base, int r, int c, float4 v) {
+  uint32_t lo[NP], hi[NP];
+  split2<NP>(v.x, v.y, lo);
+  split2<NP>(v.z, v.w, hi);
+#pragma unroll
+  for (int pl = 0; pl < NP; ++pl)
+    *reinterpret_cast<uint2*>(base + ((size_t)pl * 64 + r) * PITCH + c) = make_uint2(lo[pl], hi[pl]);
+}
+
+template <int DH, int NP>
+__global__ void __launch_bounds__(128) attn_prefill_mma(const AttnArgs p) {
+  constexpr int PITCH = DH + 8;                       // bf16 elements per smem row: 16-byte aligned, conflict-free ldmatrix
+  constexpr int KC = DH / 16;                         // k-chunks of the QK^T product
+  constexpr int ONT = DH / 8;                         // 8-column n-tiles of the output
+  constexpr int F4 = 64 * DH / 4 / 128;               // float4 per thread per 64-row tile
+  extern __shared__ __align__(16) uint8_t smem_mma[];
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_mma);      // [NP][64][PITCH]
+  __nv_bfloat16* Ks = Qs + NP * 64 * PITCH;
+  __nv_bfloat16* Vs = Ks + NP * 64 * PITCH;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 64;
+  const float* qb = p.q + (size_t)b * p.Tq * p.ldq + h * DH;
+  const float* kb = p.k + (size_t)b * p.Tk * p.ldk + h * DH;
+  const float* vb = p.v + (size_t)b * p.Tk * p.ldv + h * DH;
+  const int klen = p.lens ? min(__ldg(p.lens + b), p.Tk) : p.Tk;
+  const uint8_t* km = p.key_mask ? p.key_mask + (size_t)b * p.Tk : nullptr;
+
+  int nkt = (klen + 63) / 64;
+  if (p.causal) nkt = min(nkt, (min(q0 + 64, p.Tq) - 1) / 64 + 1);
+
+  float4 kreg[F4], vreg[F4];
+  auto load_kv = [&](int kt) {
+#pragma unroll
+    for (int u = 0; u < F4; ++u) {
+      const int i = tid + 128 * u, r = i / (DH / 4), c = (i % (DH / 4)) * 4;
+      kreg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      vreg[u] = kreg[u];
+      if (kt * 64 + r < klen) {
+        kreg[u] = *reinterpret_cast<const float4*>(kb + (size_t)(kt * 64 + r) * p.ldk + c);
+        vreg[u] = *reinterpret_cast<const float4*>(vb + (size_t)(kt * 64 + r) * p.ldv + c);
+      }
+    }
+  };
+  if (nkt > 0) load_kv(0);
+#pragma unroll
+  for (int u = 0; u < F4; ++u) {
+    const int i = tid + 128 * u, r = i / (DH / 4), c = (i % (DH / 4)) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + r < p.Tq) v = *reinterpret_cast<const float4*>(qb + (size_t)(q0 + r) * p.ldq + c);
+    split_store4<NP, PITCH>(Qs, r, c, v);
+  }
+
+  float o[ONT][4];
+#pragma unroll
+  for (int nt = 0; nt < ONT; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  const int qrow0 = q0 + warp * 16 + (lane >> 2);     // this thread's rows: qrow0 and qrow0 + 8
+  const uint32_t qs_u = (uint32_t)__cvta_generic_to_shared(Qs), ks_u = (uint32_t)__cvta_generic_to_shared(Ks),
+                 vs_u = (uint32_t)__cvta_generic_to_shared(Vs);
+  // per-lane ldmatrix row/column offsets (elements)
+  const int a_row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, a_col = (lane >> 4) * 8;      // A (Q): m0 r0-7/c0-7, m1 r8-15, m2 c8-15, m3
+  const int bk_row = (lane & 7) + (lane >> 4) * 8, bk_col = ((lane >> 3) & 1) * 8;               // B of S (K rows = keys): two n-tiles per x4
+  const int bv_row = (lane & 7) + ((lane >> 3) & 1) * 8, bv_col = (lane >> 4) * 8;               // B of PV (V rows = keys, transposed): two n-tiles per x4
+
+  for (int kt = 0; kt < nkt; ++kt) {
+    const int k0 = kt * 64;
+    __syncthreads();                                  // previous tile fully consumed (first pass: nothing to wait for)
+#pragma unroll
+    for (int u = 0; u < F4; ++u) {
+      const int i = tid + 128 * u, r = i / (DH / 4), c = (i % (DH / 4)) * 4;
+      split_store4<NP, PITCH>(Ks, r, c, kreg[u]);
+      split_store4<NP, PITCH>(Vs, r, c, vreg[u]);
+    }
+    __syncthreads();
+    if (kt + 1 < nkt) load_kv(kt + 1);                // in flight during the MMAs below
+
+    // ---- S = Q K^T : 16 rows x 64 keys per warp
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+    for (int kc = 0; kc < KC; ++kc) {
+      uint32_t a[NP][4];
+#pragma unroll
+      for (int pa = 0; pa < NP; ++pa)
+        ldsm_x4(qs_u + (uint32_t)(((pa * 64 + a_row) * PITCH + kc * 16 + a_col) * 2), a[pa][0], a[pa][1], a[pa][2], a[pa][3]);
+#pragma unroll
+      for (int pw = NP - 1; pw >= 0; --pw) {
+#pragma unroll
+        for (int n2 = 0; n2 < 4; ++n2) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4(ks_u + (uint32_t)(((pw * 64 + n2 * 16 + bk_row) * PITCH + kc * 16 + bk_col) * 2), b0, b1, b2, b3);
+#pragma unroll
+          for (int pa = NP - 1 - pw; pa >= 0; --pa) {
+            mma_bf16(s[2 * n2], a[pa], b0, b1);
+            mma_bf16(s[2 * n2 + 1], a[pa], b2, b3);
+          }
+        }
+      }
+    }
+
+    // ---- scale, mask, online softmax (rows qrow0 -> s[.][0..1], qrow0 + 8 -> s[.][2..3])
+    float tmax[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int kj = k0 + nt * 8 + 2 * (lane & 3) + (e & 1), qi = qrow0 + (e >> 1) * 8;
+        float v = s[nt][e] * p.scale;
+        if (kj >= klen) v = -INFINITY;                                      // not a key at all
+        else if ((km && !km[kj]) || (p.causal && kj > qi)) v = -FLT_MAX;    // masked_fill(-finfo.max)
+        s[nt][e] = v;
+        tmax[e >> 1] = fmaxf(tmax[e >> 1], v);
+      }
+    }
+    float alpha[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      tmax[r] = fmaxf(tmax[r], __shfl_xor_sync(0xffffffffu, tmax[r], 1));
+      tmax[r] = fmaxf(tmax[r], __shfl_xor_sync(0xffffffffu, tmax[r], 2));
+      const float m_new = fmaxf(m_run[r], tmax[r]);
+      alpha[r] = (m_run[r] == -INFINITY) ? 0.f : expf(m_run[r] - m_new);
+      m_run[r] = m_new;
+    }
+    float psum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float pv = (s[nt][e] == -INFINITY) ? 0.f : expf(s[nt][e] - m_run[e >> 1]);
+        s[nt][e] = pv;
+        psum[e >> 1] += pv;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      psum[r] += __shfl_xor_sync(0xffffffffu, psum[r], 1);
+      psum[r] += __shfl_xor_sync(0xffffffffu, psum[r], 2);
+      l_run[r] = l_run[r] * alpha[r] + psum[r];
+    }
+#pragma unroll
+    for (int nt = 0; nt < ONT; ++nt) {
+      o[nt][0] *= alpha[0]; o[nt][1] *= alpha[0];
+      o[nt][2] *= alpha[1]; o[nt][3] *= alpha[1];
+    }
+
+    // ---- O += P V : P (registers) is the A operand, 16 keys per k-chunk
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) {
+      uint32_t a[NP][4], w[NP];
+      split2<NP>(s[2 * kc][0], s[2 * kc][1], w);
+#pragma unroll
+      for (int pl = 0; pl < NP; ++pl) a[pl][0] = w[pl];
+      split2<NP>(s[2 * kc][2], s[2 * kc][3], w);
+#pragma unroll
+      for (int pl = 0; pl < NP; ++pl) a[pl][1] = w[pl];
+      split2<NP>(s[2 * kc + 1][0], s[2 * kc + 1][1], w);
+#pragma unroll
+      for (int pl = 0; pl < NP; ++pl) a[pl][2] = w[pl];
+      split2<NP>(s[2 * kc + 1][2], s[2 * kc + 1][3], w);
+#pragma unroll
+      for (int pl = 0; pl < NP; ++pl) a[pl][3] = w[pl];
+#pragma unroll
+      for (int pw = NP - 1; pw >= 0; --pw) {
+#pragma unroll
+        for (int n2 = 0; n2 < ONT / 2; ++n2) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_t(vs_u + (uint32_t)(((pw * 64 + kc * 16 + bv_row) * PITCH + n2 * 16 + bv_col) * 2), b0, b1, b2, b3);
+#pragma unroll
+          for (int pa = NP - 1 - pw; pa >= 0; --pa) {
+            mma_bf16(o[2 * n2], a[pa], b0, b1);
+            mma_bf16(o[2 * n2 + 1], a[pa], b2, b3);
+          }
+        }
+      }
+    }
+  }
+
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int qi = qrow0 + r * 8;
+    if (qi >= p.Tq) continue;
+    const float inv = l_run[r] > 0.f ? 1.f / l_run[r] : 0.f;
+    const int cbase = h * DH + 2 * (lane & 3);
+    if (p.out) {
+      float* orow = p.out + ((size_t)b * p.Tq + qi) * p.ldo + cbase;
+#pragma unroll
+      for (int nt = 0; nt < ONT; ++nt)
+        *reinterpret_cast<float2*>(orow + nt * 8) = make_float2(o[nt][2 * r] * inv, o[nt][2 * r + 1] * inv);
+    }
+    if (p.out_p) {
+      __nv_bfloat16* prow = p.out_p + ((size_t)b * p.Tq + qi) * p.planes * p.kp + cbase;
+#pragma unroll
+      for (int nt = 0; nt < ONT; ++nt) {
+        float x = o[nt][2 * r] * inv, y = o[nt][2 * r + 1] * inv;
+        for (int pl = 0; pl < p.planes; ++pl) {
+          const __nv_bfloat16 bx = __float2bfloat16_rn(x), by = __float2bfloat16_rn(y);
+          *reinterpret_cast<uint32_t*>(prow + (size_t)pl * p.kp + nt * 8) =
+              (uint32_t)__bfloat16_as_ushort(bx) | ((uint32_t)__bfloat16_as_ushort(by) << 16);
+          x -= __bfloat162float(bx);
+          y -= __bfloat162float(by);
+        }
+      }
+    }
+  }
+}
+
 // ---- decode: one query row per (b,h) ----------------------------------------------------------------------------
 // 128 threads; a group of LPK lanes owns whole keys: every lane moves one 128-bit vector per key (4 fp32 or 8 bf16), so a
 // (b,h) head row -- 256 B fp32 / 128 B bf16, contiguous in the token-major cache -- is one fully used request.
@@ -360,6 +599,25 @@ int launch_attention_prefill(const AttnArgs& a, cudaStream_t s) {
   // algorithmic: read q,k,v once, write out once; QK^T and PV (causal: half)
   ProfScope ps(CAT_ATTN_PREFILL, s, 4.0 * a.B * a.H * a.Dh * (2.0 * a.Tq + 2.0 * a.Tk),
                4.0 * a.B * a.H * (double)a.Tq * a.Tk * a.Dh * (a.causal ? 0.5 : 1.0));
+  // tensor-core path: whenever the caller runs the plane-fused tensor-core data flow (bf16-plane output requested) with
+  // 1 plane (bf16 mode) or 3 planes (fp32-grade); DIM_ATTN_PREFILL=ffma forces the FFMA kernel (A/B tuning hook)
+  static const bool force_ffma = getenv("DIM_ATTN_PREFILL") != nullptr && std::string(getenv("DIM_ATTN_PREFILL")) == "ffma";
+  if (a.out_p != nullptr && (a.planes == 1 || a.planes == 3) && !force_ffma) {
+    typedef void (*Kern)(const AttnArgs);
+    const int np = a.planes;
+    Kern kern = a.Dh == 48 ? (np == 1 ? (Kern)attn_prefill_mma<48, 1> : (Kern)attn_prefill_mma<48, 3>)
+                           : (np == 1 ? (Kern)attn_prefill_mma<64, 1> : (Kern)attn_prefill_mma<64, 3>);
+    const size_t smem = (size_t)3 * np * 64 * (a.Dh + 8) * sizeof(__nv_bfloat16);
+    static bool configured[4] = {false, false, false, false};
+    const int slot = (a.Dh == 48 ? 0 : 2) + (np == 1 ? 0 : 1);
+    if (!configured[slot]) {
+      DIM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured[slot] = true;
+    }
+    kern<<<dim3(cdiv(a.Tq, 64), a.H, a.B), 128, smem, s>>>(a);
+    DIM_LAUNCHED();
+    return DIM_OK;
+  }
   if (a.Dh == 48) {
     constexpr size_t smem = (TQ * 52 + TKV * 52 + TKV * 48 + TQ * (TKV + 4)) * sizeof(float);
     static bool once = false;

@@ -681,13 +681,16 @@ extern "C" int dim_slmft_build(dim_handle_t h, const dim_s2s_config* cfg, int pr
 // Clips are independent, so a batch is decoded as up to 4 concurrent groups of >= 128 clips (one 128-row MMA tile each) on
 // side streams: their chains interleave on the SMs and hide each other's launch/pipeline-fill/epilogue latencies.
 // Per-row results do not depend on the grouping (no cross-row arithmetic; split-K depends on K only).
-constexpr int kGroupRows = 128, kMaxGroups = 4;
+constexpr int kMaxGroups = 8;
 int plan_groups(const S2SModel& m, int B, int* begin /*[kMaxGroups+1]*/) {
+  // tuning hooks: DIM_GROUP_ROWS (rows per group, multiple of 64; default 128), DIM_MAX_GROUPS (default 4), DIM_NO_GROUPS
+  static const int kGroupRows = getenv("DIM_GROUP_ROWS") ? std::max(64, atoi(getenv("DIM_GROUP_ROWS")) / 64 * 64) : 128;
+  static const int max_groups = getenv("DIM_MAX_GROUPS") ? std::min(kMaxGroups, std::max(1, atoi(getenv("DIM_MAX_GROUPS")))) : 4;
   int ng = 1;
-  if (tc_on(m.tc, B) && B >= 2 * kGroupRows) ng = std::min(kMaxGroups, B / kGroupRows);
+  if (tc_on(m.tc, B) && B >= 2 * kGroupRows) ng = std::min(max_groups, B / kGroupRows);
   static const bool no_groups = getenv("DIM_NO_GROUPS") != nullptr;
   if (no_groups) ng = 1;
-  const int per = (B / ng + kGroupRows - 1) / kGroupRows * kGroupRows;      // multiples of 128 rows, remainder in the last
+  const int per = (B / ng + kGroupRows - 1) / kGroupRows * kGroupRows;      // multiples of the group size, remainder in the last
   for (int g = 0; g <= ng; ++g) begin[g] = std::min(B, g * per);
   begin[ng] = B;
   return ng;

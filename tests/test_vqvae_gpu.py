@@ -101,3 +101,17 @@ def test_full_size_properties(engine, vq_sd):
     ref0 = OV.decode_indices(vq_sd, idx[:1].cpu(), CFG)
     assert torch.allclose(dec[:1].cpu(), ref0, atol=TOL)
     assert torch.isfinite(dec).all()
+
+
+def test_bf16_decoder_is_close(vq_sd):
+    """bf16 mode (BASELINE configs[2] 'bf16 fused transformer + VQ decode'): the codes -> frames decoder with plain bf16 GEMM
+    operands is NOT a parity mode; it must stay within bf16 rounding noise of the oracle (outputs are O(1))."""
+    from dim_b200.engine import PREC_BF16, Handle, VQEngine
+    h = Handle()
+    h.register(vq_sd)
+    eng = VQEngine(h, CFG, precision=PREC_BF16)
+    codes = torch.randint(0, 512, (3, 40), generator=torch.Generator().manual_seed(5))
+    dec = eng.decode(codes=codes.cuda())
+    ref = OV.decode_indices(vq_sd, codes, CFG)
+    err = float((dec.cpu() - ref).abs().max())
+    assert torch.isfinite(dec).all() and err < 5e-2 * max(1.0, float(ref.abs().max())), err
