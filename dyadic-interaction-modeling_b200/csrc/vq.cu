@@ -179,6 +179,63 @@ __global__ void __launch_bounds__(256) vq_gather_bulk_kernel(const int64_t* __re
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // smem must outlive the reads; writes complete
 }
 
+// Same contract, index stream decoupled from the row stream: a CTA walks chunks of CH codes; the int64 indices of the NEXT
+// chunk are fetched into registers before the rows of the current chunk are written and parked in shared memory after it,
+// so no row ever waits for an index read that queues behind the write stream in the memory controller.  Codebook rows come
+// from L1/L2 (256 KB codebook), each warp keeps R rows (R x 512 B) in flight.
+template <int CH, bool STREAM>
+__global__ void __launch_bounds__(256) vq_gather_pf_kernel(const int64_t* __restrict__ idx, const float* __restrict__ E,
+                                                           float* __restrict__ out, int N, int D4, int K,
+                                                           int32_t* __restrict__ bad) {
+  __shared__ int codes[2][CH];
+  constexpr int PER = CH / 256, R = 4;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nchunks = (N + CH - 1) / CH;
+  int nbad = 0;
+  auto fetch = [&](int chunk, int64_t* reg) {
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const size_t i = (size_t)chunk * CH + tid + 256 * u;
+      reg[u] = i < (size_t)N ? __ldcs(idx + i) : 0;
+    }
+  };
+  auto park = [&](int buf, const int64_t* reg) {
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      int64_t c = reg[u];
+      if (c < 0 || c >= K) { ++nbad; c = c < 0 ? 0 : K - 1; }
+      codes[buf][tid + 256 * u] = (int)c;
+    }
+  };
+  int64_t reg[PER];
+  int buf = 0;
+  if ((int)blockIdx.x < nchunks) { fetch(blockIdx.x, reg); park(0, reg); }
+  __syncthreads();
+  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const int next = chunk + gridDim.x;
+    if (next < nchunks) fetch(next, reg);                          // in flight while this chunk's rows are written
+    const size_t r0 = (size_t)chunk * CH;
+    const int rows = (int)min((size_t)CH, (size_t)N - r0);
+    for (int r = warp * R; r < rows; r += 8 * R) {
+      for (int c4 = lane; c4 < D4; c4 += 32) {
+        float4 v[R];
+#pragma unroll
+        for (int u = 0; u < R; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(E) + (size_t)codes[buf][min(r + u, rows - 1)] * D4 + c4);
+#pragma unroll
+        for (int u = 0; u < R; ++u)
+          if (r + u < rows) {
+            float4* dst = reinterpret_cast<float4*>(out) + (r0 + r + u) * D4 + c4;
+            if (STREAM) __stcs(dst, v[u]); else *dst = v[u];
+          }
+      }
+    }
+    if (next < nchunks) park(buf ^ 1, reg);
+    __syncthreads();
+    buf ^= 1;
+  }
+  if (bad && nbad) atomicAdd(bad, nbad);
+}
+
 // out[b][d][l] = E[idx[b,l]][d]   (32 codes x 32 dims per tile, transposed through shared memory)
 __global__ void __launch_bounds__(256) vq_gather_bcl_kernel(const int64_t* __restrict__ idx, const float* __restrict__ E,
                                                             float* __restrict__ out, int L, int D, int K) {
@@ -242,7 +299,9 @@ int launch_vq_argmin(const float* z, const float* E, int64_t* idx, int N, int D,
   return DIM_OK;
 }
 
-int g_vq_gather_mode = -1;     // -1: automatic; 0: warp-per-row streaming stores; 1: smem-staged TMA bulk stores (tuning hook)
+// tuning hook.  -1: automatic; 0: warp-per-row, index read in line; 1: smem-staged TMA bulk stores (measured SLOWER: 2.9 TB/s
+// vs 4.6 TB/s, profiles/r01_notes.md); 2 / 3: prefetched index stream with streaming / plain stores
+int g_vq_gather_mode = -1;
 
 int launch_vq_gather(const int64_t* idx, const float* E, float* out, int N, int D, int K, int32_t* bad, cudaStream_t s) {
   DIM_REQUIRE(N > 0 && D % 4 == 0 && K > 0, "vq_gather: bad sizes");
@@ -250,8 +309,13 @@ int launch_vq_gather(const int64_t* idx, const float* E, float* out, int N, int 
   constexpr int TR = 32, NBUF = 4;
   const size_t smem = (size_t)NBUF * TR * D * sizeof(float);
   const bool bulk_ok = ((uintptr_t)out & 15) == 0 && smem <= 96 * 1024;
-  const int mode = g_vq_gather_mode >= 0 ? g_vq_gather_mode : (N >= 8 * TR ? 1 : 0);
-  if (mode == 1 && bulk_ok) {
+  const int mode = g_vq_gather_mode >= 0 ? g_vq_gather_mode : 0;
+  if (mode == 2 || mode == 3) {
+    constexpr int CH = 512;
+    const int blocks = std::min(cdiv(N, CH), 148 * 6);
+    if (mode == 2) vq_gather_pf_kernel<CH, true><<<blocks, 256, 0, s>>>(idx, E, out, N, D / 4, K, bad);
+    else vq_gather_pf_kernel<CH, false><<<blocks, 256, 0, s>>>(idx, E, out, N, D / 4, K, bad);
+  } else if (mode == 1 && bulk_ok) {
     static size_t configured = 48 * 1024;
     if (smem > configured) {
       DIM_CHECK_CUDA(cudaFuncSetAttribute(vq_gather_bulk_kernel<TR, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
