@@ -403,17 +403,22 @@ __global__ void __launch_bounds__(128) attn_prefill_mma(const AttnArgs p) {
 }
 
 // ---- decode: one query row per (b,h) ----------------------------------------------------------------------------
-// 128 threads; a group of LPK lanes owns whole keys: every lane moves one 128-bit vector per key (4 fp32 or 8 bf16), so a
-// (b,h) head row -- 256 B fp32 / 128 B bf16, contiguous in the token-major cache -- is one fully used request.
+// A group of LPK lanes owns whole keys: every lane moves one 128-bit vector per key (4 fp32 or 8 bf16), so a (b,h) head row
+// -- 256 B fp32 / 128 B bf16, contiguous in the head-major cache -- is one fully used request and a warp reads 512 contiguous
+// bytes per instruction.  The kernel is a pure stream (0.5 FLOP/B): what limits it is bytes in flight, so every lane issues U
+// independent 128-bit loads (kept raw in registers, converted when used) before it touches the first one.
 template <bool BF16>
 struct KvIo;
 template <>
 struct KvIo<false> {
   typedef float T;
   static constexpr int EPL = 4;                       // elements per lane
-  static __device__ __forceinline__ void ld(const float* p, float* v) {
-    const float4 x = *reinterpret_cast<const float4*>(p);
-    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+  static __device__ __forceinline__ float dot(const uint4& r, const float* q) {
+    return fmaf(q[3], __uint_as_float(r.w), fmaf(q[2], __uint_as_float(r.z), fmaf(q[1], __uint_as_float(r.y), q[0] * __uint_as_float(r.x))));
+  }
+  static __device__ __forceinline__ void axpy(const uint4& r, float a, float* acc) {
+    acc[0] = fmaf(a, __uint_as_float(r.x), acc[0]); acc[1] = fmaf(a, __uint_as_float(r.y), acc[1]);
+    acc[2] = fmaf(a, __uint_as_float(r.z), acc[2]); acc[3] = fmaf(a, __uint_as_float(r.w), acc[3]);
   }
   static __device__ __forceinline__ void st(float* p, const float* v) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
@@ -423,13 +428,23 @@ template <>
 struct KvIo<true> {
   typedef __nv_bfloat16 T;
   static constexpr int EPL = 8;
-  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float* v) {
-    const uint4 u = *reinterpret_cast<const uint4*>(p);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  // a bf16 is the high half of the fp32 with the same value: element 2i = word << 16, element 2i+1 = word & 0xffff0000
+  static __device__ __forceinline__ float dot(const uint4& r, const float* q) {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    float d = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
-      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+      d = fmaf(q[2 * i], __uint_as_float(w[i] << 16), d);
+      d = fmaf(q[2 * i + 1], __uint_as_float(w[i] & 0xffff0000u), d);
+    }
+    return d;
+  }
+  static __device__ __forceinline__ void axpy(const uint4& r, float a, float* acc) {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc[2 * i] = fmaf(a, __uint_as_float(w[i] << 16), acc[2 * i]);
+      acc[2 * i + 1] = fmaf(a, __uint_as_float(w[i] & 0xffff0000u), acc[2 * i + 1]);
     }
   }
   static __device__ __forceinline__ void st(__nv_bfloat16* p, const float* v) {
@@ -443,10 +458,10 @@ struct KvIo<true> {
   }
 };
 
-template <bool BF16, int NT>
+template <bool BF16, int NT, int U>
 __global__ void __launch_bounds__(NT) attn_decode_kernel(const DecodeAttnArgs p) {
   typedef typename KvIo<BF16>::T KT;
-  constexpr int DH = 64, EPL = KvIo<BF16>::EPL, LPK = DH / EPL, NG = NT / LPK, U = 4, NW = NT / 32;
+  constexpr int DH = 64, EPL = KvIo<BF16>::EPL, LPK = DH / EPL, NG = NT / LPK, NW = NT / 32;
   extern __shared__ __align__(16) float sc[];          // [nkeys_max] scores, then [NG][64] partial outputs
   __shared__ float red[8];
   pdl_prologue();
@@ -478,34 +493,34 @@ __global__ void __launch_bounds__(NT) attn_decode_kernel(const DecodeAttnArgs p)
     __syncthreads();
   }
   const uint8_t* km = p.key_mask ? p.key_mask + (size_t)b * p.Tk : nullptr;
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
 
   // scores: U keys in flight per group
   for (int base = 0; base < nkeys; base += NG * U) {   // warp-uniform trip count: the shuffles below need all lanes
-    float kv[U][EPL];
+    uint4 raw[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int j = base + grp + NG * u;
-      if (j < nkeys) KvIo<BF16>::ld(kbase + (size_t)j * p.kv_tok_stride, kv[u]);
-      else {
-#pragma unroll
-        for (int i = 0; i < EPL; ++i) kv[u][i] = 0.f;
-      }
+      raw[u] = j < nkeys ? __ldcs(reinterpret_cast<const uint4*>(kbase + (size_t)j * p.kv_tok_stride)) : zero4;
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int j = base + grp + NG * u;
-      float d = 0.f;
-#pragma unroll
-      for (int i = 0; i < EPL; ++i) d = fmaf(q[i], kv[u][i], d);
+      float d = KvIo<BF16>::dot(raw[u], q);
 #pragma unroll
       for (int off = LPK / 2; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
-      if (lk == 0 && j < nkeys) sc[j] = (km && !km[j]) ? -FLT_MAX : d * p.scale;
+      if (lk == 0 && j < nkeys) sc[j] = d * p.scale;
     }
   }
   __syncthreads();
-  // softmax statistics
+  // key-padding mask (masked_fill(-finfo.max), applied here with coalesced byte loads instead of one dependent load per key
+  // inside the streaming loop) and softmax statistics
   float mx = -INFINITY;
-  for (int j = tid; j < nkeys; j += NT) mx = fmaxf(mx, sc[j]);
+  for (int j = tid; j < nkeys; j += NT) {
+    float v = sc[j];
+    if (km && !km[j]) { v = -FLT_MAX; sc[j] = v; }
+    mx = fmaxf(mx, v);
+  }
   mx = warp_max(mx);
   if (lane == 0) red[warp] = mx;
   __syncthreads();
@@ -532,23 +547,17 @@ __global__ void __launch_bounds__(NT) attn_decode_kernel(const DecodeAttnArgs p)
 #pragma unroll
   for (int i = 0; i < EPL; ++i) acc[i] = 0.f;
   for (int base = 0; base < nkeys; base += NG * U) {
-    float vv[U][EPL], pj[U];
+    uint4 raw[U];
+    float pj[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int j = base + grp + NG * u;
-      pj[u] = 0.f;
-      if (j < nkeys) {
-        KvIo<BF16>::ld(vbase + (size_t)j * p.kv_tok_stride, vv[u]);
-        pj[u] = sc[j];
-      } else {
-#pragma unroll
-        for (int i = 0; i < EPL; ++i) vv[u][i] = 0.f;
-      }
+      const bool ok = j < nkeys;
+      raw[u] = ok ? __ldcs(reinterpret_cast<const uint4*>(vbase + (size_t)j * p.kv_tok_stride)) : zero4;
+      pj[u] = ok ? sc[j] : 0.f;
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-      for (int i = 0; i < EPL; ++i) acc[i] = fmaf(pj[u], vv[u][i], acc[i]);
+    for (int u = 0; u < U; ++u) KvIo<BF16>::axpy(raw[u], pj[u], acc);
   }
   float* part = sc + p.sc_floats;                       // [NG][64]
 #pragma unroll
@@ -644,15 +653,15 @@ int launch_attention_decode(DecodeAttnArgs a, int max_keys, cudaStream_t s) {
   a.sc_floats = (max_keys + 3) / 4 * 4;
   size_t smem = (size_t)(a.sc_floats + 16 * 64) * sizeof(float);
   DIM_REQUIRE(smem <= 200 * 1024, "decode attention: too many keys for one CTA");
-  // 64-thread CTAs when the whole (batch x heads) grid then fits in one resident wave (32 CTAs / SM): every head streams
-  // concurrently and there is no half-empty tail wave; 128-thread CTAs for larger grids.
+  // 128-thread CTAs, 8 keys (8 x 16 B) in flight per lane; DIM_ATTN_NT=64 selects the 64-thread variant (16 keys in flight
+  // per lane for bf16 rows) -- tuning hook.  The kernel is latency-bound unless enough loads are in flight: with 4 keys per
+  // lane it took the same time for bf16 and fp32 rows (profiles/r01_notes.md).
   const bool bf = a.kv_bf16 != 0;
-  static const int force_nt = getenv("DIM_ATTN_NT") ? atoi(getenv("DIM_ATTN_NT")) : 0;      // tuning hook: 64 or 128
-  const bool small = force_nt ? force_nt == 64
-                              : bf && (long)a.B * a.H <= 148L * 32;   // (fp32 rows are twice as long: 128-thread CTAs measured faster)
+  static const int force_nt = getenv("DIM_ATTN_NT") ? atoi(getenv("DIM_ATTN_NT")) : 0;
+  const bool small = force_nt == 64;
   typedef void (*Kern)(const DecodeAttnArgs);
-  Kern kern = bf ? (small ? (Kern)attn_decode_kernel<true, 64> : (Kern)attn_decode_kernel<true, 128>)
-                 : (small ? (Kern)attn_decode_kernel<false, 64> : (Kern)attn_decode_kernel<false, 128>);
+  Kern kern = bf ? (small ? (Kern)attn_decode_kernel<true, 64, 16> : (Kern)attn_decode_kernel<true, 128, 8>)
+                 : (small ? (Kern)attn_decode_kernel<false, 64, 8> : (Kern)attn_decode_kernel<false, 128, 8>);
   static size_t configured[4] = {48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024};
   const int slot = (bf ? 2 : 0) + (small ? 1 : 0);
   if (smem > configured[slot]) {

@@ -37,5 +37,14 @@ def run(M, N, K, planes=1, splits=0, iters=50):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "decode":
+        # the seven GEMM shapes of one decode step (M = rows of one decode group), bf16 and 3-plane, automatic split-K
+        for M in (128, 256):
+            for (N, K) in ((2304, 1152), (1152, 768), (768, 1152), (4608, 1152), (1152, 4608), (512, 1152)):
+                run(M, N, K, planes=1)
+        for (N, K) in ((2304, 1152), (1152, 768), (1152, 4608)):
+            run(128, N, K, planes=3)
+            run(128, N, K, planes=1, splits=1)
+        sys.exit(0)
     run(256, 2304, 1152); run(256, 2304, 1152, splits=1); run(128, 128, 384, splits=1); run(128, 32, 384, splits=1)
     run(8192, 1152, 1152, splits=1)
