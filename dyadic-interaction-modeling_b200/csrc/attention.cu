@@ -405,8 +405,7 @@ __global__ void __launch_bounds__(128) attn_prefill_mma(const AttnArgs p) {
 // ---- decode: one query row per (b,h) ----------------------------------------------------------------------------
 // A group of LPK lanes owns whole keys: every lane moves one 128-bit vector per key (4 fp32 or 8 bf16), so a (b,h) head row
 // -- 256 B fp32 / 128 B bf16, contiguous in the head-major cache -- is one fully used request and a warp reads 512 contiguous
-// bytes per instruction.  The kernel is a pure stream (0.5 FLOP/B): what limits it is bytes in flight, so every lane issues U
-// independent 128-bit loads (kept raw in registers, converted when used) before it touches the first one.
+// bytes per instruction (pass 2 of the kernel below; pass 1 reads one whole row per thread from shared memory).
 template <bool BF16>
 struct KvIo;
 template <>
@@ -458,27 +457,41 @@ struct KvIo<true> {
   }
 };
 
-template <bool BF16, int NT, int U>
+__device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One CTA per (clip, head); the head's K block and V block are contiguous streams (head-major cache).  Keys are staged in
+// CHUNK-row tiles through a 2-stage cp.async ring in shared memory (rows padded by 16 B: conflict-free for both access
+// patterns below), so the bytes in flight per SM do not depend on registers or on instruction scheduling:
+//   pass 1 (scores): one THREAD per key -- the whole 64-element dot product is local (no shuffles), q lives in registers;
+//   softmax over the scores in shared memory (key-padding mask applied here), the first V tiles already in flight;
+//   pass 2 (P.V)   : a group of LPK lanes per key, each lane owns one 16-byte slice of the head row and accumulates it over
+//                    the keys of its group; groups are reduced through shared memory at the end.
+// ~10 warp instructions per key (the previous lane-group kernel spent ~30 and was issue-bound at 3.7 TB/s).
+template <bool BF16, int NT, int CHUNK>
 __global__ void __launch_bounds__(NT) attn_decode_kernel(const DecodeAttnArgs p) {
   typedef typename KvIo<BF16>::T KT;
   constexpr int DH = 64, EPL = KvIo<BF16>::EPL, LPK = DH / EPL, NG = NT / LPK, NW = NT / 32;
-  extern __shared__ __align__(16) float sc[];          // [nkeys_max] scores, then [NG][64] partial outputs
+  constexpr int ROWB = DH * (int)sizeof(KT), PITCH = ROWB + 16, STAGE = CHUNK * PITCH, KPG = CHUNK / NG;
+  static_assert(CHUNK <= NT && CHUNK % NG == 0, "chunk shape");
+  extern __shared__ __align__(16) uint8_t dsm[];       // [2][STAGE] ring | scores [sc_floats] | partial outputs [NG][64]
   __shared__ float red[8];
+  float* sc = reinterpret_cast<float*>(dsm + 2 * STAGE);
+  float* part = sc + p.sc_floats;
   pdl_prologue();
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int grp = tid / LPK, lk = tid % LPK;           // key group of this lane, position inside the head row
+  const int grp = tid / LPK, lk = tid % LPK;           // pass-2 role: key group, 16-byte slice inside the head row
   const int pos = p.step ? *p.step : 0;                                   // index of the token being decoded
   const int nkeys = p.append ? pos + 1 : p.Tk;
-  KT* kbase = static_cast<KT*>(p.k) + (size_t)b * p.kv_batch_stride + (size_t)h * p.kv_head_stride + lk * EPL;
-  KT* vbase = static_cast<KT*>(p.v) + (size_t)b * p.kv_batch_stride + (size_t)h * p.kv_head_stride + lk * EPL;
+  KT* khead = static_cast<KT*>(p.k) + (size_t)b * p.kv_batch_stride + (size_t)h * p.kv_head_stride;   // rows 64 elements apart
+  KT* vhead = static_cast<KT*>(p.v) + (size_t)b * p.kv_batch_stride + (size_t)h * p.kv_head_stride;
+  const uint32_t ring_u = (uint32_t)__cvta_generic_to_shared(dsm);
 
-  float q[EPL];
-#pragma unroll
-  for (int i = 0; i < EPL; i += 4) {
-    const float4 x = *reinterpret_cast<const float4*>(p.q + (size_t)b * p.ldq + h * DH + lk * EPL + i);
-    q[i] = x.x; q[i + 1] = x.y; q[i + 2] = x.z; q[i + 3] = x.w;
-  }
   if (p.append) {                                                        // cache[pos] <- this step's k, v
     if (grp < 2) {
       const float* src = (grp == 0 ? p.k_new : p.v_new) + (size_t)b * p.ld_new + h * DH + lk * EPL;
@@ -488,33 +501,50 @@ __global__ void __launch_bounds__(NT) attn_decode_kernel(const DecodeAttnArgs p)
         const float4 x = *reinterpret_cast<const float4*>(src + i);
         v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
       }
-      KvIo<BF16>::st((grp == 0 ? kbase : vbase) + (size_t)pos * p.kv_tok_stride, v);
+      KvIo<BF16>::st((grp == 0 ? khead : vhead) + (size_t)pos * DH + lk * EPL, v);
+      __threadfence();                                                   // the row is read back below through cp.async (L2)
     }
     __syncthreads();
   }
-  const uint8_t* km = p.key_mask ? p.key_mask + (size_t)b * p.Tk : nullptr;
-  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  const int nch = (nkeys + CHUNK - 1) / CHUNK;
+  auto issue = [&](const KT* head, int c, int stage) {                   // rows [c*CHUNK, ..) of a head block -> ring[stage]
+    const int row0 = c * CHUNK, pieces = min(CHUNK, nkeys - row0) * LPK;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(head + (size_t)row0 * DH);
+    const uint32_t dst = ring_u + stage * STAGE;
+    for (int q = tid; q < pieces; q += NT) cp_async_16(dst + (q / LPK) * PITCH + (q % LPK) * 16, src + (size_t)q * 16);
+    cp_async_commit();
+  };
+  if (nch > 0) issue(khead, 0, 0);
+  if (nch > 1) issue(khead, 1, 1);
 
-  // scores: U keys in flight per group
-  for (int base = 0; base < nkeys; base += NG * U) {   // warp-uniform trip count: the shuffles below need all lanes
-    uint4 raw[U];
+  float q[DH];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int j = base + grp + NG * u;
-      raw[u] = j < nkeys ? __ldcs(reinterpret_cast<const uint4*>(kbase + (size_t)j * p.kv_tok_stride)) : zero4;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int j = base + grp + NG * u;
-      float d = KvIo<BF16>::dot(raw[u], q);
-#pragma unroll
-      for (int off = LPK / 2; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
-      if (lk == 0 && j < nkeys) sc[j] = d * p.scale;
-    }
+  for (int i = 0; i < DH; i += 4) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(p.q + (size_t)b * p.ldq + h * DH + i));
+    q[i] = x.x; q[i + 1] = x.y; q[i + 2] = x.z; q[i + 3] = x.w;
   }
-  __syncthreads();
-  // key-padding mask (masked_fill(-finfo.max), applied here with coalesced byte loads instead of one dependent load per key
-  // inside the streaming loop) and softmax statistics
+
+  // ---- pass 1: scores
+  for (int c = 0; c < nch; ++c) {
+    if (c + 1 < nch) cp_async_wait<1>(); else cp_async_wait<0>();
+    __syncthreads();
+    const int j = c * CHUNK + tid;
+    if (tid < CHUNK && j < nkeys) {
+      const uint4* row = reinterpret_cast<const uint4*>(dsm + (c & 1) * STAGE + tid * PITCH);
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < LPK; ++i) d[i & 3] += KvIo<BF16>::dot(row[i], q + i * EPL);
+      sc[j] = ((d[0] + d[1]) + (d[2] + d[3])) * p.scale;
+    }
+    __syncthreads();
+    if (c + 2 < nch) issue(khead, c + 2, c & 1);
+  }
+  // first V tiles in flight while the softmax statistics are computed
+  if (nch > 0) issue(vhead, 0, 0);
+  if (nch > 1) issue(vhead, 1, 1);
+
+  // key-padding mask (masked_fill(-finfo.max)) and softmax statistics
+  const uint8_t* km = p.key_mask ? p.key_mask + (size_t)b * p.Tk : nullptr;
   float mx = -INFINITY;
   for (int j = tid; j < nkeys; j += NT) {
     float v = sc[j];
@@ -542,24 +572,22 @@ __global__ void __launch_bounds__(NT) attn_decode_kernel(const DecodeAttnArgs p)
   for (int w = 1; w < NW; ++w) tot += red[w];
   const float inv = 1.f / tot;
 
-  // out = P V
+  // ---- pass 2: out = P V
   float acc[EPL];
 #pragma unroll
   for (int i = 0; i < EPL; ++i) acc[i] = 0.f;
-  for (int base = 0; base < nkeys; base += NG * U) {
-    uint4 raw[U];
-    float pj[U];
+  for (int c = 0; c < nch; ++c) {
+    if (c + 1 < nch) cp_async_wait<1>(); else cp_async_wait<0>();
+    __syncthreads();
+    const uint8_t* tile = dsm + (c & 1) * STAGE + lk * 16;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int j = base + grp + NG * u;
-      const bool ok = j < nkeys;
-      raw[u] = ok ? __ldcs(reinterpret_cast<const uint4*>(vbase + (size_t)j * p.kv_tok_stride)) : zero4;
-      pj[u] = ok ? sc[j] : 0.f;
+    for (int i = 0; i < KPG; ++i) {
+      const int jl = grp + NG * i, j = c * CHUNK + jl;
+      if (j < nkeys) KvIo<BF16>::axpy(*reinterpret_cast<const uint4*>(tile + jl * PITCH), sc[j], acc);
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) KvIo<BF16>::axpy(raw[u], pj[u], acc);
+    __syncthreads();
+    if (c + 2 < nch) issue(vhead, c + 2, c & 1);
   }
-  float* part = sc + p.sc_floats;                       // [NG][64]
 #pragma unroll
   for (int i = 0; i < EPL; ++i) part[grp * DH + lk * EPL + i] = acc[i];
   __syncthreads();
@@ -650,29 +678,25 @@ int launch_attention_prefill(const AttnArgs& a, cudaStream_t s) {
 
 int launch_attention_decode(DecodeAttnArgs a, int max_keys, cudaStream_t s) {
   DIM_REQUIRE(a.B > 0 && a.H > 0, "decode attention: empty");
-  a.sc_floats = (max_keys + 3) / 4 * 4;
-  size_t smem = (size_t)(a.sc_floats + 16 * 64) * sizeof(float);
-  DIM_REQUIRE(smem <= 200 * 1024, "decode attention: too many keys for one CTA");
-  // 128-thread CTAs, 8 keys (8 x 16 B) in flight per lane; DIM_ATTN_NT=64 selects the 64-thread variant (16 keys in flight
-  // per lane for bf16 rows) -- tuning hook.  The kernel is latency-bound unless enough loads are in flight: with 4 keys per
-  // lane it took the same time for bf16 and fp32 rows (profiles/r01_notes.md).
+  DIM_REQUIRE(a.kv_tok_stride == 64, "decode attention: the K/V caches must be head-major ([B,H,tokens,64])");
   const bool bf = a.kv_bf16 != 0;
-  static const int force_nt = getenv("DIM_ATTN_NT") ? atoi(getenv("DIM_ATTN_NT")) : 0;
-  const bool small = force_nt == 64;
+  constexpr int NT = 128, CHUNK_BF = 128, CHUNK_F32 = 64;
+  a.sc_floats = (max_keys + 3) / 4 * 4;
+  const size_t ring = bf ? 2 * (size_t)CHUNK_BF * (128 + 16) : 2 * (size_t)CHUNK_F32 * (256 + 16);
+  const size_t smem = ring + (size_t)(a.sc_floats + 16 * 64) * sizeof(float);
+  DIM_REQUIRE(smem <= 200 * 1024, "decode attention: too many keys for one CTA");
   typedef void (*Kern)(const DecodeAttnArgs);
-  Kern kern = bf ? (small ? (Kern)attn_decode_kernel<true, 64, 16> : (Kern)attn_decode_kernel<true, 128, 8>)
-                 : (small ? (Kern)attn_decode_kernel<false, 64, 8> : (Kern)attn_decode_kernel<false, 128, 8>);
-  static size_t configured[4] = {48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024};
-  const int slot = (bf ? 2 : 0) + (small ? 1 : 0);
-  if (smem > configured[slot]) {
+  Kern kern = bf ? (Kern)attn_decode_kernel<true, NT, CHUNK_BF> : (Kern)attn_decode_kernel<false, NT, CHUNK_F32>;
+  static size_t configured[2] = {48 * 1024, 48 * 1024};
+  if (smem > configured[bf ? 1 : 0]) {
     DIM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[slot] = smem;
+    configured[bf ? 1 : 0] = smem;
   }
   {
     const double keys = a.append ? (double)(a.prof_pos + 1) : (double)a.Tk;   // K and V rows actually read
     const double esz = bf ? 2.0 : 4.0;
     ProfScope ps(CAT_ATTN_DECODE, s, a.B * (double)a.H * 64.0 * (2.0 * keys * esz + 8.0), 4.0 * a.B * a.H * 64.0 * keys);
-    DIM_CHECK_CUDA(launch_k(kern, dim3(a.B * a.H), dim3(small ? 64 : 128), smem, s, a));
+    DIM_CHECK_CUDA(launch_k(kern, dim3(a.B * a.H), dim3(NT), smem, s, a));
   }
   DIM_LAUNCHED();
   return DIM_OK;
