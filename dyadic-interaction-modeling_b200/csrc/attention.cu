@@ -457,6 +457,131 @@ struct KvIo<true> {
   }
 };
 
+// volatile: the U loads of a batch stay where they are written, back to back, ahead of the first use
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+// Lane-group variant (kept for A/B measurements, DIM_ATTN_IMPL=lanes): LPK lanes per key, U keys in flight per lane.
+template <bool BF16, int NT, int U>
+__global__ void __launch_bounds__(NT) attn_decode_lanes(const DecodeAttnArgs p) {
+  typedef typename KvIo<BF16>::T KT;
+  constexpr int DH = 64, EPL = KvIo<BF16>::EPL, LPK = DH / EPL, NG = NT / LPK, NW = NT / 32;
+  extern __shared__ __align__(16) float sc[];          // [nkeys_max] scores, then [NG][64] partial outputs
+  __shared__ float red[8];
+  pdl_prologue();
+  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grp = tid / LPK, lk = tid % LPK;           // key group of this lane, position inside the head row
+  const int pos = p.step ? *p.step : 0;                                   // index of the token being decoded
+  const int nkeys = p.append ? pos + 1 : p.Tk;
+  KT* kbase = static_cast<KT*>(p.k) + (size_t)b * p.kv_batch_stride + (size_t)h * p.kv_head_stride + lk * EPL;
+  KT* vbase = static_cast<KT*>(p.v) + (size_t)b * p.kv_batch_stride + (size_t)h * p.kv_head_stride + lk * EPL;
+
+  float q[EPL];
+#pragma unroll
+  for (int i = 0; i < EPL; i += 4) {
+    const float4 x = *reinterpret_cast<const float4*>(p.q + (size_t)b * p.ldq + h * DH + lk * EPL + i);
+    q[i] = x.x; q[i + 1] = x.y; q[i + 2] = x.z; q[i + 3] = x.w;
+  }
+  if (p.append) {                                                        // cache[pos] <- this step's k, v
+    if (grp < 2) {
+      const float* src = (grp == 0 ? p.k_new : p.v_new) + (size_t)b * p.ld_new + h * DH + lk * EPL;
+      float v[EPL];
+#pragma unroll
+      for (int i = 0; i < EPL; i += 4) {
+        const float4 x = *reinterpret_cast<const float4*>(src + i);
+        v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
+      }
+      KvIo<BF16>::st((grp == 0 ? kbase : vbase) + (size_t)pos * p.kv_tok_stride, v);
+    }
+    __syncthreads();
+  }
+  const uint8_t* km = p.key_mask ? p.key_mask + (size_t)b * p.Tk : nullptr;
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+
+  // scores: U keys in flight per group
+  for (int base = 0; base < nkeys; base += NG * U) {   // warp-uniform trip count: the shuffles below need all lanes
+    uint4 raw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = base + grp + NG * u;
+      raw[u] = zero4;
+      if (j < nkeys) raw[u] = ld_stream16(kbase + (size_t)j * p.kv_tok_stride);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = base + grp + NG * u;
+      float d = KvIo<BF16>::dot(raw[u], q);
+#pragma unroll
+      for (int off = LPK / 2; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+      if (lk == 0 && j < nkeys) sc[j] = d * p.scale;
+    }
+  }
+  __syncthreads();
+  // key-padding mask (masked_fill(-finfo.max), applied here with coalesced byte loads instead of one dependent load per key
+  // inside the streaming loop) and softmax statistics
+  float mx = -INFINITY;
+  for (int j = tid; j < nkeys; j += NT) {
+    float v = sc[j];
+    if (km && !km[j]) { v = -FLT_MAX; sc[j] = v; }
+    mx = fmaxf(mx, v);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int j = tid; j < nkeys; j += NT) {
+    float e = expf(sc[j] - mx);
+    sc[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  float tot = red[0];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) tot += red[w];
+  const float inv = 1.f / tot;
+
+  // out = P V
+  float acc[EPL];
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) acc[i] = 0.f;
+  for (int base = 0; base < nkeys; base += NG * U) {
+    uint4 raw[U];
+    float pj[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = base + grp + NG * u;
+      const bool ok = j < nkeys;
+      raw[u] = zero4;
+      if (ok) raw[u] = ld_stream16(vbase + (size_t)j * p.kv_tok_stride);
+      pj[u] = ok ? sc[j] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) KvIo<BF16>::axpy(raw[u], pj[u], acc);
+  }
+  float* part = sc + p.sc_floats;                       // [NG][64]
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) part[grp * DH + lk * EPL + i] = acc[i];
+  __syncthreads();
+  if (tid < DH) {
+    float r = 0.f;
+#pragma unroll
+    for (int w = 0; w < NG; ++w) r += part[w * DH + tid];
+    if (p.out) p.out[(size_t)b * p.ldo + h * DH + tid] = r * inv;
+    if (p.out_p) store_planes1(p.out_p + (size_t)b * p.planes * p.kp + h * DH + tid, r * inv, p.planes, p.kp);
+  }
+}
+
+
 __device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
@@ -676,6 +801,8 @@ int launch_attention_prefill(const AttnArgs& a, cudaStream_t s) {
   return DIM_OK;
 }
 
+int g_attn_impl = -1;      // -1: from DIM_ATTN_IMPL (default ring); 0: cp.async ring kernel; 1: lane-group kernel
+
 int launch_attention_decode(DecodeAttnArgs a, int max_keys, cudaStream_t s) {
   DIM_REQUIRE(a.B > 0 && a.H > 0, "decode attention: empty");
   DIM_REQUIRE(a.kv_tok_stride == 64, "decode attention: the K/V caches must be head-major ([B,H,tokens,64])");
@@ -683,14 +810,22 @@ int launch_attention_decode(DecodeAttnArgs a, int max_keys, cudaStream_t s) {
   constexpr int NT = 128, CHUNK_BF = 128, CHUNK_F32 = 64;
   a.sc_floats = (max_keys + 3) / 4 * 4;
   const size_t ring = bf ? 2 * (size_t)CHUNK_BF * (128 + 16) : 2 * (size_t)CHUNK_F32 * (256 + 16);
-  const size_t smem = ring + (size_t)(a.sc_floats + 16 * 64) * sizeof(float);
+  size_t smem = ring + (size_t)(a.sc_floats + 16 * 64) * sizeof(float);
   DIM_REQUIRE(smem <= 200 * 1024, "decode attention: too many keys for one CTA");
   typedef void (*Kern)(const DecodeAttnArgs);
-  Kern kern = bf ? (Kern)attn_decode_kernel<true, NT, CHUNK_BF> : (Kern)attn_decode_kernel<false, NT, CHUNK_F32>;
-  static size_t configured[2] = {48 * 1024, 48 * 1024};
-  if (smem > configured[bf ? 1 : 0]) {
+  if (g_attn_impl < 0) {
+    const char* e = getenv("DIM_ATTN_IMPL");
+    g_attn_impl = (e && std::string(e) == "lanes") ? 1 : 0;
+  }
+  const bool lanes = g_attn_impl == 1;
+  Kern kern = lanes ? (bf ? (Kern)attn_decode_lanes<true, NT, 8> : (Kern)attn_decode_lanes<false, NT, 8>)
+                    : (bf ? (Kern)attn_decode_kernel<true, NT, CHUNK_BF> : (Kern)attn_decode_kernel<false, NT, CHUNK_F32>);
+  if (lanes) smem = (size_t)(a.sc_floats + 16 * 64) * sizeof(float);
+  static size_t configured[4] = {48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024};
+  const int slot = (bf ? 1 : 0) + (lanes ? 2 : 0);
+  if (smem > configured[slot]) {
     DIM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[bf ? 1 : 0] = smem;
+    configured[slot] = smem;
   }
   {
     const double keys = a.append ? (double)(a.prof_pos + 1) : (double)a.Tk;   // K and V rows actually read
@@ -705,6 +840,19 @@ int launch_attention_decode(DecodeAttnArgs a, int max_keys, cudaStream_t s) {
 }  // namespace dimb
 
 using namespace dimb;
+
+// tuning hook (not part of the stable ABI): one cross-attention-shaped decode launch on caller buffers.
+// k, v: head-major [B,H,Tk,64] (fp32 or bf16); q, out: [B, H*64] fp32.  impl: 0 ring, 1 lanes.
+extern "C" int dim_debug_attn_decode(int impl, void* k, void* v, const float* q, float* out, int B, int H, int Tk, int bf16,
+                                     void* stream) {
+  if (int e = ensure_device()) return e;
+  dimb::g_attn_impl = impl;
+  DecodeAttnArgs a;
+  a.q = q; a.ldq = H * 64; a.k = k; a.v = v; a.kv_bf16 = bf16;
+  a.kv_batch_stride = (size_t)H * Tk * 64; a.kv_head_stride = (size_t)Tk * 64; a.kv_tok_stride = 64;
+  a.append = 0; a.out = out; a.ldo = H * 64; a.B = B; a.H = H; a.Tk = Tk; a.scale = 0.125f;
+  return launch_attention_decode(a, Tk, as_stream(stream));
+}
 
 extern "C" int dim_attention_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out,
                                  int ldo, const uint8_t* key_mask, const int32_t* lens, int B, int H, int Tq, int Tk, int Dh,
