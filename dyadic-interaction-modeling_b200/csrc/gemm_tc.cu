@@ -520,6 +520,7 @@ int launch_split_planes(const GemmArgs& a, __nv_bfloat16* out, int kp, int plane
 
 long long* g_tc_dbg = nullptr;
 int g_tc_force_splits = 0;
+int g_tc_force_bn = 0;
 
 int tc_pairs(int planes, int* pa, int* pw) {
   // plane 0 = high, 1 = middle, 2 = low part of the bf16 split.  Products kept: all with (index sum) < planes.
@@ -549,17 +550,32 @@ int launch_gemm_tc(const GemmArgs& e, const __nv_bfloat16* Ap, const __nv_bfloat
   p.splits = 1;
   p.dbg = g_tc_dbg;
   const int total_kb = p.kblocks * p.npairs;
-  const int bn = e.N >= 128 ? 128 : (e.N > 32 ? 64 : 32);
+  int bn = e.N >= 128 ? 128 : (e.N > 32 ? 64 : 32);
+  int splits = 1;
+  if (e.M < 2048) {
+    if (planes == 1 && e.M <= 512) {
+      // Decode-step GEMMs with plain bf16 operands (measured sweep, profiles/r01g_tc_sweep_*.txt): a CTA ingests ~60 B/clk, so
+      // its main loop costs (128 + BN) * K * 2 B / 60 and the 128-row A tile dominates; the DSMEM reduction of split-K costs
+      // ~20 B/clk per SM.  Narrow tiles with the whole K per CTA win for K <= 1152 (no cluster, 16 KB epilogue tile); a 4-way
+      // split only when the N tiles alone would leave most SMs idle, or when K is long.  Depends on (N, K) only, never on M.
+      if (kp >= 2048) { bn = 64; splits = 4; }
+      else {
+        bn = 32;
+        splits = (cdiv(e.N, 32) <= 24 && total_kb >= 16) ? 4 : 1;
+      }
+    } else {
+      // fp32-grade plane products (3-6x the k-blocks) and mid-sized M: split K over a cluster so that every CTA owns >= ~4 k-blocks.
+      const int want = total_kb / 4;
+      splits = want >= 8 ? 8 : (want >= 4 ? 4 : (want >= 2 ? 2 : 1));
+    }
+  }
+  if (g_tc_force_bn > 0) bn = g_tc_force_bn;
+  p.splits = splits;
+  if (g_tc_force_splits > 0) p.splits = g_tc_force_splits;
+  while (p.splits > 1 && p.splits > total_kb) p.splits >>= 1;
   CUtensorMap tmA, tmW;
   if (int err = make_map(Ap, e.M, planes * kp, planes * kp, BM, &tmA)) return err;
   if (int err = make_map(Wp, e.N, planes * kp, planes * kp, bn, &tmW)) return err;
-  if (e.M < 2048) {
-    // Short-M GEMMs: split K over a cluster so that every CTA owns >= ~4 k-blocks.  S depends on (K, planes) only.
-    const int want = total_kb / 4;
-    p.splits = want >= 8 ? 8 : (want >= 4 ? 4 : (want >= 2 ? 2 : 1));
-  }
-  if (g_tc_force_splits > 0) p.splits = g_tc_force_splits;
-  while (p.splits > 1 && p.splits > total_kb) p.splits >>= 1;
   if (bn == 128) return launch_tc<128, 3>(tmA, tmW, p, s);
   if (bn == 64) return launch_tc<64, 4>(tmA, tmW, p, s);
   return launch_tc<32, 4>(tmA, tmW, p, s);
@@ -591,5 +607,9 @@ extern "C" int dim_linear_bf16_planes(const void* Ap, const void* Wp, int K, int
 extern "C" int dim_debug_tc(void* dbg_buffer_64x8B, int force_splits) {
   dimb::g_tc_dbg = static_cast<long long*>(dbg_buffer_64x8B);
   dimb::g_tc_force_splits = force_splits;
+  return DIM_OK;
+}
+extern "C" int dim_debug_tc_bn(int force_bn) {
+  dimb::g_tc_force_bn = force_bn;
   return DIM_OK;
 }

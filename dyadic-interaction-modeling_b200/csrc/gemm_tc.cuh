@@ -17,5 +17,6 @@ int launch_gemm_tc(const GemmArgs& e, const __nv_bfloat16* Ap, const __nv_bfloat
 int tc_pairs(int planes, int* pa, int* pw);
 extern long long* g_tc_dbg;
 extern int g_tc_force_splits;
+extern int g_tc_force_bn;
 
 }  // namespace dimb
