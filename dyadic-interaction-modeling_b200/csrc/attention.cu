@@ -590,22 +590,26 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // One CTA per (clip, head); the head's K block and V block are contiguous streams (head-major cache).  Keys are staged in
-// CHUNK-row tiles through a 2-stage cp.async ring in shared memory (rows padded by 16 B: conflict-free for both access
-// patterns below), so the bytes in flight per SM do not depend on registers or on instruction scheduling:
+// CHUNK-row tiles through cp.async rings in shared memory (2 stages for K, 2 for V; rows padded by 16 B: conflict-free for
+// both access patterns below), so the bytes in flight per SM do not depend on registers or on instruction scheduling, and
+// the first two tiles of BOTH K and V are requested before anything is computed (one exposed DRAM round trip per CTA for
+// up to 2*CHUNK keys):
 //   pass 1 (scores): one THREAD per key -- the whole 64-element dot product is local (no shuffles), q lives in registers;
-//   softmax over the scores in shared memory (key-padding mask applied here), the first V tiles already in flight;
+//   softmax over the scores in shared memory (key-padding mask applied here);
 //   pass 2 (P.V)   : a group of LPK lanes per key, each lane owns one 16-byte slice of the head row and accumulates it over
 //                    the keys of its group; groups are reduced through shared memory at the end.
-// ~10 warp instructions per key (the previous lane-group kernel spent ~30 and was issue-bound at 3.7 TB/s).
+// ~10 warp instructions per key (the lane-group kernel above spends ~30 and is issue-bound at ~4 TB/s on bf16 rows).
+// cp.async group bookkeeping: every thread commits the same sequence of (possibly empty) groups --
+//   K0, K1, V0, V1, then K(c+2) after pass-1 tile c, then V(c+2) after pass-2 tile c -- so the waits are static.
 template <bool BF16, int NT, int CHUNK>
 __global__ void __launch_bounds__(NT) attn_decode_kernel(const DecodeAttnArgs p) {
   typedef typename KvIo<BF16>::T KT;
   constexpr int DH = 64, EPL = KvIo<BF16>::EPL, LPK = DH / EPL, NG = NT / LPK, NW = NT / 32;
   constexpr int ROWB = DH * (int)sizeof(KT), PITCH = ROWB + 16, STAGE = CHUNK * PITCH, KPG = CHUNK / NG;
   static_assert(CHUNK <= NT && CHUNK % NG == 0, "chunk shape");
-  extern __shared__ __align__(16) uint8_t dsm[];       // [2][STAGE] ring | scores [sc_floats] | partial outputs [NG][64]
+  extern __shared__ __align__(16) uint8_t dsm[];       // K ring [2][STAGE] | V ring [2][STAGE] | scores | partial outputs [NG][64]
   __shared__ float red[8];
-  float* sc = reinterpret_cast<float*>(dsm + 2 * STAGE);
+  float* sc = reinterpret_cast<float*>(dsm + 4 * STAGE);
   float* part = sc + p.sc_floats;
   pdl_prologue();
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
@@ -632,15 +636,20 @@ __global__ void __launch_bounds__(NT) attn_decode_kernel(const DecodeAttnArgs p)
     __syncthreads();
   }
   const int nch = (nkeys + CHUNK - 1) / CHUNK;
-  auto issue = [&](const KT* head, int c, int stage) {                   // rows [c*CHUNK, ..) of a head block -> ring[stage]
-    const int row0 = c * CHUNK, pieces = min(CHUNK, nkeys - row0) * LPK;
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(head + (size_t)row0 * DH);
-    const uint32_t dst = ring_u + stage * STAGE;
-    for (int q = tid; q < pieces; q += NT) cp_async_16(dst + (q / LPK) * PITCH + (q % LPK) * 16, src + (size_t)q * 16);
+  // rows [c*CHUNK, ..) of a head block -> ring stage `stage` (0,1: K ring; 2,3: V ring); an empty group when c >= nch
+  auto issue = [&](const KT* head, int c, int stage) {
+    if (c < nch) {
+      const int row0 = c * CHUNK, pieces = min(CHUNK, nkeys - row0) * LPK;
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(head + (size_t)row0 * DH);
+      const uint32_t dst = ring_u + stage * STAGE;
+      for (int q = tid; q < pieces; q += NT) cp_async_16(dst + (q / LPK) * PITCH + (q % LPK) * 16, src + (size_t)q * 16);
+    }
     cp_async_commit();
   };
-  if (nch > 0) issue(khead, 0, 0);
-  if (nch > 1) issue(khead, 1, 1);
+  issue(khead, 0, 0);
+  issue(khead, 1, 1);
+  issue(vhead, 0, 2);
+  issue(vhead, 1, 3);
 
   float q[DH];
 #pragma unroll
@@ -649,9 +658,9 @@ __global__ void __launch_bounds__(NT) attn_decode_kernel(const DecodeAttnArgs p)
     q[i] = x.x; q[i + 1] = x.y; q[i + 2] = x.z; q[i + 3] = x.w;
   }
 
-  // ---- pass 1: scores
+  // ---- pass 1: scores.  Tile c < 2 may leave {K1, V0, V1} (+ refills) pending; later tiles only the newest refill.
   for (int c = 0; c < nch; ++c) {
-    if (c + 1 < nch) cp_async_wait<1>(); else cp_async_wait<0>();
+    if (c < 2) cp_async_wait<3>(); else cp_async_wait<1>();
     __syncthreads();
     const int j = c * CHUNK + tid;
     if (tid < CHUNK && j < nkeys) {
@@ -662,11 +671,8 @@ __global__ void __launch_bounds__(NT) attn_decode_kernel(const DecodeAttnArgs p)
       sc[j] = ((d[0] + d[1]) + (d[2] + d[3])) * p.scale;
     }
     __syncthreads();
-    if (c + 2 < nch) issue(khead, c + 2, c & 1);
+    issue(khead, c + 2, c & 1);
   }
-  // first V tiles in flight while the softmax statistics are computed
-  if (nch > 0) issue(vhead, 0, 0);
-  if (nch > 1) issue(vhead, 1, 1);
 
   // key-padding mask (masked_fill(-finfo.max)) and softmax statistics
   const uint8_t* km = p.key_mask ? p.key_mask + (size_t)b * p.Tk : nullptr;
@@ -697,22 +703,23 @@ __global__ void __launch_bounds__(NT) attn_decode_kernel(const DecodeAttnArgs p)
   for (int w = 1; w < NW; ++w) tot += red[w];
   const float inv = 1.f / tot;
 
-  // ---- pass 2: out = P V
+  // ---- pass 2: out = P V.  Every K group is complete; at most the newest V group may still be pending.
   float acc[EPL];
 #pragma unroll
   for (int i = 0; i < EPL; ++i) acc[i] = 0.f;
   for (int c = 0; c < nch; ++c) {
-    if (c + 1 < nch) cp_async_wait<1>(); else cp_async_wait<0>();
+    cp_async_wait<1>();
     __syncthreads();
-    const uint8_t* tile = dsm + (c & 1) * STAGE + lk * 16;
+    const uint8_t* tile = dsm + (2 + (c & 1)) * STAGE + lk * 16;
 #pragma unroll
     for (int i = 0; i < KPG; ++i) {
       const int jl = grp + NG * i, j = c * CHUNK + jl;
       if (j < nkeys) KvIo<BF16>::axpy(*reinterpret_cast<const uint4*>(tile + jl * PITCH), sc[j], acc);
     }
     __syncthreads();
-    if (c + 2 < nch) issue(vhead, c + 2, c & 1);
+    issue(vhead, c + 2, 2 + (c & 1));
   }
+  cp_async_wait<0>();
 #pragma unroll
   for (int i = 0; i < EPL; ++i) part[grp * DH + lk * EPL + i] = acc[i];
   __syncthreads();
@@ -807,9 +814,10 @@ int launch_attention_decode(DecodeAttnArgs a, int max_keys, cudaStream_t s) {
   DIM_REQUIRE(a.B > 0 && a.H > 0, "decode attention: empty");
   DIM_REQUIRE(a.kv_tok_stride == 64, "decode attention: the K/V caches must be head-major ([B,H,tokens,64])");
   const bool bf = a.kv_bf16 != 0;
-  constexpr int NT = 128, CHUNK_BF = 128, CHUNK_F32 = 64;
+  // tile rows chosen so that the 4 ring stages + scores leave room for 3 CTAs per SM (bytes in flight >= 3 x 60 KB per SM)
+  constexpr int NT = 128, CHUNK_BF = 112, CHUNK_F32 = 56;
   a.sc_floats = (max_keys + 3) / 4 * 4;
-  const size_t ring = bf ? 2 * (size_t)CHUNK_BF * (128 + 16) : 2 * (size_t)CHUNK_F32 * (256 + 16);
+  const size_t ring = bf ? 4 * (size_t)CHUNK_BF * (128 + 16) : 4 * (size_t)CHUNK_F32 * (256 + 16);   // K ring + V ring
   size_t smem = ring + (size_t)(a.sc_floats + 16 * 64) * sizeof(float);
   DIM_REQUIRE(smem <= 200 * 1024, "decode attention: too many keys for one CTA");
   typedef void (*Kern)(const DecodeAttnArgs);
