@@ -590,26 +590,25 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // One CTA per (clip, head); the head's K block and V block are contiguous streams (head-major cache).  Keys are staged in
-// CHUNK-row tiles through cp.async rings in shared memory (2 stages for K, 2 for V; rows padded by 16 B: conflict-free for
-// both access patterns below), so the bytes in flight per SM do not depend on registers or on instruction scheduling, and
-// the first two tiles of BOTH K and V are requested before anything is computed (one exposed DRAM round trip per CTA for
-// up to 2*CHUNK keys):
+// CHUNK-row tiles through a 2-stage cp.async ring in shared memory (rows padded by 16 B: conflict-free for both access
+// patterns below), so the bytes in flight per SM do not depend on registers or on instruction scheduling:
 //   pass 1 (scores): one THREAD per key -- the whole 64-element dot product is local (no shuffles), q lives in registers;
-//   softmax over the scores in shared memory (key-padding mask applied here);
+//   softmax over the scores in shared memory (key-padding mask applied here), the first V tiles already in flight;
 //   pass 2 (P.V)   : a group of LPK lanes per key, each lane owns one 16-byte slice of the head row and accumulates it over
 //                    the keys of its group; groups are reduced through shared memory at the end.
 // ~10 warp instructions per key (the lane-group kernel above spends ~30 and is issue-bound at ~4 TB/s on bf16 rows).
-// cp.async group bookkeeping: every thread commits the same sequence of (possibly empty) groups --
-//   K0, K1, V0, V1, then K(c+2) after pass-1 tile c, then V(c+2) after pass-2 tile c -- so the waits are static.
+// Measured alone (scripts/attn_roofline.py, 256 clips): bf16 rows 5.2 TB/s at 300 keys, 6.2 TB/s at 1024 keys; fp32 rows
+// 6.2-6.6 TB/s.  A variant with separate K and V rings (everything requested up front, 79 KB per CTA) was SLOWER (4.1 TB/s):
+// resident CTAs per SM matter more than the second exposed round trip.
 template <bool BF16, int NT, int CHUNK>
 __global__ void __launch_bounds__(NT) attn_decode_kernel(const DecodeAttnArgs p) {
   typedef typename KvIo<BF16>::T KT;
   constexpr int DH = 64, EPL = KvIo<BF16>::EPL, LPK = DH / EPL, NG = NT / LPK, NW = NT / 32;
   constexpr int ROWB = DH * (int)sizeof(KT), PITCH = ROWB + 16, STAGE = CHUNK * PITCH, KPG = CHUNK / NG;
   static_assert(CHUNK <= NT && CHUNK % NG == 0, "chunk shape");
-  extern __shared__ __align__(16) uint8_t dsm[];       // K ring [2][STAGE] | V ring [2][STAGE] | scores | partial outputs [NG][64]
+  extern __shared__ __align__(16) uint8_t dsm[];       // [2][STAGE] ring | scores [sc_floats] | partial outputs [NG][64]
   __shared__ float red[8];
-  float* sc = reinterpret_cast<float*>(dsm + 4 * STAGE);
+  float* sc = reinterpret_cast<float*>(dsm + 2 * STAGE);
   float* part = sc + p.sc_floats;
   pdl_prologue();
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
@@ -636,20 +635,15 @@ __global__ void __launch_bounds__(NT) attn_decode_kernel(const DecodeAttnArgs p)
     __syncthreads();
   }
   const int nch = (nkeys + CHUNK - 1) / CHUNK;
-  // rows [c*CHUNK, ..) of a head block -> ring stage `stage` (0,1: K ring; 2,3: V ring); an empty group when c >= nch
-  auto issue = [&](const KT* head, int c, int stage) {
-    if (c < nch) {
-      const int row0 = c * CHUNK, pieces = min(CHUNK, nkeys - row0) * LPK;
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(head + (size_t)row0 * DH);
-      const uint32_t dst = ring_u + stage * STAGE;
-      for (int q = tid; q < pieces; q += NT) cp_async_16(dst + (q / LPK) * PITCH + (q % LPK) * 16, src + (size_t)q * 16);
-    }
+  auto issue = [&](const KT* head, int c, int stage) {                   // rows [c*CHUNK, ..) of a head block -> ring[stage]
+    const int row0 = c * CHUNK, pieces = min(CHUNK, nkeys - row0) * LPK;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(head + (size_t)row0 * DH);
+    const uint32_t dst = ring_u + stage * STAGE;
+    for (int q = tid; q < pieces; q += NT) cp_async_16(dst + (q / LPK) * PITCH + (q % LPK) * 16, src + (size_t)q * 16);
     cp_async_commit();
   };
-  issue(khead, 0, 0);
-  issue(khead, 1, 1);
-  issue(vhead, 0, 2);
-  issue(vhead, 1, 3);
+  if (nch > 0) issue(khead, 0, 0);
+  if (nch > 1) issue(khead, 1, 1);
 
   float q[DH];
 #pragma unroll
@@ -658,9 +652,9 @@ __global__ void __launch_bounds__(NT) attn_decode_kernel(const DecodeAttnArgs p)
     q[i] = x.x; q[i + 1] = x.y; q[i + 2] = x.z; q[i + 3] = x.w;
   }
 
-  // ---- pass 1: scores.  Tile c < 2 may leave {K1, V0, V1} (+ refills) pending; later tiles only the newest refill.
+  // ---- pass 1: scores
   for (int c = 0; c < nch; ++c) {
-    if (c < 2) cp_async_wait<3>(); else cp_async_wait<1>();
+    if (c + 1 < nch) cp_async_wait<1>(); else cp_async_wait<0>();
     __syncthreads();
     const int j = c * CHUNK + tid;
     if (tid < CHUNK && j < nkeys) {
@@ -671,8 +665,11 @@ __global__ void __launch_bounds__(NT) attn_decode_kernel(const DecodeAttnArgs p)
       sc[j] = ((d[0] + d[1]) + (d[2] + d[3])) * p.scale;
     }
     __syncthreads();
-    issue(khead, c + 2, c & 1);
+    if (c + 2 < nch) issue(khead, c + 2, c & 1);
   }
+  // first V tiles in flight while the softmax statistics are computed
+  if (nch > 0) issue(vhead, 0, 0);
+  if (nch > 1) issue(vhead, 1, 1);
 
   // key-padding mask (masked_fill(-finfo.max)) and softmax statistics
   const uint8_t* km = p.key_mask ? p.key_mask + (size_t)b * p.Tk : nullptr;
@@ -703,23 +700,22 @@ __global__ void __launch_bounds__(NT) attn_decode_kernel(const DecodeAttnArgs p)
   for (int w = 1; w < NW; ++w) tot += red[w];
   const float inv = 1.f / tot;
 
-  // ---- pass 2: out = P V.  Every K group is complete; at most the newest V group may still be pending.
+  // ---- pass 2: out = P V
   float acc[EPL];
 #pragma unroll
   for (int i = 0; i < EPL; ++i) acc[i] = 0.f;
   for (int c = 0; c < nch; ++c) {
-    cp_async_wait<1>();
+    if (c + 1 < nch) cp_async_wait<1>(); else cp_async_wait<0>();
     __syncthreads();
-    const uint8_t* tile = dsm + (2 + (c & 1)) * STAGE + lk * 16;
+    const uint8_t* tile = dsm + (c & 1) * STAGE + lk * 16;
 #pragma unroll
     for (int i = 0; i < KPG; ++i) {
       const int jl = grp + NG * i, j = c * CHUNK + jl;
       if (j < nkeys) KvIo<BF16>::axpy(*reinterpret_cast<const uint4*>(tile + jl * PITCH), sc[j], acc);
     }
     __syncthreads();
-    issue(vhead, c + 2, 2 + (c & 1));
+    if (c + 2 < nch) issue(vhead, c + 2, c & 1);
   }
-  cp_async_wait<0>();
 #pragma unroll
   for (int i = 0; i < EPL; ++i) part[grp * DH + lk * EPL + i] = acc[i];
   __syncthreads();
@@ -814,23 +810,30 @@ int launch_attention_decode(DecodeAttnArgs a, int max_keys, cudaStream_t s) {
   DIM_REQUIRE(a.B > 0 && a.H > 0, "decode attention: empty");
   DIM_REQUIRE(a.kv_tok_stride == 64, "decode attention: the K/V caches must be head-major ([B,H,tokens,64])");
   const bool bf = a.kv_bf16 != 0;
-  // tile rows chosen so that the 4 ring stages + scores leave room for 3 CTAs per SM (bytes in flight >= 3 x 60 KB per SM)
-  constexpr int NT = 128, CHUNK_BF = 112, CHUNK_F32 = 56;
-  a.sc_floats = (max_keys + 3) / 4 * 4;
-  const size_t ring = bf ? 4 * (size_t)CHUNK_BF * (128 + 16) : 4 * (size_t)CHUNK_F32 * (256 + 16);   // K ring + V ring
-  size_t smem = ring + (size_t)(a.sc_floats + 16 * 64) * sizeof(float);
-  DIM_REQUIRE(smem <= 200 * 1024, "decode attention: too many keys for one CTA");
-  typedef void (*Kern)(const DecodeAttnArgs);
   if (g_attn_impl < 0) {
     const char* e = getenv("DIM_ATTN_IMPL");
-    g_attn_impl = (e && std::string(e) == "lanes") ? 1 : 0;
+    g_attn_impl = (e && std::string(e) == "lanes") ? 1 : (e && atoi(e) > 0 ? atoi(e) : 0);
   }
-  const bool lanes = g_attn_impl == 1;
-  Kern kern = lanes ? (bf ? (Kern)attn_decode_lanes<true, NT, 8> : (Kern)attn_decode_lanes<false, NT, 8>)
-                    : (bf ? (Kern)attn_decode_kernel<true, NT, CHUNK_BF> : (Kern)attn_decode_kernel<false, NT, CHUNK_F32>);
-  if (lanes) smem = (size_t)(a.sc_floats + 16 * 64) * sizeof(float);
-  static size_t configured[4] = {48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024};
-  const int slot = (bf ? 1 : 0) + (lanes ? 2 : 0);
+  // impl 0: ring kernel, 128 threads, 128-key (bf16) / 64-key (fp32) tiles; 1: lane-group kernel; 2, 3: ring-kernel shapes
+  // kept for A/B sweeps (scripts/attn_roofline.py)
+  typedef void (*Kern)(const DecodeAttnArgs);
+  Kern kern;
+  int nt = 128;
+  size_t ring = 0;
+  switch (g_attn_impl) {
+    case 1: kern = bf ? (Kern)attn_decode_lanes<true, 128, 8> : (Kern)attn_decode_lanes<false, 128, 8>; break;
+    case 2: nt = 64; ring = bf ? 2 * 64 * 144 : 2 * 32 * 272;
+            kern = bf ? (Kern)attn_decode_kernel<true, 64, 64> : (Kern)attn_decode_kernel<false, 64, 32>; break;
+    case 3: ring = bf ? 2 * 64 * 144 : 2 * 32 * 272;
+            kern = bf ? (Kern)attn_decode_kernel<true, 128, 64> : (Kern)attn_decode_kernel<false, 128, 32>; break;
+    default: ring = bf ? 2 * 128 * 144 : 2 * 64 * 272;
+            kern = bf ? (Kern)attn_decode_kernel<true, 128, 128> : (Kern)attn_decode_kernel<false, 128, 64>; break;
+  }
+  a.sc_floats = (max_keys + 3) / 4 * 4;
+  const size_t smem = ring + (size_t)(a.sc_floats + 16 * 64) * sizeof(float);
+  DIM_REQUIRE(smem <= 200 * 1024, "decode attention: too many keys for one CTA");
+  static size_t configured[8] = {48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024};
+  const int slot = (bf ? 1 : 0) + 2 * (g_attn_impl & 3);
   if (smem > configured[slot]) {
     DIM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[slot] = smem;
@@ -839,7 +842,7 @@ int launch_attention_decode(DecodeAttnArgs a, int max_keys, cudaStream_t s) {
     const double keys = a.append ? (double)(a.prof_pos + 1) : (double)a.Tk;   // K and V rows actually read
     const double esz = bf ? 2.0 : 4.0;
     ProfScope ps(CAT_ATTN_DECODE, s, a.B * (double)a.H * 64.0 * (2.0 * keys * esz + 8.0), 4.0 * a.B * a.H * 64.0 * keys);
-    DIM_CHECK_CUDA(launch_k(kern, dim3(a.B * a.H), dim3(NT), smem, s, a));
+    DIM_CHECK_CUDA(launch_k(kern, dim3(a.B * a.H), dim3(nt), smem, s, a));
   }
   DIM_LAUNCHED();
   return DIM_OK;

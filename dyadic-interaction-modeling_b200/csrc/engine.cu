@@ -154,7 +154,12 @@ int tc_add_weight(dim_handle_s* h, TcCtx& tc, const float* W, int N, int K) {
 // to fill 128-row MMA tiles, otherwise the fp32 FFMA kernels.
 inline bool tc_on(const TcCtx& tc, int M) { return tc.planes > 0 && M >= 64; }
 
-int run_gemm(const TcCtx& tc, const GemmArgs& a, __nv_bfloat16* scratch, cudaStream_t s) {
+// split_hint: DIM_SPLIT_NEVER for every prefill GEMM (M = clips x frames), DIM_SPLIT_DECODE for the per-step GEMMs (M = clips).
+// The split-K factor then depends on the call site and on (N, K) only -- never on how many clips share the batch -- so a
+// clip's bits do not depend on the batch it is decoded in (test_concurrent_group_decoding_is_bit_identical).
+int run_gemm(const TcCtx& tc, const GemmArgs& a_in, __nv_bfloat16* scratch, cudaStream_t s, int split_hint = DIM_SPLIT_NEVER) {
+  GemmArgs a = a_in;
+  a.split_hint = split_hint;
   auto it = tc.wmap.find(a.W);
   const bool tc_ok = tc_on(tc, a.M) && it != tc.wmap.end() && (scratch != nullptr || a.Ap != nullptr);
   if (!tc_ok) {
@@ -776,7 +781,7 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
         GemmArgs a;
         a.A = w.ln; a.lda = D; a.Ap = tcp ? w.ap : nullptr; a.W = SA.wqkv; a.C = w.qkv; a.ldc = 3 * inner; a.M = B; a.N = 3 * inner;
         a.K = D;
-        if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
+        if (int e = run_gemm(m.tc, a, w.ap, s, DIM_SPLIT_DECODE)) return e;
       }
       {
         DecodeAttnArgs a;
@@ -792,7 +797,7 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
         GemmArgs a;
         a.A = w.att; a.lda = inner; a.Ap = tcp ? w.ap : nullptr; a.W = SA.wo; a.residual = w.x; a.ldr = D; a.C = w.x; a.ldc = D;
         a.M = B; a.N = D; a.K = inner;
-        if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
+        if (int e = run_gemm(m.tc, a, w.ap, s, DIM_SPLIT_DECODE)) return e;
       }
       // --- cross attention over the cached context K/V
       if (int e = launch_layer_norm(w.x, CA.norm_g, CA.norm_b, tcp ? nullptr : w.ln, nullptr, B, D, 1e-5f, s, tcp ? w.ap : nullptr, P, D))
@@ -800,7 +805,7 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
       {
         GemmArgs a;
         a.A = w.ln; a.lda = D; a.Ap = tcp ? w.ap : nullptr; a.W = CA.wq; a.C = w.qkv; a.ldc = inner; a.M = B; a.N = inner; a.K = D;
-        if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
+        if (int e = run_gemm(m.tc, a, w.ap, s, DIM_SPLIT_DECODE)) return e;
       }
       {
         DecodeAttnArgs a;
@@ -817,7 +822,7 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
         GemmArgs a;
         a.A = w.att; a.lda = inner; a.Ap = tcp ? w.ap : nullptr; a.W = CA.wo; a.residual = w.x; a.ldr = D; a.C = w.x; a.ldc = D;
         a.M = B; a.N = D; a.K = inner;
-        if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
+        if (int e = run_gemm(m.tc, a, w.ap, s, DIM_SPLIT_DECODE)) return e;
       }
       // --- feed forward
       if (int e = launch_layer_norm(w.x, FF.norm_g, FF.norm_b, tcp ? nullptr : w.ln, nullptr, B, D, 1e-5f, s, tcp ? w.ap : nullptr, P, D))
@@ -827,13 +832,13 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
         a.A = w.ln; a.lda = D; a.Ap = tcp ? w.ap : nullptr; a.W = FF.w1; a.bias = FF.b1; a.M = B; a.N = F; a.K = D;
         a.act = DIM_ACT_GELU_ERF;
         if (tcp) { a.Cp = w.ap2; a.cp_planes = P; a.cp_kp = F; } else { a.C = w.ff; a.ldc = F; }
-        if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
+        if (int e = run_gemm(m.tc, a, w.ap, s, DIM_SPLIT_DECODE)) return e;
       }
       {
         GemmArgs a;
         a.A = w.ff; a.lda = F; a.Ap = tcp ? w.ap2 : nullptr; a.W = FF.w2; a.bias = FF.b2; a.residual = w.x; a.ldr = D; a.C = w.x;
         a.ldc = D; a.M = B; a.N = D; a.K = F;
-        if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
+        if (int e = run_gemm(m.tc, a, w.ap, s, DIM_SPLIT_DECODE)) return e;
       }
     }
     if (int e = launch_layer_norm(w.x, m.final_g, m.final_b, tcp ? nullptr : w.ln, nullptr, B, D, 1e-5f, s, tcp ? w.ap : nullptr, P, D))
@@ -841,7 +846,7 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
     {
       GemmArgs a;
       a.A = w.ln; a.lda = D; a.Ap = tcp ? w.ap : nullptr; a.W = m.logits_w; a.bias = m.logits_b; a.C = w.logits; a.ldc = V; a.M = B; a.N = V; a.K = D;
-      if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
+      if (int e = run_gemm(m.tc, a, w.ap, s, DIM_SPLIT_DECODE)) return e;
     }
     if (int e = launch_sample(w.logits, B, V, temperature, top_k, uniforms, steps, w.step, w.tokens, steps + 1, 1,
                               logits_out, steps * V, s))

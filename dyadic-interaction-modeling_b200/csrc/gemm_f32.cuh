@@ -6,6 +6,8 @@
 
 namespace dimb {
 
+enum { DIM_SPLIT_AUTO = 0, DIM_SPLIT_NEVER = 1, DIM_SPLIT_DECODE = 2 };
+
 struct GemmArgs {
   const float* A = nullptr; int lda = 0;      // [M,K] rows lda apart (conv mode: frames (B,T,Cin), lda = Cin)
   const float* W = nullptr;                   // [N,K] row-major
@@ -25,6 +27,7 @@ struct GemmArgs {
   int tab_mode = 0;                           //   1: row tab_index[r / tab_T] (or r / tab_T)  -- pe[batch]  (F4 quirk)
   const int32_t* tab_index = nullptr;         //   2: row (r % tab_T)                          -- pos_emb[t] * tab_scale
   int tab_T = 1; float tab_scale = 1.f;
+  int split_hint = 0;                         // tensor-core path: DIM_SPLIT_AUTO (by M) / _NEVER / _DECODE (see launch_gemm_tc)
 };
 
 int launch_gemm_f32(const GemmArgs& a, cudaStream_t s);

@@ -552,8 +552,9 @@ int launch_gemm_tc(const GemmArgs& e, const __nv_bfloat16* Ap, const __nv_bfloat
   const int total_kb = p.kblocks * p.npairs;
   int bn = e.N >= 128 ? 128 : (e.N > 32 ? 64 : 32);
   int splits = 1;
-  if (e.M < 2048) {
-    if (planes == 1 && e.M <= 512) {
+  const bool skinny = e.split_hint == DIM_SPLIT_DECODE || (e.split_hint == DIM_SPLIT_AUTO && e.M < 2048);
+  if (skinny) {
+    if (planes == 1 && (e.split_hint == DIM_SPLIT_DECODE || e.M <= 512)) {
       // Decode-step GEMMs with plain bf16 operands (measured sweep, profiles/r01g_tc_sweep_*.txt): a CTA ingests ~60 B/clk, so
       // its main loop costs (128 + BN) * K * 2 B / 60 and the 128-row A tile dominates; the DSMEM reduction of split-K costs
       // ~20 B/clk per SM.  Narrow tiles with the whole K per CTA win for K <= 1152 (no cluster, 16 KB epilogue tile); a 4-way

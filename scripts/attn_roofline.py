@@ -19,18 +19,19 @@ PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if 
 def main():
     lib = _lib.load()
     fn = lib.dim_debug_attn_decode
+    fn.restype = C.c_int
     fn.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     s = torch.cuda.current_stream().cuda_stream
     H, NB = 12, 6
     for bf16 in (1, 0):
         dt = torch.bfloat16 if bf16 else torch.float32
-        for B, Tk in ((128, 300), (256, 300), (256, 150), (256, 1024)):
+        for B, Tk in ((256, 300), (256, 150), (256, 40), (256, 1024)):
             ks = [torch.randn(B, H, Tk, 64, device="cuda").to(dt) for _ in range(NB)]
             vs = [torch.randn(B, H, Tk, 64, device="cuda").to(dt) for _ in range(NB)]
             q = torch.randn(B, H * 64, device="cuda")
             out = torch.empty(B, H * 64, device="cuda")
             ref = None
-            for impl, name in ((0, "ring"), (1, "lanes")):
+            for impl, name in ((0, "ring nt128 tile128/64"), (2, "ring nt64 tile64/32"), (3, "ring nt128 tile64/32"), (1, "lanes")):
                 def call(i):
                     _lib.check(fn(impl, ks[i % NB].data_ptr(), vs[i % NB].data_ptr(), q.data_ptr(), out.data_ptr(), B, H, Tk, bf16, s))
                 for i in range(3):
