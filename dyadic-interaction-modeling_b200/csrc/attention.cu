@@ -814,8 +814,9 @@ int launch_attention_decode(DecodeAttnArgs a, int max_keys, cudaStream_t s) {
     const char* e = getenv("DIM_ATTN_IMPL");
     g_attn_impl = (e && std::string(e) == "lanes") ? 1 : (e && atoi(e) > 0 ? atoi(e) : 0);
   }
-  // impl 0: ring kernel, 128 threads, 128-key (bf16) / 64-key (fp32) tiles; 1: lane-group kernel; 2, 3: ring-kernel shapes
-  // kept for A/B sweeps (scripts/attn_roofline.py)
+  // impl 0 (default): ring kernel -- bf16 rows: 64 threads, 64-key tiles (24 KB / CTA, ~10 CTAs per SM: fewest waves, 5.4 TB/s
+  // at 300 keys); fp32 rows: 128 threads, 64-key tiles (6.2 TB/s).  1: lane-group kernel; 2, 3, 4: other ring-kernel shapes kept
+  // for A/B sweeps (scripts/attn_roofline.py; profiles/r01j_attn_roofline.jsonl)
   typedef void (*Kern)(const DecodeAttnArgs);
   Kern kern;
   int nt = 128;
@@ -826,14 +827,18 @@ int launch_attention_decode(DecodeAttnArgs a, int max_keys, cudaStream_t s) {
             kern = bf ? (Kern)attn_decode_kernel<true, 64, 64> : (Kern)attn_decode_kernel<false, 64, 32>; break;
     case 3: ring = bf ? 2 * 64 * 144 : 2 * 32 * 272;
             kern = bf ? (Kern)attn_decode_kernel<true, 128, 64> : (Kern)attn_decode_kernel<false, 128, 32>; break;
-    default: ring = bf ? 2 * 128 * 144 : 2 * 64 * 272;
+    case 4: ring = bf ? 2 * 128 * 144 : 2 * 64 * 272;
             kern = bf ? (Kern)attn_decode_kernel<true, 128, 128> : (Kern)attn_decode_kernel<false, 128, 64>; break;
+    default:
+      if (bf) { nt = 64; ring = 2 * 64 * 144; kern = (Kern)attn_decode_kernel<true, 64, 64>; }
+      else { ring = 2 * 64 * 272; kern = (Kern)attn_decode_kernel<false, 128, 64>; }
+      break;
   }
   a.sc_floats = (max_keys + 3) / 4 * 4;
   const size_t smem = ring + (size_t)(a.sc_floats + 16 * 64) * sizeof(float);
   DIM_REQUIRE(smem <= 200 * 1024, "decode attention: too many keys for one CTA");
   static size_t configured[8] = {48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024};
-  const int slot = (bf ? 1 : 0) + 2 * (g_attn_impl & 3);
+  const int slot = (bf ? 1 : 0) + 2 * (g_attn_impl == 4 ? 0 : (g_attn_impl & 3));
   if (smem > configured[slot]) {
     DIM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[slot] = smem;

@@ -688,11 +688,13 @@ extern "C" int dim_slmft_build(dim_handle_t h, const dim_s2s_config* cfg, int pr
 // Per-row results do not depend on the grouping (no cross-row arithmetic; split-K depends on K only).
 constexpr int kMaxGroups = 8;
 int plan_groups(const S2SModel& m, int B, int* begin /*[kMaxGroups+1]*/) {
-  // tuning hooks: DIM_GROUP_ROWS (rows per group, multiple of 64; default 128), DIM_MAX_GROUPS (default 1: one chain --
-  // with the cp.async attention kernel and the narrow-tile decode GEMMs a single chain measured faster than 2 concurrent
-  // groups, 271 vs 282 ms per step, profiles/r01_notes.md), DIM_NO_GROUPS
+  // tuning hooks: DIM_GROUP_ROWS (rows per group, multiple of 64; default 128), DIM_MAX_GROUPS, DIM_NO_GROUPS.
+  // Default: plain bf16 operands decode as ONE chain (with the cp.async attention kernel and the narrow-tile decode GEMMs a
+  // single chain measured faster than 2 concurrent groups: 271 vs 282 ms per step); the fp32-grade mode (3-6x longer GEMM
+  // main loops) keeps up to 4 concurrent groups (160 k vs 151 k frames/s).  profiles/r01_notes.md
   static const int kGroupRows = getenv("DIM_GROUP_ROWS") ? std::max(64, atoi(getenv("DIM_GROUP_ROWS")) / 64 * 64) : 128;
-  static const int max_groups = getenv("DIM_MAX_GROUPS") ? std::min(kMaxGroups, std::max(1, atoi(getenv("DIM_MAX_GROUPS")))) : 1;
+  static const int env_groups = getenv("DIM_MAX_GROUPS") ? std::min(kMaxGroups, std::max(1, atoi(getenv("DIM_MAX_GROUPS")))) : 0;
+  const int max_groups = env_groups ? env_groups : (m.tc.planes == 1 ? 1 : 4);
   int ng = 1;
   if (tc_on(m.tc, B) && B >= 2 * kGroupRows) ng = std::min(max_groups, B / kGroupRows);
   static const bool no_groups = getenv("DIM_NO_GROUPS") != nullptr;

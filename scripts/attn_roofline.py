@@ -31,7 +31,7 @@ def main():
             q = torch.randn(B, H * 64, device="cuda")
             out = torch.empty(B, H * 64, device="cuda")
             ref = None
-            for impl, name in ((0, "ring nt128 tile128/64"), (2, "ring nt64 tile64/32"), (3, "ring nt128 tile64/32"), (1, "lanes")):
+            for impl, name in ((0, "ring (default: bf16 nt64 tile64; fp32 nt128 tile64)"), (4, "ring nt128 tile128/64"), (2, "ring nt64 tile64/32"), (3, "ring nt128 tile64/32"), (1, "lanes")):
                 def call(i):
                     _lib.check(fn(impl, ks[i % NB].data_ptr(), vs[i % NB].data_ptr(), q.data_ptr(), out.data_ptr(), B, H, Tk, bf16, s))
                 for i in range(3):
