@@ -814,8 +814,9 @@ int launch_attention_decode(DecodeAttnArgs a, int max_keys, cudaStream_t s) {
     const char* e = getenv("DIM_ATTN_IMPL");
     g_attn_impl = (e && std::string(e) == "lanes") ? 1 : (e && atoi(e) > 0 ? atoi(e) : 0);
   }
-  // impl 0 (default): ring kernel -- bf16 rows: 64 threads, 64-key tiles (24 KB / CTA, ~10 CTAs per SM: fewest waves, 5.4 TB/s
-  // at 300 keys); fp32 rows: 128 threads, 64-key tiles (6.2 TB/s).  1: lane-group kernel; 2, 3, 4: other ring-kernel shapes kept
+  // impl 0 (default): bf16 rows: ring kernel, 64 threads, 64-key tiles (24 KB / CTA, ~10 CTAs per SM: fewest waves, 5.4 TB/s
+  // at 300 keys); fp32 rows: lane-group kernel (6.2 TB/s, co-resides with the concurrent decode groups of the fp32-grade
+  // mode).  1: lane-group kernel; 2, 3, 4: ring-kernel shapes kept
   // for A/B sweeps (scripts/attn_roofline.py; profiles/r01j_attn_roofline.jsonl)
   typedef void (*Kern)(const DecodeAttnArgs);
   Kern kern;
@@ -831,7 +832,7 @@ int launch_attention_decode(DecodeAttnArgs a, int max_keys, cudaStream_t s) {
             kern = bf ? (Kern)attn_decode_kernel<true, 128, 128> : (Kern)attn_decode_kernel<false, 128, 64>; break;
     default:
       if (bf) { nt = 64; ring = 2 * 64 * 144; kern = (Kern)attn_decode_kernel<true, 64, 64>; }
-      else { ring = 2 * 64 * 272; kern = (Kern)attn_decode_kernel<false, 128, 64>; }
+      else kern = (Kern)attn_decode_lanes<false, 128, 8>;     // fp32 rows: equal bandwidth (6.2 TB/s), 5 KB of smem per CTA
       break;
   }
   a.sc_floats = (max_keys + 3) / 4 * 4;

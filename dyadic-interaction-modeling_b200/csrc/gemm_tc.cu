@@ -432,15 +432,23 @@ int launch_tc_act(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcParams
   cfg.blockDim = dim3(192);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
+  // the S K-slices of one output tile form a cluster; un-split launches carry NO cluster attribute (plain CTA launch path)
   cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;     // the S K-slices of one output tile form a cluster
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = p.splits;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  int na = 0;
+  if (p.splits > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = p.splits;
+    ++na;
+  }
+  if (g_pdl_on) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = g_pdl_on ? 2 : 1;
+  cfg.numAttrs = na;
   // algorithmic traffic: every operand plane once + the fp32 result; skinny (M < 2048: decode-step) launches are reported
   // separately because their roofline is HBM (weights streamed once per step), not the tensor pipe
   const int planes_n = p.npairs == 1 ? 1 : (p.npairs == 3 ? 2 : 3);
