@@ -563,15 +563,12 @@ int launch_gemm_tc(const GemmArgs& e, const __nv_bfloat16* Ap, const __nv_bfloat
   const bool skinny = e.split_hint == DIM_SPLIT_DECODE || (e.split_hint == DIM_SPLIT_AUTO && e.M < 2048);
   if (skinny) {
     if (planes == 1 && (e.split_hint == DIM_SPLIT_DECODE || e.M <= 512)) {
-      // Decode-step GEMMs with plain bf16 operands (measured sweep, profiles/r01g_tc_sweep_*.txt): a CTA ingests ~60 B/clk, so
-      // its main loop costs (128 + BN) * K * 2 B / 60 and the 128-row A tile dominates; the DSMEM reduction of split-K costs
-      // ~20 B/clk per SM.  Narrow tiles with the whole K per CTA win for K <= 1152 (no cluster, 16 KB epilogue tile); a 4-way
-      // split only when the N tiles alone would leave most SMs idle, or when K is long.  Depends on (N, K) only, never on M.
+      // Decode-step GEMMs with plain bf16 operands (measured: profiles/r01g_tc_sweep_*.txt, r01l_graph_gap.txt): a CTA ingests
+      // ~60 B/clk, so its main loop costs (128 + BN) * K * 2 B / 60 and the 128-row A tile dominates; the DSMEM reduction of a
+      // split costs ~20 B/clk per SM and a cluster launch is slower to schedule.  Narrow tiles with the whole K per CTA and no
+      // cluster win for K <= 1152; long K (FF2, 4608) takes 64-wide tiles split 4 ways.  Depends on K only, never on M or N.
       if (kp >= 2048) { bn = 64; splits = 4; }
-      else {
-        bn = 32;
-        splits = (cdiv(e.N, 32) <= 24 && total_kb >= 16) ? 4 : 1;
-      }
+      else { bn = 32; splits = 1; }
     } else {
       // fp32-grade plane products (3-6x the k-blocks) and mid-sized M: split K over a cluster so that every CTA owns >= ~4 k-blocks.
       const int want = total_kb / 4;
