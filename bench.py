@@ -123,6 +123,49 @@ def cpu_oracle_sample(frames, threads=None, repeats=1, warm=True):
     return (frames - 1) / best, best
 
 
+def attn_decode_alone(lib, B, H, T, steps_ar, bf16, dev):
+    """Time the decode-attention kernel alone at the launch shapes of one decode step (see the roofline comment in run_native).
+    Algorithmic bytes per launch = K and V head rows read once: B*H*keys*64*2*elem_size."""
+    import ctypes as C
+    try:
+        fn = lib.dim_debug_attn_decode
+    except AttributeError:
+        return None
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    dt = torch.bfloat16 if bf16 else torch.float32
+    esz = 2 if bf16 else 4
+    NB = 6
+    ks = [torch.randn(B, H, T, 64, device=dev).to(dt) for _ in range(NB)]
+    vs = [torch.randn(B, H, T, 64, device=dev).to(dt) for _ in range(NB)]
+    q = torch.randn(B, H * 64, device=dev)
+    out = torch.empty(B, H * 64, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    quart = [max(1, int(steps_ar * f)) for f in (0.125, 0.375, 0.625, 0.875)]       # self attention: pos+1 keys at quartile midpoints
+    shapes = [(T, 4.0)] + [(k, 1.0) for k in quart]                                   # (keys, launches per step of this shape): 4 layers
+    tot_t = tot_b = tot_n = 0.0
+    for keys, weight in shapes:
+        def call(i):
+            rc = fn(-1, ks[i % NB].data_ptr(), vs[i % NB].data_ptr(), q.data_ptr(), out.data_ptr(), B, H, keys, 1 if bf16 else 0, s)
+            if rc != 0:
+                raise RuntimeError("dim_debug_attn_decode failed")
+        for i in range(3):
+            call(i)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(12):
+            call(i)
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) / 12 * 1e-3
+        tot_t += weight * t
+        tot_b += weight * B * H * keys * 64 * 2 * esz
+        tot_n += weight
+    return {"GB/s": tot_b / tot_t / 1e9, "avg_launch_us": 1e6 * tot_t / tot_n,
+            "shapes": f"{B} clips x {H} heads, cross {T} keys x4, self {quart} keys (one launch each), {'bf16' if bf16 else 'fp32'} K/V"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (restated oracle: x-transformers is not installable offline and
     seq2seq_pretrain.py hard-codes .cuda()) on this box's host cores.  Rank 0 only."""
@@ -265,13 +308,34 @@ def run_native(args):
     value = frames_total * args.steps / (ms / 1e3)
     e2e_value = frames_total * args.steps / (ms_e2e / 1e3)
     peaks = load_peaks()
-    tot_ms = sum(p["ms"] for p in prof) or 1.0
-    prof.sort(key=lambda p: -p["ms"])
+    # The profiled step brackets EVERY launch with two CUDA events; that costs several microseconds per launch, which is
+    # most of what a 3-8 us decode-step kernel "takes" in that mode.  Calibrate it (same bracketing around a 1-row LayerNorm,
+    # a ~2 us kernel) and report both the raw and the corrected time of every category; shares use the corrected times.
+    ovh_us = 0.0
+    try:
+        from dim_b200 import ops as _ops
+        xx, gg = torch.randn(1, 64, device=dev), torch.ones(64, device=dev)
+        for _ in range(20):
+            _ops.layer_norm(xx, gg)
+        _lib.profile_enable(True)
+        for _ in range(200):
+            _ops.layer_norm(xx, gg)
+        cal = [p for p in _lib.profile_collect() if p["category"] == "layer_norm"]
+        _lib.profile_enable(False)
+        if cal:
+            ovh_us = max(0.0, 1e3 * cal[0]["ms"] / cal[0]["launches"] - 2.0)
+    except Exception:
+        ovh_us = 0.0
+    for p in prof:
+        p["ms_corr"] = max(p["ms"] - p["launches"] * ovh_us * 1e-3, 0.05 * p["ms"])
+    tot_ms = sum(p["ms_corr"] for p in prof) or 1.0
+    prof.sort(key=lambda p: -p["ms_corr"])
     top = prof[0]
     hbm_cats = {"attn_decode", "vq_gather", "layer_norm", "instance_norm", "gemm_f32_skinny", "gemm_bf16_tcgen05_skinny", "misc",
                 "sample"}
-    per_launch_ms = top["ms"] / top["launches"]
-    tensor_peak = peaks["tensor_sustained"]
+    per_launch_ms = top["ms_corr"] / top["launches"]
+    how = ("one extra profiled step (CUDA events around every launch on the launching stream), per-launch bracketing cost of "
+           f"{ovh_us:.1f} us (calibrated live) subtracted")
     if top["category"] in hbm_cats:
         ach = top["bytes"] / top["launches"] / (per_launch_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"]}
@@ -279,15 +343,25 @@ def run_native(args):
         ach = top["flops"] / top["launches"] / (per_launch_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": peaks["tensor_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tensor_sustained"]}
+    if top["category"] == "attn_decode":
+        # the dominant kernel timed ALONE: the launch shapes of one decode step (cross attention over T keys, self attention
+        # over pos+1 keys at the quartile midpoints of the decode), back to back on this stream, CUDA events around each batch,
+        # K/V buffers cycled so that every launch streams from HBM (6 x 2 x B*H*T*64 elements >> L2)
+        alone = attn_decode_alone(_lib.load(), B, S2SConfig().heads, T, steps_ar, prec == PREC_BF16, dev)
+        if alone:
+            roof = {"bound": "hbm", "achieved": alone["GB/s"], "peak": peaks["hbm"], "unit": "GB/s", "frac": alone["GB/s"] / peaks["hbm"]}
+            per_launch_ms = alone["avg_launch_us"] * 1e-3
+            how = ("decode-attention launches of one step replayed alone, back to back on the launching stream, CUDA events around "
+                   "each batch of 12 launches, K/V buffers cycled (HBM-resident); shapes: " + alone["shapes"])
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(top["category"])
     roof.update(traffic=traffic, kernel=top["category"], launches_per_step=top["launches"], avg_launch_us=1e3 * per_launch_ms,
-                share_of_step=top["ms"] / tot_ms, peak_source=peaks["source"],
-                how="CUDA events around every launch of one extra (untimed-for-value) step, on the launching stream")
-    kernels = [{"kernel": p["category"], "launches": p["launches"], "ms": round(p["ms"], 3), "share": round(p["ms"] / tot_ms, 4),
-                "GB/s": round(p["bytes"] / (p["ms"] * 1e-3) / 1e9, 1), "TFLOP/s": round(p["flops"] / (p["ms"] * 1e-3) / 1e12, 2)}
+                share_of_step=top["ms_corr"] / tot_ms, peak_source=peaks["source"], how=how)
+    kernels = [{"kernel": p["category"], "launches": p["launches"], "ms_raw": round(p["ms"], 3), "ms": round(p["ms_corr"], 3),
+                "share": round(p["ms_corr"] / tot_ms, 4),
+                "GB/s": round(p["bytes"] / (p["ms_corr"] * 1e-3) / 1e9, 1), "TFLOP/s": round(p["flops"] / (p["ms_corr"] * 1e-3) / 1e12, 2)}
                for p in prof]
 
     # second arm, same workload: the fp32-grade parity mode (every GEMM operand split exactly into 3 bf16 planes, fp32 KV

@@ -863,7 +863,7 @@ using namespace dimb;
 extern "C" int dim_debug_attn_decode(int impl, void* k, void* v, const float* q, float* out, int B, int H, int Tk, int bf16,
                                      void* stream) {
   if (int e = ensure_device()) return e;
-  dimb::g_attn_impl = impl;
+  if (impl >= 0) dimb::g_attn_impl = impl;          // impl < 0: whatever the library would use (default / DIM_ATTN_IMPL)
   DecodeAttnArgs a;
   a.q = q; a.ldq = H * 64; a.k = k; a.v = v; a.kv_bf16 = bf16;
   a.kv_batch_stride = (size_t)H * Tk * 64; a.kv_head_stride = (size_t)Tk * 64; a.kv_tok_stride = 64;
