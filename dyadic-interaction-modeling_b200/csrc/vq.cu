@@ -184,18 +184,18 @@ __global__ void __launch_bounds__(256) vq_gather_bulk_kernel(const int64_t* __re
 // so no row ever waits for an index read that queues behind the write stream in the memory controller.  Codebook rows come
 // from L1/L2 (256 KB codebook), each warp keeps R rows (R x 512 B) in flight.
 template <int CH, bool STREAM>
-__global__ void __launch_bounds__(256) vq_gather_pf_kernel(const int64_t* __restrict__ idx, const float* __restrict__ E,
+__global__ void __launch_bounds__(CH < 256 ? CH : 256) vq_gather_pf_kernel(const int64_t* __restrict__ idx, const float* __restrict__ E,
                                                            float* __restrict__ out, int N, int D4, int K,
                                                            int32_t* __restrict__ bad) {
   __shared__ int codes[2][CH];
-  constexpr int PER = CH / 256, R = 4;
+  constexpr int NTH = CH < 256 ? CH : 256, PER = CH / NTH, R = 4, NWARP = NTH / 32;      // launched with NTH threads
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nchunks = (N + CH - 1) / CH;
   int nbad = 0;
   auto fetch = [&](int chunk, int64_t* reg) {
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
-      const size_t i = (size_t)chunk * CH + tid + 256 * u;
+      const size_t i = (size_t)chunk * CH + tid + NTH * u;
       reg[u] = i < (size_t)N ? __ldcs(idx + i) : 0;
     }
   };
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(256) vq_gather_pf_kernel(const int64_t* __rest
     for (int u = 0; u < PER; ++u) {
       int64_t c = reg[u];
       if (c < 0 || c >= K) { ++nbad; c = c < 0 ? 0 : K - 1; }
-      codes[buf][tid + 256 * u] = (int)c;
+      codes[buf][tid + NTH * u] = (int)c;
     }
   };
   int64_t reg[PER];
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256) vq_gather_pf_kernel(const int64_t* __rest
     if (next < nchunks) fetch(next, reg);                          // in flight while this chunk's rows are written
     const size_t r0 = (size_t)chunk * CH;
     const int rows = (int)min((size_t)CH, (size_t)N - r0);
-    for (int r = warp * R; r < rows; r += 8 * R) {
+    for (int r = warp * R; r < rows; r += NWARP * R) {
       for (int c4 = lane; c4 < D4; c4 += 32) {
         float4 v[R];
 #pragma unroll
@@ -299,8 +299,9 @@ int launch_vq_argmin(const float* z, const float* E, int64_t* idx, int N, int D,
   return DIM_OK;
 }
 
-// tuning hook.  -1: automatic; 0: warp-per-row, index read in line; 1: smem-staged TMA bulk stores (measured SLOWER: 2.9 TB/s
-// vs 4.6 TB/s, profiles/r01_notes.md); 2 / 3: prefetched index stream with streaming / plain stores
+// tuning hook.  -1: automatic (256-code chunks with a prefetched index stream: 5.7-5.9 TB/s = 89-92 % of the measured copy peak
+// at 1-4 M codes, profiles/r01o_vq_roofline.jsonl); 0: warp-per-row, index read in line (4.6 TB/s: every row waits for an
+// index read that queues behind the write stream); 1: smem-staged TMA bulk stores (2.9 TB/s); 2..6: prefetched-index variants
 int g_vq_gather_mode = -1;
 
 int launch_vq_gather(const int64_t* idx, const float* E, float* out, int N, int D, int K, int32_t* bad, cudaStream_t s) {
@@ -309,12 +310,16 @@ int launch_vq_gather(const int64_t* idx, const float* E, float* out, int N, int 
   constexpr int TR = 32, NBUF = 4;
   const size_t smem = (size_t)NBUF * TR * D * sizeof(float);
   const bool bulk_ok = ((uintptr_t)out & 15) == 0 && smem <= 96 * 1024;
-  const int mode = g_vq_gather_mode >= 0 ? g_vq_gather_mode : 0;
-  if (mode == 2 || mode == 3) {
-    constexpr int CH = 512;
-    const int blocks = std::min(cdiv(N, CH), 148 * 6);
-    if (mode == 2) vq_gather_pf_kernel<CH, true><<<blocks, 256, 0, s>>>(idx, E, out, N, D / 4, K, bad);
-    else vq_gather_pf_kernel<CH, false><<<blocks, 256, 0, s>>>(idx, E, out, N, D / 4, K, bad);
+  const int mode = g_vq_gather_mode >= 0 ? g_vq_gather_mode : (N >= 1024 ? 6 : 0);
+  if (mode >= 2) {
+    // 2: 512-code chunks, streaming stores; 3: same, plain stores; 4 / 5 / 6: 128 / 64 / 256-code chunks (tuning sweep)
+    const int ch = mode == 4 ? 128 : (mode == 5 ? 64 : (mode == 6 ? 256 : 512));
+    const int blocks = std::min(cdiv(N, ch), 148 * 8);
+    if (mode == 3) vq_gather_pf_kernel<512, false><<<std::min(cdiv(N, 512), 148 * 6), 256, 0, s>>>(idx, E, out, N, D / 4, K, bad);
+    else if (mode == 4) vq_gather_pf_kernel<128, true><<<blocks, 128, 0, s>>>(idx, E, out, N, D / 4, K, bad);
+    else if (mode == 5) vq_gather_pf_kernel<64, true><<<blocks, 64, 0, s>>>(idx, E, out, N, D / 4, K, bad);
+    else if (mode == 6) vq_gather_pf_kernel<256, true><<<blocks, 256, 0, s>>>(idx, E, out, N, D / 4, K, bad);
+    else vq_gather_pf_kernel<512, true><<<std::min(cdiv(N, 512), 148 * 6), 256, 0, s>>>(idx, E, out, N, D / 4, K, bad);
   } else if (mode == 1 && bulk_ok) {
     static size_t configured = 48 * 1024;
     if (smem > configured) {

@@ -45,7 +45,8 @@ def main():
         print(json.dumps({"kernel": "write_only_ceiling(torch zero_)", "codes": N, "us": t * 1e6, "GB/s": N * 512 / t / 1e9,
                           "frac_of_hbm_peak": N * 512 / t / 1e9 / PEAK}))
         for mode, name in ((0, "warp-per-row st.cs"), (1, "smem-staged TMA bulk store"), (2, "prefetched idx + st.cs"),
-                           (3, "prefetched idx + plain st"), (-1, "default")):
+                           (3, "prefetched idx + plain st"), (6, "prefetched idx, 256-code chunks"), (4, "prefetched idx, 128-code chunks"),
+                           (5, "prefetched idx, 64-code chunks"), (-1, "default")):
             lib.dim_debug_vq_gather_mode(mode)
             out.zero_()
             t = timeit(lambda: lib.dim_vq_gather(idx.data_ptr(), E.data_ptr(), out.data_ptr(), N, 128, 512, None, s))
