@@ -386,9 +386,9 @@ def run_native(args):
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        fps, secs = cpu_oracle_sample(T if T <= 300 else 300, threads=cores, repeats=2)
+        fps, secs = cpu_oracle_sample(T if T <= 300 else 300, threads=cores, repeats=10)
         cpu = {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"1 clip x {min(T, 300)} frames, best of 2 ({secs:.1f} s), oracle/slmft.py forward_val (restated reference, "
+               "sample": f"1 clip x {min(T, 300)} frames, best of 10 runs ({secs:.1f} s each, ~10 s of CPU work), oracle/slmft.py forward_val (restated reference, "
                          f"cross-KV once, discarded work skipped), PyTorch CPU fp32"}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
