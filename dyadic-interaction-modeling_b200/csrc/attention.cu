@@ -297,17 +297,39 @@ __global__ void __launch_bounds__(128) attn_prefill_mma(const AttnArgs p) {
     }
 
     // ---- scale, mask, online softmax (rows qrow0 -> s[.][0..1], qrow0 + 8 -> s[.][2..3])
+    // Interior tiles (all 64 keys exist, none padded, entirely below this warp's diagonal) skip the per-element tests; the
+    // key-padding mask of the tile is fetched once per warp (2 bytes per lane) and turned into a 64-bit ballot.
+    unsigned long long keep = ~0ull;                    // bit j: key k0 + j is not padding
+    if (km) {
+      const int ka = k0 + lane, kb2 = k0 + 32 + lane;
+      const unsigned lo = __ballot_sync(0xffffffffu, ka < klen ? km[ka] != 0 : true);
+      const unsigned hi = __ballot_sync(0xffffffffu, kb2 < klen ? km[kb2] != 0 : true);
+      keep = (unsigned long long)lo | ((unsigned long long)hi << 32);
+    }
+    const bool interior = (k0 + 64 <= klen) && keep == ~0ull && (!p.causal || k0 + 63 <= q0 + warp * 16);
     float tmax[2] = {-INFINITY, -INFINITY};
+    if (interior) {
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int kj = k0 + nt * 8 + 2 * (lane & 3) + (e & 1), qi = qrow0 + (e >> 1) * 8;
-        float v = s[nt][e] * p.scale;
-        if (kj >= klen) v = -INFINITY;                                      // not a key at all
-        else if ((km && !km[kj]) || (p.causal && kj > qi)) v = -FLT_MAX;    // masked_fill(-finfo.max)
-        s[nt][e] = v;
-        tmax[e >> 1] = fmaxf(tmax[e >> 1], v);
+        for (int e = 0; e < 4; ++e) {
+          const float v = s[nt][e] * p.scale;
+          s[nt][e] = v;
+          tmax[e >> 1] = fmaxf(tmax[e >> 1], v);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int jj = nt * 8 + 2 * (lane & 3) + (e & 1), kj = k0 + jj, qi = qrow0 + (e >> 1) * 8;
+          float v = s[nt][e] * p.scale;
+          if (kj >= klen) v = -INFINITY;                                      // not a key at all
+          else if (!((keep >> jj) & 1ull) || (p.causal && kj > qi)) v = -FLT_MAX;    // masked_fill(-finfo.max)
+          s[nt][e] = v;
+          tmax[e >> 1] = fmaxf(tmax[e >> 1], v);
+        }
       }
     }
     float alpha[2];
@@ -324,7 +346,9 @@ __global__ void __launch_bounds__(128) attn_prefill_mma(const AttnArgs p) {
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float pv = (s[nt][e] == -INFINITY) ? 0.f : expf(s[nt][e] - m_run[e >> 1]);
+        // NP == 1 is the plain-bf16 mode (P is rounded to bf16 right below): the 2-instruction exp is exact enough there
+        const float x = s[nt][e] - m_run[e >> 1];
+        const float pv = (s[nt][e] == -INFINITY) ? 0.f : (NP == 1 ? __expf(x) : expf(x));
         s[nt][e] = pv;
         psum[e >> 1] += pv;
       }

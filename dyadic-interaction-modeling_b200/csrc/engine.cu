@@ -77,7 +77,8 @@ struct S2SModel {
   const float *final_g = nullptr, *final_b = nullptr, *logits_w = nullptr, *logits_b = nullptr;
   // CUDA graph of ONE decode step (the step index lives in device memory, so every step replays the same graph)
   struct StepGraph {
-    cudaGraphExec_t exec = nullptr;
+    cudaGraphExec_t exec = nullptr;      // one decode step
+    cudaGraphExec_t exec_u = nullptr;    // kUnroll decode steps back to back (fewer graph launches per generate)
     std::vector<uintptr_t> key;
     cudaStream_t stream = nullptr;       // side stream the graph runs on (capture is not allowed on the legacy stream)
     cudaEvent_t fork = nullptr, join = nullptr;
@@ -872,24 +873,36 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
       DIM_CHECK_CUDA(cudaEventCreateWithFlags(&G.fork, cudaEventDisableTiming));
       DIM_CHECK_CUDA(cudaEventCreateWithFlags(&G.join, cudaEventDisableTiming));
     }
+    // steps per graph launch (DIM_GRAPH_UNROLL, default 1).  Measured: 1, 13, 23 and 299 steps per graph all give 260.5-261.3 ms
+    // per bench step -- the gap between consecutive graph launches is not what limits the decode (profiles/r01_notes.md).
+    static const int unroll = getenv("DIM_GRAPH_UNROLL") ? std::max(1, atoi(getenv("DIM_GRAPH_UNROLL"))) : 1;
     if (G.exec == nullptr || G.key != key) {
       if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+      if (G.exec_u) { cudaGraphExecDestroy(G.exec_u); G.exec_u = nullptr; }
       if (int e = enqueue_step(0, s)) return e;                       // warm (lazy attribute setup, tensor maps) outside capture
       if (int e = launch_set_step(w.step, 0, s)) return e;            // ... and rewind the step counter it advanced
       DIM_CHECK_CUDA(cudaStreamSynchronize(s));
-      cudaGraph_t graph = nullptr;
-      DIM_CHECK_CUDA(cudaStreamBeginCapture(G.stream, cudaStreamCaptureModeThreadLocal));
-      int rc = enqueue_step(0, G.stream);
-      cudaError_t ce = cudaStreamEndCapture(G.stream, &graph);
-      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-      DIM_CHECK_CUDA(ce);
-      DIM_CHECK_CUDA(cudaGraphInstantiate(&G.exec, graph, 0));
-      cudaGraphDestroy(graph);
+      for (int pass = 0; pass < 2; ++pass) {
+        const int n = pass == 0 ? 1 : unroll;
+        if (pass == 1 && (unroll <= 1 || steps < unroll)) break;
+        cudaGraph_t graph = nullptr;
+        DIM_CHECK_CUDA(cudaStreamBeginCapture(G.stream, cudaStreamCaptureModeThreadLocal));
+        int rc = 0;
+        for (int i = 0; i < n && rc == 0; ++i) rc = enqueue_step(i, G.stream);
+        cudaError_t ce = cudaStreamEndCapture(G.stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        DIM_CHECK_CUDA(ce);
+        DIM_CHECK_CUDA(cudaGraphInstantiate(pass == 0 ? &G.exec : &G.exec_u, graph, 0));
+        cudaGraphDestroy(graph);
+      }
       G.key = key;
     }
     DIM_CHECK_CUDA(cudaEventRecord(G.fork, s));
     DIM_CHECK_CUDA(cudaStreamWaitEvent(G.stream, G.fork, 0));
-    for (int st = 0; st < steps; ++st) DIM_CHECK_CUDA(cudaGraphLaunch(G.exec, G.stream));
+    int st = 0;
+    if (G.exec_u)
+      for (; st + unroll <= steps; st += unroll) DIM_CHECK_CUDA(cudaGraphLaunch(G.exec_u, G.stream));
+    for (; st < steps; ++st) DIM_CHECK_CUDA(cudaGraphLaunch(G.exec, G.stream));
     g_launches.fetch_add((uint64_t)steps * (uint64_t)(5 + c.depth * 11), std::memory_order_relaxed);
     DIM_CHECK_CUDA(cudaEventRecord(G.join, G.stream));
     DIM_CHECK_CUDA(cudaStreamWaitEvent(s, G.join, 0));
