@@ -771,15 +771,22 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
   const int max_keys = std::max(T, steps + 1);
   const bool tcp = tc_on(m.tc, B);
   const int P = m.tc.planes;
-  auto enqueue_step = [&](int st, cudaStream_t s) -> int {
+  // Head of the very first step: embedding of the prompt token and layer 0's self-attention LayerNorm.  Every later step gets
+  // both from the tail kernel of the step before it (sample_next_kernel).
+  auto enqueue_prologue = [&](cudaStream_t s) -> int {
     if (int e = launch_embed_tokens(w.tokens, steps + 1, w.step, m.token_emb, w.x, B, D, V, s)) return e;
+    const XtAttn& SA0 = m.self_attn[0];
+    return launch_layer_norm(w.x, SA0.norm_g, SA0.norm_b, tcp ? nullptr : w.ln, nullptr, B, D, 1e-5f, s, tcp ? w.ap : nullptr, P, D);
+  };
+  auto enqueue_step = [&](int st, cudaStream_t s) -> int {
     for (int l = 0; l < c.depth; ++l) {
       const XtAttn& SA = m.self_attn[l];
       const XtAttn& CA = m.cross_attn[l];
       const XtFF& FF = m.ff[l];
-      // --- causal self attention with KV cache
-      if (int e = launch_layer_norm(w.x, SA.norm_g, SA.norm_b, tcp ? nullptr : w.ln, nullptr, B, D, 1e-5f, s, tcp ? w.ap : nullptr, P, D))
-        return e;
+      // --- causal self attention with KV cache (layer 0's LayerNorm was written by the previous step's tail / the prologue)
+      if (l > 0)
+        if (int e = launch_layer_norm(w.x, SA.norm_g, SA.norm_b, tcp ? nullptr : w.ln, nullptr, B, D, 1e-5f, s, tcp ? w.ap : nullptr, P, D))
+          return e;
       {
         GemmArgs a;
         a.A = w.ln; a.lda = D; a.Ap = tcp ? w.ap : nullptr; a.W = SA.wqkv; a.C = w.qkv; a.ldc = 3 * inner; a.M = B; a.N = 3 * inner;
@@ -851,17 +858,20 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
       a.A = w.ln; a.lda = D; a.Ap = tcp ? w.ap : nullptr; a.W = m.logits_w; a.bias = m.logits_b; a.C = w.logits; a.ldc = V; a.M = B; a.N = V; a.K = D;
       if (int e = run_gemm(m.tc, a, w.ap, s, DIM_SPLIT_DECODE)) return e;
     }
-    if (int e = launch_sample(w.logits, B, V, temperature, top_k, uniforms, steps, w.step, w.tokens, steps + 1, 1,
-                              logits_out, steps * V, s))
+    // tail: sample this step's token, advance the step counter, and produce the next step's embedding + layer-0 LayerNorm
+    const XtAttn& SA0 = m.self_attn[0];
+    if (int e = launch_sample_next(w.logits, B, V, temperature, top_k, uniforms, steps, w.step,
+                                   reinterpret_cast<unsigned int*>(w.step + 16), w.tokens, steps + 1, 1, logits_out, steps * V,
+                                   m.token_emb, w.x, D, SA0.norm_g, SA0.norm_b, tcp ? nullptr : w.ln, tcp ? w.ap : nullptr, P, 1e-5f, s))
       return e;
-    if (int e = launch_advance_step(w.step, s)) return e;
     return DIM_OK;
   };
 
-  // One decode step = 49 short, strictly dependent launches: replay it as a CUDA graph (captured once per distinct call
+  // One decode step = 46 short, strictly dependent launches: replay it as a CUDA graph (captured once per distinct call
   // signature) to remove the per-launch submission cost; DIM_NO_GRAPH=1 or profiling falls back to plain launches.
   static const bool no_graph = getenv("DIM_NO_GRAPH") != nullptr;
   if (no_graph || g_prof_on) {
+    if (int e = enqueue_prologue(s)) return e;
     for (int st = 0; st < steps; ++st)
       if (int e = enqueue_step(st, s)) return e;
   } else {
@@ -879,6 +889,7 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
     if (G.exec == nullptr || G.key != key) {
       if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
       if (G.exec_u) { cudaGraphExecDestroy(G.exec_u); G.exec_u = nullptr; }
+      if (int e = enqueue_prologue(s)) return e;
       if (int e = enqueue_step(0, s)) return e;                       // warm (lazy attribute setup, tensor maps) outside capture
       if (int e = launch_set_step(w.step, 0, s)) return e;            // ... and rewind the step counter it advanced
       DIM_CHECK_CUDA(cudaStreamSynchronize(s));
@@ -899,11 +910,12 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
     }
     DIM_CHECK_CUDA(cudaEventRecord(G.fork, s));
     DIM_CHECK_CUDA(cudaStreamWaitEvent(G.stream, G.fork, 0));
+    if (int e = enqueue_prologue(G.stream)) return e;
     int st = 0;
     if (G.exec_u)
       for (; st + unroll <= steps; st += unroll) DIM_CHECK_CUDA(cudaGraphLaunch(G.exec_u, G.stream));
     for (; st < steps; ++st) DIM_CHECK_CUDA(cudaGraphLaunch(G.exec, G.stream));
-    g_launches.fetch_add((uint64_t)steps * (uint64_t)(5 + c.depth * 11), std::memory_order_relaxed);
+    g_launches.fetch_add((uint64_t)steps * (uint64_t)(2 + c.depth * 11), std::memory_order_relaxed);
     DIM_CHECK_CUDA(cudaEventRecord(G.join, G.stream));
     DIM_CHECK_CUDA(cudaStreamWaitEvent(s, G.join, 0));
   }

@@ -152,18 +152,16 @@ __global__ void embed_tokens_kernel(const int64_t* __restrict__ tok, int tok_str
 // One block (256 threads) per row of logits [V <= 1024].  Greedy: first maximal index (torch.argmax on CPU returns the
 // first occurrence).  Sampling: keep the top_k largest logits (ties broken toward the lower index, like a stable
 // descending sort), softmax(l / temperature) over them in fp32, inverse-CDF draw in index order with the supplied uniform.
-__global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ logits, int V, float temperature, int top_k,
-                                                     const float* __restrict__ uniforms, int u_stride,
-                                                     const int* __restrict__ step, int64_t* __restrict__ out,
-                                                     int out_stride, int out_offset, float* __restrict__ logits_out,
-                                                     int lo_stride) {
+// Returns the chosen token to EVERY thread of the block (and stores it at out[b, out_offset + st]).
+__device__ __forceinline__ int sample_row(const float* __restrict__ logits, int V, float temperature, int top_k,
+                                          const float* __restrict__ uniforms, int u_stride, int st, int64_t* __restrict__ out,
+                                          int out_stride, int out_offset, float* __restrict__ logits_out, int lo_stride) {
   __shared__ __align__(16) float sl[1024];
   __shared__ __align__(16) float sp[1024];
   __shared__ float redf[8];
   __shared__ int redi[8];
-  pdl_prologue();
+  __shared__ int tok_s;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int st = step ? *step : 0;
   const float* lr = logits + (size_t)b * V;
   for (int i = tid; i < V; i += 256) {
     float v = lr[i];
@@ -190,9 +188,11 @@ __global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ l
     if (tid == 0) {
       for (int w = 1; w < 8; ++w)
         if (redf[w] > best || (redf[w] == best && redi[w] < bi)) { best = redf[w]; bi = redi[w]; }
-      *dst = bi == 0x7fffffff ? 0 : bi;
+      tok_s = bi == 0x7fffffff ? 0 : bi;
+      *dst = tok_s;
     }
-    return;
+    __syncthreads();
+    return tok_s;
   }
   // rank of element i = #{j : l_j > l_i or (l_j == l_i and j < i)} ; kept iff rank < top_k.
   // Each thread ranks its elements against the row held in shared memory, 4 comparisons per 128-bit read.
@@ -269,14 +269,113 @@ __global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ l
     }
   }
   __syncthreads();
-  if (tid == 0) *dst = pick_s == 0x7fffffff ? last_s : pick_s;
+  if (tid == 0) {
+    tok_s = pick_s == 0x7fffffff ? last_s : pick_s;
+    *dst = tok_s;
+  }
+  __syncthreads();
+  return tok_s;
 }
+
+__global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ logits, int V, float temperature, int top_k,
+                                                     const float* __restrict__ uniforms, int u_stride,
+                                                     const int* __restrict__ step, int64_t* __restrict__ out,
+                                                     int out_stride, int out_offset, float* __restrict__ logits_out,
+                                                     int lo_stride) {
+  pdl_prologue();
+  sample_row(logits, V, temperature, top_k, uniforms, u_stride, step ? *step : 0, out, out_stride, out_offset, logits_out, lo_stride);
+}
+
+// The tail of decode step t and the head of step t+1 in one launch, one block per clip:
+//   token = sample(logits[b])  ->  x[b,:] = token_emb[token]  ->  LayerNorm of layer 0's self-attention (fp32 and/or bf16 planes)
+//   -> the last block to finish advances the device step counter.
+// Replaces 4 launches of the per-step chain (sample, step++, embed, LayerNorm).  D <= 256 * 4 * MAXV.
+template <int MAXV>
+__global__ void __launch_bounds__(256) sample_next_kernel(const float* __restrict__ logits, int V, float temperature, int top_k,
+                                                          const float* __restrict__ uniforms, int u_stride, int* step,
+                                                          unsigned int* ticket, int64_t* __restrict__ out, int out_stride,
+                                                          int out_offset, float* __restrict__ logits_out, int lo_stride,
+                                                          const float* __restrict__ emb, float* __restrict__ x, int D,
+                                                          const float* __restrict__ gain, const float* __restrict__ bias,
+                                                          float* __restrict__ y, __nv_bfloat16* __restrict__ yp, int planes, float eps) {
+  __shared__ float redn[8];
+  pdl_prologue();
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int st = *step;
+  int tok = sample_row(logits, V, temperature, top_k, uniforms, u_stride, st, out, out_stride, out_offset, logits_out, lo_stride);
+  tok = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
+  const int n4 = D >> 2;
+  const float4* src = reinterpret_cast<const float4*>(emb + (size_t)tok * D);
+  float4 v[MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = tid + 256 * i;
+    if (c < n4) {
+      v[i] = __ldg(src + c);
+      reinterpret_cast<float4*>(x + (size_t)b * D)[c] = v[i];
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) redn[warp] = sum;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += redn[w];
+  const float mean = tot / (float)D;
+  __syncthreads();
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = tid + 256 * i;
+    if (c < n4) {
+      const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+      q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+  }
+  q = warp_sum(q);
+  if (lane == 0) redn[warp] = q;
+  __syncthreads();
+  float qt = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) qt += redn[w];
+  const float rstd = rsqrtf(qt / (float)D + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = tid + 256 * i;
+    if (c < n4) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gain) + c);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x; o.y = (v[i].y - mean) * rstd * g.y;
+      o.z = (v[i].z - mean) * rstd * g.z; o.w = (v[i].w - mean) * rstd * g.w;
+      if (bias) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + c);
+        o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+      }
+      if (y) reinterpret_cast<float4*>(y + (size_t)b * D)[c] = o;
+      if (yp) store_planes4(yp + (size_t)b * planes * D + c * 4, o, planes, D);
+    }
+  }
+  // every block has read *step long before the LAST one gets here
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+      *step = st + 1;
+      *ticket = 0u;
+    }
+  }
+}
+
 
 __global__ void advance_step_kernel(int* step) {
   pdl_prologue();
   *step += 1;
 }
-__global__ void set_step_kernel(int* step, int v) { *step = v; }
+__global__ void set_step_kernel(int* step, int v) {
+  *step = v;
+  step[16] = 0;          // the block ticket of sample_next_kernel lives 64 bytes behind the counter
+}
 
 }  // namespace
 
@@ -328,6 +427,24 @@ int launch_sample(const float* logits, int B, int V, float temperature, int top_
   ProfScope ps(CAT_SAMPLE, s, 4.0 * B * V + 8.0 * B, 0);
   DIM_CHECK_CUDA(launch_k(sample_kernel, dim3(B), dim3(256), 0, s, logits, V, temperature, top_k, uniforms, u_stride, step, out,
                           out_stride, out_offset, logits_out, lo_stride));
+  DIM_LAUNCHED();
+  return DIM_OK;
+}
+
+int launch_sample_next(const float* logits, int B, int V, float temperature, int top_k, const float* uniforms, int u_stride,
+                       int* step, unsigned int* ticket, int64_t* out, int out_stride, int out_offset, float* logits_out,
+                       int lo_stride, const float* emb, float* x, int D, const float* gain, const float* bias, float* y,
+                       __nv_bfloat16* yp, int planes, float eps, cudaStream_t s) {
+  DIM_REQUIRE(V > 0 && V <= 1024, "sample: vocabulary must be <= 1024");
+  DIM_REQUIRE(temperature == 0.f || (uniforms != nullptr && top_k > 0), "sample: sampling needs uniforms and top_k");
+  DIM_REQUIRE(D % 4 == 0 && D <= 256 * 4 * 4, "sample_next: model dim must be a multiple of 4, <= 4096");
+  ProfScope ps(CAT_SAMPLE, s, 4.0 * B * V + 8.0 * B + 12.0 * B * D, 8.0 * B * D);
+  if (D <= 256 * 4 * 2)
+    DIM_CHECK_CUDA(launch_k(sample_next_kernel<2>, dim3(B), dim3(256), 0, s, logits, V, temperature, top_k, uniforms, u_stride, step,
+                            ticket, out, out_stride, out_offset, logits_out, lo_stride, emb, x, D, gain, bias, y, yp, planes, eps));
+  else
+    DIM_CHECK_CUDA(launch_k(sample_next_kernel<4>, dim3(B), dim3(256), 0, s, logits, V, temperature, top_k, uniforms, u_stride, step,
+                            ticket, out, out_stride, out_offset, logits_out, lo_stride, emb, x, D, gain, bias, y, yp, planes, eps));
   DIM_LAUNCHED();
   return DIM_OK;
 }

@@ -15,6 +15,11 @@ int launch_embed_tokens(const int64_t* tok, int tok_stride, const int* step, con
 int launch_sample(const float* logits, int B, int V, float temperature, int top_k, const float* uniforms, int u_stride,
                   const int* step, int64_t* out, int out_stride, int out_offset, float* logits_out, int lo_stride,
                   cudaStream_t s);
+// sample + step++ + next step's token embedding + layer-0 LayerNorm in one launch (see rowops.cu)
+int launch_sample_next(const float* logits, int B, int V, float temperature, int top_k, const float* uniforms, int u_stride,
+                       int* step, unsigned int* ticket, int64_t* out, int out_stride, int out_offset, float* logits_out,
+                       int lo_stride, const float* emb, float* x, int D, const float* gain, const float* bias, float* y,
+                       __nv_bfloat16* yp, int planes, float eps, cudaStream_t s);
 int launch_advance_step(int* step, cudaStream_t s);
 int launch_set_step(int* step, int v, cudaStream_t s);
 }  // namespace dimb
