@@ -165,10 +165,14 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_f32_tiled(const Ge
 // Skinny GEMM: one warp per output column, all MT rows; W streamed once with 128-bit loads, A served by L1.
 template <int MT>
 __global__ void __launch_bounds__(128) gemm_f32_skinny(const GemmArgs p) {
+  // One CTA per output column n: its 128 lanes split the K-long weight row, every lane keeps up to U 128-bit loads in flight
+  // (the whole row of a K <= 2048 problem is requested before the first FMA), so the N * K * 4 B weight stream -- all there
+  // is to a GEMV -- runs with N * K * 4 B / 16 independent requests instead of 4 per warp.  Partial sums: warp shuffle, then
+  // 4 warps through shared memory.
+  __shared__ float part[4][MT];
   pdl_prologue();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.x * 4 + warp;
-  if (n >= p.N) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int n = blockIdx.x;
   const int k4n = p.K >> 2;
   const float4* w = reinterpret_cast<const float4*>(p.W + (size_t)n * p.K);
   float acc[MT];
@@ -176,16 +180,16 @@ __global__ void __launch_bounds__(128) gemm_f32_skinny(const GemmArgs p) {
   for (int m = 0; m < MT; ++m) acc[m] = 0.f;
 
   constexpr int U = 4;
-  for (int k4 = lane; k4 < k4n; k4 += 32 * U) {
+  for (int k4 = tid; k4 < k4n; k4 += 128 * U) {
     float4 wv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      int kk = k4 + u * 32;
+      int kk = k4 + u * 128;
       wv[u] = kk < k4n ? __ldcs(w + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      int kk = k4 + u * 32;
+      int kk = k4 + u * 128;
       if (kk < k4n) {
         float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.a_add) e = __ldg(reinterpret_cast<const float4*>(p.a_add) + kk);
@@ -203,16 +207,17 @@ __global__ void __launch_bounds__(128) gemm_f32_skinny(const GemmArgs p) {
     }
   }
 #pragma unroll
-  for (int m = 0; m < MT; ++m) acc[m] = warp_sum(acc[m]);
-  if (lane == 0) {
-#pragma unroll
-    for (int m = 0; m < MT; ++m) {
-      if (m < p.M) {
-        float o = epilogue_elem(p, acc[m], m, n);
-        if (p.C) p.C[(size_t)m * p.ldc + n] = o;
-        if (p.Cb) p.Cb[(size_t)m * p.ldcb + n] = __float2bfloat16_rn(o);
-      }
-    }
+  for (int m = 0; m < MT; ++m) {
+    acc[m] = warp_sum(acc[m]);
+    if (lane == 0) part[warp][m] = acc[m];
+  }
+  __syncthreads();
+  if (tid < MT && tid < p.M) {
+    const int m = tid;
+    const float tot = (part[0][m] + part[1][m]) + (part[2][m] + part[3][m]);
+    float o = epilogue_elem(p, tot, m, n);
+    if (p.C) p.C[(size_t)m * p.ldc + n] = o;
+    if (p.Cb) p.Cb[(size_t)m * p.ldcb + n] = __float2bfloat16_rn(o);
   }
 }
 
@@ -245,7 +250,7 @@ int launch_gemm_f32(const GemmArgs& a, cudaStream_t s) {
   DIM_REQUIRE(a.C != nullptr || a.Cb != nullptr, "gemm: no output");
   if (a.conv_T > 0) DIM_REQUIRE(a.conv_C % BK == 0 && a.K == 5 * a.conv_C, "gemm: conv mode needs Cin % 16 == 0");
   if (a.M <= 8 && a.conv_T == 0) {
-    dim3 grid(cdiv(a.N, 4));
+    dim3 grid(a.N);                                    // one CTA per output column
     ProfScope ps(CAT_GEMM_SKINNY, s, 4.0 * ((double)a.M * a.K + (double)a.N * a.K + (double)a.M * a.N),
                  2.0 * a.M * (double)a.N * a.K);
     if (a.M == 1) DIM_CHECK_CUDA(launch_k(gemm_f32_skinny<1>, grid, dim3(128), 0, s, a));
