@@ -1,7 +1,8 @@
 #!/bin/bash
 # One gpurun call: GPU parity tests, benches, the VQ-lookup roofline, and the ncu evidence (launch list + --set full captures).
 # Usage (from the repo root on the GPU box):  bash scripts/gpu_round.sh [tag] [sections]
-#   sections: any of  tests bench variants vq ncu_list ncu_full   (default: all but variants)
+#   sections: any of  tests bench variants vq ncu_list ncu_full   (default: all but variants); vq also runs the decode-attention
+#   roofline and the in-graph per-kernel cost script
 # gpurun copies gpurun_out/ back only when it is <= 64 MiB: every .ncu-rep is reduced to its raw-page CSV on the box and
 # dropped when large; the directory is pruned to < 48 MiB at the end.
 set -u
@@ -55,6 +56,10 @@ fi
 if has vq; then
   timeout 300 python scripts/vq_roofline.py > $OUT/${TAG}_vq_roofline.jsonl 2> $OUT/${TAG}_vq_roofline.err
   cut -c1-330 $OUT/${TAG}_vq_roofline.jsonl
+  timeout 300 python scripts/attn_roofline.py > $OUT/${TAG}_attn_roofline.jsonl 2> $OUT/${TAG}_attn_roofline.err
+  grep default $OUT/${TAG}_attn_roofline.jsonl | cut -c1-260
+  timeout 300 python scripts/graph_gap.py 256 > $OUT/${TAG}_graph_gap.txt 2>&1
+  cat $OUT/${TAG}_graph_gap.txt
 fi
 NCU="ncu --clock-control none"
 BENCH_NCU="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity-leg"
@@ -80,7 +85,7 @@ if has ncu_full; then
   full gemm_decode_bf16 gemm_bf16_tcgen05 9000 6 $BENCH_NCU
   full gemm_prefill gemm_bf16_tcgen05 1 6 $BENCH_NCU
   full prefill_misc "attn_prefill|layer_norm|instance_norm" 20 6 $BENCH_NCU
-  VQ_NCU=1 full vq "vq_gather|vq_argmin" 0 6 python scripts/vq_roofline.py
+  VQ_NCU=1 full vq "vq_gather|vq_argmin" 0 9 python scripts/vq_roofline.py
 fi
 # keep the directory under the copy-back limit
 while [ "$(du -sm $OUT | cut -f1)" -gt 48 ]; do
