@@ -55,3 +55,45 @@ def slmft_forward_val(s2s_engine, vq_engine, v_speaker, v_listener, v_audio, mas
     if return_codes:
         return l_cont, d, pred, codes
     return l_cont, d, pred
+
+
+_copy_streams = {}
+
+
+@torch.no_grad()
+def slmft_forward_val_host(s2s_engine, vq_engine, host, device, temperature=1.0, uniforms=None, batch_index=None,
+                           vq_decode_engine=None, out_host=None):
+    """Same forward as slmft_forward_val, fed from (pinned) HOST tensors: host = dict(v_speaker, v_listener, v_audio, mask).
+
+    The host->device copies run on a side stream in the order the stages need them (listener motion, speaker motion + mask,
+    then the 768-d audio features, by far the largest), so the listener VQ encode and the speaker encoders overlap the audio
+    copy; the decoded frames are copied back into `out_host` (pinned) when given.  Returns (loss, dict, pred[, codes])
+    like slmft_forward_val(return_codes=True)."""
+    dev = torch.device(device)
+    main = torch.cuda.current_stream(dev)
+    cs = _copy_streams.setdefault(dev.index, torch.cuda.Stream(dev))
+    cs.wait_stream(main)                                  # buffers of the previous call are free
+    dv, ev = {}, {}
+    with torch.cuda.stream(cs):
+        for k in ("v_listener", "mask", "v_speaker", "v_audio"):
+            dv[k] = host[k].to(dev, non_blocking=True)
+            ev[k] = torch.cuda.Event()
+            ev[k].record(cs)
+    for k in ("v_listener", "mask"):
+        main.wait_event(ev[k])
+    B, T, _ = dv["v_listener"].shape
+    z_l = listener_codes(vq_engine, dv["v_listener"], dv["mask"])
+    main.wait_event(ev["v_speaker"])
+    main.wait_event(ev["v_audio"])
+    ctx = s2s_engine.context(dv["v_speaker"], dv["v_audio"], dv["mask"])
+    if uniforms is None:
+        uniforms = torch.rand(B, T - 1, device=dev)
+    codes = s2s_engine.generate(ctx, dv["mask"], z_l[:, 0], T - 1, temperature=temperature, uniforms=uniforms)
+    pred = (vq_decode_engine or vq_engine).decode(codes=codes, batch_index=batch_index)
+    if out_host is not None:
+        out_host.copy_(pred, non_blocking=True)
+    l_cont = continuous_loss(pred, dv["v_listener"], dv["mask"])
+    for t in dv.values():
+        t.record_stream(main)
+    d = {"l_ce_s": 0, "l_ce_l": 0.0, "l_cont_s": 0, "l_cont_l": l_cont, "nce": 0, "c_acc": 0}
+    return l_cont, d, pred, codes

@@ -156,3 +156,23 @@ def test_concurrent_group_decoding_is_bit_identical(slmft_sd):
                                      uniforms=u[sl].contiguous(), return_logits=True)
     assert torch.equal(part, full[sl]) and torch.equal(part_logits, full_logits[sl])
     assert len(full.unique()) > 8
+
+
+def test_host_buffer_entry_point_equals_device_call(engines):
+    """compat_api.slmft_forward_val_host (pinned host inputs, H2D copies on a side stream overlapping the VQ encode, frames copied
+    back to pinned memory) must return exactly what slmft_forward_val returns on resident inputs."""
+    from dim_b200.compat_api import slmft_forward_val, slmft_forward_val_host
+    s2s, vq = engines
+    B, T = 3, 24
+    c = dim_b200.synth.make_clips(B, T, seed=12, ragged=True)
+    u = torch.rand(B, T - 1, generator=torch.Generator().manual_seed(5)).cuda()
+    host = {k: c[k].pin_memory() for k in ("v_speaker", "v_listener", "v_audio", "mask")}
+    out_host = torch.empty(B, T - 1, 56).pin_memory()
+    for _ in range(2):                                   # twice: the second call reuses the side stream and buffers
+        l1, _, p1, c1 = slmft_forward_val_host(s2s, vq, host, torch.device("cuda", torch.cuda.current_device()), uniforms=u,
+                                               out_host=out_host)
+    torch.cuda.synchronize()
+    l2, _, p2, c2 = slmft_forward_val(s2s, vq, c["v_speaker"].cuda(), c["v_listener"].cuda(), c["v_audio"].cuda(), c["mask"].cuda(),
+                                      uniforms=u, return_codes=True)
+    assert torch.equal(c1, c2) and torch.equal(p1, p2) and torch.equal(out_host, p2.cpu())
+    assert float(l1) == float(l2)
