@@ -569,8 +569,14 @@ int launch_gemm_tc(const GemmArgs& e, const __nv_bfloat16* Ap, const __nv_bfloat
       // cluster win for K <= 1152; long K (FF2, 4608) takes 64-wide tiles split 4 ways.  Depends on K only, never on M or N.
       if (kp >= 2048) { bn = 64; splits = 4; }
       else { bn = 32; splits = 1; }
+    } else if (planes == 3 && e.split_hint == DIM_SPLIT_DECODE && kp <= 2048) {
+      // fp32-grade decode-step GEMMs, K <= 1152 (108 plane-pair k-blocks): 64-wide tiles split 4 ways beat 128-wide tiles
+      // split 8 ways (profiles/r01x_tc_sweep3_m128.txt: 18.7 vs 22.9 us QKV, 12.9 vs 14.7 us out-proj, 20.9 vs 35.9 us FF1
+      // with a 2-way split -- 288 clusters of 8 do not fit one wave).  Depends on (N, K) only.
+      bn = 64;
+      splits = e.N >= 4096 ? 2 : 4;
     } else {
-      // fp32-grade plane products (3-6x the k-blocks) and mid-sized M: split K over a cluster so that every CTA owns >= ~4 k-blocks.
+      // fp32-grade plane products with long K, and mid-sized M: split K over a cluster so that every CTA owns >= ~4 k-blocks.
       const int want = total_kb / 4;
       splits = want >= 8 ? 8 : (want >= 4 ? 4 : (want >= 2 ? 2 : 1));
     }

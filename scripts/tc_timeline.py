@@ -40,6 +40,15 @@ def run(M, N, K, planes=1, splits=0, iters=50, quiet=None):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "sweep3":
+        # same sweep for the fp32-grade mode (3 bf16 planes, 6 plane products): M = 128 rows of one decode group
+        for (N, K) in ((2304, 1152), (1152, 768), (768, 1152), (4608, 1152), (1152, 4608), (512, 1152)):
+            for bn in (128, 64, 32):
+                for sp in (1, 2, 4, 8):
+                    lib.dim_debug_tc_bn(bn)
+                    run(int(sys.argv[2]) if len(sys.argv) > 2 else 128, N, K, planes=3, splits=sp, quiet=f"planes=3 bn={bn}")
+        lib.dim_debug_tc_bn(0)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "sweep":
         # tile width x split-K sweep for the decode-step GEMM shapes (M = 128 rows of one decode group)
         for (N, K) in ((2304, 1152), (1152, 768), (768, 1152), (4608, 1152), (1152, 4608), (512, 1152)):
