@@ -131,6 +131,14 @@ class SLMFT(nn.Module):
         z_l = compat_api.listener_codes(vq, v_listener.float(), mask)
         return torch.zeros_like(z_l), z_l
 
+    def forward_val_samples(self, v_speaker, v_listener, v_audio, mask, samples, uniforms=None, batch_index=None):
+        """`samples` stochastic mode='val' generations per clip in one pass -> (pred (B,samples,T-1,56), codes (B,samples,T-1)).
+        Equal, sample by sample, to calling forward(mode='val') `samples` times (x_engine_pt.py:257-258) with the same draws;
+        the encoders and the cross-attention K/V projection run once per clip instead of once per call."""
+        s2s, vq = self.engines()
+        return compat_api.slmft_forward_val_samples(s2s, vq, v_speaker.float(), v_listener.float(), v_audio.float(), mask, samples,
+                                                    uniforms=uniforms, batch_index=batch_index)
+
     def forward(self, v_speaker, v_listener, v_audio, mask, mode="train", speaker_ids=None, listener_ids=None,
                 batch_index=None):
         if mode == "train":

@@ -2,8 +2,13 @@
 
 Same loop contract: for every batch draw `beam_size` = 10 stochastic generations, and per clip keep the sample whose
 Frechet distance to the ground truth is smallest.  Returns (y_trues, y_preds, x_all, data_ids) as lists of numpy arrays
-of shape (src_len-1, 56).  The FD selection stays on the host (numpy/scipy) like the reference; predictions are copied to
-the host once per sample instead of twice per clip."""
+of shape (src_len-1, 56).
+
+When the model offers `forward_val_samples` (the B200 SLMFT does) the 10 generations of a batch are ONE pass -- the
+encoders and the cross-attention K/V projection run once per clip, the decode runs 10 x B rows sharing each clip's K/V --
+and the Frechet-distance selection happens on the device (dim_b200.compat_api.best_of_n: fp64 covariances + two `eigh`
+instead of scipy's sqrtm), so only the winning sample of each clip is copied to the host.  Any other model object falls
+back to the reference's loop (10 model calls, host-side numpy/scipy selection)."""
 import numpy as np
 import torch
 
@@ -35,6 +40,12 @@ def evaluate_test_epoch(model, loader, device, beam_size=10):
                 data_ids_all.append(data_ids[j])
                 x_all.append(x_np[j, :n])
                 truth_stats.append(calculate_activation_statistics(y_true[j][:n]))
+            if hasattr(model, "forward_val_samples"):
+                from dim_b200.compat_api import best_of_n
+                preds, _ = model.forward_val_samples(src_s_v.contiguous(), tgt, src_s_a.contiguous(), mask, beam_size)
+                picked, _, _ = best_of_n(preds, tgt[:, 1:, :], [int(n) - 1 for n in src_len])
+                y_preds_all.extend(p.cpu().numpy() for p in picked)
+                continue
             best, keep = [float("inf")] * B, [None] * B
             for _ in range(beam_size):
                 _, _, y_preds = model(src_s_v.contiguous(), tgt, src_s_a.contiguous(), mask, mode="val")

@@ -97,3 +97,59 @@ def slmft_forward_val_host(s2s_engine, vq_engine, host, device, temperature=1.0,
         t.record_stream(main)
     d = {"l_ce_s": 0, "l_ce_l": 0.0, "l_cont_s": 0, "l_cont_l": l_cont, "nce": 0, "c_acc": 0}
     return l_cont, d, pred, codes
+
+
+@torch.no_grad()
+def slmft_forward_val_samples(s2s_engine, vq_engine, v_speaker, v_listener, v_audio, mask, samples, uniforms=None,
+                              temperature=1.0, batch_index=None, vq_decode_engine=None):
+    """`samples` stochastic generations per clip in ONE pass (what x_engine_pt.py:255-270 obtains with `samples` model calls):
+    the listener VQ encode, the speaker encoders and the cross-attention K/V projection run once per clip, only the decode and
+    the VQ decode run per sample.  uniforms (B,samples,T-1) or None.  Returns (pred (B,samples,T-1,56), codes (B,samples,T-1));
+    pred[:, j] is bit-identical to slmft_forward_val(..., uniforms=uniforms[:, j])'s prediction."""
+    B, T, _ = v_speaker.shape
+    z_l = listener_codes(vq_engine, v_listener, mask)
+    ctx = s2s_engine.context(v_speaker, v_audio, mask)
+    if uniforms is None:
+        uniforms = torch.rand(B, samples, T - 1, device=v_speaker.device)
+    codes = s2s_engine.generate_samples(ctx, mask, z_l[:, 0], T - 1, samples, uniforms, temperature=temperature)
+    if batch_index is None:
+        batch_index = torch.arange(B, dtype=torch.int32, device=v_speaker.device)
+    # sample j of clip b sits in batch slot b of "its" model call: the VQ decoder's batch-index positional encoding (SURVEY F4)
+    bi = batch_index.to(torch.int32).repeat_interleave(samples)
+    pred = (vq_decode_engine or vq_engine).decode(codes=codes.reshape(B * samples, T - 1), batch_index=bi)
+    return pred.reshape(B, samples, T - 1, -1), codes
+
+
+def frechet_distance_torch(x, y):
+    """Frechet distance between the Gaussians fitted to the rows of x (n,d) and of y (..., n, d), on the tensors' device in fp64:
+    |mu1-mu2|^2 + tr(S1) + tr(S2) - 2 tr(sqrtm(S1 S2))  with np.cov's n-1 normalisation (metrics/eval_utils.py:6-44).
+    tr(sqrtm(S1 S2)) = sum of the square roots of the eigenvalues of S1^(1/2) S2 S1^(1/2), a symmetric PSD matrix: two `eigh`
+    calls instead of scipy's Schur-based sqrtm of a non-symmetric product (identical value, no complex round-off)."""
+    x, y = x.double(), y.double()
+    n = x.shape[-2]
+    mu1, mu2 = x.mean(-2), y.mean(-2)
+    xc, yc = x - mu1.unsqueeze(-2), y - mu2.unsqueeze(-2)
+    s1 = xc.transpose(-1, -2) @ xc / (n - 1)
+    s2 = yc.transpose(-1, -2) @ yc / (y.shape[-2] - 1)
+    w, v = torch.linalg.eigh(s1)
+    r1 = (v * w.clamp_min(0).sqrt().unsqueeze(-2)) @ v.transpose(-1, -2)          # S1^(1/2)
+    ev = torch.linalg.eigvalsh(r1 @ s2 @ r1)
+    tr = ev.clamp_min(0).sqrt().sum(-1)
+    d = mu1 - mu2
+    return (d * d).sum(-1) + torch.diagonal(s1, dim1=-2, dim2=-1).sum(-1) + torch.diagonal(s2, dim1=-2, dim2=-1).sum(-1) - 2 * tr
+
+
+@torch.no_grad()
+def best_of_n(pred, target, lengths):
+    """Per clip, the sample whose Frechet distance to the ground truth is smallest (x_engine_pt.py:260-268), selected on the
+    device: pred (B,S,L,56), target (B,L,56), lengths[b] = valid frames.  Returns (list of (n_b,56) tensors, chosen (B,), fd (B,S))."""
+    B, S = pred.shape[:2]
+    keep, chosen, fds = [], [], []
+    for b in range(B):
+        n = int(lengths[b])
+        fd = frechet_distance_torch(target[b, :n], pred[b, :, :n])
+        j = int(torch.argmin(fd))                       # first minimum, like the reference's strict `<` scan
+        keep.append(pred[b, j, :n])
+        chosen.append(j)
+        fds.append(fd)
+    return keep, torch.tensor(chosen), torch.stack(fds)

@@ -501,8 +501,9 @@ __global__ void __launch_bounds__(NT) attn_decode_lanes(const DecodeAttnArgs p) 
   const int grp = tid / LPK, lk = tid % LPK;           // key group of this lane, position inside the head row
   const int pos = p.step ? *p.step : 0;                                   // index of the token being decoded
   const int nkeys = p.append ? pos + 1 : p.Tk;
-  KT* kbase = static_cast<KT*>(p.k) + (size_t)b * p.kv_batch_stride + (size_t)h * p.kv_head_stride + lk * EPL;
-  KT* vbase = static_cast<KT*>(p.v) + (size_t)b * p.kv_batch_stride + (size_t)h * p.kv_head_stride + lk * EPL;
+  const int bkv = b / p.kv_group;                      // cache row (samples of one clip share the cross-attention K/V)
+  KT* kbase = static_cast<KT*>(p.k) + (size_t)bkv * p.kv_batch_stride + (size_t)h * p.kv_head_stride + lk * EPL;
+  KT* vbase = static_cast<KT*>(p.v) + (size_t)bkv * p.kv_batch_stride + (size_t)h * p.kv_head_stride + lk * EPL;
 
   float q[EPL];
 #pragma unroll
@@ -523,7 +524,7 @@ __global__ void __launch_bounds__(NT) attn_decode_lanes(const DecodeAttnArgs p) 
     }
     __syncthreads();
   }
-  const uint8_t* km = p.key_mask ? p.key_mask + (size_t)b * p.Tk : nullptr;
+  const uint8_t* km = p.key_mask ? p.key_mask + (size_t)bkv * p.Tk : nullptr;
   const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
 
   // scores: U keys in flight per group
@@ -640,8 +641,9 @@ __global__ void __launch_bounds__(NT) attn_decode_kernel(const DecodeAttnArgs p)
   const int grp = tid / LPK, lk = tid % LPK;           // pass-2 role: key group, 16-byte slice inside the head row
   const int pos = p.step ? *p.step : 0;                                   // index of the token being decoded
   const int nkeys = p.append ? pos + 1 : p.Tk;
-  KT* khead = static_cast<KT*>(p.k) + (size_t)b * p.kv_batch_stride + (size_t)h * p.kv_head_stride;   // rows 64 elements apart
-  KT* vhead = static_cast<KT*>(p.v) + (size_t)b * p.kv_batch_stride + (size_t)h * p.kv_head_stride;
+  const int bkv = b / p.kv_group;                      // cache row (samples of one clip share the cross-attention K/V)
+  KT* khead = static_cast<KT*>(p.k) + (size_t)bkv * p.kv_batch_stride + (size_t)h * p.kv_head_stride;   // rows 64 elements apart
+  KT* vhead = static_cast<KT*>(p.v) + (size_t)bkv * p.kv_batch_stride + (size_t)h * p.kv_head_stride;
   const uint32_t ring_u = (uint32_t)__cvta_generic_to_shared(dsm);
 
   if (p.append) {                                                        // cache[pos] <- this step's k, v
@@ -696,7 +698,7 @@ __global__ void __launch_bounds__(NT) attn_decode_kernel(const DecodeAttnArgs p)
   if (nch > 1) issue(vhead, 1, 1);
 
   // key-padding mask (masked_fill(-finfo.max)) and softmax statistics
-  const uint8_t* km = p.key_mask ? p.key_mask + (size_t)b * p.Tk : nullptr;
+  const uint8_t* km = p.key_mask ? p.key_mask + (size_t)bkv * p.Tk : nullptr;
   float mx = -INFINITY;
   for (int j = tid; j < nkeys; j += NT) {
     float v = sc[j];
@@ -831,7 +833,8 @@ int launch_attention_prefill(const AttnArgs& a, cudaStream_t s) {
 int g_attn_impl = -1;      // -1: from DIM_ATTN_IMPL (default ring); 0: cp.async ring kernel; 1: lane-group kernel
 
 int launch_attention_decode(DecodeAttnArgs a, int max_keys, cudaStream_t s) {
-  DIM_REQUIRE(a.B > 0 && a.H > 0, "decode attention: empty");
+  DIM_REQUIRE(a.B > 0 && a.H > 0 && a.kv_group >= 1, "decode attention: empty");
+  DIM_REQUIRE(a.kv_group == 1 || a.append == 0, "decode attention: only read-only caches can be shared between rows");
   DIM_REQUIRE(a.kv_tok_stride == 64, "decode attention: the K/V caches must be head-major ([B,H,tokens,64])");
   const bool bf = a.kv_bf16 != 0;
   if (g_attn_impl < 0) {

@@ -30,6 +30,8 @@ struct DecodeAttnArgs {
   float* out = nullptr; int ldo = 0;                      // (B, H*64)  (nullable when out_p is given)
   __nv_bfloat16* out_p = nullptr; int planes = 0, kp = 0; // optional bf16-plane copy [B, planes*kp]
   int B = 0, H = 0, Tk = 0;                               // Tk: number of keys when append == 0
+  int kv_group = 1;                                       // rows b*kv_group .. +kv_group-1 share cache row b (and its key mask):
+                                                          //   several samples per clip over one cross-attention K/V
   float scale = 1.f;
   int sc_floats = 0;                                      // set by the launcher
   int prof_pos = 0;                                       // host copy of *step, for profiling byte counts only

@@ -424,8 +424,10 @@ struct GenWs {
   __nv_bfloat16 *ap, *ap2;                 // A-operand plane scratch for the tensor-core GEMMs
   size_t bytes;
 };
-GenWs carve_gen(const dim_s2s_config& c, int planes, bool kv_bf16, int B, int T, int steps, void* base) {
+// B clips, S samples per clip: the cross-attention K/V exist once per clip, everything else once per decode row (R = B*S).
+GenWs carve_gen(const dim_s2s_config& c, int planes, bool kv_bf16, int B, int T, int steps, void* base, int S = 1) {
   const int inner = c.heads * c.dim_head, D = c.dim + c.dim_audio;
+  const size_t R = (size_t)B * S;
   char* p = static_cast<char*>(base);
   GenWs w{};
   auto take = [&](size_t nfloat) {
@@ -437,15 +439,15 @@ GenWs carve_gen(const dim_s2s_config& c, int planes, bool kv_bf16, int B, int T,
   for (int l = 0; l < c.depth; ++l) w.cross_kv.push_back(take((size_t)B * T * 2 * inner / kvdiv));
   w.kv_tmp = take((size_t)B * T * 2 * inner / kvdiv);
   for (int l = 0; l < c.depth; ++l) {
-    w.self_k.push_back(take((size_t)B * (steps + 1) * inner / kvdiv));
-    w.self_v.push_back(take((size_t)B * (steps + 1) * inner / kvdiv));
+    w.self_k.push_back(take(R * (steps + 1) * inner / kvdiv));
+    w.self_v.push_back(take(R * (steps + 1) * inner / kvdiv));
   }
-  w.x = take((size_t)B * D); w.ln = take((size_t)B * D); w.qkv = take((size_t)B * 3 * inner);
-  w.att = take((size_t)B * inner); w.ff = take((size_t)B * c.ff_mult * D); w.logits = take((size_t)B * c.num_tokens);
-  w.tokens = reinterpret_cast<int64_t*>(take((size_t)B * (steps + 1) * 2));
+  w.x = take(R * D); w.ln = take(R * D); w.qkv = take(R * 3 * inner);
+  w.att = take(R * inner); w.ff = take(R * c.ff_mult * D); w.logits = take(R * c.num_tokens);
+  w.tokens = reinterpret_cast<int64_t*>(take(R * (steps + 1) * 2));
   w.step = reinterpret_cast<int*>(take(64));
   {
-    const size_t rows_ctx = (size_t)B * T, rows_step = (size_t)B;
+    const size_t rows_ctx = (size_t)B * T, rows_step = R;
     const size_t need = std::max(rows_ctx * tc_round_k(D), rows_step * tc_round_k(c.ff_mult * D)) * planes;
     w.ap = planes ? reinterpret_cast<__nv_bfloat16*>(take(need / 2 + 64)) : nullptr;
     w.ap2 = planes ? reinterpret_cast<__nv_bfloat16*>(take(rows_step * tc_round_k(c.ff_mult * D) * planes / 2 + 64)) : nullptr;
@@ -745,27 +747,29 @@ extern "C" int dim_slmft_context(dim_handle_t h, int model, const float* v_speak
 
 namespace {
 // Decode `B` clips on stream `s` (one group).  G: this group's cached step graph.
+// samples > 1: every clip is decoded `samples` times (rows b*samples + j, their own uniforms) over ONE projection of its
+// context: the cross-attention K/V of a clip are shared by its rows (the 10-sample best-of-N eval loop).
 int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, const uint8_t* mask, const int64_t* prompt,
-                   int B, int T, int steps, float temperature, int top_k, const float* uniforms, int64_t* out_codes,
-                   float* logits_out, void* ws, size_t ws_bytes, cudaStream_t s) {
+                   int Bc, int T, int steps, float temperature, int top_k, const float* uniforms, int64_t* out_codes,
+                   float* logits_out, void* ws, size_t ws_bytes, cudaStream_t s, int samples = 1) {
+  const int B = Bc * samples;                        // decode rows
   const dim_s2s_config& c = m.cfg;
   const int inner = c.heads * c.dim_head, D = c.dim + c.dim_audio, F = c.ff_mult * D, V = c.num_tokens;
   const bool kv16 = m.precision == DIM_PREC_BF16;   // bf16 mode keeps both KV caches in bf16 (half the decode-attention bytes)
-  GenWs w = carve_gen(c, m.tc.planes, kv16, B, T, steps, ws);
+  GenWs w = carve_gen(c, m.tc.planes, kv16, Bc, T, steps, ws, samples);
   if (ws == nullptr || ws_bytes < w.bytes) return fail(DIM_EWORKSPACE, "dim_slmft_generate: workspace too small");
   const float scale = 1.0f / sqrtf((float)c.dim_head);
 
   for (int l = 0; l < c.depth; ++l) {  // cross-attention K/V of the whole context, once
     GemmArgs a;
-    a.A = ctx; a.lda = D; a.W = m.cross_attn[l].wkv; a.M = B * T; a.N = 2 * inner; a.K = D;
+    a.A = ctx; a.lda = D; a.W = m.cross_attn[l].wkv; a.M = Bc * T; a.N = 2 * inner; a.K = D;
     if (kv16) { a.Cb = reinterpret_cast<__nv_bfloat16*>(w.kv_tmp); a.ldcb = 2 * inner; }
     else { a.C = w.kv_tmp; a.ldc = 2 * inner; }
     if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
     // head-major: each (clip, head) K / V block is one contiguous stream for the per-step attention (DRAM page locality)
-    if (int e = launch_kv_head_major(w.kv_tmp, w.cross_kv[l], B, T, c.heads, kv16, s)) return e;
+    if (int e = launch_kv_head_major(w.kv_tmp, w.cross_kv[l], Bc, T, c.heads, kv16, s)) return e;
   }
-  DIM_CHECK_CUDA(cudaMemcpy2DAsync(w.tokens, (size_t)(steps + 1) * sizeof(int64_t), prompt, sizeof(int64_t), sizeof(int64_t),
-                                   B, cudaMemcpyDeviceToDevice, s));
+  if (int e = launch_init_tokens(w.tokens, steps + 1, prompt, B, samples, s)) return e;      // tokens[r, 0] = prompt[r / samples]
   if (int e = launch_set_step(w.step, 0, s)) return e;
 
   const int max_keys = std::max(T, steps + 1);
@@ -820,12 +824,12 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
       {
         DecodeAttnArgs a;
         a.q = w.qkv; a.ldq = inner; a.kv_bf16 = kv16; a.k = w.cross_kv[l];
-        const size_t vplane = (size_t)B * T * inner;     // V block follows the K block
+        const size_t vplane = (size_t)Bc * T * inner;    // V block follows the K block (one per clip)
         a.v = kv16 ? static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(w.cross_kv[l]) + vplane) : static_cast<void*>(w.cross_kv[l] + vplane);
         a.kv_batch_stride = (size_t)T * inner; a.kv_head_stride = (size_t)T * c.dim_head; a.kv_tok_stride = c.dim_head;
         a.append = 0; a.step = w.step;
         a.key_mask = mask; a.out = tcp ? nullptr : w.att; a.ldo = inner; a.out_p = tcp ? w.ap : nullptr; a.planes = P;
-        a.kp = inner; a.B = B; a.H = c.heads; a.Tk = T; a.scale = scale;
+        a.kp = inner; a.B = B; a.H = c.heads; a.Tk = T; a.scale = scale; a.kv_group = samples;
         if (int e = launch_attention_decode(a, max_keys, s)) return e;
       }
       {
@@ -876,7 +880,7 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
       if (int e = enqueue_step(st, s)) return e;
   } else {
     std::vector<uintptr_t> key = {(uintptr_t)ctx, (uintptr_t)mask, (uintptr_t)uniforms, (uintptr_t)logits_out, (uintptr_t)ws,
-                                  (uintptr_t)B, (uintptr_t)T, (uintptr_t)steps, (uintptr_t)top_k,
+                                  (uintptr_t)B, (uintptr_t)samples, (uintptr_t)T, (uintptr_t)steps, (uintptr_t)top_k,
                                   (uintptr_t)(temperature * 65536.0f)};
     if (!G.stream) {
       DIM_CHECK_CUDA(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
@@ -939,7 +943,7 @@ extern "C" int dim_slmft_generate(dim_handle_t h, int model, const float* ctx, c
   cudaStream_t s = as_stream(stream);
   int begin[kMaxGroups + 1];
   const int ng = plan_groups(m, B, begin);
-  if ((int)m.graphs.size() < kMaxGroups) m.graphs.resize(kMaxGroups);
+  if ((int)m.graphs.size() < kMaxGroups + 1) m.graphs.resize(kMaxGroups + 1);     // last slot: multi-sample decoding
   if (ng == 1 || g_prof_on) {
     if (ng > 1) {   // profiling: same groups, sequentially on the caller's stream (events need one stream)
       char* wsp = static_cast<char*>(ws);
@@ -984,4 +988,25 @@ extern "C" int dim_slmft_generate(dim_handle_t h, int model, const float* ctx, c
     wsp += need;
   }
   return DIM_OK;
+}
+
+// ---- several samples per clip over one context projection (evaluate_test_epoch's best-of-N loop) -----------
+extern "C" size_t dim_slmft_samples_workspace_bytes(dim_handle_t h, int model, int B, int T, int steps, int samples) {
+  if (!h || model < 0 || model >= (int)h->s2s.size() || B <= 0 || T <= 0 || steps <= 0 || samples <= 0) return 0;
+  const S2SModel& m = *h->s2s[model];
+  return carve_gen(m.cfg, m.tc.planes, m.precision == DIM_PREC_BF16, B, T, steps, nullptr, samples).bytes;
+}
+
+extern "C" int dim_slmft_generate_samples(dim_handle_t h, int model, const float* ctx, const uint8_t* mask, const int64_t* prompt,
+                                          int B, int T, int steps, int samples, float temperature, int top_k,
+                                          const float* uniforms, int64_t* out_codes, float* logits_out, void* ws,
+                                          size_t ws_bytes, void* stream) {
+  DIM_REQUIRE(h && model >= 0 && model < (int)h->s2s.size(), "dim_slmft_generate_samples: bad model");
+  DIM_REQUIRE(ctx && prompt && out_codes && B > 0 && T > 0 && steps > 0 && samples > 0, "dim_slmft_generate_samples: bad argument");
+  DIM_REQUIRE(temperature >= 0.f, "temperature must be >= 0");
+  DIM_REQUIRE(temperature == 0.f || (uniforms && top_k > 0), "sampling needs uniforms and top_k");
+  const S2SModel& m = *h->s2s[model];
+  if ((int)m.graphs.size() < kMaxGroups + 1) m.graphs.resize(kMaxGroups + 1);
+  return generate_group(m, m.graphs[kMaxGroups], ctx, mask, prompt, B, T, steps, temperature, top_k, uniforms, out_codes, logits_out,
+                        ws, ws_bytes, as_stream(stream), samples);
 }

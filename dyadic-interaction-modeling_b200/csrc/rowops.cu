@@ -368,6 +368,12 @@ __global__ void __launch_bounds__(256) sample_next_kernel(const float* __restric
 }
 
 
+// tokens[r, 0] = prompt[r / samples]   (every sample of a clip starts from the clip's prompt token)
+__global__ void init_tokens_kernel(int64_t* __restrict__ tokens, int stride, const int64_t* __restrict__ prompt, int rows, int samples) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows) tokens[(size_t)r * stride] = prompt[r / samples];
+}
+
 __global__ void advance_step_kernel(int* step) {
   pdl_prologue();
   *step += 1;
@@ -445,6 +451,14 @@ int launch_sample_next(const float* logits, int B, int V, float temperature, int
   else
     DIM_CHECK_CUDA(launch_k(sample_next_kernel<4>, dim3(B), dim3(256), 0, s, logits, V, temperature, top_k, uniforms, u_stride, step,
                             ticket, out, out_stride, out_offset, logits_out, lo_stride, emb, x, D, gain, bias, y, yp, planes, eps));
+  DIM_LAUNCHED();
+  return DIM_OK;
+}
+
+int launch_init_tokens(int64_t* tokens, int stride, const int64_t* prompt, int rows, int samples, cudaStream_t s) {
+  DIM_REQUIRE(rows > 0 && samples >= 1, "init_tokens: bad sizes");
+  ProfScope ps(CAT_MISC, s, 16.0 * rows, 0);
+  init_tokens_kernel<<<cdiv(rows, 256), 256, 0, s>>>(tokens, stride, prompt, rows, samples);
   DIM_LAUNCHED();
   return DIM_OK;
 }

@@ -158,6 +158,27 @@ class SLMFTEngine:
                    "dim_slmft_context")
         return ctx if want == "ctx" else xs
 
+    def generate_samples(self, ctx, mask, prompt, steps, samples, uniforms, temperature=1.0, top_k=None, return_logits=False):
+        """`samples` independent draws per clip over one projection of its context (x_engine_pt.py:255-270's best-of-N loop):
+        uniforms (B,samples,steps) -> codes (B,samples,steps) int64 [, logits (B,samples,steps,V)]."""
+        B, T, _ = ctx.shape
+        ctx = ctx.contiguous()
+        m8 = mask.to(torch.uint8).contiguous()
+        prompt = prompt.reshape(B).contiguous()
+        if top_k is None:
+            top_k = math.ceil(self.cfg.top_k_frac * self.cfg.num_tokens)
+        uniforms = uniforms.to(device=ctx.device, dtype=torch.float32).contiguous()
+        assert uniforms.shape == (B, samples, steps)
+        out = torch.empty(B, samples, steps, dtype=torch.int64, device=ctx.device)
+        logits = torch.empty(B, samples, steps, self.cfg.num_tokens, dtype=torch.float32, device=ctx.device) if return_logits else None
+        n = self.handle.lib.dim_slmft_samples_workspace_bytes(self.handle.h, self.model, B, T, steps, samples)
+        ws = self.ws.get(n)
+        _lib.check(self.handle.lib.dim_slmft_generate_samples(self.handle.h, self.model, ctx.data_ptr(), m8.data_ptr(),
+                                                              prompt.data_ptr(), B, T, steps, samples, float(temperature), int(top_k),
+                                                              uniforms.data_ptr(), out.data_ptr(), _ptr(logits), ws.data_ptr(), n,
+                                                              _stream()), "dim_slmft_generate_samples")
+        return (out, logits) if return_logits else out
+
     def generate(self, ctx, mask, prompt, steps, temperature=0.0, top_k=None, uniforms=None, return_logits=False):
         """prompt (B,) or (B,1) int64 -> codes (B,steps) int64 (seq2seq_pretrain.py:450)."""
         B, T, _ = ctx.shape

@@ -170,6 +170,16 @@ int dim_slmft_generate(dim_handle_t h, int model, const float* ctx, const uint8_
                        int T, int steps, float temperature, int top_k, const float* uniforms, int64_t* out_codes,
                        float* logits_out, void* ws, size_t ws_bytes, void* stream);
 
+/* The same decoding for `samples` independent draws per clip over ONE projection of the clip's context (x_engine_pt.py:255-270
+ * calls the model 10 times per batch and keeps the best sample; the context, and therefore the cross-attention K/V, are the
+ * same in all 10 calls).  Row r = b*samples + j: uniforms (B*samples, steps), out_codes (B*samples, steps),
+ * logits_out (B*samples, steps, num_tokens) nullable.  Every row equals what dim_slmft_generate returns for clip b with that
+ * row's uniforms (bit for bit: no arithmetic crosses rows). */
+size_t dim_slmft_samples_workspace_bytes(dim_handle_t h, int model, int B, int T, int steps, int samples);
+int dim_slmft_generate_samples(dim_handle_t h, int model, const float* ctx, const uint8_t* mask, const int64_t* prompt, int B,
+                               int T, int steps, int samples, float temperature, int top_k, const float* uniforms,
+                               int64_t* out_codes, float* logits_out, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

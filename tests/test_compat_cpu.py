@@ -95,3 +95,23 @@ def test_pos_embed_and_x_utils_importable(compat):
     d = {"num_tokens": 512, "max_seq_len": 2048, "depth": 4}
     assert x_utils.pick_and_pop(["num_tokens", "max_seq_len"], d) == {"num_tokens": 512, "max_seq_len": 2048} and d == {"depth": 4}
     assert x_utils.groupby_prefix_and_trim("attn_", {"attn_heads": 2, "depth": 1}) == ({"heads": 2}, {"depth": 1})
+
+
+def test_frechet_distance_torch_matches_scipy_formula():
+    """compat_api.frechet_distance_torch (fp64, two eigh) == metrics/eval_utils.py's numpy-cov + scipy-sqrtm formula, on
+    full-rank (n > d) and rank-deficient (n < d) samples; batched over the leading dimension of y."""
+    import numpy as np
+    from scipy import linalg
+    from dim_b200.compat_api import frechet_distance_torch
+    g = torch.Generator().manual_seed(0)
+    for n, d in ((200, 56), (40, 56), (12, 8)):
+        x = torch.randn(n, d, generator=g)
+        y = torch.randn(3, n, d, generator=g) * 1.3 + 0.2
+        got = frechet_distance_torch(x, y).numpy()
+        for j in range(3):
+            a, b = x.numpy().astype(np.float64), y[j].numpy().astype(np.float64)
+            mu1, s1, mu2, s2 = a.mean(0), np.cov(a, rowvar=False), b.mean(0), np.cov(b, rowvar=False)
+            cm = linalg.sqrtm(s1.dot(s2))
+            cm = cm.real if np.iscomplexobj(cm) else cm
+            ref = (mu1 - mu2).dot(mu1 - mu2) + np.trace(s1) + np.trace(s2) - 2 * np.trace(cm)
+            assert abs(got[j] - ref) <= 1e-6 * max(1.0, abs(ref)) + (1e-3 if n < d else 0.0), (n, d, got[j], ref)

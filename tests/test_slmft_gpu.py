@@ -176,3 +176,57 @@ def test_host_buffer_entry_point_equals_device_call(engines):
                                       uniforms=u, return_codes=True)
     assert torch.equal(c1, c2) and torch.equal(p1, p2) and torch.equal(out_host, p2.cpu())
     assert float(l1) == float(l2)
+
+
+def test_generate_samples_equals_separate_calls(engines, slmft_sd):
+    """`samples` draws per clip over ONE context projection (shared cross-attention K/V) must equal, bit for
+    bit, `samples` separate generate calls with the same uniforms -- codes and logits (no arithmetic crosses rows)."""
+    s2s, _ = engines
+    B, T, S = 3, 20, 4
+    c = dim_b200.synth.make_clips(B, T, seed=31, ragged=True)
+    ctx = s2s.context(c["v_speaker"].cuda(), c["v_audio"].cuda(), c["mask"].cuda())
+    m = c["mask"].cuda()
+    prompt = torch.randint(0, 512, (B,), generator=torch.Generator().manual_seed(8)).cuda()
+    u = torch.rand(B, S, T - 1, generator=torch.Generator().manual_seed(9)).cuda()
+    codes, logits = s2s.generate_samples(ctx, m, prompt, T - 1, S, u, return_logits=True)
+    again = s2s.generate_samples(ctx, m, prompt, T - 1, S, u)                       # graph replay path
+    assert torch.equal(codes, again)
+    for j in range(S):
+        cj, lj = s2s.generate(ctx, m, prompt, T - 1, temperature=1.0, uniforms=u[:, j].contiguous(), return_logits=True)
+        assert torch.equal(codes[:, j], cj), f"sample {j}: codes differ"
+        assert torch.equal(logits[:, j], lj), f"sample {j}: logits differ"
+    assert len(codes.unique()) > 8
+
+
+def test_forward_val_samples_equals_forward_val(engines):
+    from dim_b200.compat_api import best_of_n, frechet_distance_torch, slmft_forward_val, slmft_forward_val_samples
+    s2s, vq = engines
+    B, T, S = 2, 24, 3
+    c = dim_b200.synth.make_clips(B, T, seed=41, ragged=True)
+    d = {k: c[k].cuda() for k in ("v_speaker", "v_listener", "v_audio", "mask")}
+    u = torch.rand(B, S, T - 1, generator=torch.Generator().manual_seed(2)).cuda()
+    pred, codes = slmft_forward_val_samples(s2s, vq, d["v_speaker"], d["v_listener"], d["v_audio"], d["mask"], S, uniforms=u)
+    assert pred.shape == (B, S, T - 1, 56)
+    for j in range(S):
+        _, _, pj, cj = slmft_forward_val(s2s, vq, d["v_speaker"], d["v_listener"], d["v_audio"], d["mask"],
+                                         uniforms=u[:, j].contiguous(), return_codes=True)
+        assert torch.equal(codes[:, j], cj) and torch.equal(pred[:, j], pj)
+    # device-side best-of-N == the reference's host-side selection (numpy cov + scipy sqrtm, x_engine_pt.py:260-268)
+    import numpy as np
+    from scipy import linalg
+    lengths = [int(v) - 1 for v in c["lengths"]]
+    picked, chosen, fd = best_of_n(pred, d["v_listener"][:, 1:], lengths)
+    for b in range(B):
+        n = lengths[b]
+        t = c["v_listener"][b, 1:n + 1].numpy().astype(np.float64)
+        ref = []
+        for j in range(S):
+            p = pred[b, j, :n].cpu().numpy().astype(np.float64)
+            mu1, s1, mu2, s2 = t.mean(0), np.cov(t, rowvar=False), p.mean(0), np.cov(p, rowvar=False)
+            cm = linalg.sqrtm(s1.dot(s2))
+            cm = cm.real if np.iscomplexobj(cm) else cm
+            ref.append(float((mu1 - mu2).dot(mu1 - mu2) + np.trace(s1) + np.trace(s2) - 2 * np.trace(cm)))
+        assert int(np.argmin(ref)) == int(chosen[b])
+        # n < 56 frames: rank-deficient covariances, where scipy's sqrtm itself carries ~1e-4 of round-off
+        assert np.allclose(fd[b].cpu().numpy(), ref, rtol=1e-3, atol=1e-3), (fd[b], ref)
+        assert torch.equal(picked[b], pred[b, int(chosen[b]), :n])
