@@ -78,7 +78,7 @@ class _Workspace:
 
 class VQEngine:
     def __init__(self, handle: Handle, cfg: VQConfig = VQConfig(), prefix: str = "", precision: int = PREC_FP32):
-        self.handle, self.cfg, self.prefix = handle, cfg, prefix
+        self.handle, self.cfg, self.prefix, self.precision = handle, cfg, prefix, precision
         cc = _lib.VQConfigC(cfg.in_dim, cfg.hidden_size, cfg.num_hidden_layers, cfg.num_attention_heads,
                             cfg.intermediate_size, cfg.n_embed, cfg.zquant_dim * cfg.face_quan_num, cfg.pe_max_len, cfg.neg)
         torch.cuda.synchronize(handle.device)
@@ -126,7 +126,7 @@ class VQEngine:
 
 class SLMFTEngine:
     def __init__(self, handle: Handle, cfg: S2SConfig = S2SConfig(), precision: int = PREC_FP32):
-        self.handle, self.cfg = handle, cfg
+        self.handle, self.cfg, self.precision = handle, cfg, precision
         cc = _lib.S2SConfigC(cfg.dim_in, cfg.dim, cfg.dim_audio, cfg.depth, cfg.heads, cfg.dim_head, cfg.max_seq_len,
                              cfg.num_tokens, cfg.ff_mult)
         torch.cuda.synchronize(handle.device)

@@ -38,7 +38,7 @@ def host_select(preds, tgt, lengths):
 
 
 def main():
-    B, T, S = int(os.environ.get("B", 26)), int(os.environ.get("T", 300)), 10
+    B, T, S = int(os.environ.get("B", 64)), int(os.environ.get("T", 300)), 10      # >= 64 clips: both arms on the tensor cores
     bf16 = os.environ.get("PREC", "bf16") == "bf16"
     h = Handle()
     h.register(dim_b200.synth.make_slmft_state_dict(131))
