@@ -221,7 +221,9 @@ def test_forward_val_samples_equals_forward_val(engines):
     for j in range(S):
         _, _, pj, cj = slmft_forward_val(s2s, vq, d["v_speaker"], d["v_listener"], d["v_audio"], d["mask"],
                                          uniforms=u[:, j].contiguous(), return_codes=True)
-        assert torch.equal(codes[:, j], cj) and torch.equal(pred[:, j], pj)
+        # codes: same GEMV kernel on both sides -> identical; frames: the VQ decode of 3x the rows may cross the FFMA / tensor-core
+        # boundary (64 rows), so the decoded coefficients agree to fp32 accumulation order
+        assert torch.equal(codes[:, j], cj) and torch.allclose(pred[:, j], pj, atol=2e-5)
     # device-side best-of-N == the reference's host-side selection (numpy cov + scipy sqrtm, x_engine_pt.py:260-268)
     import numpy as np
     from scipy import linalg
