@@ -101,6 +101,8 @@ SIGNATURES = {
     "dim_slmft_generate": (I, [P, I, P, P, P, I, I, I, F, I, P, P, P, P, SZ, P]),
     "dim_slmft_samples_workspace_bytes": (SZ, [P, I, I, I, I, I]),
     "dim_slmft_generate_samples": (I, [P, I, P, P, P, I, I, I, I, F, I, P, P, P, P, SZ, P]),
+    "dim_slmft_teacher_forced_workspace_bytes": (SZ, [P, I, I, I, I]),
+    "dim_slmft_teacher_forced": (I, [P, I, P, P, P, P, I, I, I, P, P, SZ, P]),
 }
 
 

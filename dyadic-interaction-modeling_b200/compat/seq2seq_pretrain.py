@@ -13,7 +13,8 @@ Differences in WORK, not in results: the speaker VQ encodes and the duplicated f
 discards, are skipped; cross-attention K/V are projected once (F9).  Sampling draws come from torch.rand on
 the device (one uniform per step and clip) instead of torch.multinomial's stream: same distribution, different stream;
 set `self.decode_uniforms` (B,T-1) or `self.greedy = True` for reproducible decoding.
-mode='train' (teacher forcing + loss for fine-tuning) is outside the hot path and raises NotImplementedError.
+mode='train' runs the teacher-forced FORWARD pass (logits, CE + continuous loss, argmax decode) like
+x_engine_pt.evaluate_finetune_epoch needs; no autograd graph is built (fine-tuning itself is out of scope).
 """
 import os
 
@@ -78,6 +79,7 @@ class SLMFT(nn.Module):
         self.greedy = False             # True: argmax decoding (deterministic parity mode)
         self.decode_uniforms = None     # optional (B, T-1) uniforms for reproducible sampling
         self.last_codes = None          # generated code sequences of the last val forward (B, T-1) int64
+        self.train_kv_mask = None       # optional (B, T-1) bool key mask for mode='train' (None: drawn at random, mask_prob 0.15)
 
     # ---- engine binding ----
     def engines(self):
@@ -110,9 +112,14 @@ class SLMFT(nn.Module):
         return s2s.context(v_speaker.float(), None, mask, want="x_s")
 
     def forward_decoder(self, x_s, z_l, x_a, mask, mode):
-        if mode == "train":
-            raise NotImplementedError("teacher-forced decoding (mode='train') is outside the inference hot path")
         x_s = torch.cat([x_s + self.patch_embed_dec_s, x_a], dim=-1)
+        if mode == "train":                                 # :447-448, forward only
+            s2s, _ = self.engines()
+            inp, target = z_l[:, :-1].clone(), z_l[:, 1:]
+            inp[inp == -100] = 0
+            kv = self.train_kv_mask if self.train_kv_mask is not None else compat_api.draw_kv_mask(inp.shape, 0.15, inp.device)
+            logits = s2s.teacher_forced(x_s.contiguous(), mask, inp, kv)
+            return torch.nn.functional.cross_entropy(logits.transpose(1, 2), target, ignore_index=-100), logits
         px_l = self.decoder_joint.generate(z_l[:, 0].unsqueeze(1), seq_len=z_l.shape[1] - 1, context=x_s, context_mask=mask)
         return 0.0, px_l
 
@@ -141,10 +148,12 @@ class SLMFT(nn.Module):
 
     def forward(self, v_speaker, v_listener, v_audio, mask, mode="train", speaker_ids=None, listener_ids=None,
                 batch_index=None):
-        if mode == "train":
-            raise NotImplementedError("SLMFT.forward(mode='train') (teacher forcing + CE loss) is outside the inference "
-                                      "hot path built here (SURVEY.md 8(f).2); use mode='val'")
         s2s, vq = self.engines()
+        if mode == "train":
+            # teacher forcing (what x_engine_pt.evaluate_finetune_epoch:217 runs): FORWARD ONLY -- the returned loss carries no
+            # autograd graph, fine-tuning (backward) is outside the path built here.  self.train_kv_mask pins the random key mask.
+            return compat_api.slmft_forward_train(s2s, vq, v_speaker.float(), v_listener.float(), v_audio.float(), mask,
+                                                  kv_mask=self.train_kv_mask, mask_prob=0.15, batch_index=batch_index)
         uniforms = None if self.greedy else (self.decode_uniforms if self.decode_uniforms is not None else
                                              torch.rand(v_speaker.shape[0], v_speaker.shape[1] - 1, device=v_speaker.device))
         loss, d, pred, codes = compat_api.slmft_forward_val(s2s, vq, v_speaker.float(), v_listener.float(), v_audio.float(),

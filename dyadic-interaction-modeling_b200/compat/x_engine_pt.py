@@ -58,3 +58,26 @@ def evaluate_test_epoch(model, loader, device, beam_size=10):
                         best[j], keep[j] = fd, yp[j][:n].copy()
             y_preds_all.extend(keep)
     return y_trues_all, y_preds_all, x_all, data_ids_all
+
+
+def evaluate_finetune_epoch(model, loader, device):
+    """Teacher-forced evaluation (reference: code/x_engine_pt.py:201-230): one mode='train' forward per batch, predictions cut to
+    src_len - 1 frames.  Returns (y_trues, y_preds, x_all, data_ids)."""
+    y_trues_all, y_preds_all, x_all, data_ids_all = [], [], [], []
+    model.eval()
+    with torch.no_grad():
+        for batch in tqdm(loader):
+            src, tgt, src_len, _, data_ids = batch
+            src, tgt = src.to(device), tgt.to(device)
+            src_s_v, src_s_a = torch.split(src, [56, 768], dim=2)
+            lens = torch.as_tensor(list(src_len), device=device)
+            mask = torch.arange(src.shape[1], device=device)[None, :] < lens[:, None]
+            _, _, y_preds = model(src_s_v.contiguous(), tgt, src_s_a.contiguous(), mask, mode="train")
+            yp, yt, xs = y_preds.cpu().numpy(), tgt[:, 1:, :].cpu().numpy(), src_s_v.cpu().numpy()
+            for j in range(len(yp)):
+                n = int(src_len[j]) - 1
+                y_preds_all.append(yp[j][:n])
+                y_trues_all.append(yt[j][:n])
+                x_all.append(xs[j, :n])
+                data_ids_all.append(data_ids[j])
+    return y_trues_all, y_preds_all, x_all, data_ids_all

@@ -153,3 +153,39 @@ def best_of_n(pred, target, lengths):
         chosen.append(j)
         fds.append(fd)
     return keep, torch.tensor(chosen), torch.stack(fds)
+
+
+def draw_kv_mask(inp_shape, mask_prob, device, generator=None):
+    """AutoregressiveWrapper.forward's random `self_attn_kv_mask` (x-transformers 1.30.16; drawn even in eval mode):
+    rand = randn(shape); rand[:, 0] = -max; the num_mask = min(int(seq * mask_prob), seq - 1) largest draws of each row are
+    masked.  Returns (B, seq) bool, True = key kept."""
+    B, seq = inp_shape
+    rand = torch.randn(B, seq, device=device, generator=generator)
+    rand[:, 0] = -torch.finfo(rand.dtype).max
+    num_mask = min(int(seq * mask_prob), seq - 1)
+    indices = rand.topk(num_mask, dim=-1).indices
+    return ~torch.zeros(B, seq, device=device).scatter(1, indices, 1.0).bool()
+
+
+@torch.no_grad()
+def slmft_forward_train(s2s_engine, vq_engine, v_speaker, v_listener, v_audio, mask, kv_mask=None, mask_prob=0.15,
+                        batch_index=None, return_logits=False):
+    """SLMFT.forward(mode='train') forward pass (seq2seq_pretrain.py:496-514 with :447-448, :456; what
+    x_engine_pt.evaluate_finetune_epoch:217 runs): teacher-forced decoder logits over the listener codes, cross-entropy against
+    the shifted codes (ignore_index -100), argmax codes -> VQ decode -> continuous loss.  kv_mask: the self-attention key mask
+    upstream draws at random (mask_prob 0.15); None draws one with draw_kv_mask.  Forward only: no autograd graph is built."""
+    B, T, _ = v_speaker.shape
+    z_l = listener_codes(vq_engine, v_listener, mask)                    # (B,T) with -100 on padding
+    ctx = s2s_engine.context(v_speaker, v_audio, mask)
+    inp, target = z_l[:, :-1].clone(), z_l[:, 1:]
+    inp[inp == -100] = 0                                                 # ignore_index -> pad_value
+    if kv_mask is None and mask_prob > 0:
+        kv_mask = draw_kv_mask(inp.shape, mask_prob, inp.device)
+    logits = s2s_engine.teacher_forced(ctx, mask, inp, kv_mask)
+    l_ce = F.cross_entropy(logits.transpose(1, 2), target, ignore_index=-100)
+    codes = torch.argmax(logits, dim=-1)
+    pred = vq_engine.decode(codes=codes, batch_index=batch_index)
+    l_cont = continuous_loss(pred, v_listener, mask)
+    d = {"l_ce_s": 0, "l_ce_l": l_ce, "l_cont_s": 0, "l_cont_l": l_cont, "nce": 0, "c_acc": 0}
+    out = (l_ce + l_cont, d, pred)
+    return out + (logits,) if return_logits else out

@@ -1010,3 +1010,130 @@ extern "C" int dim_slmft_generate_samples(dim_handle_t h, int model, const float
   return generate_group(m, m.graphs[kMaxGroups], ctx, mask, prompt, B, T, steps, temperature, top_k, uniforms, out_codes, logits_out,
                         ws, ws_bytes, as_stream(stream), samples);
 }
+
+// ---- teacher-forced decoder forward: AutoregressiveWrapper.forward(..., return_outputs=True) ----------------
+// seq2seq_pretrain.py:447-448 -> x-transformers TransformerWrapper over the WHOLE input sequence: token embedding, then per layer
+// causal self attention (optionally with the random `self_attn_kv_mask` of mask_prob, passed in as kv_mask), cross attention
+// over the context under the key-padding mask, feed forward; final norm; logits.  Forward only (no autograd).
+namespace {
+struct TfWs {
+  float *x, *ln, *qkv, *att, *ff, *ckv;
+  __nv_bfloat16 *ap, *ap2;
+  size_t bytes;
+};
+TfWs carve_tf(const dim_s2s_config& c, int planes, int B, int T, int L, void* base) {
+  const int inner = c.heads * c.dim_head, D = c.dim + c.dim_audio, F = c.ff_mult * D;
+  const size_t R = (size_t)B * L, RC = (size_t)B * T;
+  char* p = static_cast<char*>(base);
+  TfWs w{};
+  auto take = [&](size_t nfloat) {
+    float* r = reinterpret_cast<float*>(p);
+    p += align_up(nfloat * sizeof(float), 256);
+    return r;
+  };
+  w.x = take(R * D); w.ln = take(R * D); w.qkv = take(R * 3 * inner); w.att = take(R * inner); w.ff = take(R * F);
+  w.ckv = take(RC * 2 * inner);
+  const size_t need = std::max(R * (size_t)tc_round_k(F), RC * (size_t)tc_round_k(D)) * planes;
+  w.ap = planes ? reinterpret_cast<__nv_bfloat16*>(take(need / 2 + 64)) : nullptr;
+  w.ap2 = planes ? reinterpret_cast<__nv_bfloat16*>(take(R * (size_t)tc_round_k(F) * planes / 2 + 64)) : nullptr;
+  w.bytes = (size_t)(p - static_cast<char*>(base));
+  return w;
+}
+}  // namespace
+
+extern "C" size_t dim_slmft_teacher_forced_workspace_bytes(dim_handle_t h, int model, int B, int T, int L) {
+  if (!h || model < 0 || model >= (int)h->s2s.size() || B <= 0 || T <= 0 || L <= 0) return 0;
+  return carve_tf(h->s2s[model]->cfg, h->s2s[model]->tc.planes, B, T, L, nullptr).bytes;
+}
+
+extern "C" int dim_slmft_teacher_forced(dim_handle_t h, int model, const float* ctx, const uint8_t* mask, const int64_t* tokens,
+                                        const uint8_t* kv_mask, int B, int T, int L, float* logits, void* ws, size_t ws_bytes,
+                                        void* stream) {
+  DIM_REQUIRE(h && model >= 0 && model < (int)h->s2s.size(), "dim_slmft_teacher_forced: bad model");
+  DIM_REQUIRE(ctx && tokens && logits && B > 0 && T > 0 && L > 0, "dim_slmft_teacher_forced: bad argument");
+  const S2SModel& m = *h->s2s[model];
+  const dim_s2s_config& c = m.cfg;
+  const int inner = c.heads * c.dim_head, D = c.dim + c.dim_audio, F = c.ff_mult * D, V = c.num_tokens;
+  TfWs w = carve_tf(c, m.tc.planes, B, T, L, ws);
+  if (ws == nullptr || ws_bytes < w.bytes) return fail(DIM_EWORKSPACE, "dim_slmft_teacher_forced: workspace too small");
+  cudaStream_t s = as_stream(stream);
+  const int R = B * L;
+  const bool tcp = tc_on(m.tc, R);
+  const int P = m.tc.planes;
+  const float scale = 1.0f / sqrtf((float)c.dim_head);
+  // token embedding (TransformerWrapper; SLMFT has no positional embedding in the decoder, seq2seq_pretrain.py:386)
+  if (int e = launch_vq_gather(tokens, m.token_emb, w.x, R, D, V, nullptr, s)) return e;
+  for (int l = 0; l < c.depth; ++l) {
+    const XtAttn& SA = m.self_attn[l];
+    const XtAttn& CA = m.cross_attn[l];
+    const XtFF& FF = m.ff[l];
+    // --- causal self attention over the whole sequence (+ optional key mask)
+    if (int e = launch_layer_norm(w.x, SA.norm_g, SA.norm_b, tcp ? nullptr : w.ln, nullptr, R, D, 1e-5f, s, tcp ? w.ap : nullptr, P, D))
+      return e;
+    {
+      GemmArgs a;
+      a.A = w.ln; a.lda = D; a.Ap = tcp ? w.ap : nullptr; a.W = SA.wqkv; a.C = w.qkv; a.ldc = 3 * inner; a.M = R; a.N = 3 * inner; a.K = D;
+      if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
+    }
+    {
+      AttnArgs a;
+      a.q = w.qkv; a.k = w.qkv + inner; a.v = w.qkv + 2 * inner; a.ldq = a.ldk = a.ldv = 3 * inner;
+      a.out = tcp ? nullptr : w.att; a.ldo = inner; a.out_p = tcp ? w.ap : nullptr; a.planes = P; a.kp = inner;
+      a.key_mask = kv_mask; a.B = B; a.H = c.heads; a.Tq = L; a.Tk = L; a.Dh = c.dim_head; a.scale = scale; a.causal = 1;
+      if (int e = launch_attention_prefill(a, s)) return e;
+    }
+    {
+      GemmArgs a;
+      a.A = w.att; a.lda = inner; a.Ap = tcp ? w.ap : nullptr; a.W = SA.wo; a.residual = w.x; a.ldr = D; a.C = w.x; a.ldc = D;
+      a.M = R; a.N = D; a.K = inner;
+      if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
+    }
+    // --- cross attention over the context (K/V of this layer projected here; key-padding mask on the context)
+    {
+      GemmArgs a;
+      a.A = ctx; a.lda = D; a.W = CA.wkv; a.C = w.ckv; a.ldc = 2 * inner; a.M = B * T; a.N = 2 * inner; a.K = D;
+      if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
+    }
+    if (int e = launch_layer_norm(w.x, CA.norm_g, CA.norm_b, tcp ? nullptr : w.ln, nullptr, R, D, 1e-5f, s, tcp ? w.ap : nullptr, P, D))
+      return e;
+    {
+      GemmArgs a;
+      a.A = w.ln; a.lda = D; a.Ap = tcp ? w.ap : nullptr; a.W = CA.wq; a.C = w.qkv; a.ldc = inner; a.M = R; a.N = inner; a.K = D;
+      if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
+    }
+    {
+      AttnArgs a;
+      a.q = w.qkv; a.ldq = inner; a.k = w.ckv; a.v = w.ckv + inner; a.ldk = a.ldv = 2 * inner;
+      a.out = tcp ? nullptr : w.att; a.ldo = inner; a.out_p = tcp ? w.ap : nullptr; a.planes = P; a.kp = inner;
+      a.key_mask = mask; a.B = B; a.H = c.heads; a.Tq = L; a.Tk = T; a.Dh = c.dim_head; a.scale = scale; a.causal = 0;
+      if (int e = launch_attention_prefill(a, s)) return e;
+    }
+    {
+      GemmArgs a;
+      a.A = w.att; a.lda = inner; a.Ap = tcp ? w.ap : nullptr; a.W = CA.wo; a.residual = w.x; a.ldr = D; a.C = w.x; a.ldc = D;
+      a.M = R; a.N = D; a.K = inner;
+      if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
+    }
+    // --- feed forward
+    if (int e = launch_layer_norm(w.x, FF.norm_g, FF.norm_b, tcp ? nullptr : w.ln, nullptr, R, D, 1e-5f, s, tcp ? w.ap : nullptr, P, D))
+      return e;
+    {
+      GemmArgs a;
+      a.A = w.ln; a.lda = D; a.Ap = tcp ? w.ap : nullptr; a.W = FF.w1; a.bias = FF.b1; a.M = R; a.N = F; a.K = D;
+      a.act = DIM_ACT_GELU_ERF;
+      if (tcp) { a.Cp = w.ap2; a.cp_planes = P; a.cp_kp = F; } else { a.C = w.ff; a.ldc = F; }
+      if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
+    }
+    {
+      GemmArgs a;
+      a.A = w.ff; a.lda = F; a.Ap = tcp ? w.ap2 : nullptr; a.W = FF.w2; a.bias = FF.b2; a.residual = w.x; a.ldr = D; a.C = w.x;
+      a.ldc = D; a.M = R; a.N = D; a.K = F;
+      if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
+    }
+  }
+  if (int e = launch_layer_norm(w.x, m.final_g, m.final_b, tcp ? nullptr : w.ln, nullptr, R, D, 1e-5f, s, tcp ? w.ap : nullptr, P, D))
+    return e;
+  GemmArgs a;
+  a.A = w.ln; a.lda = D; a.Ap = tcp ? w.ap : nullptr; a.W = m.logits_w; a.bias = m.logits_b; a.C = logits; a.ldc = V; a.M = R; a.N = V; a.K = D;
+  return run_gemm(m.tc, a, w.ap, s);
+}

@@ -158,6 +158,23 @@ class SLMFTEngine:
                    "dim_slmft_context")
         return ctx if want == "ctx" else xs
 
+    def teacher_forced(self, ctx, mask, tokens, kv_mask=None):
+        """Teacher-forced decoder forward (seq2seq_pretrain.py:447-448): tokens (B,L) int64 decoder inputs (pad already substituted
+        for ignore_index), kv_mask (B,L) bool/uint8 or None -> logits (B,L,num_tokens) fp32.  Forward only."""
+        B, T, _ = ctx.shape
+        L = tokens.shape[1]
+        ctx = ctx.contiguous()
+        m8 = mask.to(torch.uint8).contiguous()
+        tokens = tokens.to(torch.int64).contiguous()
+        k8 = None if kv_mask is None else kv_mask.to(torch.uint8).contiguous()
+        logits = torch.empty(B, L, self.cfg.num_tokens, dtype=torch.float32, device=ctx.device)
+        n = self.handle.lib.dim_slmft_teacher_forced_workspace_bytes(self.handle.h, self.model, B, T, L)
+        ws = self.ws.get(n)
+        _lib.check(self.handle.lib.dim_slmft_teacher_forced(self.handle.h, self.model, ctx.data_ptr(), m8.data_ptr(), tokens.data_ptr(),
+                                                            _ptr(k8), B, T, L, logits.data_ptr(), ws.data_ptr(), n, _stream()),
+                   "dim_slmft_teacher_forced")
+        return logits
+
     def generate_samples(self, ctx, mask, prompt, steps, samples, uniforms, temperature=1.0, top_k=None, return_logits=False):
         """`samples` independent draws per clip over one projection of its context (x_engine_pt.py:255-270's best-of-N loop):
         uniforms (B,samples,steps) -> codes (B,samples,steps) int64 [, logits (B,samples,steps,V)]."""

@@ -180,6 +180,14 @@ int dim_slmft_generate_samples(dim_handle_t h, int model, const float* ctx, cons
                                int T, int steps, int samples, float temperature, int top_k, const float* uniforms,
                                int64_t* out_codes, float* logits_out, void* ws, size_t ws_bytes, void* stream);
 
+/* Teacher-forced decoder forward (seq2seq_pretrain.py:447-448 -> x-transformers AutoregressiveWrapper.forward(..., return_outputs=True)):
+ * tokens (B,L) int64 = the decoder INPUT sequence (z_l[:, :-1] with ignore_index already replaced by pad_value), ctx (B,T,D) and
+ * mask (B,T) as for generate, kv_mask (B,L) uint8 nullable = the `self_attn_kv_mask` upstream draws at random when mask_prob > 0
+ * (1 = key kept).  logits (B,L,num_tokens) fp32.  Forward only. */
+size_t dim_slmft_teacher_forced_workspace_bytes(dim_handle_t h, int model, int B, int T, int L);
+int dim_slmft_teacher_forced(dim_handle_t h, int model, const float* ctx, const uint8_t* mask, const int64_t* tokens,
+                             const uint8_t* kv_mask, int B, int T, int L, float* logits, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

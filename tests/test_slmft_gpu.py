@@ -243,3 +243,39 @@ def test_forward_val_samples_equals_forward_val(engines):
         # n < 56 frames: rank-deficient covariances, where scipy's sqrtm itself carries ~1e-4 of round-off
         assert np.allclose(fd[b].cpu().numpy(), ref, rtol=1e-3, atol=1e-3), (fd[b], ref)
         assert torch.equal(picked[b], pred[b, int(chosen[b]), :n])
+
+
+@pytest.mark.parametrize("B,T,ragged,with_kv_mask", [(2, 30, True, True), (3, 70, True, False), (70, 12, False, True)])
+def test_teacher_forced_forward(engines, slmft_sd, B, T, ragged, with_kv_mask):
+    """SURVEY 8(f).2 -- SLMFT.forward(mode='train') forward pass (seq2seq_pretrain.py:447-448, x-transformers
+    AutoregressiveWrapper.forward with the random self_attn_kv_mask supplied explicitly): logits within 5e-4 of the restated
+    oracle on the valid positions, cross-entropy within 1e-4, argmax codes equal wherever the oracle's top-2 margin > 1e-3."""
+    import torch.nn.functional as F
+    from dim_b200.compat_api import draw_kv_mask, slmft_forward_train
+    s2s, vq = engines
+    c = dim_b200.synth.make_clips(B, T, seed=200 + B, ragged=ragged)
+    kv = draw_kv_mask((B, T - 1), 0.15, "cpu", generator=torch.Generator().manual_seed(3)) if with_kv_mask else None
+    total, d, pred, logits = slmft_forward_train(s2s, vq, c["v_speaker"].cuda(), c["v_listener"].cuda(), c["v_audio"].cuda(),
+                                                 c["mask"].cuda(), kv_mask=None if kv is None else kv.cuda(), mask_prob=0.0,
+                                                 return_logits=True)
+    z_l = OS.forward_vq_listener(slmft_sd, c["v_listener"], c["mask"], VQ)
+    x_s = OS.forward_encoder(slmft_sd, c["v_speaker"], c["mask"], S2S)
+    ctx = OS.decoder_context(slmft_sd, x_s, c["v_audio"])
+    ref_loss, ref_logits = OX.teacher_forced(slmft_sd, "decoder_joint.net", z_l, S2S.depth, ctx, c["mask"], kv_mask=kv)
+    valid = z_l[:, 1:] != -100                                           # positions that enter the loss
+    diff = (logits.cpu() - ref_logits)[valid].abs().max()
+    assert float(diff) < 5e-4, float(diff)
+    assert abs(float(d["l_ce_l"]) - float(ref_loss)) < 1e-4
+    top2 = torch.topk(ref_logits, 2, dim=-1).values
+    clear = valid & ((top2[..., 0] - top2[..., 1]) > 1e-3)
+    assert torch.equal(logits.argmax(-1).cpu()[clear], ref_logits.argmax(-1)[clear])
+    assert pred.shape == (B, T - 1, 56) and torch.isfinite(pred).all()
+    assert abs(float(total) - float(d["l_ce_l"]) - float(d["l_cont_l"])) < 1e-6
+
+
+def test_draw_kv_mask_follows_upstream_recipe():
+    from dim_b200.compat_api import draw_kv_mask
+    m = draw_kv_mask((5, 40), 0.15, "cuda")
+    assert m.shape == (5, 40) and m.dtype == torch.bool
+    assert bool(m[:, 0].all())                                          # the first key is never masked
+    assert (~m).sum(1).tolist() == [min(int(40 * 0.15), 39)] * 5
