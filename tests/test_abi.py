@@ -52,3 +52,25 @@ def test_no_cpu_fallback():
     from dim_b200.engine import Handle
     with pytest.raises(RuntimeError):
         Handle()
+
+
+def test_committed_ncu_captures_parse():
+    """profiles/*_ncu/*.raw.csv.gz (raw pages of the `ncu --set full` captures taken on the B200 box) stay readable by the
+    summary script, and profiles/ncu_traffic.json carries the DRAM bytes per launch bench.py reports as `roofline.traffic`."""
+    import glob
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import ncu_csv_summary as S
+    paths = glob.glob(os.path.join(ROOT, "profiles", "r01z_ncu", "*.raw.csv.gz"))
+    assert len(paths) >= 5
+    names = set()
+    for p in paths:
+        hdr, units, rows = S.read(p)
+        assert hdr and rows and "gpu__time_duration.sum" in hdr and "dram__bytes_read.sum" in hdr
+        names.update(r[hdr.index("Kernel Name")] for r in rows)
+    joined = " ".join(names)
+    for kernel in ("attn_decode_kernel", "gemm_bf16_tcgen05", "attn_prefill_mma", "vq_gather_pf_kernel", "vq_argmin_f32", "layer_norm_kernel"):
+        assert kernel in joined, kernel
+    t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    assert 1.5e8 < t["attn_decode"] < 3e8 and t["vq_gather"] > 2e9
