@@ -37,20 +37,33 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu for sm_100a into libdimb200.so next to this file (cross-compiles without a GPU)."""
+    """Compile csrc/*.cu for sm_100a into libdimb200.so next to this file (cross-compiles without a GPU).
+    Safe when several ranks start at once (torchrun): builds are serialised by a file lock, each writes its own temporary and
+    publishes it with an atomic rename; the ranks that waited find a fresh library and skip the compile."""
     if not force and not _stale():
         return SO_PATH
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    if not os.path.exists(nvcc):
-        nvcc = "nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + sources() + ["-o", SO_PATH + ".tmp"]
-    if verbose:
-        print(" ".join(cmd))
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    os.replace(SO_PATH + ".tmp", SO_PATH)
-    return SO_PATH
+    import fcntl
+    with open(SO_PATH + ".lock", "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return SO_PATH
+            nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+            if not os.path.exists(nvcc):
+                nvcc = "nvcc"
+            tmp = f"{SO_PATH}.tmp.{os.getpid()}"
+            cmd = [nvcc] + NVCC_FLAGS + sources() + ["-o", tmp]
+            if verbose:
+                print(" ".join(cmd))
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                if os.path.exists(tmp):
+                    os.unlink(tmp)
+                raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+            os.replace(tmp, SO_PATH)
+            return SO_PATH
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
 
 
 class VQConfigC(C.Structure):
