@@ -1,10 +1,15 @@
-// fp32 attention kernels (parity mode).
-//   attn_prefill_f32 : flash-style tiled attention over frames, online softmax, 64x64 score tiles in shared memory.
-//                      VQ-VAE layers (Dh 48, scale hidden^-0.5, no mask; models/lib/base_models.py:136-143) and
-//                      x-transformers encoders (Dh 64, causal + key-padding mask, -FLT_MAX fill).
-//   attn_decode      : one query per (batch, head) against a token-major K/V cache (self-attention with in-kernel
-//                      append of the new key/value, or cross-attention over the projected context); HBM-bound:
-//                      each half-warp streams whole 256-byte head rows with 128-bit loads.
+// Attention kernels.
+//   attn_prefill_mma : prefill attention on the tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate) with Q, K, V and the
+//                      probabilities split exactly into 1 (bf16 mode) or 3 (fp32-grade) bf16 planes; online softmax in
+//                      registers, 64 x 64 tiles.  VQ-VAE layers (Dh 48, scale hidden^-0.5, no mask;
+//                      models/lib/base_models.py:136-143), x-transformers encoders (Dh 64, causal + key-padding mask,
+//                      -FLT_MAX fill) and the teacher-forced decoder (self: causal + kv mask; cross: Tq != Tk).
+//   attn_prefill_f32 : the same contract on FFMA (DIM_PREC_FP32, operator-level ABI dim_attention_f32).
+//   attn_decode_kernel / attn_decode_lanes : one query per (clip, head) against a HEAD-MAJOR K/V cache [B,H,tokens,64]
+//                      (self attention with in-kernel append of the new key/value, or cross attention over the once-projected
+//                      context, optionally shared by several sample rows of a clip); HBM-bound streaming kernels, see the
+//                      comments at each kernel and DESIGN.md 5.3.
+//   kv_head_major    : token-major projection output -> head-major caches.
 #include "attention.cuh"
 
 #include <algorithm>

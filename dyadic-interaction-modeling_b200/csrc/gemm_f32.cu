@@ -162,7 +162,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_f32_tiled(const Ge
   }
 }
 
-// Skinny GEMM: one warp per output column, all MT rows; W streamed once with 128-bit loads, A served by L1.
+// GEMV-like GEMM (M <= 8 rows): one CTA per output column, all MT rows; W streamed once with 128-bit loads, A served by L1.
 template <int MT>
 __global__ void __launch_bounds__(128) gemm_f32_skinny(const GemmArgs p) {
   // One CTA per output column n: its 128 lanes split the K-long weight row, every lane keeps up to U 128-bit loads in flight

@@ -2,8 +2,9 @@
 //   vq_argmin_f32 : exact fp32 nearest neighbour.  d_j = (|z|^2 + |e_j|^2) - 2 (z . e_j), first minimum wins
 //                   (models/lib/quantizer.py:38-45).  64 tokens x 64 codes per CTA tile, fp32 FFMA.
 //   vq_gather     : codes -> codebook rows (replaces the one-hot matmul of quantizer.py:79-90 and
-//                   seq2seq_pretrain.py:457-461): 8 B index in, D*4 B row out per code; pure HBM streaming,
-//                   one warp per row, 128-bit loads/stores, 4 rows in flight per warp.
+//                   seq2seq_pretrain.py:457-461; also the decoder's token embedding): 8 B index in, D*4 B row out per code;
+//                   pure HBM streaming.  Default: vq_gather_pf_kernel (index stream prefetched one chunk ahead, 128-bit
+//                   loads/stores, 4 rows in flight per warp): 5.7-5.9 TB/s; variants kept behind dim_debug_vq_gather_mode.
 //   vq_gather_bcl / vq_rows_from_bcl : the (B,D,L) channel-major layout VQAutoEncoder.encode returns / decode accepts.
 #include "vq.cuh"
 
