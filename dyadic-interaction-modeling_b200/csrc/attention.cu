@@ -615,6 +615,9 @@ __global__ void __launch_bounds__(NT) attn_decode_lanes(const DecodeAttnArgs p) 
 __device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async_16_hint(uint32_t dst_smem, const void* src, uint64_t policy) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -666,11 +669,17 @@ __global__ void __launch_bounds__(NT) attn_decode_kernel(const DecodeAttnArgs p)
     __syncthreads();
   }
   const int nch = (nkeys + CHUNK - 1) / CHUNK;
+  uint64_t kvpol = 0;
+  if (p.kv_evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(kvpol));
   auto issue = [&](const KT* head, int c, int stage) {                   // rows [c*CHUNK, ..) of a head block -> ring[stage]
     const int row0 = c * CHUNK, pieces = min(CHUNK, nkeys - row0) * LPK;
     const uint8_t* src = reinterpret_cast<const uint8_t*>(head + (size_t)row0 * DH);
     const uint32_t dst = ring_u + stage * STAGE;
-    for (int q = tid; q < pieces; q += NT) cp_async_16(dst + (q / LPK) * PITCH + (q % LPK) * 16, src + (size_t)q * 16);
+    if (p.kv_evict_first) {                                              // read-once stream: do not displace L2-resident weights
+      for (int q = tid; q < pieces; q += NT) cp_async_16_hint(dst + (q / LPK) * PITCH + (q % LPK) * 16, src + (size_t)q * 16, kvpol);
+    } else {
+      for (int q = tid; q < pieces; q += NT) cp_async_16(dst + (q / LPK) * PITCH + (q % LPK) * 16, src + (size_t)q * 16);
+    }
     cp_async_commit();
   };
   if (nch > 0) issue(khead, 0, 0);
@@ -839,6 +848,8 @@ int g_attn_impl = -1;      // -1: from DIM_ATTN_IMPL (default ring); 0: cp.async
 
 int launch_attention_decode(DecodeAttnArgs a, int max_keys, cudaStream_t s) {
   DIM_REQUIRE(a.B > 0 && a.H > 0 && a.kv_group >= 1, "decode attention: empty");
+  static const bool evict_first = getenv("DIM_L2_WEIGHT_KEEP") != nullptr && atof(getenv("DIM_L2_WEIGHT_KEEP")) > 0.0;   // tuning hook
+  a.kv_evict_first = evict_first ? 1 : 0;
   DIM_REQUIRE(a.kv_group == 1 || a.append == 0, "decode attention: only read-only caches can be shared between rows");
   DIM_REQUIRE(a.kv_tok_stride == 64, "decode attention: the K/V caches must be head-major ([B,H,tokens,64])");
   const bool bf = a.kv_bf16 != 0;

@@ -34,6 +34,7 @@ struct DecodeAttnArgs {
                                                           //   several samples per clip over one cross-attention K/V
   float scale = 1.f;
   int sc_floats = 0;                                      // set by the launcher
+  int kv_evict_first = 0;                                 // set by the launcher: K/V loads carry an L2 evict_first policy
   int prof_pos = 0;                                       // host copy of *step, for profiling byte counts only
 };
 int launch_attention_decode(DecodeAttnArgs a, int max_keys, cudaStream_t s);

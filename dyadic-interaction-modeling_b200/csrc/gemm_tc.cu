@@ -21,6 +21,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -59,6 +60,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(x), "r"(y), "r"(bar)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
+      "l"(map), "r"(x), "r"(y), "r"(bar), "l"(policy)
+      : "memory");
+}
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
 //   start address >> 4 | LBO (=1, unused for swizzled K-major) << 16 | SBO (1024 B between 8-row groups) >> 4 << 32 |
 //   version 1 << 46 | layout SWIZZLE_128B (2) << 61
@@ -93,6 +100,8 @@ struct TcParams {
   int kp;                     // padded K (elements) = plane stride
   int splits;                 // split-K factor = cluster size along z (1, 2, 4 or 8)
   long long* dbg;             // optional timeline of CTA (0,0,0): clock64 stamps (debug / tuning only)
+  float w_keep;               // > 0: fraction of the weight tiles loaded with an L2 evict_last policy (decode-step GEMMs:
+                              //      keep part of the per-step weight stream L2-resident across steps), rest evict_first
 };
 
 template <int ACT>
@@ -223,6 +232,9 @@ __global__ void __launch_bounds__(192) gemm_bf16_tcgen05(const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      uint64_t wpol = 0;
+      if (p.w_keep > 0.f)
+        asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(wpol) : "f"(p.w_keep));
       for (int it = it_begin; it < it_end; ++it) {
         const int pair = it / p.kblocks, kb = it - pair * p.kblocks;
         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
@@ -230,7 +242,8 @@ __global__ void __launch_bounds__(192) gemm_bf16_tcgen05(const __grid_constant__
         mbar_expect_tx(fb, STAGE_BYTES);
         const uint32_t sa = smem_base + stage * STAGE_BYTES;
         tma_load_2d(sa, &tmA, p.pa[pair] * p.kp + kb * BKE, m0, fb);
-        tma_load_2d(sa + A_BYTES, &tmW, p.pw[pair] * p.kp + kb * BKE, n0, fb);
+        if (p.w_keep > 0.f) tma_load_2d_hint(sa + A_BYTES, &tmW, p.pw[pair] * p.kp + kb * BKE, n0, fb, wpol);
+        else tma_load_2d(sa + A_BYTES, &tmW, p.pw[pair] * p.kp + kb * BKE, n0, fb);
         if (dbg && it - it_begin < 16) p.dbg[8 + (it - it_begin)] = clock64();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
@@ -557,6 +570,8 @@ int launch_gemm_tc(const GemmArgs& e, const __nv_bfloat16* Ap, const __nv_bfloat
   p.npairs = tc_pairs(planes, p.pa, p.pw);
   p.splits = 1;
   p.dbg = g_tc_dbg;
+  static const float w_keep_env = getenv("DIM_L2_WEIGHT_KEEP") ? (float)atof(getenv("DIM_L2_WEIGHT_KEEP")) : 0.f;   // tuning hook
+  p.w_keep = e.split_hint == DIM_SPLIT_DECODE ? w_keep_env : 0.f;
   const int total_kb = p.kblocks * p.npairs;
   int bn = e.N >= 128 ? 128 : (e.N > 32 ? 64 : 32);
   int splits = 1;
