@@ -848,7 +848,8 @@ int g_attn_impl = -1;      // -1: from DIM_ATTN_IMPL (default ring); 0: cp.async
 
 int launch_attention_decode(DecodeAttnArgs a, int max_keys, cudaStream_t s) {
   DIM_REQUIRE(a.B > 0 && a.H > 0 && a.kv_group >= 1, "decode attention: empty");
-  static const bool evict_first = getenv("DIM_L2_WEIGHT_KEEP") != nullptr && atof(getenv("DIM_L2_WEIGHT_KEEP")) > 0.0;   // tuning hook
+  // K/V rows are read once per step: evict_first keeps them from displacing the L2-resident decode weights (see launch_gemm_tc)
+  static const bool evict_first = !(getenv("DIM_L2_WEIGHT_KEEP") != nullptr && atof(getenv("DIM_L2_WEIGHT_KEEP")) <= 0.0);
   a.kv_evict_first = evict_first ? 1 : 0;
   DIM_REQUIRE(a.kv_group == 1 || a.append == 0, "decode attention: only read-only caches can be shared between rows");
   DIM_REQUIRE(a.kv_tok_stride == 64, "decode attention: the K/V caches must be head-major ([B,H,tokens,64])");

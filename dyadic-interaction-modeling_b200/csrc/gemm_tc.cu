@@ -570,8 +570,13 @@ int launch_gemm_tc(const GemmArgs& e, const __nv_bfloat16* Ap, const __nv_bfloat
   p.npairs = tc_pairs(planes, p.pa, p.pw);
   p.splits = 1;
   p.dbg = g_tc_dbg;
-  static const float w_keep_env = getenv("DIM_L2_WEIGHT_KEEP") ? (float)atof(getenv("DIM_L2_WEIGHT_KEEP")) : 0.f;   // tuning hook
-  p.w_keep = e.split_hint == DIM_SPLIT_DECODE ? w_keep_env : 0.f;
+  // Decode-step GEMMs re-read the same weights every step (144 MB of bf16 planes per step, more than the 126 MB L2): load 70 % of
+  // the weight tiles with an L2 evict_last policy and the rest evict_first, so that most of the stream is served from L2 on the
+  // next step instead of thrashing (measured: 261.9 -> 251.8 ms per bench step; 0.4: 254.5, 1.0: 256.4; profiles/r01_notes.md).
+  // The K/V streams of the decode attention carry evict_first.  DIM_L2_WEIGHT_KEEP overrides (0 disables); plain-bf16 mode only.
+  static const float w_keep_env = getenv("DIM_L2_WEIGHT_KEEP") ? (float)atof(getenv("DIM_L2_WEIGHT_KEEP")) : -1.f;
+  const float w_keep_default = planes == 1 ? 0.7f : 0.f;
+  p.w_keep = e.split_hint == DIM_SPLIT_DECODE ? (w_keep_env >= 0.f ? w_keep_env : w_keep_default) : 0.f;
   const int total_kb = p.kblocks * p.npairs;
   int bn = e.N >= 128 ? 128 : (e.N > 32 ? 64 : 32);
   int splits = 1;
