@@ -368,6 +368,40 @@ __global__ void __launch_bounds__(256) sample_next_kernel(const float* __restric
 }
 
 
+// ---- input side: audio-feature resampling to the motion frame rate ------------------------------------------
+// mode 0: vico_preprocessing.downsample_mean (code/vico_preprocessing.py:7-19): out[i] = mean(in[i*w : i*w + w]), w = int(t / new_t)
+// mode 1: dataset/l2l.downsample_mean (code/dataset/l2l.py:23-29): F.interpolate(mode='linear', align_corners=True)
+// One thread per 4 consecutive channels of one output frame: coalesced 128-bit loads and stores, pure HBM streaming.
+__global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__ in, float* __restrict__ out, int t, int d4,
+                                                       int new_t, int window, int mode) {
+  const size_t total = (size_t)new_t * d4;
+  const float4* in4 = reinterpret_cast<const float4*>(in);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / d4), c = (int)(i - (size_t)row * d4);
+    float4 o;
+    if (mode == 0) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int start = row * window;
+      for (int k = 0; k < window; ++k) {
+        const float4 v = __ldcs(in4 + (size_t)(start + k) * d4 + c);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      const float inv = 1.0f / (float)window;
+      o = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    } else {
+      // ATen area_pixel_compute_source_index(align_corners=True): src = scale * dst, scale = (t-1)/(new_t-1) in fp32
+      const float scale = new_t > 1 ? (float)(t - 1) / (float)(new_t - 1) : 0.f;
+      const float src = scale * (float)row;
+      const int i0 = (int)src, i1 = i0 + (i0 < t - 1 ? 1 : 0);
+      const float w1 = src - (float)i0, w0 = 1.0f - w1;
+      const float4 a = __ldcs(in4 + (size_t)i0 * d4 + c), b = __ldcs(in4 + (size_t)i1 * d4 + c);
+      o = make_float4(__fadd_rn(__fmul_rn(w0, a.x), __fmul_rn(w1, b.x)), __fadd_rn(__fmul_rn(w0, a.y), __fmul_rn(w1, b.y)),
+                      __fadd_rn(__fmul_rn(w0, a.z), __fmul_rn(w1, b.z)), __fadd_rn(__fmul_rn(w0, a.w), __fmul_rn(w1, b.w)));
+    }
+    __stcs(reinterpret_cast<float4*>(out) + i, o);
+  }
+}
+
 // tokens[r, 0] = prompt[r / samples]   (every sample of a clip starts from the clip's prompt token)
 __global__ void init_tokens_kernel(int64_t* __restrict__ tokens, int stride, const int64_t* __restrict__ prompt, int rows, int samples) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -455,6 +489,17 @@ int launch_sample_next(const float* logits, int B, int V, float temperature, int
   return DIM_OK;
 }
 
+int launch_resample(const float* in, float* out, int t, int d, int new_t, int window, int mode, cudaStream_t s) {
+  DIM_REQUIRE(in && out && t > 0 && d > 0 && d % 4 == 0 && new_t > 0, "resample: bad sizes (d must be a multiple of 4)");
+  DIM_REQUIRE(mode == 1 || (window >= 1 && (long)new_t * window <= t), "resample: window mean reads past the input");
+  const size_t total = (size_t)new_t * (d / 4);
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 16);
+  ProfScope ps(CAT_MISC, s, 4.0 * d * ((mode == 0 ? (double)new_t * window : 2.0 * new_t) + new_t), 0);
+  resample_kernel<<<blocks, 256, 0, s>>>(in, out, t, d / 4, new_t, window, mode);
+  DIM_LAUNCHED();
+  return DIM_OK;
+}
+
 int launch_init_tokens(int64_t* tokens, int stride, const int64_t* prompt, int rows, int samples, cudaStream_t s) {
   DIM_REQUIRE(rows > 0 && samples >= 1, "init_tokens: bad sizes");
   ProfScope ps(CAT_MISC, s, 16.0 * rows, 0);
@@ -479,6 +524,11 @@ int launch_set_step(int* step, int v, cudaStream_t s) {
 }  // namespace dimb
 
 using namespace dimb;
+
+extern "C" int dim_resample_features(const float* in, int t, int d, int new_t, int window, int mode, float* out, void* stream) {
+  if (int e = ensure_device()) return e;
+  return launch_resample(in, out, t, d, new_t, window, mode, as_stream(stream));
+}
 
 extern "C" int dim_layer_norm_f32(const float* x, const float* gain, const float* bias, float* y, int rows, int dim,
                                   float eps, void* stream) {

@@ -20,6 +20,7 @@ int launch_sample_next(const float* logits, int B, int V, float temperature, int
                        int* step, unsigned int* ticket, int64_t* out, int out_stride, int out_offset, float* logits_out,
                        int lo_stride, const float* emb, float* x, int D, const float* gain, const float* bias, float* y,
                        __nv_bfloat16* yp, int planes, float eps, cudaStream_t s);
+int launch_resample(const float* in, float* out, int t, int d, int new_t, int window, int mode, cudaStream_t s);
 int launch_init_tokens(int64_t* tokens, int stride, const int64_t* prompt, int rows, int samples, cudaStream_t s);
 int launch_advance_step(int* step, cudaStream_t s);
 int launch_set_step(int* step, int v, cudaStream_t s);

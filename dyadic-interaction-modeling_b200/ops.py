@@ -130,5 +130,27 @@ def attention(qkv, heads, dim_head, scale, key_mask=None, lens=None, causal=Fals
     return out
 
 
+def resample_window_mean(x, factor=0.6):
+    """vico_preprocessing.downsample_mean (code/vico_preprocessing.py:7-19): x (t,d) fp32 -> (int(t*factor), d); each output frame
+    is the mean of `int(t / new_t)` consecutive input frames starting at i*window (window = 1 at factor 0.6: the reference's
+    50 -> 30 fps "downsampling" keeps the first 60 % of the frames)."""
+    _req(x, torch.float32, "x")
+    t, d = x.shape
+    new_t = int(t * factor)
+    window = int(t / new_t)
+    out = torch.empty(new_t, d, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().dim_resample_features(_ptr(x), t, d, new_t, window, 0, _ptr(out), _stream()), "dim_resample_features")
+    return out
+
+
+def resample_linear(x, new_t):
+    """dataset/l2l.downsample_mean (code/dataset/l2l.py:23-29): linear interpolation, align_corners=True.  x (t,d) -> (new_t,d)."""
+    _req(x, torch.float32, "x")
+    t, d = x.shape
+    out = torch.empty(new_t, d, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().dim_resample_features(_ptr(x), t, d, new_t, 1, 1, _ptr(out), _stream()), "dim_resample_features")
+    return out
+
+
 def launch_count() -> int:
     return int(_lib.load().dim_launch_count())

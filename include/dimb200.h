@@ -102,6 +102,12 @@ int dim_repack_conv_weight(const float* w_oik /*[Cout][Cin][5]*/, float* w_oki /
  * t < lens[b] (or T).  Replaces stage1_BIWI.py:268 / :334. */
 int dim_instance_norm_f32(float* x, const int32_t* lens, int B, int T, int C, float eps, void* stream);
 
+/* Audio-feature resampling to the motion frame rate, (t,d) fp32 -> (new_t,d) fp32, d % 4 == 0.
+ * mode 0: window mean, out[i] = mean(in[i*window : (i+1)*window])  -- vico_preprocessing.downsample_mean
+ *         (code/vico_preprocessing.py:7-19: new_t = int(t*0.6), window = int(t/new_t), i.e. 1 for the 50->30 fps case);
+ * mode 1: linear interpolation with align_corners=True -- dataset/l2l.downsample_mean (code/dataset/l2l.py:23-29). */
+int dim_resample_features(const float* in, int t, int d, int new_t, int window, int mode, float* out, void* stream);
+
 /* LayerNorm over the last dim (eps), gain, optional bias.  base_models.py:14 ; x-transformers bias-free LayerNorm. */
 int dim_layer_norm_f32(const float* x, const float* gain, const float* bias, float* y, int rows, int dim, float eps,
                        void* stream);

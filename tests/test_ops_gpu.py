@@ -201,3 +201,36 @@ def test_split_planes_is_exact():
     assert torch.equal(p[:, 0, :56], x.bfloat16().float())
     rec = p[:, 0, :56] + p[:, 1, :56] + p[:, 2, :56]
     assert float((rec - x).abs().max()) <= 2e-7 * float(x.abs().max())
+
+
+@pytest.mark.parametrize("case", ["vico_120x64", "short_7x8", "odd_333x16"])
+def test_feature_resampling_matches_reference_golden(case):
+    """SURVEY 8(f).3 -- dim_resample_features vs outputs of the reference's own functions (tests/golden/resample_reference.pt, made
+    by tests/golden/make_resample_golden.py): the window mean (code/vico_preprocessing.py:7-19) is exact in fp32 for a window of 1
+    and within fp32 rounding of the reference's float64 mean otherwise; the linear resampler (code/dataset/l2l.py:23-29, ATen
+    align_corners=True index arithmetic restated in the kernel) within 1e-6 abs."""
+    import os
+    from dim_b200 import ops
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resample_reference.pt"), weights_only=False)
+    c = g["cases"][case]
+    x = c["x"].cuda()
+    out = ops.resample_window_mean(x, 0.6).cpu()
+    assert torch.equal(out.double(), c["window_mean_0.6"])                       # window of 1: a copy of the first 60 %
+    out = ops.resample_window_mean(x, 0.25).cpu()
+    assert out.shape == c["window_mean_0.25"].shape
+    assert torch.allclose(out.double(), c["window_mean_0.25"], atol=1e-6)
+    for n, ref in c["linear_new_t"].items():
+        out = ops.resample_linear(x, n).cpu()
+        assert out.shape == ref.shape and torch.allclose(out, ref, atol=1e-6), (n, float((out - ref).abs().max()))
+
+
+def test_feature_resampling_full_size():
+    """HuBERT-shape input (50 fps x 20 s, 768-d) -> 30 fps: properties at a size the goldens do not cover."""
+    from dim_b200 import ops
+    x = torch.randn(1000, 768, generator=_g(4)).cuda()
+    y = ops.resample_linear(x, 600)
+    assert torch.equal(y[0], x[0]) and torch.allclose(y[-1], x[-1], atol=1e-6)   # align_corners: end points map to end points
+    assert torch.equal(ops.resample_linear(x, 1000), x)                          # identity when new_t == t
+    ref = torch.nn.functional.interpolate(x.t()[None], size=600, mode="linear", align_corners=True)[0].t()
+    assert torch.allclose(y, ref, atol=1e-6)
+    assert torch.equal(ops.resample_window_mean(x, 0.6), x[:600])

@@ -2,6 +2,7 @@
 self-consistency of the restated x-transformers half (cache vs no cache, cross-KV once vs every step)."""
 import hashlib
 import math
+import os
 
 import torch
 
@@ -116,3 +117,17 @@ def test_forward_val_shapes_and_as_reference_equivalence(slmft_sd):
     b = OS.forward_val(slmft_sd, c["v_speaker"], c["v_listener"], c["v_audio"], c["mask"], S2S, VQ, as_reference=True,
                        cross_kv_once=False)
     assert a[2].shape == (2, 9, 56) and torch.equal(a[2], b[2]) and set(a[1]) == {"l_ce_s", "l_ce_l", "l_cont_s", "l_cont_l", "nce", "c_acc"}
+
+
+def test_feature_resamplers_match_reference_golden():
+    """oracle/features.py vs the outputs of the reference's own functions (tests/golden/make_resample_golden.py)."""
+    import numpy as np
+    from oracle import features as OF
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resample_reference.pt"), weights_only=False)
+    for name, c in g["cases"].items():
+        x = c["x"].numpy()
+        assert np.array_equal(OF.window_mean(x), c["window_mean_0.6"].numpy()), name
+        assert np.array_equal(OF.window_mean(x, factor=0.25), c["window_mean_0.25"].numpy()), name
+        assert np.array_equal(OF.window_mean(x), x[: int(len(x) * 0.6)].astype(np.float64))        # the window-of-1 quirk
+        for n, ref in c["linear_new_t"].items():
+            assert np.array_equal(OF.linear(x, n), ref.numpy()), (name, n)
