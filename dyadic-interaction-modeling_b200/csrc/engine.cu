@@ -421,6 +421,8 @@ struct GenWs {
   float *x, *ln, *qkv, *att, *ff, *logits;
   int64_t* tokens;                         // [B, steps+1]
   int* step;
+  uint8_t* mask_stage;                     // [B,T] copy of the caller's key-padding mask   } what the captured step graph reads:
+  float* u_stage;                          // [R,steps] copy of the caller's uniforms       } the graph never holds caller pointers
   __nv_bfloat16 *ap, *ap2;                 // A-operand plane scratch for the tensor-core GEMMs
   size_t bytes;
 };
@@ -446,6 +448,8 @@ GenWs carve_gen(const dim_s2s_config& c, int planes, bool kv_bf16, int B, int T,
   w.att = take(R * inner); w.ff = take(R * c.ff_mult * D); w.logits = take(R * c.num_tokens);
   w.tokens = reinterpret_cast<int64_t*>(take(R * (steps + 1) * 2));
   w.step = reinterpret_cast<int*>(take(64));
+  w.mask_stage = reinterpret_cast<uint8_t*>(take(((size_t)B * T + 3) / 4 + 1));
+  w.u_stage = take(R * (size_t)steps + 1);
   {
     const size_t rows_ctx = (size_t)B * T, rows_step = R;
     const size_t need = std::max(rows_ctx * tc_round_k(D), rows_step * tc_round_k(c.ff_mult * D)) * planes;
@@ -770,6 +774,12 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
     if (int e = launch_kv_head_major(w.kv_tmp, w.cross_kv[l], Bc, T, c.heads, kv16, s)) return e;
   }
   if (int e = launch_init_tokens(w.tokens, steps + 1, prompt, B, samples, s)) return e;      // tokens[r, 0] = prompt[r / samples]
+  // the step graph reads the mask and the uniforms from the workspace, so a cached graph stays valid whatever buffers the
+  // caller passes next time
+  if (mask) DIM_CHECK_CUDA(cudaMemcpyAsync(w.mask_stage, mask, (size_t)Bc * T, cudaMemcpyDeviceToDevice, s));
+  if (uniforms) DIM_CHECK_CUDA(cudaMemcpyAsync(w.u_stage, uniforms, (size_t)B * steps * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  const uint8_t* mask_g = mask ? w.mask_stage : nullptr;
+  const float* uniforms_g = uniforms ? w.u_stage : nullptr;
   if (int e = launch_set_step(w.step, 0, s)) return e;
 
   const int max_keys = std::max(T, steps + 1);
@@ -828,7 +838,7 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
         a.v = kv16 ? static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(w.cross_kv[l]) + vplane) : static_cast<void*>(w.cross_kv[l] + vplane);
         a.kv_batch_stride = (size_t)T * inner; a.kv_head_stride = (size_t)T * c.dim_head; a.kv_tok_stride = c.dim_head;
         a.append = 0; a.step = w.step;
-        a.key_mask = mask; a.out = tcp ? nullptr : w.att; a.ldo = inner; a.out_p = tcp ? w.ap : nullptr; a.planes = P;
+        a.key_mask = mask_g; a.out = tcp ? nullptr : w.att; a.ldo = inner; a.out_p = tcp ? w.ap : nullptr; a.planes = P;
         a.kp = inner; a.B = B; a.H = c.heads; a.Tk = T; a.scale = scale; a.kv_group = samples;
         if (int e = launch_attention_decode(a, max_keys, s)) return e;
       }
@@ -864,7 +874,7 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
     }
     // tail: sample this step's token, advance the step counter, and produce the next step's embedding + layer-0 LayerNorm
     const XtAttn& SA0 = m.self_attn[0];
-    if (int e = launch_sample_next(w.logits, B, V, temperature, top_k, uniforms, steps, w.step,
+    if (int e = launch_sample_next(w.logits, B, V, temperature, top_k, uniforms_g, steps, w.step,
                                    reinterpret_cast<unsigned int*>(w.step + 16), w.tokens, steps + 1, 1, logits_out, steps * V,
                                    m.token_emb, w.x, D, SA0.norm_g, SA0.norm_b, tcp ? nullptr : w.ln, tcp ? w.ap : nullptr, P, 1e-5f, s))
       return e;
@@ -879,7 +889,7 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
     for (int st = 0; st < steps; ++st)
       if (int e = enqueue_step(st, s)) return e;
   } else {
-    std::vector<uintptr_t> key = {(uintptr_t)ctx, (uintptr_t)mask, (uintptr_t)uniforms, (uintptr_t)logits_out, (uintptr_t)ws,
+    std::vector<uintptr_t> key = {(uintptr_t)(mask != nullptr), (uintptr_t)(uniforms != nullptr), (uintptr_t)logits_out, (uintptr_t)ws,
                                   (uintptr_t)B, (uintptr_t)samples, (uintptr_t)T, (uintptr_t)steps, (uintptr_t)top_k,
                                   (uintptr_t)(temperature * 65536.0f)};
     if (!G.stream) {
