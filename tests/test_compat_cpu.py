@@ -115,3 +115,20 @@ def test_frechet_distance_torch_matches_scipy_formula():
             cm = cm.real if np.iscomplexobj(cm) else cm
             ref = (mu1 - mu2).dot(mu1 - mu2) + np.trace(s1) + np.trace(s2) - 2 * np.trace(cm)
             assert abs(got[j] - ref) <= 1e-6 * max(1.0, abs(ref)) + (1e-3 if n < d else 0.0), (n, d, got[j], ref)
+
+
+def test_mymetrics_print_metrics_matches_reference_golden(compat, capsys):
+    """compat/mymetrics.print_metrics prints the reference's lines (mymetrics.py:7-88) with the golden values of
+    tests/golden/make_metrics_golden.py and returns (fid_pose, fid_exp) like the reference."""
+    import mymetrics
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "metrics_reference.pt"), weights_only=False)
+    to_np = lambda seq: [t.numpy() for t in seq]
+    if torch.cuda.is_available():
+        pytest.skip("device placement is covered by tests/test_metrics.py on the GPU box")
+    fp, fe = mymetrics.print_metrics(to_np(g["gt"]), to_np(g["pred"]), to_np(g["x"]))
+    assert abs(fp - g["ref"]["fid_pose"]) < 1e-5 * g["ref"]["fid_pose"] and abs(fe - g["ref"]["fid_exp"]) < 1e-5 * g["ref"]["fid_exp"]
+    lines = capsys.readouterr().out.strip().splitlines()
+    assert [l.split(":")[0] for l in lines] == ["fid_pose", "fid_exp", "pfid_pose", "pfid_exp", "mse_pose", "mse_exp", "sid_pose",
+                                                "sid_exp", "var_pose", "var_exp", "rpcc pose", "rpcc exp", "sts pose", "sts exp"]
+    mymetrics.print_metrics_full(to_np(g["gt"]), to_np(g["pred"]), to_np(g["x"]))
+    assert [l.split(":")[0] for l in capsys.readouterr().out.strip().splitlines()] == ["fid", "pfid", "mse", "var"]
