@@ -157,6 +157,9 @@ int tc_add_weight(dim_handle_s* h, TcCtx& tc, const float* W, int N, int K) {
 // tiled FFMA kernel: 3.1 s per 1023-step batch, profiles/r01_notes.md.)
 inline bool tc_on(const TcCtx& tc, int M) { return tc.planes > 0 && M > 8; }
 
+// split_hint: DIM_SPLIT_NEVER for every prefill GEMM (M = clips x frames), DIM_SPLIT_DECODE for the per-step GEMMs (M = clips).
+// The split-K factor then depends on the call site and on (N, K) only -- never on how many clips share the batch -- so a
+// clip's bits do not depend on the batch it is decoded in (test_concurrent_group_decoding_is_bit_identical).
 int run_gemm(const TcCtx& tc, const GemmArgs& a_in, __nv_bfloat16* scratch, cudaStream_t s, int split_hint = DIM_SPLIT_NEVER) {
   GemmArgs a = a_in;
   a.split_hint = split_hint;
