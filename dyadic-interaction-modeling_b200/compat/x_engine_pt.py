@@ -81,3 +81,9 @@ def evaluate_finetune_epoch(model, loader, device):
                 x_all.append(xs[j, :n])
                 data_ids_all.append(data_ids[j])
     return y_trues_all, y_preds_all, x_all, data_ids_all
+
+
+def train_epoch(model, loader, optimizer, device, scheduler=None, clip=1.0, print_freq=10, epoch=0):
+    """Name kept for `from x_engine_pt import train_epoch, ...` (test_s2s_pretrain.py:6; the call is commented out there).
+    Training needs the backward pass, which is out of scope."""
+    raise NotImplementedError("train_epoch: fine-tuning (backward pass) is outside the inference path built here")

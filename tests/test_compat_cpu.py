@@ -132,3 +132,22 @@ def test_mymetrics_print_metrics_matches_reference_golden(compat, capsys):
                                                 "sid_exp", "var_pose", "var_exp", "rpcc pose", "rpcc exp", "sts pose", "sts exp"]
     mymetrics.print_metrics_full(to_np(g["gt"]), to_np(g["pred"]), to_np(g["x"]))
     assert [l.split(":")[0] for l in capsys.readouterr().out.strip().splitlines()] == ["fid", "pfid", "mse", "var"]
+
+
+def test_compat_eval_utils_numpy_api_matches_reference_golden(compat):
+    """compat/metrics/eval_utils.py keeps the reference's numpy-in / float-out helpers (sts, calcuate_sid, calculate_variance,
+    FD) that test_l2l.py and mymetrics import; values against tests/golden/metrics_reference.pt."""
+    import numpy as np
+    from metrics import eval_utils as EU
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "metrics_reference.pt"), weights_only=False)
+    gt, pred = [t.numpy() for t in g["gt"]], [t.numpy() for t in g["pred"]]
+    G, P = np.concatenate(gt, 0), np.concatenate(pred, 0)
+    assert abs(EU.sts(G[:, 0:6], P[:, 0:6]) - g["ref"]["sts_pose"]) < 1e-5 * g["ref"]["sts_pose"]
+    assert abs(EU.sts(G[:, 6:], P[:, 6:]) - g["ref"]["sts_exp"]) < 1e-5 * g["ref"]["sts_exp"]
+    if not torch.cuda.is_available():
+        assert abs(EU.calcuate_sid(gt, pred, type="pose") - g["ref"]["sid_pose"][0]) < 1e-9
+        assert abs(EU.calcuate_sid(gt, gt, type="exp") - g["ref"]["sid_exp"][1]) < 1e-9
+    assert abs(EU.calculate_variance(G) - float(np.sum(np.var(G, axis=0)))) < 1e-12
+    mu1, s1 = EU.calculate_activation_statistics(gt[0][:, 0:6])
+    mu2, s2 = EU.calculate_activation_statistics(pred[0][:, 0:6])
+    assert EU.calculate_frechet_distance(mu1, s1, mu2, s2) > 0
