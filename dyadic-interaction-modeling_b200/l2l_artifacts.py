@@ -55,3 +55,29 @@ def write_l2l_fixtures(data_root, data_ids, first, second, split="test"):
     os.makedirs(data_root, exist_ok=True)
     pd.DataFrame(rows, columns=["sentiment", "uuid", "listener", "speaker", "listener_id", "speaker_id", "split"]).to_csv(
         os.path.join(data_root, "RLD_data.csv"), index=False)
+
+
+def write_vico_fixtures(data_root, clips, ids=None, split="test"):
+    """Synthetic ViCo inputs in the layout the reference's loader reads (dataset/data_loader.py:110-152, get_vico_dataloaders
+    :461-475): `<data_root>/RLD_data.csv` (positional columns [0] sentiment, [1] clip id, [4] listener id, [5] speaker id,
+    [6] split) and `<data_root>/vico_processed_30fps/<clip id>.pkl` = {'video_speaker' (T,56), 'audio' (T,768),
+    'video_listener' (T,56)}.  clips: dict with v_speaker / v_audio / v_listener (B,T,.) tensors or arrays and `lengths` (B).
+    split: one name for all clips or a list per clip (get_vico_dataloaders builds a 'train' AND a 'test' dataset and fails on an
+    empty one)."""
+    import pandas as pd
+    B = len(clips["v_listener"])
+    ids = ids or [f"vico{i:03d}" for i in range(B)]
+    d = os.path.join(data_root, "vico_processed_30fps")
+    os.makedirs(d, exist_ok=True)
+    rows = []
+    for i, cid in enumerate(ids):
+        n = int(clips["lengths"][i]) if "lengths" in clips else len(clips["v_listener"][i])
+        rec = {"video_speaker": np.asarray(clips["v_speaker"][i][:n], dtype=np.float32),
+               "audio": np.asarray(clips["v_audio"][i][:n], dtype=np.float32),
+               "video_listener": np.asarray(clips["v_listener"][i][:n], dtype=np.float32)}
+        with open(os.path.join(d, cid + ".pkl"), "wb") as f:
+            pickle.dump(rec, f)
+        rows.append(["neutral", cid, f"{cid}_l", f"{cid}_s", i, 100 + i, split if isinstance(split, str) else split[i]])
+    pd.DataFrame(rows, columns=["sentiment", "uuid", "listener", "speaker", "listener_id", "speaker_id", "split"]).to_csv(
+        os.path.join(data_root, "RLD_data.csv"), index=False)
+    return ids
