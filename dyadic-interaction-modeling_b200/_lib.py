@@ -51,15 +51,36 @@ def build(force: bool = False, verbose: bool = False) -> str:
             nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
             if not os.path.exists(nvcc):
                 nvcc = "nvcc"
+            # one object per source, compiled in parallel and only when stale (build/ is git-ignored), then one link
+            from concurrent.futures import ThreadPoolExecutor
+            objdir = os.path.join(_HERE, "build")
+            os.makedirs(objdir, exist_ok=True)
+            hdr_t = max(os.path.getmtime(d) for d in glob.glob(os.path.join(CSRC, "*.cuh")) + [HEADER])
+
+            def compile_one(src):
+                obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+                if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
+                    return obj, None
+                cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-c", src, "-o", obj]
+                if verbose:
+                    print(" ".join(cmd))
+                r = subprocess.run(cmd, capture_output=True, text=True)
+                return obj, (r.stdout + r.stderr if r.returncode != 0 else None)
+
+            with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+                results = list(ex.map(compile_one, sources()))
+            errs = [e for _, e in results if e]
+            if errs:
+                raise RuntimeError("nvcc failed:\n" + "\n".join(errs))
             tmp = f"{SO_PATH}.tmp.{os.getpid()}"
-            cmd = [nvcc] + NVCC_FLAGS + sources() + ["-o", tmp]
+            cmd = [nvcc, "-shared", "-o", tmp] + [o for o, _ in results]
             if verbose:
                 print(" ".join(cmd))
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:
                 if os.path.exists(tmp):
                     os.unlink(tmp)
-                raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+                raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
             os.replace(tmp, SO_PATH)
             return SO_PATH
         finally:
@@ -117,6 +138,9 @@ SIGNATURES = {
     "dim_slmft_generate_samples": (I, [P, I, P, P, P, I, I, I, I, F, I, P, P, P, P, SZ, P]),
     "dim_slmft_teacher_forced_workspace_bytes": (SZ, [P, I, I, I, I]),
     "dim_slmft_teacher_forced": (I, [P, I, P, P, P, P, I, I, I, P, P, SZ, P]),
+    "dim_decode_trace_enable": (I, [I]),
+    "dim_decode_trace_collect": (I, [C.POINTER(C.c_double), C.POINTER(C.c_int32), I, C.POINTER(I)]),
+    "dim_decode_set_impl": (I, [I]),
 }
 
 
@@ -161,3 +185,24 @@ def profile_collect():
     check(lib.dim_profile_collect(arr, 32, C.byref(n)), "dim_profile_collect")
     return [dict(category=lib.dim_profile_category_name(arr[i].category).decode(), launches=arr[i].launches,
                  ms=arr[i].ms, bytes=arr[i].bytes, flops=arr[i].flops) for i in range(n.value)]
+
+
+MK_TYPE_NAMES = {1: "gemm", 2: "attention", 3: "residual_layernorm", 4: "gelu", 5: "sample_embed_layernorm"}
+
+
+def decode_trace_enable(on: bool):
+    check(load().dim_decode_trace_enable(int(on)), "dim_decode_trace_enable")
+
+
+def decode_trace_collect():
+    """-> list of (type name, ms) per phase of one decode step, summed over the steps of the last generate call."""
+    lib = load()
+    ms = (C.c_double * 64)()
+    ty = (C.c_int32 * 64)()
+    n = C.c_int(0)
+    check(lib.dim_decode_trace_collect(ms, ty, 64, C.byref(n)), "dim_decode_trace_collect")
+    return [(MK_TYPE_NAMES.get(ty[i], str(ty[i])), ms[i]) for i in range(n.value)]
+
+
+def decode_set_impl(impl: int):
+    check(load().dim_decode_set_impl(int(impl)), "dim_decode_set_impl")

@@ -157,12 +157,13 @@ def best_of_n(pred, target, lengths):
 
 def draw_kv_mask(inp_shape, mask_prob, device, generator=None):
     """AutoregressiveWrapper.forward's random `self_attn_kv_mask` (x-transformers 1.30.16; drawn even in eval mode):
-    rand = randn(shape); rand[:, 0] = -max; the num_mask = min(int(seq * mask_prob), seq - 1) largest draws of each row are
-    masked.  Returns (B, seq) bool, True = key kept."""
+    rand = randn(inp.shape); rand[:, 0] = -max; with T = inp.shape[1] + 1 (the length before the shift) the
+    num_mask = min(int(T * mask_prob), T - 1) largest draws of each row are masked.  Returns (B, seq) bool, True = key kept."""
     B, seq = inp_shape
     rand = torch.randn(B, seq, device=device, generator=generator)
     rand[:, 0] = -torch.finfo(rand.dtype).max
-    num_mask = min(int(seq * mask_prob), seq - 1)
+    # upstream reads `seq` from x BEFORE the shift (x.shape[1] = len(inp) + 1): num_mask = min(int(T * mask_prob), T - 1)
+    num_mask = min(int((seq + 1) * mask_prob), seq)
     indices = rand.topk(num_mask, dim=-1).indices
     return ~torch.zeros(B, seq, device=device).scatter(1, indices, 1.0).bool()
 

@@ -42,7 +42,7 @@ int ensure_device();   // DIM_OK when the current device is sm_100; DIM_ENODEVIC
 // ---- optional per-kernel-category timing (dim_profile_*): CUDA events around each launch on the launching stream ----
 enum ProfCat {
   CAT_GEMM_TILED = 0, CAT_GEMM_SKINNY, CAT_CONV, CAT_LAYERNORM, CAT_INSTNORM, CAT_ATTN_PREFILL, CAT_ATTN_DECODE,
-  CAT_VQ_ARGMIN, CAT_VQ_GATHER, CAT_SAMPLE, CAT_MISC, CAT_GEMM_TC, CAT_GEMM_TC_SKINNY, CAT_COUNT
+  CAT_VQ_ARGMIN, CAT_VQ_GATHER, CAT_SAMPLE, CAT_MISC, CAT_GEMM_TC, CAT_GEMM_TC_SKINNY, CAT_DECODE_MK, CAT_COUNT
 };
 extern bool g_prof_on;
 void prof_begin(int cat, cudaStream_t s, double bytes, double flops);

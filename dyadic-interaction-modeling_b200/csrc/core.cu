@@ -46,7 +46,8 @@ cudaEvent_t get_event() {
 }
 const char* kCatNames[CAT_COUNT] = {"gemm_f32_tiled", "gemm_f32_skinny", "conv5_implicit_gemm", "layer_norm",
                                     "instance_norm", "attn_prefill_f32", "attn_decode", "vq_argmin", "vq_gather",
-                                    "sample", "misc", "gemm_bf16_tcgen05", "gemm_bf16_tcgen05_skinny"};
+                                    "sample", "misc", "gemm_bf16_tcgen05", "gemm_bf16_tcgen05_skinny",
+                                    "decode_megakernel"};
 }  // namespace
 void prof_begin(int cat, cudaStream_t s, double bytes, double flops) {
   ProfRec r{cat, get_event(), get_event(), bytes, flops};

@@ -1,0 +1,775 @@
+// Persistent decode kernel for sm_100a: every autoregressive step of decoder_joint.generate (seq2seq_pretrain.py:450;
+// x-transformers AutoregressiveWrapper.generate / Decoder) inside ONE cooperative launch.
+//
+// Why: one decode step used to be 46 dependent kernel launches (CUDA graph); each paid ~4-5 us of launch gap, barrier/TMEM
+// prologue, first-TMA round trip and epilogue drain, so a 256-clip step took ~670 us against an HBM floor of ~240 us
+// (profiles/r01z_graph_gap.txt).  Here the grid is one CTA per SM, resident for the whole generate call; the
+// launches become PHASES of a small program interpreted by every CTA, separated by a grid-wide barrier (one atomic + an
+// acquire spin, < 1 us).  mbarriers, TMEM and the TMA descriptors are set up once.
+//
+// Phase types (MkPhase::type):
+//   MK_GEMM       split-K tcgen05 GEMM.  Work unit = (128-row tile of decode rows, bn-wide tile of output features, K slice z);
+//                 units are dealt round-robin to the CTAs.  warp 0 = TMA producer (A and W tiles, 128B swizzle, 6-slot
+//                 full/empty mbarrier ring), warp 1 = tcgen05.mma issuer (fp32 accumulator in TMEM), warps 4-7 move the
+//                 accumulator TMEM -> smem, then all 12 warps store it as coalesced rows of the fp32 PARTIAL part[z][row][col].
+//                 No epilogue arithmetic here: the consumer phase sums the K slices in a fixed order (deterministic, and a row's
+//                 bits never depend on which other rows share the batch: the split factor depends on (N, K, planes) only).
+//   MK_ATTN       decode attention, one (row, head) work item per 64-thread sub-group (6 per CTA), items of a CTA handed out
+//                 through a shared-memory counter.  q and the step's new k, v rows are summed from the QKV partials, the new row is
+//                 appended to the head-major cache, K then V tiles stream through a 2-stage cp.async ring (same algorithm as
+//                 attn_decode_kernel in attention.cu, which stays the stand-alone / per-kernel-path version).
+//   MK_ROW_RESLN  x += bias + sum_z part[z]; LayerNorm(x) -> bf16 planes (the next GEMM's A operand).  One warp per row.
+//   MK_ROW_GELU   gelu_erf(bias + sum_z part[z]) -> bf16 planes (FF2's A operand).  Elementwise.
+//   MK_ROW_SAMPLE logits = bias + sum_z part[z]; argmax or top-k / softmax / inverse-CDF draw (same arithmetic as
+//                 sample_row in rowops.cu); token embedding -> x; layer 0's LayerNorm -> planes.  One warp per row.
+//
+// Every wait (mbarrier, grid barrier) is bounded: after ~4 s it traps, so a logic error surfaces as a launch failure instead
+// of wedging the GPU.
+#include <algorithm>
+#include <cstdlib>
+
+#include "decode_mk.cuh"
+#include "kvio.cuh"
+#include "tc_ptx.cuh"
+
+namespace dimb {
+
+namespace {
+
+constexpr int MK_THREADS = 384;                     // 12 warps
+constexpr int MK_WARPS = MK_THREADS / 32;
+constexpr int MK_NSUB = MK_THREADS / 64;            // attention sub-groups per CTA
+constexpr int MK_STAGES = 6;
+constexpr uint32_t MK_A_BYTES = 128 * 64 * 2;       // one A tile: 128 rows x 64 bf16 (128-byte swizzle rows)
+constexpr uint32_t MK_SLOT = 2 * MK_A_BYTES;        // ring slot: A tile + W tile of up to 128 rows
+constexpr uint32_t MK_RING = MK_STAGES * MK_SLOT;   // 192 KB, also the attention / staging scratch
+constexpr uint32_t MK_SUB_BYTES = MK_RING / MK_NSUB;
+constexpr int MK_TMEM_COLS = 128;
+constexpr int MK_MAXS = 9;                          // largest split-K factor (engine.cu: mk_gemm_cfg)
+constexpr unsigned long long MK_TIMEOUT_NS = 4000000000ull;
+
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// mbarrier wait with a watchdog
+__device__ __forceinline__ void mbar_wait_guard(uint32_t bar, uint32_t parity) {
+  unsigned long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (it == 64) t0 = gtime_ns();
+    if (it > 64 && (it & 255) == 0 && gtime_ns() - t0 > MK_TIMEOUT_NS) __trap();
+  }
+}
+
+__device__ __forceinline__ void bar_sub(int sub) {   // named barrier of one 64-thread attention sub-group
+  asm volatile("bar.sync %0, 64;" ::"r"(sub + 1) : "memory");
+}
+
+// Grid-wide barrier: CTA barrier, then thread 0 publishes with a gpu-scope RELEASE reduction (cumulative over the CTA's writes
+// through the barrier before it) and spins with gpu-scope ACQUIRE loads; a second CTA barrier releases the other threads.
+// to_tma: the next phase reads this phase's generic-proxy global writes through TMA (async proxy) -> proxy fences on both sides.
+__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& target, bool to_tma) {
+  if (to_tma) asm volatile("fence.proxy.async;" ::: "memory");
+  __syncthreads();
+  target += gridDim.x;
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    unsigned long long t0 = 0;
+    for (uint32_t it = 0;; ++it) {
+      unsigned int v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      if ((int)(v - target) >= 0) break;
+      if (it == 64) t0 = gtime_ns();
+      if (it > 64 && (it & 63) == 0 && gtime_ns() - t0 > MK_TIMEOUT_NS) __trap();
+    }
+  }
+  __syncthreads();
+  if (to_tma) asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+struct Pipe {            // ring / accumulator barrier positions; they persist across units, phases and steps
+  uint32_t p_stage = 0, p_phase = 0;     // producer
+  uint32_t c_stage = 0, c_phase = 0;     // MMA issuer
+  uint32_t acc_phase = 0;                // accumulator barrier parity (all threads track it)
+};
+
+struct Ctl {             // static shared memory
+  uint64_t full_bar[MK_STAGES];
+  uint64_t empty_bar[MK_STAGES];
+  uint64_t accum_bar;
+  uint32_t tmem_slot;
+  int attn_ctr;
+  int sub_item[MK_NSUB];
+  float red[2 * MK_WARPS];               // block reductions of the row phases
+  int tok[2];
+};
+
+// ---- MK_GEMM ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mk_gemm(const MkPlan& P, const MkPhase& ph, uint8_t* smem, uint32_t smem_base, Ctl& ctl,
+                                        Pipe& pipe, uint32_t tmem_base) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int M = ph.M, N = ph.N, bn = ph.bn, S = ph.splits;
+  const int mt = (M + 127) >> 7, nt = (N + bn - 1) / bn;
+  const int units = mt * nt * S;
+  const int total_it = ph.kblocks * ph.npairs;
+  const uint32_t stage_bytes = MK_A_BYTES + (uint32_t)bn * 128u;
+  const int CP = bn + 4;                                // fp32 staging pitch (floats): conflict-free 128-bit accesses
+  float* stage_tile = reinterpret_cast<float*>(smem);
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    // the m tiles that share a weight tile are neighbours in the unit order: they run at the same time on different SMs and the
+    // second one finds the tile in L2
+    const int m_i = u % mt, r1 = u / mt, n_i = r1 % nt, z = r1 / nt;
+    const int m0 = m_i * 128, n0 = n_i * bn;
+    const int it_begin = (int)(((long long)z * total_it) / S), it_end = (int)(((long long)(z + 1) * total_it) / S);
+    if (warp == 0) {
+      if (lane == 0) {
+        const CUtensorMap* tmA = &P.maps[ph.mapA];
+        const CUtensorMap* tmW = &P.maps[ph.mapW];
+        uint64_t wpol = 0;
+        const bool hint = ph.w_keep > 0.f;
+        if (hint) asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(wpol) : "f"(ph.w_keep));
+        uint32_t stage = pipe.p_stage, phase = pipe.p_phase;
+        for (int it = it_begin; it < it_end; ++it) {
+          const int pair = it / ph.kblocks, kb = it - pair * ph.kblocks;
+          mbar_wait_guard(smem_u32(&ctl.empty_bar[stage]), phase ^ 1u);
+          const uint32_t fb = smem_u32(&ctl.full_bar[stage]);
+          mbar_expect_tx(fb, stage_bytes);
+          const uint32_t sa = smem_base + stage * MK_SLOT;
+          if (hint) tma_load_2d_hint(sa + MK_A_BYTES, tmW, ph.pw[pair] * ph.kp + kb * 64, n0, fb, wpol);
+          else tma_load_2d(sa + MK_A_BYTES, tmW, ph.pw[pair] * ph.kp + kb * 64, n0, fb);
+          tma_load_2d(sa, tmA, ph.pa[pair] * ph.kp + kb * 64, m0, fb);
+          if (++stage == MK_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        pipe.p_stage = stage; pipe.p_phase = phase;
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      if (lane == 0) {
+        // instruction descriptor: D fp32 (1<<4), A bf16 (1<<7), B bf16 (1<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        uint32_t stage = pipe.c_stage, phase = pipe.c_phase;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");     // the previous unit's TMEM reads are done (CTA barrier)
+        for (int it = it_begin; it < it_end; ++it) {
+          mbar_wait_guard(smem_u32(&ctl.full_bar[stage]), phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_base + stage * MK_SLOT;
+          const uint64_t adesc = make_sdesc(sa), bdesc = make_sdesc(sa + MK_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)                   // UMMA_K = 16 bf16 = 32 bytes: +2 in the (addr >> 4) field
+            umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it > it_begin || k > 0) ? 1u : 0u);
+          umma_commit(smem_u32(&ctl.empty_bar[stage]));
+          if (++stage == MK_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(smem_u32(&ctl.accum_bar));
+        pipe.c_stage = stage; pipe.c_phase = phase;
+      }
+      __syncwarp();
+    } else if (warp >= 4 && warp < 8) {
+      // accumulator -> staging tile (the ring is idle once accum_bar fires: every MMA, hence every TMA write, has completed)
+      const int q = warp & 3;                            // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+      mbar_wait_guard(smem_u32(&ctl.accum_bar), pipe.acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float* my_row = stage_tile + (size_t)(q * 32 + lane) * CP;
+      const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < bn; c0 += 16) {
+        float v[16];
+        tmem_ld16(tlane + (uint32_t)c0, v);
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<float4*>(my_row + c0 + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    pipe.acc_phase ^= 1u;
+    __syncthreads();
+    {  // staging tile -> part[z][m0 + r][n0 + c], whole rows per warp instruction
+      const int LPR = bn >> 2, RPI = 32 / LPR;
+      const int c = (lane % LPR) * 4, col = n0 + c;
+      const int rows = min(128, M - m0);
+      float* dst = ph.part + ((size_t)z * M + m0) * N + col;
+      if (col < N)
+        for (int r = warp * RPI + lane / LPR; r < rows; r += MK_WARPS * RPI)
+          *reinterpret_cast<float4*>(dst + (size_t)r * N) = *reinterpret_cast<const float4*>(stage_tile + (size_t)r * CP + c);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic accesses to the ring before the next TMA writes
+    __syncthreads();
+  }
+}
+
+// ---- MK_ATTN ------------------------------------------------------------------------------------------------------------
+template <bool BF16>
+__device__ __forceinline__ void mk_attn_item(const MkPhase& ph, int Brows, int H, int planes, int sc_floats, uint8_t* reg, int sub,
+                                             int tid, int item, int pos) {
+  typedef typename KvIo<BF16>::T KT;
+  constexpr int NT = 64, DH = 64, EPL = KvIo<BF16>::EPL, LPK = DH / EPL, NG = NT / LPK, CHUNK = BF16 ? 64 : 32;
+  constexpr int ROWB = DH * (int)sizeof(KT), PITCH = ROWB + 16, STAGE = CHUNK * PITCH, KPG = CHUNK / NG;
+  float* sc = reinterpret_cast<float*>(reg + 2 * STAGE);
+  float* part = sc + sc_floats;                        // [NG][64]
+  float* qs = part + NG * DH;                          // [64]
+  float* red = qs + DH;                                // [4]
+  float* knew = red + 4;                               // [64] this step's key row (append)
+  float* vnew = knew + DH;                             // [64]
+  const int lane = tid & 31, warp = tid >> 5;
+  const int grp = tid / LPK, lk = tid % LPK;
+  const int b = item / H, h = item - b * H;
+  const int nkeys = ph.append ? pos + 1 : ph.Tk;     // keys attended, the step's own key included
+  const int bkv = b / ph.kv_group;
+  KT* khead = static_cast<KT*>(ph.kcache) + (size_t)bkv * ph.kv_batch_stride + (size_t)h * ph.kv_head_stride;
+  KT* vhead = static_cast<KT*>(ph.vcache) + (size_t)bkv * ph.kv_batch_stride + (size_t)h * ph.kv_head_stride;
+  const uint32_t ring_u = smem_u32(reg);
+  // keys already in the cache; the key/value of THIS step (append) never takes the round trip through global memory: it is
+  // written to the cache for the later steps and used here from shared memory (rounded to the cache's element type first)
+  const int nold = ph.append ? pos : ph.Tk;
+  const int nch = (nold + CHUNK - 1) / CHUNK;
+  uint64_t kvpol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(kvpol));
+  auto issue = [&](const KT* head, int c, int stage) {                   // rows [c*CHUNK, ..) of a head block -> ring[stage]
+    const int row0 = c * CHUNK, pieces = min(CHUNK, nold - row0) * LPK;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(head + (size_t)row0 * DH);
+    const uint32_t dst = ring_u + stage * STAGE;
+    for (int q = tid; q < pieces; q += NT) cp_async_16_hint(dst + (q / LPK) * PITCH + (q % LPK) * 16, src + (size_t)q * 16, kvpol);
+    cp_async_commit();
+  };
+  if (nch > 0) issue(khead, 0, 0);                     // the first K tiles travel while the projection partials are summed
+  if (nch > 1) issue(khead, 1, 1);
+  {  // q (and this step's k, v) = sum of the K slices of the projection, in slice order; thread t owns element t of the head row.
+     // All loads are issued before the first add (one L2 round trip, not one per slice).
+    const size_t mn = (size_t)Brows * ph.q_ld;
+    const float* base = reinterpret_cast<const float*>(ph.part) + (size_t)b * ph.q_ld + h * DH + tid;
+    float pq[MK_MAXS], pk[MK_MAXS], pv[MK_MAXS];
+#pragma unroll
+    for (int z = 0; z < MK_MAXS; ++z) {
+      const bool on = z < ph.q_splits;
+      pq[z] = on ? base[z * mn + ph.q_col] : 0.f;
+      pk[z] = (on && ph.append) ? base[z * mn + ph.k_col] : 0.f;
+      pv[z] = (on && ph.append) ? base[z * mn + ph.v_col] : 0.f;
+    }
+    float qv = pq[0], kv = pk[0], vv = pv[0];
+#pragma unroll
+    for (int z = 1; z < MK_MAXS; ++z)
+      if (z < ph.q_splits) { qv += pq[z]; kv += pk[z]; vv += pv[z]; }
+    qs[tid] = qv;
+    if (ph.append) {
+      if (BF16) {
+        const __nv_bfloat16 kb = __float2bfloat16_rn(kv), vb = __float2bfloat16_rn(vv);
+        reinterpret_cast<__nv_bfloat16*>(khead)[(size_t)pos * DH + tid] = kb;
+        reinterpret_cast<__nv_bfloat16*>(vhead)[(size_t)pos * DH + tid] = vb;
+        kv = __bfloat162float(kb);
+        vv = __bfloat162float(vb);
+      } else {
+        reinterpret_cast<float*>(khead)[(size_t)pos * DH + tid] = kv;
+        reinterpret_cast<float*>(vhead)[(size_t)pos * DH + tid] = vv;
+      }
+      knew[tid] = kv;
+      vnew[tid] = vv;
+    }
+  }
+  bar_sub(sub);
+
+  float q[DH];
+#pragma unroll
+  for (int i = 0; i < DH; i += 4) {
+    const float4 x = *reinterpret_cast<const float4*>(qs + i);
+    q[i] = x.x; q[i + 1] = x.y; q[i + 2] = x.z; q[i + 3] = x.w;
+  }
+  if (ph.append && tid == NT - 1) {                    // score of the step's own key, from shared memory
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < DH; ++i) d[i & 3] = fmaf(q[i], knew[i], d[i & 3]);
+    sc[pos] = ((d[0] + d[1]) + (d[2] + d[3])) * ph.scale;
+  }
+  // ---- pass 1: scores of the cached keys, one thread per key
+  for (int c = 0; c < nch; ++c) {
+    if (c + 1 < nch) cp_async_wait<1>(); else cp_async_wait<0>();
+    bar_sub(sub);
+    const int j = c * CHUNK + tid;
+    if (tid < CHUNK && j < nold) {
+      const uint4* row = reinterpret_cast<const uint4*>(reg + (c & 1) * STAGE + tid * PITCH);
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < LPK; ++i) d[i & 3] += KvIo<BF16>::dot(row[i], q + i * EPL);
+      sc[j] = ((d[0] + d[1]) + (d[2] + d[3])) * ph.scale;
+    }
+    bar_sub(sub);
+    if (c + 2 < nch) issue(khead, c + 2, c & 1);
+  }
+  if (nch > 0) issue(vhead, 0, 0);
+  if (nch > 1) issue(vhead, 1, 1);
+  bar_sub(sub);                                        // the own key's score is visible (covers the no-tile first step too)
+  // key-padding mask (masked_fill(-finfo.max)) and softmax statistics
+  const uint8_t* km = ph.key_mask ? ph.key_mask + (size_t)bkv * ph.Tk : nullptr;
+  float mx = -INFINITY;
+  for (int j = tid; j < nkeys; j += NT) {
+    float v = sc[j];
+    if (km && !km[j]) { v = -FLT_MAX; sc[j] = v; }
+    mx = fmaxf(mx, v);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  bar_sub(sub);
+  mx = fmaxf(red[0], red[1]);
+  bar_sub(sub);
+  float sum = 0.f;
+  for (int j = tid; j < nkeys; j += NT) {
+    const float e = expf(sc[j] - mx);
+    sc[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  bar_sub(sub);
+  const float inv = 1.f / (red[0] + red[1]);
+  // ---- pass 2: out = P V, a group of LPK lanes per key
+  float acc[EPL];
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) acc[i] = 0.f;
+  for (int c = 0; c < nch; ++c) {
+    if (c + 1 < nch) cp_async_wait<1>(); else cp_async_wait<0>();
+    bar_sub(sub);
+    const uint8_t* tile = reg + (c & 1) * STAGE + lk * 16;
+#pragma unroll
+    for (int i = 0; i < KPG; ++i) {
+      const int jl = grp + NG * i, j = c * CHUNK + jl;
+      if (j < nold) KvIo<BF16>::axpy(*reinterpret_cast<const uint4*>(tile + jl * PITCH), sc[j], acc);
+    }
+    bar_sub(sub);
+    if (c + 2 < nch) issue(vhead, c + 2, c & 1);
+  }
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) part[grp * DH + lk * EPL + i] = acc[i];
+  bar_sub(sub);
+  {
+    float r = 0.f;
+#pragma unroll
+    for (int w = 0; w < NG; ++w) r += part[w * DH + tid];
+    if (ph.append) r = fmaf(sc[pos], vnew[tid], r);
+    store_planes1(ph.outp + (size_t)b * planes * ph.out_kp + h * DH + tid, r * inv, planes, ph.out_kp);
+  }
+}
+
+__device__ __forceinline__ void mk_attn(const MkPlan& P, const MkPhase& ph, uint8_t* smem, Ctl& ctl, int pos) {
+  const int items = P.B * P.H;
+  const int mine = (int)blockIdx.x < items ? (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  if (threadIdx.x == 0) ctl.attn_ctr = 0;
+  __syncthreads();
+  const int sub = threadIdx.x >> 6, tid = threadIdx.x & 63;
+  uint8_t* reg = smem + (size_t)sub * MK_SUB_BYTES;
+  for (;;) {
+    if (tid == 0) ctl.sub_item[sub] = atomicAdd(&ctl.attn_ctr, 1);
+    bar_sub(sub);
+    const int k = ctl.sub_item[sub];
+    if (k >= mine) break;
+    const int item = (int)blockIdx.x + k * (int)gridDim.x;
+    if (P.kv_bf16) mk_attn_item<true>(ph, P.B, P.H, P.planes, P.sc_floats, reg, sub, tid, item, pos);
+    else mk_attn_item<false>(ph, P.B, P.H, P.planes, P.sc_floats, reg, sub, tid, item, pos);
+    bar_sub(sub);
+  }
+}
+
+// ---- row phases ----------------------------------------------------------------------------------------------------------
+// A row (<= 384 float4 = 1536 floats) is spread over the WHOLE CTA, one float4 per thread, and a CTA handles two rows at a
+// time (rows r and r + gridDim.x: at 256 decode rows every CTA has at most two), so that every load of the phase -- all K
+// slices of both rows -- is in flight before the first add: the phase costs one L2 round trip, not one per slice.
+
+// block-wide sums of two values; every thread of the CTA must call it
+__device__ __forceinline__ void block_sum2(float& a, float& b, float* red) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (lane == 0) { red[warp] = a; red[MK_WARPS + warp] = b; }
+  __syncthreads();
+  float sa = 0.f, sb = 0.f;
+#pragma unroll
+  for (int w = 0; w < MK_WARPS; ++w) { sa += red[w]; sb += red[MK_WARPS + w]; }
+  __syncthreads();
+  a = sa;
+  b = sb;
+}
+
+// sum of the K slices of one float4, slice order; all loads first
+__device__ __forceinline__ float4 sum_slices(const float* p, size_t slice_stride, int splits) {
+  float4 t[MK_MAXS];
+#pragma unroll
+  for (int z = 0; z < MK_MAXS; ++z)
+    t[z] = z < splits ? *reinterpret_cast<const float4*>(p + z * slice_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 a = t[0];
+#pragma unroll
+  for (int z = 1; z < MK_MAXS; ++z)
+    if (z < splits) { a.x += t[z].x; a.y += t[z].y; a.z += t[z].z; a.w += t[z].w; }
+  return a;
+}
+
+// LayerNorm of two rows held one float4 per thread (thread c < n4 owns columns 4c..4c+3; on[k]: row k exists) -> bf16 planes
+__device__ __forceinline__ void ln_pair(const float4 (&v)[2], const bool (&on)[2], int c, int n4, int dim, const float* gain,
+                                        const float* beta, __nv_bfloat16* const (&out)[2], int planes, int kp, float* red) {
+  const bool mine = c < n4;
+  float s0 = (mine && on[0]) ? (v[0].x + v[0].y) + (v[0].z + v[0].w) : 0.f;
+  float s1 = (mine && on[1]) ? (v[1].x + v[1].y) + (v[1].z + v[1].w) : 0.f;
+  block_sum2(s0, s1, red);
+  const float mean[2] = {s0 / (float)dim, s1 / (float)dim};
+  float q[2] = {0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+    if (mine && on[k]) {
+      const float a = v[k].x - mean[k], b = v[k].y - mean[k], cc = v[k].z - mean[k], d = v[k].w - mean[k];
+      q[k] = (a * a + b * b) + (cc * cc + d * d);
+    }
+  block_sum2(q[0], q[1], red);
+  if (!mine) return;
+  const float4 g = __ldg(reinterpret_cast<const float4*>(gain) + c);
+  float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (beta) bb = __ldg(reinterpret_cast<const float4*>(beta) + c);
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+    if (on[k]) {
+      const float rstd = rsqrtf(q[k] / (float)dim + 1e-5f);
+      float4 o;
+      o.x = (v[k].x - mean[k]) * rstd * g.x; o.y = (v[k].y - mean[k]) * rstd * g.y;
+      o.z = (v[k].z - mean[k]) * rstd * g.z; o.w = (v[k].w - mean[k]) * rstd * g.w;
+      if (beta) { o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
+      store_planes4(out[k] + c * 4, o, planes, kp);
+    }
+}
+
+__device__ __forceinline__ void mk_row_resln(const MkPlan& P, const MkPhase& ph, Ctl& ctl) {
+  const int N = ph.N, n4 = N >> 2, c = threadIdx.x;
+  const size_t mn = (size_t)ph.M * N;
+  for (int r0 = (int)blockIdx.x; r0 < ph.M; r0 += 2 * (int)gridDim.x) {
+    const int row[2] = {r0, r0 + (int)gridDim.x};
+    const bool on[2] = {true, row[1] < ph.M};
+    float4 v[2], res[2];
+    v[0] = v[1] = res[0] = res[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < n4) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        if (on[k]) {
+          res[k] = *reinterpret_cast<const float4*>(ph.x + (size_t)row[k] * N + c * 4);
+          v[k] = sum_slices(ph.part + (size_t)row[k] * N + c * 4, mn, ph.in_splits);
+        }
+      float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ph.bias) bb = __ldg(reinterpret_cast<const float4*>(ph.bias) + c);
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        if (on[k]) {
+          float4 a = v[k];
+          a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+          a.x = __fadd_rn(a.x, res[k].x); a.y = __fadd_rn(a.y, res[k].y); a.z = __fadd_rn(a.z, res[k].z); a.w = __fadd_rn(a.w, res[k].w);
+          *reinterpret_cast<float4*>(ph.x + (size_t)row[k] * N + c * 4) = a;
+          v[k] = a;
+        }
+    }
+    __nv_bfloat16* const out[2] = {ph.outp + (size_t)row[0] * P.planes * ph.out_kp, ph.outp + (size_t)row[1] * P.planes * ph.out_kp};
+    ln_pair(v, on, c, n4, N, ph.gain, ph.beta, out, P.planes, ph.out_kp, ctl.red);
+  }
+}
+
+// gelu_erf(bias + sum of the K slices) -> planes.  U float4 per thread per batch, all loads of a batch in flight together.
+__device__ __forceinline__ void mk_row_gelu(const MkPlan& P, const MkPhase& ph) {
+  constexpr int U = 3;
+  const int N = ph.N, n4 = N >> 2;
+  const size_t mn = (size_t)ph.M * N;
+  const int total = ph.M * n4, stride = (int)gridDim.x * MK_THREADS;
+  for (int i0 = (int)blockIdx.x * MK_THREADS + (int)threadIdx.x; i0 < total; i0 += U * stride) {
+    float4 a[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * stride;
+      if (i < total) a[u] = sum_slices(ph.part + (size_t)i * 4, mn, ph.in_splits);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * stride;
+      if (i >= total) continue;
+      const int row = i / n4, c = i - row * n4;
+      float4 v = a[u];
+      if (ph.bias) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(ph.bias) + c);
+        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+      }
+      v.x = act_apply(v.x, DIM_ACT_GELU_ERF, 0.f); v.y = act_apply(v.y, DIM_ACT_GELU_ERF, 0.f);
+      v.z = act_apply(v.z, DIM_ACT_GELU_ERF, 0.f); v.w = act_apply(v.w, DIM_ACT_GELU_ERF, 0.f);
+      store_planes4(ph.outp + (size_t)row * P.planes * ph.out_kp + c * 4, v, P.planes, ph.out_kp);
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t order_key(float v) {      // unsigned key with the order of the floats (-0 == +0)
+  const uint32_t u = __float_as_uint(v + 0.0f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// One warp samples one row of logits held in shared memory.  Lane l owns the NPL = V/32 consecutive logits [l*NPL, (l+1)*NPL):
+// index order is (lane, slot) order.  Same decisions as sample_row (rowops.cu): greedy = first maximal index; sampling = keep the
+// top_k logits with ties toward the lower index, softmax(l / temperature) over them in fp32, inverse-CDF draw in index order
+// with fp64 running sums whose association (chunks of V/256 entries, 8 chunks per lane, Hillis-Steele scan over lanes) equals
+// the block kernel's.
+template <int NPL>
+__device__ __forceinline__ int mk_sample_row(const MkPlan& P, const float* lg, int row, int st, int lane) {
+  constexpr int PER = NPL / 8;                           // entries per chunk of the block kernel (V / 256)
+  constexpr int V = NPL * 32;
+  float l[NPL];
+#pragma unroll
+  for (int j = 0; j < NPL; j += 4) {
+    const float4 a = *reinterpret_cast<const float4*>(lg + lane * NPL + j);
+    l[j] = a.x; l[j + 1] = a.y; l[j + 2] = a.z; l[j + 3] = a.w;
+  }
+  int tok;
+  if (P.temperature == 0.f) {
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+      const int i = lane * NPL + j;
+      if (l[j] > best || (l[j] == best && i < bi)) { best = l[j]; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    tok = bi == 0x7fffffff ? 0 : bi;
+  } else {
+    // k-th largest key by bitwise binary search: T = max{t : #(key >= t) >= k}
+    uint32_t key[NPL];
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) key[j] = order_key(l[j]);
+    const int k = min(P.top_k, V);
+    uint32_t T = 0;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = T | (1u << bit);
+      int cnt = 0;
+#pragma unroll
+      for (int j = 0; j < NPL; ++j) cnt += key[j] >= cand;
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if (cnt >= k) T = cand;
+    }
+    int gt = 0, eq = 0;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) { gt += key[j] > T; eq += key[j] == T; }
+    const int need = k - __reduce_add_sync(0xffffffffu, gt);        // how many of the entries equal to T are kept (lowest indices)
+    int eq_before = eq;                                              // exclusive prefix of eq over lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, eq_before, o);
+      if (lane >= o) eq_before += up;
+    }
+    eq_before -= eq;
+    float sp[NPL];
+    float mx = -INFINITY;
+    int seen = 0;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+      bool keep = key[j] > T;
+      if (key[j] == T) { keep = eq_before + seen < need; ++seen; }
+      sp[j] = keep ? l[j] / P.temperature : -INFINITY;
+      if (keep) mx = fmaxf(mx, sp[j]);
+    }
+    mx = warp_max(mx);
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) sp[j] = sp[j] == -INFINITY ? 0.f : expf(sp[j] - mx);
+    double loc[8], run = 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      double mine = 0.0;
+#pragma unroll
+      for (int e = 0; e < PER; ++e) mine += (double)sp[c * PER + e];
+      loc[c] = run;
+      run += mine;
+    }
+    double incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    const double excl = incl - run;
+    const double total = __shfl_sync(0xffffffffu, incl, 31);
+    const double target = (double)P.uniforms[(size_t)row * P.u_stride + st] * total;
+    int pick = 0x7fffffff, last = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      double cum = excl + loc[c];
+#pragma unroll
+      for (int e = 0; e < PER; ++e) {
+        const float pv = sp[c * PER + e];
+        const int i = lane * NPL + c * PER + e;
+        if (pv > 0.f) {
+          last = max(last, i);
+          cum += (double)pv;
+          if (cum > target) pick = min(pick, i);
+        }
+      }
+    }
+    pick = __reduce_min_sync(0xffffffffu, pick);
+    last = __reduce_max_sync(0xffffffffu, last);
+    tok = pick == 0x7fffffff ? last : pick;
+  }
+  if (lane == 0) P.tokens[(size_t)row * P.tok_stride + st + 1] = tok;
+  return tok;
+}
+
+// logits = bias + sum of the K slices (whole CTA, into shared memory) -> one warp per row samples -> token embedding -> x and
+// layer 0's LayerNorm -> planes (whole CTA again).  Two rows per pass.
+__device__ __forceinline__ void mk_row_sample(const MkPlan& P, const MkPhase& ph, float* lg /*[2][V] shared*/, Ctl& ctl, int st) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int V = ph.N, v4 = V >> 2, D = ph.D, n4 = D >> 2, c = threadIdx.x;
+  const size_t mn = (size_t)ph.M * V;
+  for (int r0 = (int)blockIdx.x; r0 < ph.M; r0 += 2 * (int)gridDim.x) {
+    const int row[2] = {r0, r0 + (int)gridDim.x};
+    const bool on[2] = {true, row[1] < ph.M};
+    for (int f = c; f < 2 * v4; f += MK_THREADS) {
+      const int k = f / v4, j = f - k * v4;
+      if (!on[k]) continue;
+      float4 a = sum_slices(ph.part + (size_t)row[k] * V + j * 4, mn, ph.in_splits);
+      if (ph.bias) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(ph.bias) + j);
+        a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+      }
+      *reinterpret_cast<float4*>(lg + k * V + j * 4) = a;
+      if (P.logits_out) *reinterpret_cast<float4*>(P.logits_out + (size_t)row[k] * P.lo_stride + (size_t)st * V + j * 4) = a;
+    }
+    __syncthreads();
+    if (warp < 2 && on[warp]) {
+      int tok;
+      if (V == 512) tok = mk_sample_row<16>(P, lg + warp * V, row[warp], st, lane);
+      else if (V == 1024) tok = mk_sample_row<32>(P, lg + warp * V, row[warp], st, lane);
+      else tok = mk_sample_row<8>(P, lg + warp * V, row[warp], st, lane);
+      if (lane == 0) ctl.tok[warp] = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
+    }
+    __syncthreads();
+    // next step's input: token embedding -> x, layer 0's LayerNorm -> planes
+    float4 v[2];
+    v[0] = v[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < n4) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        if (on[k]) {
+          v[k] = __ldg(reinterpret_cast<const float4*>(ph.emb + (size_t)ctl.tok[k] * D) + c);
+          *reinterpret_cast<float4*>(ph.x + (size_t)row[k] * D + c * 4) = v[k];
+        }
+    }
+    __nv_bfloat16* const out[2] = {ph.outp + (size_t)row[0] * P.planes * ph.out_kp, ph.outp + (size_t)row[1] * P.planes * ph.out_kp};
+    ln_pair(v, on, c, n4, D, ph.gain, ph.beta, out, P.planes, ph.out_kp, ctl.red);
+  }
+}
+
+__global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const __grid_constant__ MkPlan P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) Ctl ctl;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < MK_STAGES; ++s) {
+      mbar_init(smem_u32(&ctl.full_bar[s]), 1);
+      mbar_init(smem_u32(&ctl.empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&ctl.accum_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl.tmem_slot)), "r"(MK_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = ctl.tmem_slot;
+
+  Pipe pipe;
+  unsigned int bar_target = 0;
+  const int nph = P.nphases, steps = P.steps;
+  if ((int)threadIdx.x < P.nmaps) asm volatile("prefetch.tensormap [%0];" ::"l"(&P.maps[threadIdx.x]) : "memory");
+  unsigned long long t_prev = 0;
+  const bool tracing = P.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  if (tracing) t_prev = gtime_ns();
+  for (int st = 0; st < steps; ++st) {
+    for (int i = 0; i < nph; ++i) {
+      const MkPhase& ph = P.phases[i];                 // kernel-parameter space: uniform constant-bank reads
+      const int nxt = i + 1 < nph ? i + 1 : 0;
+      if (threadIdx.x == 32 && P.phases[nxt].type == MK_GEMM) {     // descriptors of the next GEMM phase
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&P.maps[P.phases[nxt].mapA]) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&P.maps[P.phases[nxt].mapW]) : "memory");
+      }
+      switch (ph.type) {
+        case MK_GEMM: mk_gemm(P, ph, smem, smem_base, ctl, pipe, tmem_base); break;
+        case MK_ATTN: mk_attn(P, ph, smem, ctl, st); break;
+        case MK_ROW_RESLN: mk_row_resln(P, ph, ctl); break;
+        case MK_ROW_GELU: mk_row_gelu(P, ph); break;
+        case MK_ROW_SAMPLE: mk_row_sample(P, ph, reinterpret_cast<float*>(smem), ctl, st); break;
+        default: break;
+      }
+      grid_sync(P.bar, bar_target, P.phases[nxt].type == MK_GEMM);
+      if (tracing) {
+        const unsigned long long t = gtime_ns();
+        P.trace[i] += t - t_prev;
+        t_prev = t;
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(MK_TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace
+
+bool mk_supported(int D, int inner, int F, int V, int H, int planes, int max_keys) {
+  static const bool off = getenv("DIM_DECODE_IMPL") != nullptr && std::string(getenv("DIM_DECODE_IMPL")) == "graph";
+  if (off) return false;
+  if (planes < 1 || planes > 3) return false;
+  if (D % 64 || inner % 64 || F % 64 || D > 4 * MK_THREADS || inner != H * 64) return false;
+  if (!(V == 256 || V == 512 || V == 1024)) return false;
+  // per attention sub-group: 2-stage K/V ring + scores + partial outputs + q + reduction slots
+  const size_t need = 2 * 64 * 144 + (size_t)((max_keys + 3) / 4 * 4) * 4 + 8 * 64 * 4 + 3 * 64 * 4 + 16;
+  return need <= MK_SUB_BYTES;
+}
+
+int launch_decode_megakernel(const MkPlan& plan, cudaStream_t s) {
+  static_assert(sizeof(MkPlan) <= 32000, "the plan travels as a kernel parameter (limit 32764 bytes)");
+  DIM_REQUIRE(plan.nphases > 0 && plan.nphases <= MK_MAX_PHASES && plan.steps > 0 && plan.bar != nullptr, "decode megakernel: bad plan");
+  constexpr size_t smem = MK_RING + 1024;
+  int dev = 0, sms = 0;
+  DIM_CHECK_CUDA(cudaGetDevice(&dev));
+  DIM_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  DIM_CHECK_CUDA(cudaFuncSetAttribute(decode_megakernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  DIM_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_megakernel, MK_THREADS, smem));
+  DIM_REQUIRE(per_sm >= 1, "decode megakernel: one CTA does not fit an SM");
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(sms);
+  cfg.blockDim = dim3(MK_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;         // all CTAs co-resident: the grid barrier cannot deadlock
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ProfScope ps(CAT_DECODE_MK, s, 0, 0);
+  DIM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_megakernel, plan));
+  DIM_LAUNCHED();
+  return DIM_OK;
+}
+
+}  // namespace dimb

@@ -1,0 +1,73 @@
+// Persistent decode kernel ("megakernel"): every autoregressive step of decoder_joint.generate in ONE cooperative launch.
+// See decode_mk.cu.  The host (engine.cu) fills an MkPlan -- a phase program for one decode step plus the TMA descriptors it
+// needs -- and launches decode_megakernel with it as the kernel parameter.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace dimb {
+
+enum { MK_GEMM = 1, MK_ATTN = 2, MK_ROW_RESLN = 3, MK_ROW_GELU = 4, MK_ROW_SAMPLE = 5, MK_NTYPES = 6 };
+
+constexpr int MK_MAX_PHASES = 64;
+constexpr int MK_MAX_MAPS = 48;
+constexpr int MK_PART_FLOATS = 9216;     // split-K partial columns per decode row (max over the GEMMs of splits * N)
+
+struct MkPhase {
+  int type;
+  int M, N;                                  // rows (decode rows), output columns
+  // ---- MK_GEMM: part[z][M][N] = A_planes[M, :] . W_planes[N, :]^T over the z-th slice of the (plane pair, k-block) iterations
+  int mapA, mapW;                            // indices into MkPlan::maps
+  int kblocks, npairs, splits, bn, kp;
+  int pa[6], pw[6];
+  float w_keep;                              // > 0: fraction of the weight tiles loaded with L2 evict_last
+  float* part;
+  // ---- MK_ATTN: one query row per (decode row, head) over a head-major K/V cache
+  int q_splits, q_ld, q_col, k_col, v_col;   // the producing GEMM's partials: pitch and column offsets of q / new k / new v
+  int append, Tk, kv_group;
+  void *kcache, *vcache;
+  unsigned long long kv_batch_stride, kv_head_stride;
+  const uint8_t* key_mask;
+  float scale;
+  // ---- row phases (also the outputs of MK_ATTN): bf16 planes [M, planes * out_kp] = the next GEMM's A operand
+  __nv_bfloat16* outp;
+  int out_kp;
+  int in_splits;                             // partial slices to sum (row phases)
+  const float* bias;                         // [N] nullable
+  float* x;                                  // residual stream [M, N]
+  const float *gain, *beta;                  // LayerNorm (beta nullable)
+  const float* emb;                          // MK_ROW_SAMPLE: token embedding [V, D]
+  int D;                                     // MK_ROW_SAMPLE: model width (N = vocabulary)
+};
+
+struct alignas(128) MkPlan {
+  CUtensorMap maps[MK_MAX_MAPS];
+  MkPhase phases[MK_MAX_PHASES];
+  int nphases;
+  int nmaps;
+  int B;                                     // decode rows
+  int H;
+  int planes;
+  int kv_bf16;
+  int steps;
+  int sc_floats;                             // score slots per attention work item (>= max keys, multiple of 4)
+  unsigned int* bar;                         // grid barrier counter, zero at launch
+  unsigned long long* trace;                 // nullable: [MK_MAX_PHASES] ns spent per phase (summed over steps), CTA 0's view
+  int64_t* tokens;                           // [B, tok_stride]; column 0 = prompt, column st+1 = token of step st
+  int tok_stride;
+  const float* uniforms;                     // [B, u_stride] (sampling)
+  int u_stride;
+  float* logits_out;                         // nullable [B, lo_stride]
+  long long lo_stride;
+  float temperature;
+  int top_k;
+};
+
+// True when the persistent kernel can decode this configuration (otherwise the caller keeps the per-kernel path).
+bool mk_supported(int D, int inner, int F, int V, int H, int planes, int max_keys);
+// Cooperative launch of the persistent kernel; the plan travels as a __grid_constant__ kernel parameter (TMA descriptors
+// included).  The barrier counter (plan.bar) must have been zeroed on the same stream.
+int launch_decode_megakernel(const MkPlan& plan, cudaStream_t s);
+
+}  // namespace dimb

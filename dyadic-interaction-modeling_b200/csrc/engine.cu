@@ -5,6 +5,7 @@
 //   * decoder_joint.generate                   (seq2seq_pretrain.py:450; x-transformers 1.30.16)
 // Everything is enqueued on the caller's stream; no host synchronisation inside.
 #include <cstdlib>
+#include <cstring>
 #include <memory>
 #include <string>
 #include <unordered_map>
@@ -12,6 +13,7 @@
 
 #include "attention.cuh"
 #include "common.cuh"
+#include "decode_mk.cuh"
 #include "gemm_f32.cuh"
 #include "gemm_tc.cuh"
 #include "rowops.cuh"
@@ -20,6 +22,11 @@
 using namespace dimb;
 
 namespace {
+
+bool g_mk_trace_on = false;
+int g_decode_impl = 0;                                    // 0: persistent kernel when supported; 1: per-kernel CUDA-graph path
+std::vector<unsigned long long> g_mk_trace_host;     // last collected trace, ns per phase
+std::vector<int> g_mk_trace_types;
 
 struct TensorRef {
   const void* p = nullptr;
@@ -426,6 +433,11 @@ struct GenWs {
   uint8_t* mask_stage;                     // [B,T] copy of the caller's key-padding mask   } what the captured step graph reads:
   float* u_stage;                          // [R,steps] copy of the caller's uniforms       } the graph never holds caller pointers
   __nv_bfloat16 *ap, *ap2;                 // A-operand plane scratch for the tensor-core GEMMs
+  // persistent decode kernel (decode_mk.cu): split-K partials [MK_PART_FLOATS per row], attention-output planes, grid barrier, trace
+  float* mk_part;
+  __nv_bfloat16* mk_attp;
+  unsigned int* mk_bar;
+  unsigned long long* mk_trace;
   size_t bytes;
 };
 // B clips, S samples per clip: the cross-attention K/V exist once per clip, everything else once per decode row (R = B*S).
@@ -458,6 +470,10 @@ GenWs carve_gen(const dim_s2s_config& c, int planes, bool kv_bf16, int B, int T,
     w.ap = planes ? reinterpret_cast<__nv_bfloat16*>(take(need / 2 + 64)) : nullptr;
     w.ap2 = planes ? reinterpret_cast<__nv_bfloat16*>(take(rows_step * tc_round_k(c.ff_mult * D) * planes / 2 + 64)) : nullptr;
   }
+  w.mk_part = planes ? take(R * MK_PART_FLOATS) : nullptr;
+  w.mk_attp = planes ? reinterpret_cast<__nv_bfloat16*>(take(R * (size_t)tc_round_k(inner) * planes / 2 + 64)) : nullptr;
+  w.mk_bar = reinterpret_cast<unsigned int*>(take(64));
+  w.mk_trace = reinterpret_cast<unsigned long long*>(take(2 * MK_MAX_PHASES));
   w.bytes = (size_t)(p - static_cast<char*>(base));
   return w;
 }
@@ -478,6 +494,17 @@ extern "C" int dim_create(dim_handle_t* out, int device) {
 
 extern "C" int dim_destroy(dim_handle_t h) {
   if (!h) return DIM_OK;
+  cudaSetDevice(h->device);
+  for (auto& m : h->s2s) {
+    for (auto& G : m->graphs) {
+      if (G.exec) cudaGraphExecDestroy(G.exec);
+      if (G.exec_u) cudaGraphExecDestroy(G.exec_u);
+      if (G.fork) cudaEventDestroy(G.fork);
+      if (G.join) cudaEventDestroy(G.join);
+      if (G.stream) cudaStreamDestroy(G.stream);
+    }
+    if (m->fork_ev) cudaEventDestroy(m->fork_ev);
+  }
   for (void* p : h->owned) cudaFree(p);
   delete h;
   return DIM_OK;
@@ -696,7 +723,17 @@ extern "C" int dim_slmft_build(dim_handle_t h, const dim_s2s_config* cfg, int pr
 // side streams: their chains interleave on the SMs and hide each other's launch/pipeline-fill/epilogue latencies.
 // Per-row results do not depend on the grouping (no cross-row arithmetic; split-K depends on K only).
 constexpr int kMaxGroups = 8;
-int plan_groups(const S2SModel& m, int B, int* begin /*[kMaxGroups+1]*/) {
+int plan_groups(const S2SModel& m, int B, int max_keys, int* begin /*[kMaxGroups+1]*/) {
+  {  // the persistent decode kernel owns every SM: one chain
+    const dim_s2s_config& c = m.cfg;
+    const int D = c.dim + c.dim_audio;
+    if (g_decode_impl == 0 && m.tc.planes > 0 &&
+        mk_supported(D, c.heads * c.dim_head, c.ff_mult * D, c.num_tokens, c.heads, m.tc.planes, max_keys)) {
+      begin[0] = 0;
+      begin[1] = B;
+      return 1;
+    }
+  }
   // tuning hooks: DIM_GROUP_ROWS (rows per group, multiple of 64; default 128), DIM_MAX_GROUPS, DIM_NO_GROUPS.
   // Default: plain bf16 operands decode as ONE chain (with the cp.async attention kernel and the narrow-tile decode GEMMs a
   // single chain measured faster than 2 concurrent groups: 271 vs 282 ms per step); the fp32-grade mode (3-6x longer GEMM
@@ -709,6 +746,7 @@ int plan_groups(const S2SModel& m, int B, int* begin /*[kMaxGroups+1]*/) {
   static const bool no_groups = getenv("DIM_NO_GROUPS") != nullptr;
   if (no_groups) ng = 1;
   const int per = (B / ng + kGroupRows - 1) / kGroupRows * kGroupRows;      // multiples of the group size, remainder in the last
+  ng = std::min(ng, (B + per - 1) / per);                                   // rounding up may leave fewer non-empty groups
   for (int g = 0; g <= ng; ++g) begin[g] = std::min(B, g * per);
   begin[ng] = B;
   return ng;
@@ -722,7 +760,7 @@ extern "C" size_t dim_slmft_workspace_bytes(dim_handle_t h, int model, int B, in
   size_t b = 0;
   if (steps > 0) {
     int begin[kMaxGroups + 1];
-    const int ng = plan_groups(*h->s2s[model], B, begin);
+    const int ng = plan_groups(*h->s2s[model], B, std::max(T, steps + 1), begin);
     for (int g = 0; g < ng; ++g)
       b += carve_gen(c, planes, h->s2s[model]->precision == DIM_PREC_BF16, begin[g + 1] - begin[g], T, steps, nullptr).bytes;
   }
@@ -752,6 +790,145 @@ extern "C" int dim_slmft_context(dim_handle_t h, int model, const float* v_speak
 }
 
 namespace {
+
+// ---- persistent decode kernel: the phase program of ONE decode step (decode_mk.cu) -------------------------------------------
+// Tile width and split-K factor of a decode-step GEMM: ~72 work units per 128-row tile of decode rows (144 at 256 rows: one per
+// SM).  A function of (N, K, planes) only -- never of the number of rows -- so a row's bits do not depend on its batch.
+void mk_gemm_cfg(int N, int K, int planes, int* bn, int* splits) {
+  const int kp = tc_round_k(K), npairs = planes == 1 ? 1 : (planes == 2 ? 3 : 6);
+  const int total_it = kp / 64 * npairs;
+  *bn = (N >= 2048 || kp >= 2048) ? 128 : 64;
+  const int nt = cdiv(N, *bn);
+  int sp = (72 + nt / 2) / nt;
+  sp = std::max(1, std::min(sp, 9));
+  sp = std::min(sp, total_it);
+  while (sp > 1 && sp * N > MK_PART_FLOATS) --sp;
+  *splits = sp;
+}
+
+struct MkBuilder {
+  MkPlan& P;
+  const S2SModel& m;
+  int nmaps = 0;
+  int rows;
+  MkBuilder(MkPlan& p, const S2SModel& mm, int r) : P(p), m(mm), rows(r) {}
+  int add_map(const __nv_bfloat16* ptr, int nrows, int cols, int box_rows, int* idx) {
+    if (nmaps >= MK_MAX_MAPS) return fail(DIM_EINVAL, "decode plan: too many tensor maps");
+    if (int e = tc_make_map(ptr, nrows, cols, cols, box_rows, &P.maps[nmaps])) return e;
+    *idx = nmaps++;
+    return DIM_OK;
+  }
+  MkPhase* next(int type) {
+    if (P.nphases >= MK_MAX_PHASES) return nullptr;
+    MkPhase* ph = &P.phases[P.nphases++];
+    ph->type = type;
+    ph->M = rows;
+    return ph;
+  }
+  // part[z][rows][N] = A_planes . W^T ; returns the split factor
+  int gemm(int mapA, const float* W, int N, int K, float* part, float w_keep, int* splits_out) {
+    auto it = m.tc.wmap.find(W);
+    if (it == m.tc.wmap.end()) return fail(DIM_EINVAL, "decode plan: weight without bf16 planes");
+    MkPhase* ph = next(MK_GEMM);
+    if (!ph) return fail(DIM_EINVAL, "decode plan: too many phases");
+    const int planes = m.tc.planes, kp = tc_round_k(K);
+    ph->N = N; ph->kp = kp; ph->kblocks = kp / 64;
+    ph->npairs = tc_pairs(planes, ph->pa, ph->pw);
+    mk_gemm_cfg(N, K, planes, &ph->bn, &ph->splits);
+    ph->mapA = mapA;
+    if (int e = add_map(it->second, N, planes * kp, ph->bn, &ph->mapW)) return e;
+    ph->part = part;
+    ph->w_keep = w_keep;
+    *splits_out = ph->splits;
+    return DIM_OK;
+  }
+};
+
+// x-transformers Decoder layer order (a, c, f) x depth, final norm, to_logits, sampling: 12 phases per layer + 2.
+int build_mk_plan(const S2SModel& m, const GenWs& w, int B, int Bc, int T, int steps, int samples, float temperature, int top_k,
+                  const uint8_t* mask, const float* uniforms, float* logits_out, MkPlan& P) {
+  const dim_s2s_config& c = m.cfg;
+  const int inner = c.heads * c.dim_head, D = c.dim + c.dim_audio, F = c.ff_mult * D, V = c.num_tokens;
+  const int planes = m.tc.planes;
+  const bool kv16 = m.precision == DIM_PREC_BF16;
+  memset(&P, 0, sizeof(P));
+  MkBuilder b(P, m, B);
+  int mapLn, mapAtt, mapFf;
+  if (int e = b.add_map(w.ap, B, planes * D, 128, &mapLn)) return e;
+  if (int e = b.add_map(w.mk_attp, B, planes * inner, 128, &mapAtt)) return e;
+  if (int e = b.add_map(w.ap2, B, planes * F, 128, &mapFf)) return e;
+  static const float w_keep_env = getenv("DIM_L2_WEIGHT_KEEP") ? (float)atof(getenv("DIM_L2_WEIGHT_KEEP")) : -1.f;
+  const float w_keep = w_keep_env >= 0.f ? w_keep_env : (planes == 1 ? 0.7f : 0.f);
+  const float scale = 1.0f / sqrtf((float)c.dim_head);
+  auto resln = [&](int in_splits, const float* bias, const float* gain, const float* beta) -> int {
+    MkPhase* ph = b.next(MK_ROW_RESLN);
+    if (!ph) return fail(DIM_EINVAL, "decode plan: too many phases");
+    ph->N = D; ph->part = w.mk_part; ph->in_splits = in_splits; ph->bias = bias; ph->x = w.x; ph->gain = gain; ph->beta = beta;
+    ph->outp = w.ap; ph->out_kp = D;
+    return DIM_OK;
+  };
+  for (int l = 0; l < c.depth; ++l) {
+    const XtAttn& SA = m.self_attn[l];
+    const XtAttn& CA = m.cross_attn[l];
+    const XtFF& FF = m.ff[l];
+    int sp = 1;
+    // --- causal self attention with KV cache
+    if (int e = b.gemm(mapLn, SA.wqkv, 3 * inner, D, w.mk_part, w_keep, &sp)) return e;
+    {
+      MkPhase* ph = b.next(MK_ATTN);
+      if (!ph) return fail(DIM_EINVAL, "decode plan: too many phases");
+      ph->part = w.mk_part; ph->q_splits = sp; ph->q_ld = 3 * inner; ph->q_col = 0; ph->k_col = inner; ph->v_col = 2 * inner;
+      ph->append = 1; ph->Tk = 0; ph->kv_group = 1; ph->kcache = w.self_k[l]; ph->vcache = w.self_v[l];
+      ph->kv_batch_stride = (size_t)(steps + 1) * inner; ph->kv_head_stride = (size_t)(steps + 1) * c.dim_head;
+      ph->scale = scale; ph->outp = w.mk_attp; ph->out_kp = inner;
+    }
+    if (int e = b.gemm(mapAtt, SA.wo, D, inner, w.mk_part, w_keep, &sp)) return e;
+    if (int e = resln(sp, nullptr, CA.norm_g, CA.norm_b)) return e;
+    // --- cross attention over the once-projected context K/V
+    if (int e = b.gemm(mapLn, CA.wq, inner, D, w.mk_part, w_keep, &sp)) return e;
+    {
+      MkPhase* ph = b.next(MK_ATTN);
+      if (!ph) return fail(DIM_EINVAL, "decode plan: too many phases");
+      ph->part = w.mk_part; ph->q_splits = sp; ph->q_ld = inner; ph->q_col = 0;
+      ph->append = 0; ph->Tk = T; ph->kv_group = samples; ph->kcache = w.cross_kv[l];
+      const size_t vplane = (size_t)Bc * T * inner;      // V block follows the K block (one per clip)
+      ph->vcache = kv16 ? static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(w.cross_kv[l]) + vplane)
+                        : static_cast<void*>(w.cross_kv[l] + vplane);
+      ph->kv_batch_stride = (size_t)T * inner; ph->kv_head_stride = (size_t)T * c.dim_head;
+      ph->key_mask = mask; ph->scale = scale; ph->outp = w.mk_attp; ph->out_kp = inner;
+    }
+    if (int e = b.gemm(mapAtt, CA.wo, D, inner, w.mk_part, w_keep, &sp)) return e;
+    if (int e = resln(sp, nullptr, FF.norm_g, FF.norm_b)) return e;
+    // --- feed forward
+    if (int e = b.gemm(mapLn, FF.w1, F, D, w.mk_part, w_keep, &sp)) return e;
+    {
+      MkPhase* ph = b.next(MK_ROW_GELU);
+      if (!ph) return fail(DIM_EINVAL, "decode plan: too many phases");
+      ph->N = F; ph->part = w.mk_part; ph->in_splits = sp; ph->bias = FF.b1; ph->outp = w.ap2; ph->out_kp = F;
+    }
+    if (int e = b.gemm(mapFf, FF.w2, D, F, w.mk_part, w_keep, &sp)) return e;
+    const bool last = l + 1 == c.depth;
+    if (int e = resln(sp, FF.b2, last ? m.final_g : m.self_attn[l + 1].norm_g, last ? m.final_b : m.self_attn[l + 1].norm_b)) return e;
+  }
+  {
+    int sp = 1;
+    if (int e = b.gemm(mapLn, m.logits_w, V, D, w.mk_part, w_keep, &sp)) return e;
+    MkPhase* ph = b.next(MK_ROW_SAMPLE);
+    if (!ph) return fail(DIM_EINVAL, "decode plan: too many phases");
+    ph->N = V; ph->D = D; ph->part = w.mk_part; ph->in_splits = sp; ph->bias = m.logits_b; ph->emb = m.token_emb; ph->x = w.x;
+    ph->gain = m.self_attn[0].norm_g; ph->beta = m.self_attn[0].norm_b; ph->outp = w.ap; ph->out_kp = D;
+  }
+  P.nmaps = b.nmaps;
+  P.B = B; P.H = c.heads; P.planes = planes; P.kv_bf16 = kv16 ? 1 : 0; P.steps = steps;
+  P.sc_floats = (std::max(T, steps + 1) + 3) / 4 * 4;
+  P.bar = w.mk_bar; P.trace = g_mk_trace_on ? w.mk_trace : nullptr;
+  P.tokens = w.tokens; P.tok_stride = steps + 1;
+  P.uniforms = uniforms; P.u_stride = steps;
+  P.logits_out = logits_out; P.lo_stride = (long long)steps * V;
+  P.temperature = temperature; P.top_k = top_k;
+  return DIM_OK;
+}
+
 // Decode `B` clips on stream `s` (one group).  G: this group's cached step graph.
 // samples > 1: every clip is decoded `samples` times (rows b*samples + j, their own uniforms) over ONE projection of its
 // context: the cross-attention K/V of a clip are shared by its rows (the 10-sample best-of-N eval loop).
@@ -785,6 +962,27 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
   if (int e = launch_set_step(w.step, 0, s)) return e;
 
   const int max_keys = std::max(T, steps + 1);
+  if (g_decode_impl == 0 && m.tc.planes > 0 && mk_supported(D, inner, F, V, c.heads, m.tc.planes, max_keys)) {
+    // persistent decode kernel: prompt embedding + layer 0's LayerNorm here, then every step inside ONE cooperative launch
+    const XtAttn& SA0 = m.self_attn[0];
+    if (int e = launch_embed_tokens(w.tokens, steps + 1, w.step, m.token_emb, w.x, B, D, V, s)) return e;
+    if (int e = launch_layer_norm(w.x, SA0.norm_g, SA0.norm_b, nullptr, nullptr, B, D, 1e-5f, s, w.ap, m.tc.planes, D)) return e;
+    DIM_CHECK_CUDA(cudaMemsetAsync(w.mk_bar, 0, 256, s));
+    if (g_mk_trace_on) DIM_CHECK_CUDA(cudaMemsetAsync(w.mk_trace, 0, MK_MAX_PHASES * sizeof(unsigned long long), s));
+    static thread_local MkPlan plan;
+    if (int e = build_mk_plan(m, w, B, Bc, T, steps, samples, temperature, top_k, mask, uniforms, logits_out, plan)) return e;
+    if (int e = launch_decode_megakernel(plan, s)) return e;
+    if (g_mk_trace_on) {
+      g_mk_trace_host.assign(MK_MAX_PHASES, 0ull);
+      g_mk_trace_types.assign(MK_MAX_PHASES, 0);
+      for (int i = 0; i < plan.nphases; ++i) g_mk_trace_types[i] = plan.phases[i].type;
+      DIM_CHECK_CUDA(cudaMemcpyAsync(g_mk_trace_host.data(), w.mk_trace, MK_MAX_PHASES * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    }
+    DIM_CHECK_CUDA(cudaMemcpy2DAsync(out_codes, (size_t)steps * sizeof(int64_t), w.tokens + 1,
+                                     (size_t)(steps + 1) * sizeof(int64_t), (size_t)steps * sizeof(int64_t), B,
+                                     cudaMemcpyDeviceToDevice, s));
+    return DIM_OK;
+  }
   const bool tcp = tc_on(m.tc, B);
   const int P = m.tc.planes;
   // Head of the very first step: embedding of the prompt token and layer 0's self-attention LayerNorm.  Every later step gets
@@ -954,7 +1152,7 @@ extern "C" int dim_slmft_generate(dim_handle_t h, int model, const float* ctx, c
   const int D = c.dim + c.dim_audio, V = c.num_tokens;
   cudaStream_t s = as_stream(stream);
   int begin[kMaxGroups + 1];
-  const int ng = plan_groups(m, B, begin);
+  const int ng = plan_groups(m, B, std::max(T, steps + 1), begin);
   if ((int)m.graphs.size() < kMaxGroups + 1) m.graphs.resize(kMaxGroups + 1);     // last slot: multi-sample decoding
   if (ng == 1 || g_prof_on) {
     if (ng > 1) {   // profiling: same groups, sequentially on the caller's stream (events need one stream)
@@ -1148,4 +1346,30 @@ extern "C" int dim_slmft_teacher_forced(dim_handle_t h, int model, const float* 
   GemmArgs a;
   a.A = w.ln; a.lda = D; a.Ap = tcp ? w.ap : nullptr; a.W = m.logits_w; a.bias = m.logits_b; a.C = logits; a.ldc = V; a.M = R; a.N = V; a.K = D;
   return run_gemm(m.tc, a, w.ap, s);
+}
+
+// ---- persistent decode kernel: phase trace and implementation switch ----------------------------------------------------------
+extern "C" int dim_decode_trace_enable(int on) {
+  g_mk_trace_on = on != 0;
+  return DIM_OK;
+}
+
+extern "C" int dim_decode_trace_collect(double* ms_per_phase, int32_t* type_per_phase, int max_phases, int* n_out) {
+  DIM_REQUIRE(ms_per_phase && type_per_phase && n_out && max_phases > 0, "dim_decode_trace_collect: bad argument");
+  if (cudaDeviceSynchronize() != cudaSuccess) return fail(DIM_ECUDA, "decode trace: device synchronize failed");
+  int n = 0;
+  for (size_t i = 0; i < g_mk_trace_types.size() && n < max_phases; ++i) {
+    if (g_mk_trace_types[i] == 0) break;
+    ms_per_phase[n] = (double)g_mk_trace_host[i] * 1e-6;
+    type_per_phase[n] = g_mk_trace_types[i];
+    ++n;
+  }
+  *n_out = n;
+  return DIM_OK;
+}
+
+extern "C" int dim_decode_set_impl(int impl) {
+  DIM_REQUIRE(impl == 0 || impl == 1, "dim_decode_set_impl: 0 = persistent kernel, 1 = per-kernel graph path");
+  g_decode_impl = impl;
+  return DIM_OK;
 }

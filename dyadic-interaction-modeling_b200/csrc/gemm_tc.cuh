@@ -1,5 +1,7 @@
 // tcgen05 (5th-gen tensor core) GEMM on bf16 plane operands + the fp32 -> bf16-plane split.  See gemm_tc.cu.
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 #include "gemm_f32.cuh"
 
@@ -15,6 +17,8 @@ int launch_split_planes(const GemmArgs& a, __nv_bfloat16* out, int kp, int plane
 int launch_gemm_tc(const GemmArgs& e, const __nv_bfloat16* Ap, const __nv_bfloat16* Wp, int kp, int planes, cudaStream_t s);
 
 int tc_pairs(int planes, int* pa, int* pw);
+// TMA descriptor of a bf16 matrix [rows, cols] with row pitch ld (elements): box = 64 columns x box_rows rows, 128-byte swizzle
+int tc_make_map(const __nv_bfloat16* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out);
 extern long long* g_tc_dbg;
 extern int g_tc_force_splits;
 extern int g_tc_force_bn;

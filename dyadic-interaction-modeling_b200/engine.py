@@ -27,6 +27,26 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+def _index_arg(t, B, device, name, lo, hi):
+    """Normalise an optional per-clip int32 argument of the C ABI (`lens`, `batch_index`): the library reads DEVICE int32 memory,
+    so an int64 or host tensor must never reach it as a raw pointer.  Shape (B,) is enforced; values are range-checked here when
+    the tensor lives on the host (no synchronisation) -- device tensors are clamped into range by the kernels instead
+    (lens to [1, T], batch_index to [0, pe_max_len)), so a bad value can never read outside the buffers."""
+    if t is None:
+        return None
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(t)
+    if t.shape != (B,):
+        raise ValueError(f"{name} must have shape ({B},), got {tuple(t.shape)}")
+    if t.is_floating_point() or t.dtype == torch.bool:
+        raise ValueError(f"{name} must be an integer tensor")
+    if not t.is_cuda and B > 0:
+        mn, mx = int(t.min()), int(t.max())
+        if mn < lo or mx >= hi:
+            raise ValueError(f"{name} values must lie in [{lo}, {hi}), got [{mn}, {mx}]")
+    return t.to(device=device, dtype=torch.int32).contiguous()
+
+
 class Handle:
     """dim_handle_t with the registered tensors kept alive."""
 
@@ -98,6 +118,8 @@ class VQEngine:
         x = x.contiguous()
         B, T, _ = x.shape
         dev = x.device
+        lens = _index_arg(lens, B, dev, "lens", 1, T + 1)            # an empty clip has no replicate-padding source (reference raises too)
+        batch_index = _index_arg(batch_index, B, dev, "batch_index", 0, self.cfg.pe_max_len)
         idx = torch.empty(B, T, dtype=torch.int64, device=dev)
         z = torch.empty(B, T, self.cfg.zquant_dim, dtype=torch.float32, device=dev) if want_z else None
         q = torch.empty(B, self.cfg.zquant_dim, T, dtype=torch.float32, device=dev) if want_quant else None
@@ -117,6 +139,7 @@ class VQEngine:
         else:
             quant = quant.contiguous()
             B, _, L = quant.shape
+        batch_index = _index_arg(batch_index, B, src.device, "batch_index", 0, self.cfg.pe_max_len)
         out = torch.empty(B, L, self.cfg.in_dim, dtype=torch.float32, device=src.device)
         ws, n = self._workspace(B, L)
         _lib.check(self.handle.lib.dim_vqvae_decode(self.handle.h, self.model, _ptr(codes), _ptr(quant), _ptr(batch_index),

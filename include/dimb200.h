@@ -194,6 +194,18 @@ size_t dim_slmft_teacher_forced_workspace_bytes(dim_handle_t h, int model, int B
 int dim_slmft_teacher_forced(dim_handle_t h, int model, const float* ctx, const uint8_t* mask, const int64_t* tokens,
                              const uint8_t* kv_mask, int B, int T, int L, float* logits, void* ws, size_t ws_bytes, void* stream);
 
+/* The decode loop of dim_slmft_generate* runs as ONE persistent cooperative kernel (csrc/decode_mk.cu) whenever the model was
+ * built for the tensor cores; its launches-turned-phases cannot be timed from outside, so the kernel itself can record the time
+ * CTA 0 spends in every phase of the step program (summed over the steps of a call).
+ *   dim_decode_trace_enable(1) before the generate call; dim_decode_trace_collect afterwards (synchronises the device):
+ *   ms_per_phase[i], type_per_phase[i] for the i-th phase of one step (1 GEMM, 2 attention, 3 residual+LayerNorm, 4 GELU,
+ *   5 sampling + embedding + LayerNorm).
+ * dim_decode_set_impl(1) selects the per-kernel CUDA-graph decode path instead (0 = persistent kernel, the default): the two
+ * implementations are each other's cross-check in the parity tests. */
+int dim_decode_trace_enable(int on);
+int dim_decode_trace_collect(double* h_ms_per_phase, int32_t* h_type_per_phase, int max_phases, int* h_n_out);
+int dim_decode_set_impl(int impl);
+
 #ifdef __cplusplus
 }
 #endif

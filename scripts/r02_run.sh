@@ -1,0 +1,37 @@
+#!/bin/bash
+# Round-2 GPU session helper: bash scripts/r02_run.sh TAG "sections"
+set -u
+TAG=${1:-r02a}
+SECTIONS=${2:-"mk slmft bench"}
+OUT=gpurun_out
+mkdir -p $OUT
+has() { [[ " $SECTIONS " == *" $1 "* ]]; }
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_gpu.txt 2>&1
+if has mk; then
+  timeout 900 python -m pytest tests/test_decode_mk_gpu.py -x -q > $OUT/${TAG}_mk.log 2>&1; echo "exit $?" >> $OUT/${TAG}_mk.log
+  tail -25 $OUT/${TAG}_mk.log
+fi
+if has slmft; then
+  timeout 1200 python -m pytest tests/test_slmft_gpu.py -x -q > $OUT/${TAG}_slmft.log 2>&1; echo "exit $?" >> $OUT/${TAG}_slmft.log
+  tail -15 $OUT/${TAG}_slmft.log
+fi
+if has alltests; then
+  timeout 1800 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_tests.log 2>&1; echo "exit $?" >> $OUT/${TAG}_tests.log
+  tail -15 $OUT/${TAG}_tests.log
+fi
+if has bench; then
+  timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench_bf16.json 2> $OUT/${TAG}_bench_bf16.err
+  tail -c 3000 $OUT/${TAG}_bench_bf16.json; tail -5 $OUT/${TAG}_bench_bf16.err
+fi
+if has trace; then
+  timeout 600 python scripts/decode_trace.py > $OUT/${TAG}_trace.txt 2>&1
+  cat $OUT/${TAG}_trace.txt
+fi
+if has b1; then
+  timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-parity-leg --workload vico_b1 > $OUT/${TAG}_bench_b1.json 2> $OUT/${TAG}_bench_b1.err
+  tail -c 1500 $OUT/${TAG}_bench_b1.json; tail -5 $OUT/${TAG}_bench_b1.err
+fi
+if has trace1; then
+  timeout 600 python scripts/decode_trace.py 1 300 > $OUT/${TAG}_trace_b1.txt 2>&1
+  grep -v "  phase" $OUT/${TAG}_trace_b1.txt
+fi

@@ -12,6 +12,7 @@ import dim_b200  # noqa: E402
 from dim_b200.schema import S2SConfig, VQConfig  # noqa: E402
 from oracle import slmft as OS  # noqa: E402
 from oracle import xt as OX  # noqa: E402
+from parity_util import explain_first_difference  # noqa: E402
 
 S2S, VQ = S2SConfig(), VQConfig()
 TOL = 1e-4
@@ -73,17 +74,15 @@ def test_generate_sampled_with_uniforms(engines, slmft_sd):
     ctx = OS.decoder_context(slmft_sd, x_s, c["v_audio"])
     prompt = torch.tensor([[3], [400]])
     u = torch.rand(B, T - 1, generator=torch.Generator().manual_seed(77))
-    ref = OX.generate(slmft_sd, "decoder_joint.net", prompt, T - 1, S2S.depth, ctx, c["mask"], temperature=1.0, uniforms=u)
-    out = s2s.generate(ctx.cuda(), c["mask"].cuda(), prompt.cuda(), T - 1, temperature=1.0, uniforms=u.cuda(),
-                       top_k=math.ceil(0.1 * 512)).cpu()
-    agree = (out == ref).float().mean()
-    # a draw within ~1e-6 of a CDF boundary may legitimately flip and then the sequences diverge; demand the
-    # common prefix be long and the first difference (if any) be explainable
-    if not torch.equal(out, ref):
-        for b in range(B):
-            neq = (out[b] != ref[b]).nonzero()
-            if len(neq):
-                assert int(neq[0]) > 5, f"early divergence at {int(neq[0])} (agreement {float(agree):.2f})"
+    ref, ref_logits = OX.generate(slmft_sd, "decoder_joint.net", prompt, T - 1, S2S.depth, ctx, c["mask"], temperature=1.0, uniforms=u,
+                                  return_logits=True)
+    out, logits = s2s.generate(ctx.cuda(), c["mask"].cuda(), prompt.cuda(), T - 1, temperature=1.0, uniforms=u.cuda(),
+                               top_k=math.ceil(0.1 * 512), return_logits=True)
+    out, logits = out.cpu(), logits.cpu()
+    # a draw may legitimately flip only when it sits at a CDF boundary of the oracle's distribution (within the logit tolerance):
+    # explain_first_difference proves that, and that the logits agree up to the flip
+    for b in range(B):
+        explain_first_difference(out[b], logits[b], ref[b], ref_logits[b], u[b])
     assert len(out.unique()) > 8                                    # sampling really explores the codebook
 
 
@@ -278,7 +277,7 @@ def test_draw_kv_mask_follows_upstream_recipe():
     m = draw_kv_mask((5, 40), 0.15, "cuda")
     assert m.shape == (5, 40) and m.dtype == torch.bool
     assert bool(m[:, 0].all())                                          # the first key is never masked
-    assert (~m).sum(1).tolist() == [min(int(40 * 0.15), 39)] * 5
+    assert (~m).sum(1).tolist() == [min(int(41 * 0.15), 40)] * 5     # T = 41 before the shift
 
 
 def test_long_clip_T1024_lm_listener_shape(engines, slmft_sd):
@@ -297,9 +296,13 @@ def test_long_clip_T1024_lm_listener_shape(engines, slmft_sd):
     from dim_b200.compat_api import listener_codes
     assert torch.equal(listener_codes(vq, c["v_listener"].cuda(), c["mask"].cuda()).cpu(), z_l)      # 1024 VQ codes bit-exact
     got, ref = codes.cpu()[0], inter["codes"][0]
-    neq = (got != ref).nonzero()
-    if len(neq) == 0:
+    if torch.equal(got, ref):
         assert torch.allclose(pred.cpu(), ref_pred, atol=TOL), float((pred.cpu() - ref_pred).abs().max())
-    else:                                                                # 1023 dependent steps: tolerate one oracle near-tie
-        t = int(neq[0])
-        assert t > 200, f"codes diverge at step {t}"
+    else:
+        # 1023 dependent steps: a difference is accepted only as a proven oracle near-tie (top-2 margin below the logit tolerance,
+        # logits equal within tolerance up to that step) -- never because it happens late
+        ctx = s2s.context(c["v_speaker"].cuda(), c["v_audio"].cuda(), c["mask"].cuda())
+        codes2, logits = s2s.generate(ctx, c["mask"].cuda(), z_l[:, 0].cuda(), T - 1, return_logits=True)
+        assert torch.equal(codes2.cpu()[0], got)
+        _, ref_logits = OX.generate(slmft_sd, "decoder_joint.net", z_l[:, 0:1], T - 1, S2S.depth, inter["ctx"], c["mask"], return_logits=True)
+        explain_first_difference(got, logits[0].cpu(), ref, ref_logits[0])
