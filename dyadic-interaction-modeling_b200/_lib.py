@@ -187,7 +187,7 @@ def profile_collect():
                  ms=arr[i].ms, bytes=arr[i].bytes, flops=arr[i].flops) for i in range(n.value)]
 
 
-MK_TYPE_NAMES = {1: "gemm", 2: "attention", 3: "residual_layernorm", 4: "gelu", 5: "sample_embed_layernorm"}
+MK_TYPE_NAMES = {1: "gemm", 2: "attention", 3: "residual_layernorm", 4: "gelu", 5: "sample_embed_layernorm", 6: "nop"}
 
 
 def decode_trace_enable(on: bool):

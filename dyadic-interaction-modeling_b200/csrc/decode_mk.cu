@@ -361,6 +361,224 @@ __device__ __forceinline__ void mk_attn_item(const MkPhase& ph, int Brows, int H
   }
 }
 
+// ---- MK_ATTN, bf16 caches: the two products of an item on the (legacy) tensor pipe -----------------------------------------
+// The FFMA item above spends ~14 warp instructions per key and is issue-bound with the 12 warps of this kernel (51.8 us per
+// 256-clip cross-attention phase against 36 us of HBM time).  With bf16 K/V rows the dot products map onto mma.sync m16n8k16:
+//   S = q K^T : A = q (row 0: bf16 high part, row 1: low part -- q = hi + lo to 2^-17, the other 14 rows are zero),
+//               B = a K tile straight from the padded smem rows (ldmatrix, conflict-free with the 144-byte pitch);
+//   O = P V   : A = p (rows 0/1: high / low part of the fp32 probabilities), B = the V tile (ldmatrix.trans).
+// fp32 accumulation; rows 0 and 1 of the result are added with one shuffle.  ~4 warp instructions per key.  Warp w of the
+// sub-group owns keys [32w, 32w+32) of every 64-key tile.  Rows of a tile past the last cached key are ZERO-filled (cp.async
+// src-size 0): the tensor core multiplies whole tiles, and 0 * stale-NaN would poison the sum.
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async_16_zfill(uint32_t dst_smem, const void* src, uint32_t src_bytes, uint64_t policy) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst_smem), "l"(src), "r"(src_bytes), "l"(policy)
+               : "memory");
+}
+// (x, y) -> packed bf16x2 of the high parts (sel == 0), of the low parts x - bf16(x) (sel == 1), or 0
+__device__ __forceinline__ uint32_t pack_part(float x, float y, int sel) {
+  __nv_bfloat16 bx = __float2bfloat16_rn(x), by = __float2bfloat16_rn(y);
+  if (sel == 1) {
+    bx = __float2bfloat16_rn(x - __bfloat162float(bx));
+    by = __float2bfloat16_rn(y - __bfloat162float(by));
+  }
+  const uint32_t w = (uint32_t)__bfloat16_as_ushort(bx) | ((uint32_t)__bfloat16_as_ushort(by) << 16);
+  return sel <= 1 ? w : 0u;
+}
+
+__device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, int H, int planes, int sc_floats, uint8_t* reg, int sub,
+                                                 int tid, int item, int pos) {
+  constexpr int NT = 64, DH = 64, CHUNK = 64, PITCH = 144, STAGE = CHUNK * PITCH;
+  float* sc = reinterpret_cast<float*>(reg + 2 * STAGE);
+  float* part = sc + sc_floats;                        // [2][64] partial outputs of the two warps (sized [8][64] by the carve)
+  float* qs = part + 8 * DH;                           // [64]
+  float* red = qs + DH;                                // [4]
+  float* knew = red + 4;                               // [64] this step's key row (append)
+  float* vnew = knew + DH;                             // [64]
+  const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+  const int b = item / H, h = item - b * H;
+  const int nkeys = ph.append ? pos + 1 : ph.Tk;       // keys attended, the step's own key included
+  const int nold = ph.append ? pos : ph.Tk;            // keys already in the cache
+  const int bkv = b / ph.kv_group;
+  __nv_bfloat16* khead = static_cast<__nv_bfloat16*>(ph.kcache) + (size_t)bkv * ph.kv_batch_stride + (size_t)h * ph.kv_head_stride;
+  __nv_bfloat16* vhead = static_cast<__nv_bfloat16*>(ph.vcache) + (size_t)bkv * ph.kv_batch_stride + (size_t)h * ph.kv_head_stride;
+  const uint32_t ring_u = smem_u32(reg);
+  const int nch = (nold + CHUNK - 1) / CHUNK;
+  uint64_t kvpol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(kvpol));
+  // thread -> 8 fixed 16-byte pieces of a tile: rows tid/8 + 8i, chunk tid%8
+  const uint32_t dst0 = (uint32_t)((tid >> 3) * PITCH + (tid & 7) * 16);
+  const int row_t = tid >> 3;
+  auto issue = [&](const __nv_bfloat16* head, int c, int stage) {         // rows [c*64, c*64+64) of a head block -> ring[stage]
+    const int row0 = c * CHUNK, valid = nold - row0;                     // rows >= valid are zero-filled
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(head + (size_t)row0 * DH) + tid * 16;
+    const uint32_t dst = ring_u + stage * STAGE + dst0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool ok = row_t + 8 * i < valid;
+      cp_async_16_zfill(dst + i * 8 * PITCH, ok ? src + i * 1024 : reinterpret_cast<const uint8_t*>(head), ok ? 16u : 0u, kvpol);
+    }
+    cp_async_commit();
+  };
+  if (nch > 0) issue(khead, 0, 0);                     // the first K tiles travel while the projection partials are summed
+  if (nch > 1) issue(khead, 1, 1);
+  {  // q (and this step's k, v) = sum of the K slices of the projection, in slice order; thread t owns element t of the head row
+    const size_t mn = (size_t)Brows * ph.q_ld;
+    const float* base = reinterpret_cast<const float*>(ph.part) + (size_t)b * ph.q_ld + h * DH + tid;
+    float pq[MK_MAXS], pk[MK_MAXS], pv[MK_MAXS];
+#pragma unroll
+    for (int z = 0; z < MK_MAXS; ++z) {
+      const bool on = z < ph.q_splits;
+      pq[z] = on ? base[z * mn + ph.q_col] : 0.f;
+      pk[z] = (on && ph.append) ? base[z * mn + ph.k_col] : 0.f;
+      pv[z] = (on && ph.append) ? base[z * mn + ph.v_col] : 0.f;
+    }
+    float qv = pq[0], kv = pk[0], vv = pv[0];
+#pragma unroll
+    for (int z = 1; z < MK_MAXS; ++z)
+      if (z < ph.q_splits) { qv += pq[z]; kv += pk[z]; vv += pv[z]; }
+    qs[tid] = qv;
+    if (ph.append) {
+      const __nv_bfloat16 kb = __float2bfloat16_rn(kv), vb = __float2bfloat16_rn(vv);
+      khead[(size_t)pos * DH + tid] = kb;
+      vhead[(size_t)pos * DH + tid] = vb;
+      knew[tid] = __bfloat162float(kb);
+      vnew[tid] = __bfloat162float(vb);
+    }
+  }
+  bar_sub(sub);
+  // A fragments of q: lanes g == 0 carry the high parts (row 0), lanes g == 1 the low parts (row 1), every other row is zero
+  uint32_t aq[4][4];
+#pragma unroll
+  for (int kc = 0; kc < 4; ++kc) {
+    const float2 x0 = *reinterpret_cast<const float2*>(qs + kc * 16 + 2 * t4);
+    const float2 x1 = *reinterpret_cast<const float2*>(qs + kc * 16 + 8 + 2 * t4);
+    aq[kc][0] = pack_part(x0.x, x0.y, g);
+    aq[kc][1] = 0u;
+    aq[kc][2] = pack_part(x1.x, x1.y, g);
+    aq[kc][3] = 0u;
+  }
+  if (ph.append && tid == NT - 1) {                    // score of the step's own key, from shared memory (fp32)
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < DH; ++i) d[i & 3] = fmaf(qs[i], knew[i], d[i & 3]);
+    sc[pos] = ((d[0] + d[1]) + (d[2] + d[3])) * ph.scale;
+  }
+  // per-lane ldmatrix offsets (bytes), as in attn_prefill_mma
+  const uint32_t bk_off = (uint32_t)(((lane & 7) + (lane >> 4) * 8) * PITCH + ((lane >> 3) & 1) * 16);
+  const uint32_t bv_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (lane >> 4) * 16);
+  // ---- pass 1: S = q K^T; warp w owns keys 32w .. 32w+31 of the tile
+  for (int c = 0; c < nch; ++c) {
+    if (c + 1 < nch) cp_async_wait<1>(); else cp_async_wait<0>();
+    bar_sub(sub);
+    const uint32_t tile = ring_u + (c & 1) * STAGE;
+    float s[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+    for (int n2 = 0; n2 < 2; ++n2) {
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(tile + (uint32_t)((warp * 32 + n2 * 16) * PITCH + kc * 32) + bk_off, b0, b1, b2, b3);
+        mma_bf16(s[2 * n2], aq[kc], b0, b1);
+        mma_bf16(s[2 * n2 + 1], aq[kc], b2, b3);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const float s0 = s[nt][0] + __shfl_xor_sync(0xffffffffu, s[nt][0], 4);      // row 0 (high part of q) + row 1 (low part)
+      const float s1 = s[nt][1] + __shfl_xor_sync(0xffffffffu, s[nt][1], 4);
+      const int j = c * CHUNK + warp * 32 + nt * 8 + 2 * t4;
+      if (g == 0) {
+        if (j < nold) sc[j] = s0 * ph.scale;
+        if (j + 1 < nold) sc[j + 1] = s1 * ph.scale;
+      }
+    }
+    bar_sub(sub);
+    if (c + 2 < nch) issue(khead, c + 2, c & 1);
+  }
+  if (nch > 0) issue(vhead, 0, 0);
+  if (nch > 1) issue(vhead, 1, 1);
+  bar_sub(sub);                                        // the own key's score is visible (covers the no-tile first step too)
+  // key-padding mask (masked_fill(-finfo.max)) and softmax statistics
+  const uint8_t* km = ph.key_mask ? ph.key_mask + (size_t)bkv * ph.Tk : nullptr;
+  float mx = -INFINITY;
+  for (int j = tid; j < nkeys; j += NT) {
+    float v = sc[j];
+    if (km && !km[j]) { v = -FLT_MAX; sc[j] = v; }
+    mx = fmaxf(mx, v);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  bar_sub(sub);
+  mx = fmaxf(red[0], red[1]);
+  bar_sub(sub);
+  float sum = 0.f;
+  for (int j = tid; j < nkeys; j += NT) {
+    const float e = expf(sc[j] - mx);
+    sc[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  bar_sub(sub);
+  const float inv = 1.f / (red[0] + red[1]);
+  // ---- pass 2: O = P V; warp w owns keys 32w .. 32w+31 of the tile (two 16-key k-steps), all 64 output columns
+  float o[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+  for (int c = 0; c < nch; ++c) {
+    if (c + 1 < nch) cp_async_wait<1>(); else cp_async_wait<0>();
+    bar_sub(sub);
+    const uint32_t tile = ring_u + (c & 1) * STAGE;
+#pragma unroll
+    for (int k2 = 0; k2 < 2; ++k2) {
+      const int kb = warp * 32 + k2 * 16, j0 = c * CHUNK + kb + 2 * t4;     // this lane's key columns: j0, j0+1, j0+8, j0+9
+      uint32_t ap[4];
+      {
+        const float p0 = j0 < nold ? sc[j0] : 0.f, p1 = j0 + 1 < nold ? sc[j0 + 1] : 0.f;
+        const float p2 = j0 + 8 < nold ? sc[j0 + 8] : 0.f, p3 = j0 + 9 < nold ? sc[j0 + 9] : 0.f;
+        ap[0] = pack_part(p0, p1, g);
+        ap[1] = 0u;
+        ap[2] = pack_part(p2, p3, g);
+        ap[3] = 0u;
+      }
+#pragma unroll
+      for (int n2 = 0; n2 < 4; ++n2) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(tile + (uint32_t)(kb * PITCH + n2 * 32) + bv_off, b0, b1, b2, b3);
+        mma_bf16(o[2 * n2], ap, b0, b1);
+        mma_bf16(o[2 * n2 + 1], ap, b2, b3);
+      }
+    }
+    bar_sub(sub);
+    if (c + 2 < nch) issue(vhead, c + 2, c & 1);
+  }
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const float o0 = o[nt][0] + __shfl_xor_sync(0xffffffffu, o[nt][0], 4);
+    const float o1 = o[nt][1] + __shfl_xor_sync(0xffffffffu, o[nt][1], 4);
+    if (g == 0) *reinterpret_cast<float2*>(part + warp * DH + nt * 8 + 2 * t4) = make_float2(o0, o1);
+  }
+  bar_sub(sub);
+  {
+    float r = part[tid] + part[DH + tid];
+    if (ph.append) r = fmaf(sc[pos], vnew[tid], r);
+    store_planes1(ph.outp + (size_t)b * planes * ph.out_kp + h * DH + tid, r * inv, planes, ph.out_kp);
+  }
+}
+
 __device__ __forceinline__ void mk_attn(const MkPlan& P, const MkPhase& ph, uint8_t* smem, Ctl& ctl, int pos) {
   const int items = P.B * P.H;
   const int mine = (int)blockIdx.x < items ? (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -374,7 +592,8 @@ __device__ __forceinline__ void mk_attn(const MkPlan& P, const MkPhase& ph, uint
     const int k = ctl.sub_item[sub];
     if (k >= mine) break;
     const int item = (int)blockIdx.x + k * (int)gridDim.x;
-    if (P.kv_bf16) mk_attn_item<true>(ph, P.B, P.H, P.planes, P.sc_floats, reg, sub, tid, item, pos);
+    if (P.kv_bf16 && P.attn_mma) mk_attn_item_mma(ph, P.B, P.H, P.planes, P.sc_floats, reg, sub, tid, item, pos);
+    else if (P.kv_bf16) mk_attn_item<true>(ph, P.B, P.H, P.planes, P.sc_floats, reg, sub, tid, item, pos);
     else mk_attn_item<false>(ph, P.B, P.H, P.planes, P.sc_floats, reg, sub, tid, item, pos);
     bar_sub(sub);
   }

@@ -8,7 +8,7 @@
 
 namespace dimb {
 
-enum { MK_GEMM = 1, MK_ATTN = 2, MK_ROW_RESLN = 3, MK_ROW_GELU = 4, MK_ROW_SAMPLE = 5, MK_NTYPES = 6 };
+enum { MK_GEMM = 1, MK_ATTN = 2, MK_ROW_RESLN = 3, MK_ROW_GELU = 4, MK_ROW_SAMPLE = 5, MK_NOP = 6, MK_NTYPES = 7 };
 
 constexpr int MK_MAX_PHASES = 64;
 constexpr int MK_MAX_MAPS = 48;
@@ -51,6 +51,7 @@ struct alignas(128) MkPlan {
   int planes;
   int kv_bf16;
   int steps;
+  int attn_mma;                              // bf16 caches: 1 = mma.sync attention items, 0 = FFMA items (A/B hook DIM_MK_ATTN_FFMA)
   int sc_floats;                             // score slots per attention work item (>= max keys, multiple of 4)
   unsigned int* bar;                         // grid barrier counter, zero at launch
   unsigned long long* trace;                 // nullable: [MK_MAX_PHASES] ns spent per phase (summed over steps), CTA 0's view

@@ -921,6 +921,13 @@ int build_mk_plan(const S2SModel& m, const GenWs& w, int B, int Bc, int T, int s
   P.nmaps = b.nmaps;
   P.B = B; P.H = c.heads; P.planes = planes; P.kv_bf16 = kv16 ? 1 : 0; P.steps = steps;
   P.sc_floats = (std::max(T, steps + 1) + 3) / 4 * 4;
+  {  // measurement hooks: DIM_MK_ATTN_FFMA=1 keeps the FFMA attention items for bf16 caches; DIM_MK_NOPS=k appends k empty phases
+    static const bool ffma = getenv("DIM_MK_ATTN_FFMA") != nullptr;
+    static const int nops = getenv("DIM_MK_NOPS") ? atoi(getenv("DIM_MK_NOPS")) : 0;
+    P.attn_mma = ffma ? 0 : 1;
+    for (int i = 0; i < nops; ++i)
+      if (!b.next(MK_NOP)) break;
+  }
   P.bar = w.mk_bar; P.trace = g_mk_trace_on ? w.mk_trace : nullptr;
   P.tokens = w.tokens; P.tok_stride = steps + 1;
   P.uniforms = uniforms; P.u_stride = steps;

@@ -35,3 +35,27 @@ if has trace1; then
   timeout 600 python scripts/decode_trace.py 1 300 > $OUT/${TAG}_trace_b1.txt 2>&1
   grep -v "  phase" $OUT/${TAG}_trace_b1.txt
 fi
+if has barab; then
+  for m in 0 1; do
+    DIM_MK_NOPS=8 DIM_MK_BAR=$m timeout 300 python scripts/decode_trace.py 256 300 bf16 > $OUT/${TAG}_barab_$m.txt 2>&1
+    echo "bar mode $m"; grep -v "  phase" $OUT/${TAG}_barab_$m.txt; grep "nop" $OUT/${TAG}_barab_$m.txt | head -3
+  done
+fi
+if has stages2; then
+  DIM_MK_ATTN_STAGES=2 timeout 300 python scripts/decode_trace.py 256 300 bf16 > $OUT/${TAG}_stages2.txt 2>&1
+  echo "2-stage ring"; grep -v "  phase" $OUT/${TAG}_stages2.txt
+fi
+if has attnffma; then
+  DIM_MK_ATTN_FFMA=1 timeout 300 python scripts/decode_trace.py 256 300 bf16 > $OUT/${TAG}_attnffma.txt 2>&1
+  echo "FFMA attention items"; grep -v "  phase" $OUT/${TAG}_attnffma.txt
+fi
+if has ncumk; then
+  # one --set full capture of the persistent decode kernel (bf16, 256 x 300): where do the warps stall?
+  timeout 900 ncu --set full --import-source on --clock-control none -k regex:decode_megakernel -c 1 -o $OUT/${TAG}_ncu_mk -f \
+      python scripts/decode_trace.py 256 ${NCU_T:-300} bf16 > $OUT/${TAG}_ncu_mk.log 2>&1
+  ncu -i $OUT/${TAG}_ncu_mk.ncu-rep --page raw --csv > $OUT/${TAG}_ncu_mk.raw.csv 2>/dev/null
+  ncu -i $OUT/${TAG}_ncu_mk.ncu-rep --page source --csv --print-source cuda,sass > $OUT/${TAG}_ncu_mk.source.csv 2>/dev/null
+  ncu -i $OUT/${TAG}_ncu_mk.ncu-rep --page details > $OUT/${TAG}_ncu_mk.details.txt 2>/dev/null
+  ls -la $OUT/${TAG}_ncu_mk*; tail -3 $OUT/${TAG}_ncu_mk.log
+  gzip -f $OUT/${TAG}_ncu_mk.source.csv
+fi
