@@ -430,8 +430,22 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
     }
     cp_async_commit();
   };
-  if (nch > 0) issue(khead, 0, 0);                     // the first K tiles travel while the projection partials are summed
-  if (nch > 1) issue(khead, 1, 1);
+  // K tiles then V tiles form ONE stream of 2*nch tiles through the 2-stage ring (stream tile s -> stage s & 1): the first V tiles
+  // are already in flight while the softmax statistics are computed
+  auto issue_stream = [&](int s2) {
+    if (s2 < nch) issue(khead, s2, s2 & 1);
+    else if (s2 < 2 * nch) issue(vhead, s2 - nch, s2 & 1);
+  };
+  // key-padding mask bytes of this thread's keys (tid, tid + 64, ...), fetched now: the softmax below must not wait for them
+  const uint8_t* km = ph.key_mask ? ph.key_mask + (size_t)bkv * ph.Tk : nullptr;
+  uint32_t kmbits = 0xffffffffu;                       // bit i: key tid + 64 i is kept
+  if (km) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (tid + 64 * i < nkeys && !km[tid + 64 * i]) kmbits &= ~(1u << i);
+  }
+  issue_stream(0);                                     // the first tiles travel while the projection partials are summed
+  issue_stream(1);
   {  // q (and this step's k, v) = sum of the K slices of the projection, in slice order; thread t owns element t of the head row
     const size_t mn = (size_t)Brows * ph.q_ld;
     const float* base = reinterpret_cast<const float*>(ph.part) + (size_t)b * ph.q_ld + h * DH + tid;
@@ -479,7 +493,7 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
   const uint32_t bv_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (lane >> 4) * 16);
   // ---- pass 1: S = q K^T; warp w owns keys 32w .. 32w+31 of the tile
   for (int c = 0; c < nch; ++c) {
-    if (c + 1 < nch) cp_async_wait<1>(); else cp_async_wait<0>();
+    cp_async_wait<1>();                                // stream tile c + 1 (a K tile or the first V tile) may still be in flight
     bar_sub(sub);
     const uint32_t tile = ring_u + (c & 1) * STAGE;
     float s[4][4];
@@ -506,17 +520,15 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
       }
     }
     bar_sub(sub);
-    if (c + 2 < nch) issue(khead, c + 2, c & 1);
+    issue_stream(c + 2);
   }
-  if (nch > 0) issue(vhead, 0, 0);
-  if (nch > 1) issue(vhead, 1, 1);
   bar_sub(sub);                                        // the own key's score is visible (covers the no-tile first step too)
   // key-padding mask (masked_fill(-finfo.max)) and softmax statistics
-  const uint8_t* km = ph.key_mask ? ph.key_mask + (size_t)bkv * ph.Tk : nullptr;
   float mx = -INFINITY;
-  for (int j = tid; j < nkeys; j += NT) {
+  for (int j = tid, i = 0; j < nkeys; j += NT, ++i) {
     float v = sc[j];
-    if (km && !km[j]) { v = -FLT_MAX; sc[j] = v; }
+    const bool keep = i < 32 ? ((kmbits >> i) & 1u) != 0 : !(km && !km[j]);
+    if (!keep) { v = -FLT_MAX; sc[j] = v; }
     mx = fmaxf(mx, v);
   }
   mx = warp_max(mx);
@@ -541,7 +553,7 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
   for (int c = 0; c < nch; ++c) {
     if (c + 1 < nch) cp_async_wait<1>(); else cp_async_wait<0>();
     bar_sub(sub);
-    const uint32_t tile = ring_u + (c & 1) * STAGE;
+    const uint32_t tile = ring_u + ((nch + c) & 1) * STAGE;
 #pragma unroll
     for (int k2 = 0; k2 < 2; ++k2) {
       const int kb = warp * 32 + k2 * 16, j0 = c * CHUNK + kb + 2 * t4;     // this lane's key columns: j0, j0+1, j0+8, j0+9
@@ -563,7 +575,7 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
       }
     }
     bar_sub(sub);
-    if (c + 2 < nch) issue(vhead, c + 2, c & 1);
+    issue_stream(nch + c + 2);
   }
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {

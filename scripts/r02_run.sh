@@ -16,7 +16,7 @@ if has slmft; then
   tail -15 $OUT/${TAG}_slmft.log
 fi
 if has alltests; then
-  timeout 1800 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_tests.log 2>&1; echo "exit $?" >> $OUT/${TAG}_tests.log
+  timeout 1800 python -m pytest tests -m gpu -q > $OUT/${TAG}_tests.log 2>&1; echo "exit $?" >> $OUT/${TAG}_tests.log
   tail -15 $OUT/${TAG}_tests.log
 fi
 if has bench; then
@@ -58,4 +58,30 @@ if has ncumk; then
   ncu -i $OUT/${TAG}_ncu_mk.ncu-rep --page details > $OUT/${TAG}_ncu_mk.details.txt 2>/dev/null
   ls -la $OUT/${TAG}_ncu_mk*; tail -3 $OUT/${TAG}_ncu_mk.log
   gzip -f $OUT/${TAG}_ncu_mk.source.csv
+fi
+if has chains1; then
+  DIM_MK_CHAINS=1 timeout 300 python scripts/decode_trace.py 256 300 bf16 > $OUT/${TAG}_chains1.txt 2>&1
+  echo "single chain"; grep -v "  phase" $OUT/${TAG}_chains1.txt
+  DIM_MK_STAGGER=0 timeout 300 python scripts/decode_trace.py 256 300 bf16 > $OUT/${TAG}_stagger0.txt 2>&1
+  echo "two chains, no stagger"; grep -v "  phase" $OUT/${TAG}_stagger0.txt
+  DIM_MK_STAGGER=5 timeout 300 python scripts/decode_trace.py 256 300 bf16 > $OUT/${TAG}_stagger5.txt 2>&1
+  echo "two chains, stagger 5"; grep -v "  phase" $OUT/${TAG}_stagger5.txt
+fi
+if has mkdebug; then
+  DIM_MK_DEBUG=1 timeout 300 python scripts/decode_trace.py 256 60 bf16 2>&1 | grep -v "  phase" | head -20
+fi
+if has mkcheck; then
+  for cfg in "2 0" "2 2" "3 0"; do
+    set -- $cfg
+    echo "== chains=$1 stagger=$2"
+    DIM_MK_CHAINS=$1 DIM_MK_STAGGER=$2 timeout 300 python scripts/mk_check.py 130 10 fp32_tc 2>&1 | tail -3
+    DIM_MK_CHAINS=$1 DIM_MK_STAGGER=$2 timeout 300 python scripts/mk_check.py 256 8 fp32_tc 2>&1 | tail -3
+  done
+fi
+if has chainsab; then
+  for cfg in "2 0" "2 2" "2 5" "2 12" "3 0" "1 0"; do
+    set -- $cfg
+    echo "== chains=$1 stagger=$2"
+    DIM_MK_CHAINS=$1 DIM_MK_STAGGER=$2 timeout 300 python scripts/decode_trace.py 256 300 bf16 2>&1 | grep -v "  phase"
+  done
 fi

@@ -74,7 +74,8 @@ def test_config1_single_clip_T300(engines, slmft_sd, config1_oracle, mode):
         pred = vq.decode(codes=codes)
         ref_pred = OV.decode_indices(slmft_sd, ref_codes, VQ, None, prefix="listener_vq.")
         assert float((pred.cpu() - ref_pred).abs().max()) < 1e-4
-    assert len(codes.unique()) > 8
+    if mode == "sampled":
+        assert len(codes.unique()) > 8                                                # sampling really explores the codebook
 
 
 def test_config2_rows_of_the_full_batch(slmft_sd):

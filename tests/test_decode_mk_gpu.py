@@ -167,3 +167,4 @@ def test_phase_trace(engine_tc):
     kinds = [k for k, _ in tr]
     assert kinds.count("gemm") == 6 * S2S.depth + 1 and kinds.count("attention") == 2 * S2S.depth
     assert all(ms > 0 for _, ms in tr)
+
