@@ -11,8 +11,10 @@ encoders -> (T-1)-step KV-cached autoregressive decode with top-k(52) sampling f
 
 Prints ONE JSON line on rank 0 (contract in the task statement): value = whole-job frames/s with inputs resident in HBM;
 e2e = same metric through the public API with pinned-host inputs (H2D + D2H inside the timed region); roofline = the
-kernel category that dominates the step, timed with CUDA events on the launching stream in one extra profiled step;
-cpu_baseline = the CPU oracle (restated reference, oracle/) on a bounded sample on this box's host cores.
+kernel that dominates the step (the persistent decode kernel), timed with CUDA events on the launching stream in one extra
+profiled step, with the in-kernel per-phase clock beside it; cpu_baseline = the CPU oracle (restated reference, oracle/) on a
+bounded sample on this box's host cores; fp32_parity_mode = the same workload in the fp32-grade mode (value, e2e, roofline);
+vq_lookup = the codebook gather / argmin alone at 1 M codes; other_workloads = the other BASELINE configurations.
 """
 from __future__ import annotations
 
@@ -98,8 +100,8 @@ class ClockSampler:
         return out
 
 
-def cpu_oracle_sample(frames, threads=None, repeats=1, warm=True):
-    """Time the CPU oracle (oracle/slmft.py, PyTorch fp32, all host threads) on ONE clip of `frames` frames.
+def cpu_oracle_sample(frames, threads=None, repeats=1, warm=True, clips=1):
+    """Time the CPU oracle (oracle/slmft.py, PyTorch fp32, all host threads) on `clips` clips of `frames` frames in ONE call.
     Variant timed: cross-attention K/V projected once and none of the work the reference discards (the FASTEST
     restatement of the reference; its real code path does strictly more work: SURVEY F9/F10)."""
     import dim_b200
@@ -108,86 +110,86 @@ def cpu_oracle_sample(frames, threads=None, repeats=1, warm=True):
     if threads:
         torch.set_num_threads(threads)
     sd = dim_b200.synth.make_slmft_state_dict(131)
-    c = dim_b200.synth.make_clips(1, frames, seed=0)
-    u = torch.rand(1, frames - 1, generator=torch.Generator().manual_seed(1))
+    c = dim_b200.synth.make_clips(clips, frames, seed=0)
+    u = torch.rand(clips, frames - 1, generator=torch.Generator().manual_seed(1))
     run = lambda cc, uu: OS.forward_val(sd, cc["v_speaker"], cc["v_listener"], cc["v_audio"], cc["mask"], S2SConfig(),
                                         VQConfig(), temperature=1.0, uniforms=uu)
     if warm:
-        w = dim_b200.synth.make_clips(1, 16, seed=1)
-        run(w, torch.rand(1, 15))
+        w = dim_b200.synth.make_clips(clips, 16, seed=1)
+        run(w, torch.rand(clips, 15))
     best = float("inf")
     for _ in range(repeats):
         t0 = time.perf_counter()
         run(c, u)
         best = min(best, time.perf_counter() - t0)
-    return (frames - 1) / best, best
+    return clips * (frames - 1) / best, best
 
 
-def attn_decode_alone(lib, B, H, T, steps_ar, bf16, dev):
-    """Time the decode-attention kernel alone at the launch shapes of one decode step (see the roofline comment in run_native).
-    Algorithmic bytes per launch = K and V head rows read once: B*H*keys*64*2*elem_size."""
-    import ctypes as C
-    try:
-        fn = lib.dim_debug_attn_decode
-    except AttributeError:
-        return None
-    fn.restype = C.c_int
-    fn.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
-    dt = torch.bfloat16 if bf16 else torch.float32
-    esz = 2 if bf16 else 4
-    NB = 6
-    ks = [torch.randn(B, H, T, 64, device=dev).to(dt) for _ in range(NB)]
-    vs = [torch.randn(B, H, T, 64, device=dev).to(dt) for _ in range(NB)]
-    q = torch.randn(B, H * 64, device=dev)
-    out = torch.empty(B, H * 64, device=dev)
-    s = torch.cuda.current_stream().cuda_stream
-    quart = [max(1, int(steps_ar * f)) for f in (0.125, 0.375, 0.625, 0.875)]       # self attention: pos+1 keys at quartile midpoints
-    shapes = [(T, 4.0)] + [(k, 1.0) for k in quart]                                   # (keys, launches per step of this shape): 4 layers
-    tot_t = tot_b = tot_n = 0.0
-    for keys, weight in shapes:
-        def call(i):
-            rc = fn(-1, ks[i % NB].data_ptr(), vs[i % NB].data_ptr(), q.data_ptr(), out.data_ptr(), B, H, keys, 1 if bf16 else 0, s)
-            if rc != 0:
-                raise RuntimeError("dim_debug_attn_decode failed")
-        for i in range(3):
-            call(i)
+def decode_algorithmic_bytes(cfg, B, T, steps, kv_bytes, planes):
+    """Algorithmic HBM bytes of ONE generate call ('Decode step'): per step the decoder weights once (shared by the
+    batch: bf16 planes) and, per clip, the cross-attention K/V of the T context frames plus the self-attention K/V of the
+    st + 1 frames decoded so far, every layer, every head."""
+    D, inner = cfg.dec_dim, cfg.inner
+    w_params = cfg.depth * (3 * inner * D + inner * D + inner * D + inner * D + 2 * cfg.ff_mult * D * D) + cfg.num_tokens * D
+    kv = sum(cfg.depth * 2 * inner * (T + st + 1) * kv_bytes for st in range(steps))
+    return B * kv + steps * w_params * 2 * planes, B * kv, steps * w_params * 2 * planes
+
+
+def vq_lookup_record(dev, peaks, n=1 << 20):
+    """BASELINE.json's 'VQ-lookup HBM GB/s vs peak': the codebook gather (decode-side lookup, 520 B per code) and the codebook
+    argmin (encode-side lookup, 520 B and 131 kFLOP per token) alone at `n` codes, CUDA events around 20 back-to-back launches."""
+    from dim_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    E = (torch.randn(512, 128, generator=g) * 0.5).to(dev)
+    idx = torch.randint(0, 512, (n,), generator=g).to(dev)
+    z = torch.randn(n, 128, generator=g).to(dev)
+    out = {}
+    for name, fn, flops in (("gather", lambda: ops.vq_gather(idx, E), 0.0), ("argmin", lambda: ops.vq_argmin(z, E), 2.0 * 128 * 512)):
+        for _ in range(3):
+            fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
-        for i in range(12):
-            call(i)
+        for _ in range(20):
+            fn()
         e1.record()
         torch.cuda.synchronize()
-        t = e0.elapsed_time(e1) / 12 * 1e-3
-        tot_t += weight * t
-        tot_b += weight * B * H * keys * 64 * 2 * esz
-        tot_n += weight
-    return {"GB/s": tot_b / tot_t / 1e9, "avg_launch_us": 1e6 * tot_t / tot_n,
-            "shapes": f"{B} clips x {H} heads, cross {T} keys x4, self {quart} keys (one launch each), {'bf16' if bf16 else 'fp32'} K/V"}
+        t = e0.elapsed_time(e1) / 20 * 1e-3
+        gbs = n * 520 / t / 1e9
+        out[name] = {"codes": n, "us_per_launch": round(1e6 * t, 1), "GB/s": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm"], 4),
+                     "algorithmic_bytes_per_code": 520}
+        if flops:
+            out[name]["TFLOP/s"] = round(n * flops / t / 1e12, 1)
+    return out
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU path (restated oracle: x-transformers is not installable offline and
-    seq2seq_pretrain.py hard-codes .cuda()) on this box's host cores.  Rank 0 only."""
+    seq2seq_pretrain.py hard-codes .cuda()) on this box's host cores.  Rank 0 only.  A step = ONE forward(mode='val') call over a
+    bounded sample of the workload: 8 clips (or the whole batch when it is smaller) at the workload's full clip length; the
+    1-clip-per-call figure is measured and printed beside it."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     B, T, note = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    # calibrate so that the whole run stays within a few minutes
-    t0 = time.perf_counter()
-    cpu_oracle_sample(24, warm=True)
-    per_frame = (time.perf_counter() - t0) / (23 + 15)
-    budget = 240.0
+    clips = min(B, 8)
     frames = T
-    while frames > 32 and per_frame * frames * (args.steps + args.warmup) > budget:
-        frames //= 2
     import dim_b200
     from dim_b200.schema import S2SConfig, VQConfig
     from oracle import slmft as OS
     sd = dim_b200.synth.make_slmft_state_dict(131)
-    clip = dim_b200.synth.make_clips(1, frames, seed=0)
-    u = torch.rand(1, frames - 1, generator=torch.Generator().manual_seed(1))
+    # calibrate on a short call so that the whole run stays within a few minutes (the sample shrinks only if it must)
+    t0 = time.perf_counter()
+    cpu_oracle_sample(24, warm=True, clips=clips)
+    per_frame = (time.perf_counter() - t0) / (clips * (23 + 15))
+    budget = 300.0
+    while clips > 1 and per_frame * clips * frames * (args.steps + args.warmup) > budget:
+        clips //= 2
+    while frames > 32 and per_frame * clips * frames * (args.steps + args.warmup) > budget:
+        frames //= 2
+    clip = dim_b200.synth.make_clips(clips, frames, seed=0)
+    u = torch.rand(clips, frames - 1, generator=torch.Generator().manual_seed(1))
     step = lambda: OS.forward_val(sd, clip["v_speaker"], clip["v_listener"], clip["v_audio"], clip["mask"], S2SConfig(),
                                   VQConfig(), temperature=1.0, uniforms=u)
     for _ in range(args.warmup):
@@ -196,65 +198,86 @@ def run_reference(args):
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
-    val = args.steps * (frames - 1) / dt
-    sample = (f"1 clip x {frames} frames per step (of the {B}x{T} workload), PyTorch {torch.__version__} CPU fp32, "
-              f"{torch.get_num_threads()} threads; restated reference with cross-KV projected once and discarded work skipped")
+    val = args.steps * clips * (frames - 1) / dt
+    one_fps, one_s = cpu_oracle_sample(frames, threads=cores, repeats=2, warm=False, clips=1)
+    sample = (f"{clips} clips x {frames} frames per step (of the {B}x{T} workload), PyTorch {torch.__version__} CPU fp32, "
+              f"{torch.get_num_threads()} threads; restated reference with cross-KV projected once and discarded work skipped; "
+              f"1 clip per call: {one_fps:.1f} frames/s")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "clips_per_gpu": B, "frames_per_clip": T, "note": note},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "config": {"workload": args.workload, "clips_per_gpu": B, "frames_per_clip": T, "note": note,
+                       "sample_clips_per_step": clips, "sample_frames_per_clip": frames},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
+                             "one_clip_per_call": one_fps},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+class Leg:
+    """One workload in one arithmetic mode on this rank: engines, resident and host inputs, the two step functions."""
+
+    def __init__(self, h, workload, precision, rank, world, dev, speaker_ones=False):
+        import dim_b200
+        from dim_b200.engine import PREC_BF16, PREC_FP32, PREC_FP32_TC, SLMFTEngine, VQEngine
+        from dim_b200.schema import S2SConfig, VQConfig
+        self.B, self.T, self.note = WORKLOADS[workload]
+        self.workload, self.precision, self.rank, self.world, self.dev = workload, precision, rank, world, dev
+        self.steps_ar = self.T - 1
+        prec = {"bf16": PREC_BF16, "fp32": PREC_FP32, "fp32_tc": PREC_FP32_TC}[precision]
+        vq_prec = PREC_FP32 if prec == PREC_FP32 else PREC_FP32_TC   # the VQ-VAE ENCODER keeps fp32-grade maths: code indices are bit-exact
+        self.s2s = SLMFTEngine(h, S2SConfig(), precision=prec)
+        self.vq = VQEngine(h, VQConfig(), prefix="listener_vq.", precision=vq_prec)
+        # bf16 mode ("bf16 fused transformer + VQ decode"): the codes -> frames VQ decoder also runs plain bf16 GEMM operands
+        self.vq_dec = VQEngine(h, VQConfig(), prefix="listener_vq.", precision=PREC_BF16) if prec == PREC_BF16 else None
+        B, T = self.B, self.T
+        # this rank's shard of the global batch (weak scaling: B clips per GPU), global batch positions for the F4 quirk
+        clips = dim_b200.synth.make_clips(B, T, seed=1000 + rank, speaker="ones" if speaker_ones else "randn")
+        self.batch_index = torch.arange(rank * B, (rank + 1) * B, dtype=torch.int32, device=dev)
+        self.host = {k: clips[k].pin_memory() for k in ("v_speaker", "v_listener", "v_audio", "mask")}
+        self.u = torch.rand(B, self.steps_ar, generator=torch.Generator().manual_seed(7 + rank)).to(dev)
+        self.res = {k: v.to(dev) for k, v in self.host.items()}
+        self.pred_host = torch.empty(B, self.steps_ar, 56).pin_memory()
+        self.h2d = sum(v.numel() * v.element_size() for v in self.host.values())
+        self.d2h = self.pred_host.numel() * 4
+
+    def step_resident(self):
+        from dim_b200 import dist as D
+        from dim_b200.compat_api import slmft_forward_val
+        r = self.res
+        loss, d, pred, codes = slmft_forward_val(self.s2s, self.vq, r["v_speaker"], r["v_listener"], r["v_audio"], r["mask"],
+                                                 temperature=1.0, uniforms=self.u, batch_index=self.batch_index, return_codes=True,
+                                                 vq_decode_engine=self.vq_dec)
+        all_codes = D.all_gather_codes(codes, self.world * self.B) if self.world > 1 else codes     # the one collective of the path
+        return pred, all_codes
+
+    def step_e2e(self):
+        # host (pinned) inputs in, decoded frames back to pinned host memory: the public host-buffer entry point
+        from dim_b200 import dist as D
+        from dim_b200.compat_api import slmft_forward_val_host
+        loss, d, pred, codes = slmft_forward_val_host(self.s2s, self.vq, self.host, self.dev, temperature=1.0, uniforms=self.u,
+                                                      batch_index=self.batch_index, vq_decode_engine=self.vq_dec, out_host=self.pred_host)
+        if self.world > 1:
+            D.all_gather_codes(codes, self.world * self.B)
+        return pred
 
 
 def run_native(args):
     import dim_b200
     from dim_b200 import _lib
     from dim_b200 import dist as D
-    from dim_b200.compat_api import slmft_forward_val, slmft_forward_val_host
-    from dim_b200.engine import PREC_BF16, PREC_FP32, PREC_FP32_TC, Handle, SLMFTEngine, VQEngine
-    from dim_b200.schema import S2SConfig, VQConfig
+    from dim_b200.engine import Handle
+    from dim_b200.schema import S2SConfig
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (native) needs a B200: the CUDA path has no CPU fallback")
     rank, world, local = D.init_from_env()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    B, T, note = WORKLOADS[args.workload]
-    steps_ar = T - 1
-    prec = {"bf16": PREC_BF16, "fp32": PREC_FP32, "fp32_tc": PREC_FP32_TC}[args.precision]
-    vq_prec = PREC_FP32 if prec == PREC_FP32 else PREC_FP32_TC      # the VQ-VAE keeps fp32-grade maths: code indices are bit-exact
-
+    cfg = S2SConfig()
+    peaks = load_peaks()
     h = Handle()
     h.register(dim_b200.synth.make_slmft_state_dict(131))
-    s2s = SLMFTEngine(h, S2SConfig(), precision=prec)
-    vq = VQEngine(h, VQConfig(), prefix="listener_vq.", precision=vq_prec)
-    # bf16 mode ("bf16 fused transformer + VQ decode"): the codes -> frames VQ decoder also runs plain bf16 GEMM operands
-    vq_dec = VQEngine(h, VQConfig(), prefix="listener_vq.", precision=PREC_BF16) if prec == PREC_BF16 else None
-
-    # this rank's shard of the global batch (weak scaling: B clips per GPU), global batch positions for the F4 quirk
-    clips = dim_b200.synth.make_clips(B, T, seed=1000 + rank, speaker="ones" if args.speaker_ones else "randn")
-    batch_index = torch.arange(rank * B, (rank + 1) * B, dtype=torch.int32, device=dev)
-    host = {k: clips[k].pin_memory() for k in ("v_speaker", "v_listener", "v_audio", "mask")}
-    u = torch.rand(B, steps_ar, generator=torch.Generator().manual_seed(7 + rank)).to(dev)
-    res = {k: v.to(dev) for k, v in host.items()}
-    pred_host = torch.empty(B, steps_ar, 56).pin_memory()
-
-    def step_resident():
-        loss, d, pred, codes = slmft_forward_val(s2s, vq, res["v_speaker"], res["v_listener"], res["v_audio"], res["mask"],
-                                                 temperature=1.0, uniforms=u, batch_index=batch_index, return_codes=True,
-                                                 vq_decode_engine=vq_dec)
-        all_codes = D.all_gather_codes(codes, world * B) if world > 1 else codes     # the one collective of the path
-        return pred, all_codes
-
-    def step_e2e():
-        # host (pinned) inputs in, decoded frames back to pinned host memory: the public host-buffer entry point
-        loss, d, pred, codes = slmft_forward_val_host(s2s, vq, host, dev, temperature=1.0, uniforms=u, batch_index=batch_index,
-                                                      vq_decode_engine=vq_dec, out_host=pred_host)
-        if world > 1:
-            D.all_gather_codes(codes, world * B)
-        return pred
 
     def barrier():
         if world > 1:
@@ -276,27 +299,90 @@ def run_native(args):
             ms = float(t.item())
         return ms
 
+    def profiled_step(leg):
+        """One extra step with CUDA events around every launch on the launching stream (dim_profile_*) and, inside the persistent
+        decode kernel, CTA 0's clock around every phase (dim_decode_trace_*).  -> (categories, decode phases)"""
+        _lib.profile_enable(True)
+        _lib.decode_trace_enable(True)
+        leg.step_resident()
+        prof = _lib.profile_collect()
+        trace = _lib.decode_trace_collect()
+        _lib.decode_trace_enable(False)
+        _lib.profile_enable(False)
+        return prof, trace
+
+    def roofline_of(leg, prof, trace):
+        """The dominant kernel of the step is the persistent decode kernel (one launch per step).  achieved = algorithmic HBM bytes
+        of that launch (K/V head rows read once per step + decoder weights once per step) / its duration, CUDA events around the
+        launch on the launching stream.  The attention phases inside it (in-kernel clock) are reported beside it: they move
+        > 90 % of those bytes."""
+        kv_bytes = 2 if leg.precision == "bf16" else 4
+        planes = 1 if leg.precision == "bf16" else 3
+        total, kv, wts = decode_algorithmic_bytes(cfg, leg.B, leg.T, leg.steps_ar, kv_bytes, planes)
+        mk = [p for p in prof if p["category"] == "decode_megakernel"]
+        tot_ms = sum(p["ms"] for p in prof) or 1.0
+        if not mk:
+            return None
+        ms = mk[0]["ms"] / mk[0]["launches"]
+        ach = total / (ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
+                "kernel": "decode_megakernel", "launches_per_step": mk[0]["launches"], "avg_launch_us": 1e3 * ms,
+                "share_of_step": mk[0]["ms"] / tot_ms, "peak_source": peaks["source"],
+                "algorithmic_bytes_per_launch": total, "algorithmic_bytes_kv": kv, "algorithmic_bytes_weights": wts,
+                "how": "one extra profiled step: CUDA events around the launch on the launching stream; bytes = SURVEY 8(d) per-frame K/V "
+                       "bytes x clips x generated frames + decoder weights (bf16 planes) once per step"}
+        agg = {}
+        for kind, t_ms in trace:
+            agg[kind] = agg.get(kind, 0.0) + t_ms
+        if agg.get("attention"):
+            a_gbs = kv / (agg["attention"] * 1e-3) / 1e9
+            roof["phases"] = {k: {"ms": round(v, 3), "us_per_step": round(1e3 * v / leg.steps_ar, 1)} for k, v in sorted(agg.items(), key=lambda kv: -kv[1])}
+            roof["attention_phases"] = {"GB/s": a_gbs, "frac": a_gbs / peaks["hbm"], "share_of_kernel": agg["attention"] / sum(agg.values()),
+                                        "how": "in-kernel globaltimer around every phase (CTA 0), K/V bytes / time inside the attention phases"}
+            roof["phase_count_per_step"] = len(trace)
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            roof["traffic"] = tj.get("decode_megakernel_" + leg.precision)
+            roof["traffic_note"] = tj.get("_note")
+        else:
+            roof["traffic"] = None
+        return roof
+
+    leg = Leg(h, args.workload, args.precision, rank, world, dev, args.speaker_ones)
+    B, T, steps_ar = leg.B, leg.T, leg.steps_ar
     for _ in range(args.warmup):
-        step_resident()
+        leg.step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = _lib.load().dim_launch_count()
-    ms = timed(step_resident, args.steps)
+    ms = timed(leg.step_resident, args.steps)
     launches = _lib.load().dim_launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
 
-    step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    leg.step_e2e()
+    ms_e2e = timed(leg.step_e2e, args.steps)
 
-    # one extra profiled step: CUDA events around every launch, on the launching stream (rank 0 reports)
-    prof = []
-    if rank == 0 or world > 1:
-        _lib.profile_enable(True)
-        step_resident()
-        prof = _lib.profile_collect()
-        _lib.profile_enable(False)
+    prof, trace = profiled_step(leg) if (rank == 0 or world > 1) else ([], [])
     barrier()
+
+    # multi-GPU correctness on hardware (outside the timed region): rank 0 recomputes the first 4 clips of a FOREIGN shard (the
+    # last rank's) from their seeds, with the global batch positions, and compares with that shard's rows of the all-gathered codes
+    sharded_ok = None
+    if world > 1:
+        _, all_codes = leg.step_resident()
+        if rank == 0:
+            from dim_b200.compat_api import slmft_forward_val
+            fr = world - 1
+            fc = dim_b200.synth.make_clips(B, T, seed=1000 + fr, speaker="ones" if args.speaker_ones else "randn")
+            fu = torch.rand(B, steps_ar, generator=torch.Generator().manual_seed(7 + fr))[:4].to(dev)
+            sub = {k: fc[k][:4].to(dev) for k in ("v_speaker", "v_listener", "v_audio", "mask")}
+            bi = torch.arange(fr * B, fr * B + 4, dtype=torch.int32, device=dev)
+            _, _, _, codes4 = slmft_forward_val(leg.s2s, leg.vq, sub["v_speaker"], sub["v_listener"], sub["v_audio"], sub["mask"],
+                                                temperature=1.0, uniforms=fu, batch_index=bi, return_codes=True, vq_decode_engine=leg.vq_dec)
+            sharded_ok = bool(torch.equal(codes4, all_codes[fr * B: fr * B + 4]))
+        barrier()
 
     if rank != 0:
         if world > 1:
@@ -305,105 +391,86 @@ def run_native(args):
     frames_total = world * B * steps_ar
     value = frames_total * args.steps / (ms / 1e3)
     e2e_value = frames_total * args.steps / (ms_e2e / 1e3)
-    peaks = load_peaks()
-    # The profiled step brackets EVERY launch with two CUDA events; that costs several microseconds per launch, which is
-    # most of what a 3-8 us decode-step kernel "takes" in that mode.  Calibrate it (same bracketing around a 1-row LayerNorm,
-    # a ~2 us kernel) and report both the raw and the corrected time of every category; shares use the corrected times.
-    ovh_us = 0.0
-    try:
-        from dim_b200 import ops as _ops
-        xx, gg = torch.randn(1, 64, device=dev), torch.ones(64, device=dev)
-        for _ in range(20):
-            _ops.layer_norm(xx, gg)
-        _lib.profile_enable(True)
-        for _ in range(200):
-            _ops.layer_norm(xx, gg)
-        cal = [p for p in _lib.profile_collect() if p["category"] == "layer_norm"]
-        _lib.profile_enable(False)
-        if cal:
-            ovh_us = max(0.0, 1e3 * cal[0]["ms"] / cal[0]["launches"] - 2.0)
-    except Exception:
-        ovh_us = 0.0
-    for p in prof:
-        p["ms_corr"] = max(p["ms"] - p["launches"] * ovh_us * 1e-3, 0.05 * p["ms"])
-    tot_ms = sum(p["ms_corr"] for p in prof) or 1.0
-    prof.sort(key=lambda p: -p["ms_corr"])
-    top = prof[0]
-    hbm_cats = {"attn_decode", "vq_gather", "layer_norm", "instance_norm", "gemm_f32_skinny", "gemm_bf16_tcgen05_skinny", "misc",
-                "sample"}
-    per_launch_ms = top["ms_corr"] / top["launches"]
-    how = ("one extra profiled step (CUDA events around every launch on the launching stream), per-launch bracketing cost of "
-           f"{ovh_us:.1f} us (calibrated live) subtracted")
-    if top["category"] in hbm_cats:
-        ach = top["bytes"] / top["launches"] / (per_launch_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"]}
-    else:
-        ach = top["flops"] / top["launches"] / (per_launch_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "achieved": ach, "peak": peaks["tensor_sustained"], "unit": "TFLOP/s",
-                "frac": ach / peaks["tensor_sustained"]}
-    if top["category"] == "attn_decode":
-        # the dominant kernel timed ALONE: the launch shapes of one decode step (cross attention over T keys, self attention
-        # over pos+1 keys at the quartile midpoints of the decode), back to back on this stream, CUDA events around each batch,
-        # K/V buffers cycled so that every launch streams from HBM (6 x 2 x B*H*T*64 elements >> L2)
-        alone = attn_decode_alone(_lib.load(), B, S2SConfig().heads, T, steps_ar, prec == PREC_BF16, dev)
-        if alone:
-            roof = {"bound": "hbm", "achieved": alone["GB/s"], "peak": peaks["hbm"], "unit": "GB/s", "frac": alone["GB/s"] / peaks["hbm"]}
-            per_launch_ms = alone["avg_launch_us"] * 1e-3
-            how = ("decode-attention launches of one step replayed alone, back to back on the launching stream, CUDA events around "
-                   "each batch of 12 launches, K/V buffers cycled (HBM-resident); shapes: " + alone["shapes"])
-    traffic = traffic_note = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        traffic, traffic_note = tj.get(top["category"]), tj.get("_note")
-    roof.update(traffic=traffic, traffic_note=traffic_note, kernel=top["category"], launches_per_step=top["launches"], avg_launch_us=1e3 * per_launch_ms,
-                share_of_step=top["ms_corr"] / tot_ms, peak_source=peaks["source"], how=how)
-    kernels = [{"kernel": p["category"], "launches": p["launches"], "ms_raw": round(p["ms"], 3), "ms": round(p["ms_corr"], 3),
-                "share": round(p["ms_corr"] / tot_ms, 4),
-                "GB/s": round(p["bytes"] / (p["ms_corr"] * 1e-3) / 1e9, 1), "TFLOP/s": round(p["flops"] / (p["ms_corr"] * 1e-3) / 1e12, 2)}
+    tot_ms = sum(p["ms"] for p in prof) or 1.0
+    prof.sort(key=lambda p: -p["ms"])
+    kernels = [{"kernel": p["category"], "launches": p["launches"], "ms": round(p["ms"], 3), "share": round(p["ms"] / tot_ms, 4),
+                "GB/s": round(p["bytes"] / (p["ms"] * 1e-3) / 1e9, 1), "TFLOP/s": round(p["flops"] / (p["ms"] * 1e-3) / 1e12, 2)}
                for p in prof]
+    roof = roofline_of(leg, prof, trace) or {"bound": "hbm", "achieved": None, "peak": peaks["hbm"], "unit": "GB/s", "frac": None,
+                                             "traffic": None, "kernel": kernels[0]["kernel"] if kernels else None}
 
     # second arm, same workload: the fp32-grade parity mode (every GEMM operand split exactly into 3 bf16 planes, fp32 KV
     # cache) -- the mode whose outputs meet the 1e-4 / bit-exact-codes bars against the oracle end to end
     parity = None
     if world == 1 and args.precision == "bf16" and not args.no_parity_leg:
-        del s2s
+        del leg.s2s
         torch.cuda.empty_cache()
-        s2s_p = SLMFTEngine(h, S2SConfig(), precision=PREC_FP32_TC)
-
-        def step_parity():
-            return slmft_forward_val(s2s_p, vq, res["v_speaker"], res["v_listener"], res["v_audio"], res["mask"],
-                                     temperature=1.0, uniforms=u, batch_index=batch_index, return_codes=True)
+        pl = Leg(h, args.workload, "fp32_tc", rank, world, dev, args.speaker_ones)
         for _ in range(args.warmup):
-            step_parity()
-        ms_p = timed(step_parity, args.steps)
+            pl.step_resident()
+        ms_p = timed(pl.step_resident, args.steps)
+        pl.step_e2e()
+        ms_pe = timed(pl.step_e2e, args.steps)
+        pprof, ptrace = profiled_step(pl)
         parity = {"dtype": "f32 (bf16x3 split on tcgen05, fp32 accumulate, fp32 KV cache)", "value": frames_total * args.steps / (ms_p / 1e3),
-                  "unit": UNIT, "ms_per_step": ms_p / args.steps}
-        del s2s_p
+                  "unit": UNIT, "ms_per_step": ms_p / args.steps,
+                  "e2e": {"value": frames_total * args.steps / (ms_pe / 1e3), "unit": UNIT, "ms_per_step": ms_pe / args.steps,
+                          "h2d_bytes_per_step": pl.h2d, "d2h_bytes_per_step": pl.d2h},
+                  "roofline": roofline_of(pl, pprof, ptrace)}
+        del pl
+        torch.cuda.empty_cache()
+
+    # BASELINE.json's second metric: VQ-lookup HBM GB/s vs peak, at a size where the launch is not latency
+    vq_lookup = vq_lookup_record(dev, peaks) if world == 1 else None
+
+    # the other BASELINE configurations, resident inputs, same run (3 warm-up + 3 timed steps each)
+    others = {}
+    if world == 1 and not args.no_other_workloads and args.workload == "vico_b256":
+        for name, prec in (("vico_b1", "fp32_tc"), ("vico_b1", "bf16"), ("candor_b256", "bf16"), ("lm_listener_b32", "bf16")):
+            try:
+                ol = Leg(h, name, prec, rank, world, dev)
+                for _ in range(3):
+                    ol.step_resident()
+                oms = timed(ol.step_resident, 3)
+                others[f"{name}/{prec}"] = {"value": ol.B * ol.steps_ar * 3 / (oms / 1e3), "unit": UNIT, "ms_per_step": oms / 3,
+                                            "clips": ol.B, "frames_per_clip": ol.T, "note": ol.note}
+                del ol
+                torch.cuda.empty_cache()
+            except Exception as e:                                      # a side measurement must not take the headline line down
+                others[f"{name}/{prec}"] = {"error": str(e)[:200]}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        fps, secs = cpu_oracle_sample(T if T <= 300 else 300, threads=cores, repeats=10)
-        cpu = {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"1 clip x {min(T, 300)} frames, best of 10 runs ({secs:.1f} s each, ~10 s of CPU work), oracle/slmft.py forward_val (restated reference, "
-                         f"cross-KV once, discarded work skipped), PyTorch CPU fp32"}
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
+        fr = T if T <= 300 else 300
+        fps1, secs1 = cpu_oracle_sample(fr, threads=cores, repeats=5)
+        fps8, secs8 = cpu_oracle_sample(fr, threads=cores, repeats=2, clips=min(B, 8))
+        cpu = {"value": max(fps1, fps8), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "one_clip_per_call": fps1, "eight_clips_per_call": fps8,
+               "sample": f"oracle/slmft.py forward_val (restated reference, cross-KV once, discarded work skipped), PyTorch CPU fp32: 1 clip x {fr} frames "
+                         f"best of 5 ({secs1:.1f} s each) and {min(B, 8)} clips x {fr} frames best of 2 ({secs8:.1f} s each); value = the faster"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"bf16": "bf16", "fp32": "f32", "fp32_tc": "f32 (bf16x3 split on tcgen05, fp32 accumulate)"}[args.precision], "data": "synthetic",
             "config": {"workload": args.workload, "clips_per_gpu": B, "frames_per_clip": T, "generated_frames_per_clip": steps_ar,
                        "global_batch": world * B, "decode": "top-k 52 sampling, temperature 1, pre-drawn uniforms, KV cache on",
                        "parallelism": f"dp{world} (clips sharded, one all-gather of codes)" if world > 1 else "single GPU",
-                       "l2": "inputs+workspace per step >> 126 MB L2 (no explicit flush needed)", "note": note},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": pred_host.numel() * 4,
+                       "l2": "inputs+workspace per step >> 126 MB L2 (no explicit flush needed)", "note": leg.note},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": leg.h2d, "d2h_bytes_per_step": leg.d2h,
                     "ms_per_step": ms_e2e / args.steps, "api": "dim_b200.compat_api.slmft_forward_val_host (SLMFT.forward mode='val' on pinned host buffers; H2D copies overlap the VQ encode)"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernels}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernels,
+            "env": {k: v for k, v in sorted(os.environ.items()) if k.startswith("DIM_")}}
+    if sharded_ok is not None:
+        line["sharded_equals_unsharded"] = sharded_ok
     if cpu:
         line["cpu_baseline"] = cpu
     if parity:
         line["fp32_parity_mode"] = parity
+    if vq_lookup:
+        line["vq_lookup"] = vq_lookup
+    if others:
+        line["other_workloads"] = others
     print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -423,6 +490,7 @@ def main():
     ap.add_argument("--no-parity-leg", action="store_true", help="skip the extra fp32_tc measurement reported as fp32_parity_mode")
     ap.add_argument("--speaker-ones", action="store_true", help="ViCo loader behaviour: speaker motion replaced by ones")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true", help="skip the vico_b1 / candor_b256 / lm_listener_b32 side measurements")
     args = ap.parse_args()
     if args.impl == "native" and os.environ.get("DIM_BENCH_ALLOW_COLD") != "1":
         args.warmup = max(args.warmup, 3)      # timing rule: >= 3 warm-up steps (the override exists for ncu launch lists only)

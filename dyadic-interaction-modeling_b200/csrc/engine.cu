@@ -727,7 +727,7 @@ int plan_groups(const S2SModel& m, int B, int max_keys, int* begin /*[kMaxGroups
   {  // the persistent decode kernel owns every SM: one chain
     const dim_s2s_config& c = m.cfg;
     const int D = c.dim + c.dim_audio;
-    if (g_decode_impl == 0 && m.tc.planes > 0 &&
+    if (g_decode_impl == 0 && tc_on(m.tc, B) &&
         mk_supported(D, c.heads * c.dim_head, c.ff_mult * D, c.num_tokens, c.heads, m.tc.planes, max_keys)) {
       begin[0] = 0;
       begin[1] = B;
@@ -969,8 +969,9 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
   if (int e = launch_set_step(w.step, 0, s)) return e;
 
   const int max_keys = std::max(T, steps + 1);
-  if (g_decode_impl == 0 && m.tc.planes > 0 && mk_supported(D, inner, F, V, c.heads, m.tc.planes, max_keys)) {
-    // persistent decode kernel: prompt embedding + layer 0's LayerNorm here, then every step inside ONE cooperative launch
+  if (g_decode_impl == 0 && tc_on(m.tc, B) && mk_supported(D, inner, F, V, c.heads, m.tc.planes, max_keys)) {
+    // persistent decode kernel (more than 8 decode rows; fewer stay on the weight-streaming GEMV chain, which is faster there:
+    // 77.9 vs 94 ms per single 300-frame clip, profiles/r02_notes.md): prompt embedding + layer 0's LayerNorm here, then every step inside ONE cooperative launch
     const XtAttn& SA0 = m.self_attn[0];
     if (int e = launch_embed_tokens(w.tokens, steps + 1, w.step, m.token_emb, w.x, B, D, V, s)) return e;
     if (int e = launch_layer_norm(w.x, SA0.norm_g, SA0.norm_b, nullptr, nullptr, B, D, 1e-5f, s, w.ap, m.tc.planes, D)) return e;

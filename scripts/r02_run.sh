@@ -85,3 +85,28 @@ if has chainsab; then
     DIM_MK_CHAINS=$1 DIM_MK_STAGGER=$2 timeout 300 python scripts/decode_trace.py 256 300 bf16 2>&1 | grep -v "  phase"
   done
 fi
+if has smoke; then
+  timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "exit $?" >> $OUT/${TAG}_smoke.log; tail -3 $OUT/${TAG}_smoke.log
+fi
+if has benchfull; then
+  timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/${TAG}_bench_bf16.json 2> $OUT/${TAG}_bench_bf16.err
+  tail -c 600 $OUT/${TAG}_bench_bf16.err
+  python - $OUT/${TAG}_bench_bf16.json <<'PY'
+import json, sys
+d = json.loads([l for l in open(sys.argv[1]) if l.startswith("{")][-1])
+print("value %.0f ms %.1f e2e %.0f launches %s" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["gpu_launches"]))
+r = d["roofline"]; print("roofline", r["kernel"], "frac %.3f" % r["frac"], "attn phases", r.get("attention_phases", {}).get("frac"), "share", r["share_of_step"])
+print("phases", r.get("phases"))
+p = d.get("fp32_parity_mode"); print("parity", p and (p["value"], p["ms_per_step"], p["e2e"]["value"], p["roofline"]["frac"]))
+print("vq", d.get("vq_lookup")); print("others", d.get("other_workloads")); print("cpu", d.get("cpu_baseline")); print("clocks", d["clocks"])
+for k in d["kernels"][:8]: print("   ", k)
+PY
+fi
+if has benchref; then
+  timeout 900 python bench.py --steps 3 --warmup 1 --impl reference > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err
+  cut -c1-700 $OUT/${TAG}_bench_reference.json
+fi
+if has bf16contract; then
+  timeout 900 python -m pytest tests/test_bf16_contract_gpu.py tests/test_decode_mk_gpu.py -q -s > $OUT/${TAG}_bf16contract.log 2>&1; echo "exit $?" >> $OUT/${TAG}_bf16contract.log
+  grep -E "bf16|passed|failed|Error|assert" $OUT/${TAG}_bf16contract.log | head -30
+fi
