@@ -110,3 +110,9 @@ if has bf16contract; then
   timeout 900 python -m pytest tests/test_bf16_contract_gpu.py tests/test_decode_mk_gpu.py -q -s > $OUT/${TAG}_bf16contract.log 2>&1; echo "exit $?" >> $OUT/${TAG}_bf16contract.log
   grep -E "bf16|passed|failed|Error|assert" $OUT/${TAG}_bf16contract.log | head -30
 fi
+if has argmintc; then
+  timeout 900 python -m pytest tests/test_vq_argmin_tc_gpu.py tests/test_ops_gpu.py tests/test_vqvae_gpu.py -q -s -x > $OUT/${TAG}_argmintc.log 2>&1; echo "exit $?" >> $OUT/${TAG}_argmintc.log
+  grep -E "tokens with|passed|failed|Error|assert|exit" $OUT/${TAG}_argmintc.log | head -20
+  timeout 300 python scripts/vq_roofline.py > $OUT/${TAG}_vq_roofline.jsonl 2> $OUT/${TAG}_vq_roofline.err
+  grep argmin $OUT/${TAG}_vq_roofline.jsonl | cut -c1-300; tail -2 $OUT/${TAG}_vq_roofline.err
+fi

@@ -56,13 +56,24 @@ def main():
                               "bit_exact_vs_index_select": bool(torch.equal(out, ref))}))
         lib.dim_debug_vq_gather_mode(-1)
         del out, ref
-    for N in ((1 << 20,) if NCU else (76800, 1 << 20)):
+    import ctypes as C
+    lib.dim_debug_vq_argmin_impl.argtypes = [C.c_int]
+    tc_peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json"))).get("bf16_tflops", 1675.8)
+    for N in ((1 << 20,) if NCU else (76800, 1 << 20, 1 << 22)):
         z = (torch.randn(N, 128, generator=g) * 0.7).cuda()
         o = torch.empty(N, dtype=torch.int64, device="cuda")
-        t = timeit(lambda: lib.dim_vq_argmin(z.data_ptr(), E.data_ptr(), o.data_ptr(), N, 128, 512, s))
-        gbs = N * 520 / t / 1e9
-        print(json.dumps({"kernel": "vq_argmin_f32", "tokens": N, "us": t * 1e6, "GB/s": gbs, "frac_of_hbm_peak": gbs / PEAK,
-                          "TFLOP/s": N * 131072 / t / 1e12, "algorithmic_bytes_per_token": 520}))
+        res = {}
+        for impl, name in ((1, "vq_argmin_f32 (exact FFMA)"), (0, "vq_argmin_tc (fp16 tcgen05 shortlist + exact fp32 re-rank)")):
+            lib.dim_debug_vq_argmin_impl(impl)
+            t = timeit(lambda: lib.dim_vq_argmin(z.data_ptr(), E.data_ptr(), o.data_ptr(), N, 128, 512, s))
+            res[impl] = o.clone()
+            gbs = N * 520 / t / 1e9
+            print(json.dumps({"kernel": name, "tokens": N, "us": t * 1e6, "GB/s": gbs, "frac_of_hbm_peak": gbs / PEAK,
+                              "TFLOP/s": N * 131072 / t / 1e12, "frac_of_tensor_peak": N * 131072 / t / 1e12 / tc_peak if impl == 0 else None,
+                              "algorithmic_bytes_per_token": 520,
+                              "note": "time includes the 2 small codebook-preparation launches" if impl == 0 else ""}))
+        lib.dim_debug_vq_argmin_impl(0)
+        print(json.dumps({"check": "tensor-core indices == exact-kernel indices", "tokens": N, "equal": bool(torch.equal(res[0], res[1]))}))
 
 
 if __name__ == "__main__":
