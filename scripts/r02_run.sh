@@ -116,3 +116,21 @@ if has argmintc; then
   timeout 300 python scripts/vq_roofline.py > $OUT/${TAG}_vq_roofline.jsonl 2> $OUT/${TAG}_vq_roofline.err
   grep argmin $OUT/${TAG}_vq_roofline.jsonl | cut -c1-300; tail -2 $OUT/${TAG}_vq_roofline.err
 fi
+if has argmindbg; then
+  VQ_TC_DBG=${VQ_TC_DBG:-0,1,2,4,8,9,11,15} timeout 300 python scripts/vq_roofline.py 2>&1 | grep ablation
+fi
+if has argmintrace; then
+  timeout 300 python scripts/vq_tc_trace.py 2>&1 | tail -30
+fi
+if has argmintrace2; then
+  for d in ${VQ_TC_DBGS:-9 4 13}; do echo "== dbg $d"; VQ_TC_DBG=$d timeout 300 python scripts/vq_tc_trace.py 2>&1 | tail -20 | grep "tile  [89]"; done
+fi
+if has ncuargmin; then
+  VQ_NCU=1 timeout 600 ncu --set full --import-source on --clock-control none -k regex:vq_argmin_tc -c 1 -o $OUT/${TAG}_ncu_argmin -f \
+      python scripts/vq_roofline.py > $OUT/${TAG}_ncu_argmin.log 2>&1
+  ncu -i $OUT/${TAG}_ncu_argmin.ncu-rep --page raw --csv > $OUT/${TAG}_ncu_argmin.raw.csv 2>/dev/null
+  ncu -i $OUT/${TAG}_ncu_argmin.ncu-rep --page details > $OUT/${TAG}_ncu_argmin.details.txt 2>/dev/null
+  ncu -i $OUT/${TAG}_ncu_argmin.ncu-rep --page source --csv --print-source sass > $OUT/${TAG}_ncu_argmin.source.csv 2>/dev/null
+  gzip -f $OUT/${TAG}_ncu_argmin.source.csv
+  ls -la $OUT/${TAG}_ncu_argmin*; tail -3 $OUT/${TAG}_ncu_argmin.log
+fi

@@ -59,6 +59,16 @@ def main():
     import ctypes as C
     lib.dim_debug_vq_argmin_impl.argtypes = [C.c_int]
     tc_peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json"))).get("bf16_tflops", 1675.8)
+    if os.environ.get("VQ_TC_DBG"):                # timing ablations of the tensor-core kernel (results wrong by construction)
+        N = 1 << 20
+        z = (torch.randn(N, 128, generator=g) * 0.7).cuda()
+        o = torch.empty(N, dtype=torch.int64, device="cuda")
+        for dbg in [int(x) for x in os.environ["VQ_TC_DBG"].split(",")]:
+            lib.dim_debug_vq_argmin_impl(dbg << 8)
+            t = timeit(lambda: lib.dim_vq_argmin(z.data_ptr(), E.data_ptr(), o.data_ptr(), N, 128, 512, s))
+            print(json.dumps({"ablation": dbg, "us": t * 1e6}))
+        lib.dim_debug_vq_argmin_impl(0)
+        return
     for N in ((1 << 20,) if NCU else (76800, 1 << 20, 1 << 22)):
         z = (torch.randn(N, 128, generator=g) * 0.7).cuda()
         o = torch.empty(N, dtype=torch.int64, device="cuda")
