@@ -80,6 +80,8 @@ __device__ __forceinline__ void bar_sub(int sub) {   // named barrier of one 64-
 
 // Grid-wide barrier: CTA barrier, then thread 0 publishes with a gpu-scope RELEASE reduction (cumulative over the CTA's writes
 // through the barrier before it) and spins with gpu-scope ACQUIRE loads; a second CTA barrier releases the other threads.
+// (A variant in which the last arriver publishes a generation flag on its own line and everyone polls that line measured
+// SLOWER: +1.2 us per barrier -- the extra release store and its propagation cost more than the contention they avoid.)
 // to_tma: the next phase reads this phase's generic-proxy global writes through TMA (async proxy) -> proxy fences on both sides.
 __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& target, bool to_tma) {
   if (to_tma) asm volatile("fence.proxy.async;" ::: "memory");
@@ -200,10 +202,24 @@ __device__ __forceinline__ void mk_gemm(const MkPlan& P, const MkPhase& ph, uint
       const int LPR = bn >> 2, RPI = 32 / LPR;
       const int c = (lane % LPR) * 4, col = n0 + c;
       const int rows = min(128, M - m0);
-      float* dst = ph.part + ((size_t)z * M + m0) * N + col;
-      if (col < N)
-        for (int r = warp * RPI + lane / LPR; r < rows; r += MK_WARPS * RPI)
-          *reinterpret_cast<float4*>(dst + (size_t)r * N) = *reinterpret_cast<const float4*>(stage_tile + (size_t)r * CP + c);
+      if (ph.epi == 1) {
+        // unsplit GEMM with the consumer's row phase folded in: gelu_erf(acc + bias) -> bf16 planes (FF1 -> FF2's A operand)
+        if (col < N) {
+          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ph.bias) bb = __ldg(reinterpret_cast<const float4*>(ph.bias + col));
+          for (int r = warp * RPI + lane / LPR; r < rows; r += MK_WARPS * RPI) {
+            float4 v = *reinterpret_cast<const float4*>(stage_tile + (size_t)r * CP + c);
+            v.x = act_apply(v.x + bb.x, DIM_ACT_GELU_ERF, 0.f); v.y = act_apply(v.y + bb.y, DIM_ACT_GELU_ERF, 0.f);
+            v.z = act_apply(v.z + bb.z, DIM_ACT_GELU_ERF, 0.f); v.w = act_apply(v.w + bb.w, DIM_ACT_GELU_ERF, 0.f);
+            store_planes4(ph.outp + (size_t)(m0 + r) * P.planes * ph.out_kp + col, v, P.planes, ph.out_kp);
+          }
+        }
+      } else {
+        float* dst = ph.part + ((size_t)z * M + m0) * N + col;
+        if (col < N)
+          for (int r = warp * RPI + lane / LPR; r < rows; r += MK_WARPS * RPI)
+            *reinterpret_cast<float4*>(dst + (size_t)r * N) = *reinterpret_cast<const float4*>(stage_tile + (size_t)r * CP + c);
+      }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic accesses to the ring before the next TMA writes
     __syncthreads();
@@ -396,10 +412,16 @@ __device__ __forceinline__ uint32_t pack_part(float x, float y, int sel) {
   return sel <= 1 ? w : 0u;
 }
 
+// The K tiles then the V tiles of an item form one stream of 2*nch tiles through an NST-slot cp.async ring, and the stream runs on
+// into the NEXT item of the sub-group (every item of a phase has the same tile count): while an item finishes (softmax tail, output
+// reduction, store) and the next one sums its projection partials, the next item's first tiles are already in flight.  `issued`
+// counts the cp.async groups committed by this sub-group in this phase (one per stream position, empty past the last item), `g0` is
+// the stream position of this item's first tile; slot = position % NST.
+template <int NST>
 __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, int H, int planes, int sc_floats, uint8_t* reg, int sub,
-                                                 int tid, int item, int pos) {
+                                                 int tid, int item, int next_item, int pos, int& issued, int& g0) {
   constexpr int NT = 64, DH = 64, CHUNK = 64, PITCH = 144, STAGE = CHUNK * PITCH;
-  float* sc = reinterpret_cast<float*>(reg + 2 * STAGE);
+  float* sc = reinterpret_cast<float*>(reg + NST * STAGE);
   float* part = sc + sc_floats;                        // [2][64] partial outputs of the two warps (sized [8][64] by the carve)
   float* qs = part + 8 * DH;                           // [64]
   float* red = qs + DH;                                // [4]
@@ -419,22 +441,37 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
   // thread -> 8 fixed 16-byte pieces of a tile: rows tid/8 + 8i, chunk tid%8
   const uint32_t dst0 = (uint32_t)((tid >> 3) * PITCH + (tid & 7) * 16);
   const int row_t = tid >> 3;
-  auto issue = [&](const __nv_bfloat16* head, int c, int stage) {         // rows [c*64, c*64+64) of a head block -> ring[stage]
+  const int n = 2 * nch;                                // tiles of one item's stream
+  // head blocks of the next item (its first tiles are prefetched at the end of this one): computed once, not per tile
+  const __nv_bfloat16 *knext = khead, *vnext = vhead;
+  if (next_item >= 0) {
+    const int nb = next_item / H, nh = next_item - nb * H, nbkv = nb / ph.kv_group;
+    const size_t off = (size_t)nbkv * ph.kv_batch_stride + (size_t)nh * ph.kv_head_stride;
+    knext = static_cast<const __nv_bfloat16*>(ph.kcache) + off;
+    vnext = static_cast<const __nv_bfloat16*>(ph.vcache) + off;
+  }
+  auto issue_tile = [&](const __nv_bfloat16* head, int c, int slot) {     // rows [c*64, c*64+64) of a head block -> ring[slot]
     const int row0 = c * CHUNK, valid = nold - row0;                     // rows >= valid are zero-filled
     const uint8_t* src = reinterpret_cast<const uint8_t*>(head + (size_t)row0 * DH) + tid * 16;
-    const uint32_t dst = ring_u + stage * STAGE + dst0;
+    const uint32_t dst = ring_u + slot * STAGE + dst0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const bool ok = row_t + 8 * i < valid;
       cp_async_16_zfill(dst + i * 8 * PITCH, ok ? src + i * 1024 : reinterpret_cast<const uint8_t*>(head), ok ? 16u : 0u, kvpol);
     }
-    cp_async_commit();
   };
-  // K tiles then V tiles form ONE stream of 2*nch tiles through the 2-stage ring (stream tile s -> stage s & 1): the first V tiles
-  // are already in flight while the softmax statistics are computed
-  auto issue_stream = [&](int s2) {
-    if (s2 < nch) issue(khead, s2, s2 & 1);
-    else if (s2 < 2 * nch) issue(vhead, s2 - nch, s2 & 1);
+  int slot_next = issued % NST;                         // ring slot of stream position `issued`
+  auto issue_upto = [&](int limit) {                    // commit one group per stream position below `limit`
+    while (issued < limit) {
+      const int idx = issued - g0;
+      if (idx < nch) issue_tile(khead, idx, slot_next);
+      else if (idx < n) issue_tile(vhead, idx - nch, slot_next);
+      else if (next_item >= 0 && idx < n + nch) issue_tile(knext, idx - n, slot_next);
+      else if (next_item >= 0 && idx < 2 * n) issue_tile(vnext, idx - n - nch, slot_next);
+      cp_async_commit();
+      ++issued;
+      if (++slot_next == NST) slot_next = 0;
+    }
   };
   // key-padding mask bytes of this thread's keys (tid, tid + 64, ...), fetched now: the softmax below must not wait for them
   const uint8_t* km = ph.key_mask ? ph.key_mask + (size_t)bkv * ph.Tk : nullptr;
@@ -444,8 +481,9 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
     for (int i = 0; i < 32; ++i)
       if (tid + 64 * i < nkeys && !km[tid + 64 * i]) kmbits &= ~(1u << i);
   }
-  issue_stream(0);                                     // the first tiles travel while the projection partials are summed
-  issue_stream(1);
+  int slot_cur = g0 % NST;                             // ring slot of this item's next tile to consume
+  issue_upto(g0 + NST);                                // the first tiles travel while the projection partials are summed (a no-op
+                                                       // when the previous item of this sub-group has already sent them)
   {  // q (and this step's k, v) = sum of the K slices of the projection, in slice order; thread t owns element t of the head row
     const size_t mn = (size_t)Brows * ph.q_ld;
     const float* base = reinterpret_cast<const float*>(ph.part) + (size_t)b * ph.q_ld + h * DH + tid;
@@ -493,9 +531,10 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
   const uint32_t bv_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (lane >> 4) * 16);
   // ---- pass 1: S = q K^T; warp w owns keys 32w .. 32w+31 of the tile
   for (int c = 0; c < nch; ++c) {
-    cp_async_wait<1>();                                // stream tile c + 1 (a K tile or the first V tile) may still be in flight
+    cp_async_wait<NST - 1>();                          // the NST - 1 stream positions after this tile may still be in flight
     bar_sub(sub);
-    const uint32_t tile = ring_u + (c & 1) * STAGE;
+    const uint32_t tile = ring_u + slot_cur * STAGE;
+    if (++slot_cur == NST) slot_cur = 0;
     float s[4][4];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
@@ -520,7 +559,7 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
       }
     }
     bar_sub(sub);
-    issue_stream(c + 2);
+    issue_upto(g0 + c + 1 + NST);
   }
   bar_sub(sub);                                        // the own key's score is visible (covers the no-tile first step too)
   // key-padding mask (masked_fill(-finfo.max)) and softmax statistics
@@ -551,9 +590,10 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
   for (int c = 0; c < nch; ++c) {
-    if (c + 1 < nch) cp_async_wait<1>(); else cp_async_wait<0>();
+    cp_async_wait<NST - 1>();
     bar_sub(sub);
-    const uint32_t tile = ring_u + ((nch + c) & 1) * STAGE;
+    const uint32_t tile = ring_u + slot_cur * STAGE;
+    if (++slot_cur == NST) slot_cur = 0;
 #pragma unroll
     for (int k2 = 0; k2 < 2; ++k2) {
       const int kb = warp * 32 + k2 * 16, j0 = c * CHUNK + kb + 2 * t4;     // this lane's key columns: j0, j0+1, j0+8, j0+9
@@ -575,8 +615,9 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
       }
     }
     bar_sub(sub);
-    issue_stream(nch + c + 2);
+    issue_upto(g0 + nch + c + 1 + NST);                // past this item's last tile: the next item's first tiles
   }
+  g0 += n;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
     const float o0 = o[nt][0] + __shfl_xor_sync(0xffffffffu, o[nt][0], 4);
@@ -591,6 +632,28 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
   }
 }
 
+template <int NST>
+__device__ __forceinline__ void mk_attn_mma_loop(const MkPlan& P, const MkPhase& ph, uint8_t* reg, Ctl& ctl, int sub, int tid, int mine, int pos) {
+  auto fetch = [&]() {                                 // next entry of this CTA's item list, handed out to whichever sub-group asks
+    if (tid == 0) ctl.sub_item[sub] = atomicAdd(&ctl.attn_ctr, 1);
+    bar_sub(sub);
+    const int k = ctl.sub_item[sub];
+    bar_sub(sub);
+    return k;
+  };
+  int issued = 0, g0 = 0;
+  int k = fetch();
+  while (k < mine) {
+    const int kn = fetch();
+    const int item = (int)blockIdx.x + k * (int)gridDim.x;
+    const int next = kn < mine ? (int)blockIdx.x + kn * (int)gridDim.x : -1;
+    mk_attn_item_mma<NST>(ph, P.B, P.H, P.planes, P.sc_floats, reg, sub, tid, item, next, pos, issued, g0);
+    bar_sub(sub);
+    k = kn;
+  }
+  cp_async_wait<0>();                                  // only empty groups can be pending here
+}
+
 __device__ __forceinline__ void mk_attn(const MkPlan& P, const MkPhase& ph, uint8_t* smem, Ctl& ctl, int pos) {
   const int items = P.B * P.H;
   const int mine = (int)blockIdx.x < items ? (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -598,14 +661,18 @@ __device__ __forceinline__ void mk_attn(const MkPlan& P, const MkPhase& ph, uint
   __syncthreads();
   const int sub = threadIdx.x >> 6, tid = threadIdx.x & 63;
   uint8_t* reg = smem + (size_t)sub * MK_SUB_BYTES;
+  if (P.kv_bf16 && P.attn_mma) {
+    if (P.attn_stages == 3) mk_attn_mma_loop<3>(P, ph, reg, ctl, sub, tid, mine, pos);
+    else mk_attn_mma_loop<2>(P, ph, reg, ctl, sub, tid, mine, pos);
+    return;
+  }
   for (;;) {
     if (tid == 0) ctl.sub_item[sub] = atomicAdd(&ctl.attn_ctr, 1);
     bar_sub(sub);
     const int k = ctl.sub_item[sub];
     if (k >= mine) break;
     const int item = (int)blockIdx.x + k * (int)gridDim.x;
-    if (P.kv_bf16 && P.attn_mma) mk_attn_item_mma(ph, P.B, P.H, P.planes, P.sc_floats, reg, sub, tid, item, pos);
-    else if (P.kv_bf16) mk_attn_item<true>(ph, P.B, P.H, P.planes, P.sc_floats, reg, sub, tid, item, pos);
+    if (P.kv_bf16) mk_attn_item<true>(ph, P.B, P.H, P.planes, P.sc_floats, reg, sub, tid, item, pos);
     else mk_attn_item<false>(ph, P.B, P.H, P.planes, P.sc_floats, reg, sub, tid, item, pos);
     bar_sub(sub);
   }

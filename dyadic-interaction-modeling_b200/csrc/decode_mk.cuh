@@ -22,6 +22,7 @@ struct MkPhase {
   int kblocks, npairs, splits, bn, kp;
   int pa[6], pw[6];
   float w_keep;                              // > 0: fraction of the weight tiles loaded with L2 evict_last
+  int epi;                                   // 0: fp32 partials -> part; 1 (splits == 1 only): gelu_erf(acc + bias) -> planes outp
   float* part;
   // ---- MK_ATTN: one query row per (decode row, head) over a head-major K/V cache
   int q_splits, q_ld, q_col, k_col, v_col;   // the producing GEMM's partials: pitch and column offsets of q / new k / new v
@@ -51,6 +52,7 @@ struct alignas(128) MkPlan {
   int planes;
   int kv_bf16;
   int steps;
+  int attn_stages;                           // cp.async ring slots of the mma attention items (3 when the scores fit beside them)
   int attn_mma;                              // bf16 caches: 1 = mma.sync attention items, 0 = FFMA items (A/B hook DIM_MK_ATTN_FFMA)
   int sc_floats;                             // score slots per attention work item (>= max keys, multiple of 4)
   unsigned int* bar;                         // grid barrier counter, zero at launch

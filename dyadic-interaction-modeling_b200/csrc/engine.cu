@@ -901,7 +901,14 @@ int build_mk_plan(const S2SModel& m, const GenWs& w, int B, int Bc, int T, int s
     if (int e = resln(sp, nullptr, FF.norm_g, FF.norm_b)) return e;
     // --- feed forward
     if (int e = b.gemm(mapLn, FF.w1, F, D, w.mk_part, w_keep, &sp)) return e;
-    {
+    static const bool no_fuse = getenv("DIM_MK_NO_GELU_FUSE") != nullptr;     // measurement hook
+    if (planes == 1 && cdiv(F, 64) >= 72 && !no_fuse) {        // a function of (N, K, planes) only, like every split decision
+      // bf16 operands: FF1 has enough 64-wide output tiles to fill the SMs without splitting K, so bias + GELU + the bf16
+      // rounding of FF2's A operand run in the GEMM's own epilogue and the GELU row phase (and its grid barrier) disappears
+      MkPhase* ph = &P.phases[P.nphases - 1];
+      ph->bn = 64; ph->splits = 1; ph->epi = 1; ph->bias = FF.b1; ph->outp = w.ap2; ph->out_kp = F;
+      if (int e = tc_make_map(m.tc.wmap.find(FF.w1)->second, F, planes * tc_round_k(D), planes * tc_round_k(D), 64, &P.maps[ph->mapW])) return e;
+    } else {
       MkPhase* ph = b.next(MK_ROW_GELU);
       if (!ph) return fail(DIM_EINVAL, "decode plan: too many phases");
       ph->N = F; ph->part = w.mk_part; ph->in_splits = sp; ph->bias = FF.b1; ph->outp = w.ap2; ph->out_kp = F;
@@ -921,6 +928,11 @@ int build_mk_plan(const S2SModel& m, const GenWs& w, int B, int Bc, int T, int s
   P.nmaps = b.nmaps;
   P.B = B; P.H = c.heads; P.planes = planes; P.kv_bf16 = kv16 ? 1 : 0; P.steps = steps;
   P.sc_floats = (std::max(T, steps + 1) + 3) / 4 * 4;
+  {  // attention sub-group scratch (decode_mk.cu: MK_SUB_BYTES = 32 KB): a third ring slot when the scores fit beside it
+    static const int st_env = getenv("DIM_MK_ATTN_STAGES") ? atoi(getenv("DIM_MK_ATTN_STAGES")) : 0;
+    const size_t need3 = 3 * 64 * 144 + (size_t)P.sc_floats * 4 + 8 * 64 * 4 + 3 * 64 * 4 + 16;
+    P.attn_stages = (need3 <= 32768 && st_env == 3) ? 3 : 2;     // measured: a third slot does not pay (341 vs 346 us of attention per step)
+  }
   {  // measurement hooks: DIM_MK_ATTN_FFMA=1 keeps the FFMA attention items for bf16 caches; DIM_MK_NOPS=k appends k empty phases
     static const bool ffma = getenv("DIM_MK_ATTN_FFMA") != nullptr;
     static const int nops = getenv("DIM_MK_NOPS") ? atoi(getenv("DIM_MK_NOPS")) : 0;

@@ -134,3 +134,8 @@ if has ncuargmin; then
   gzip -f $OUT/${TAG}_ncu_argmin.source.csv
   ls -la $OUT/${TAG}_ncu_argmin*; tail -3 $OUT/${TAG}_ncu_argmin.log
 fi
+if has mkab; then
+  echo "== default"; timeout 300 python scripts/decode_trace.py 256 300 bf16 2>&1 | grep -v "  phase"
+  echo "== 2-stage ring"; DIM_MK_ATTN_STAGES=2 timeout 300 python scripts/decode_trace.py 256 300 bf16 2>&1 | grep -v "  phase"
+  echo "== no gelu fuse"; DIM_MK_NO_GELU_FUSE=1 timeout 300 python scripts/decode_trace.py 256 300 bf16 2>&1 | grep -v "  phase"
+fi
