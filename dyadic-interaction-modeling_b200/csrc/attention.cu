@@ -753,31 +753,22 @@ int launch_attention_prefill(const AttnArgs& a, cudaStream_t s) {
     Kern kern = a.Dh == 48 ? (np == 1 ? (Kern)attn_prefill_mma<48, 1> : (Kern)attn_prefill_mma<48, 3>)
                            : (np == 1 ? (Kern)attn_prefill_mma<64, 1> : (Kern)attn_prefill_mma<64, 3>);
     const size_t smem = (size_t)3 * np * 64 * (a.Dh + 8) * sizeof(__nv_bfloat16);
-    static bool configured[4] = {false, false, false, false};
+    static PerDeviceOnce configured[4];
     const int slot = (a.Dh == 48 ? 0 : 2) + (np == 1 ? 0 : 1);
-    if (!configured[slot]) {
-      DIM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured[slot] = true;
-    }
+    if (configured[slot].first()) DIM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3(cdiv(a.Tq, 64), a.H, a.B), 128, smem, s>>>(a);
     DIM_LAUNCHED();
     return DIM_OK;
   }
   if (a.Dh == 48) {
     constexpr size_t smem = (TQ * 52 + TKV * 52 + TKV * 48 + TQ * (TKV + 4)) * sizeof(float);
-    static bool once = false;
-    if (!once) {
-      DIM_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_f32<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      once = true;
-    }
+    static PerDeviceOnce once;
+    if (once.first()) DIM_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_f32<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attn_prefill_f32<48><<<grid, 256, smem, s>>>(a);
   } else {
     constexpr size_t smem = (TQ * 68 + TKV * 68 + TKV * 64 + TQ * (TKV + 4)) * sizeof(float);
-    static bool once = false;
-    if (!once) {
-      DIM_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_f32<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      once = true;
-    }
+    static PerDeviceOnce once;
+    if (once.first()) DIM_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_f32<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attn_prefill_f32<64><<<grid, 256, smem, s>>>(a);
   }
   DIM_LAUNCHED();
@@ -822,11 +813,14 @@ int launch_attention_decode(DecodeAttnArgs a, int max_keys, cudaStream_t s) {
   a.sc_floats = (max_keys + 3) / 4 * 4;
   const size_t smem = ring + (size_t)(a.sc_floats + 16 * 64) * sizeof(float);
   DIM_REQUIRE(smem <= 200 * 1024, "decode attention: too many keys for one CTA");
-  static size_t configured[8] = {48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024};
+  static size_t configured[64][8];                                          // per device: largest size set so far (0 = the 48 KB default)
   const int slot = (bf ? 1 : 0) + 2 * (g_attn_impl == 4 ? 0 : (g_attn_impl & 3));
-  if (smem > configured[slot]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (smem > 48 * 1024 && smem > configured[dev][slot]) {
     DIM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[slot] = smem;
+    configured[dev][slot] = smem;
   }
   {
     const double keys = a.append ? (double)(a.prof_pos + 1) : (double)a.Tk;   // K and V rows actually read

@@ -39,6 +39,19 @@ extern std::atomic<uint64_t> g_launches;
 
 int ensure_device();   // DIM_OK when the current device is sm_100; DIM_ENODEVICE otherwise
 
+// One-time per-DEVICE set-up guard (cudaFuncSetAttribute is a per-device property; a process may hold handles on several GPUs)
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    const bool f = !done[d];
+    done[d] = true;
+    return f;
+  }
+};
+
 // ---- optional per-kernel-category timing (dim_profile_*): CUDA events around each launch on the launching stream ----
 enum ProfCat {
   CAT_GEMM_TILED = 0, CAT_GEMM_SKINNY, CAT_CONV, CAT_LAYERNORM, CAT_INSTNORM, CAT_ATTN_PREFILL, CAT_ATTN_DECODE,

@@ -522,6 +522,7 @@ extern "C" int dim_set_tensor(dim_handle_t h, const char* name, const void* ptr,
 
 extern "C" int dim_vqvae_build(dim_handle_t h, const char* prefix_c, const dim_vq_config* cfg, int precision, int* model) {
   DIM_REQUIRE(h && cfg && model, "dim_vqvae_build: null argument");
+  DIM_CHECK_CUDA(cudaSetDevice(h->device));            // the handle's device, whatever the caller's current device is
   DIM_REQUIRE(precision == DIM_PREC_FP32 || precision == DIM_PREC_FP32_TC || precision == DIM_PREC_BF16,
               "dim_vqvae_build: unknown precision");
   const dim_vq_config& c = *cfg;
@@ -594,6 +595,7 @@ extern "C" int dim_vqvae_encode(dim_handle_t h, int model, const float* x, const
                                 int B, int T, int64_t* idx, float* z, float* quant_bcl, void* ws, size_t ws_bytes,
                                 void* stream) {
   DIM_REQUIRE(h && model >= 0 && model < (int)h->vq.size(), "dim_vqvae_encode: bad model");
+  DIM_CHECK_CUDA(cudaSetDevice(h->device));            // the handle's device, whatever the caller's current device is
   DIM_REQUIRE(x && B > 0 && T > 0 && (idx || z), "dim_vqvae_encode: bad argument");
   const VqModel& m = *h->vq[model];
   const dim_vq_config& c = m.cfg;
@@ -627,6 +629,7 @@ extern "C" int dim_vqvae_decode(dim_handle_t h, int model, const int64_t* codes,
                                 const int32_t* batch_index, int B, int L, float* out, void* ws, size_t ws_bytes,
                                 void* stream) {
   DIM_REQUIRE(h && model >= 0 && model < (int)h->vq.size(), "dim_vqvae_decode: bad model");
+  DIM_CHECK_CUDA(cudaSetDevice(h->device));            // the handle's device, whatever the caller's current device is
   DIM_REQUIRE((codes != nullptr) != (quant_bcl != nullptr), "dim_vqvae_decode: pass exactly one of codes / quant");
   DIM_REQUIRE(out && B > 0 && L > 0, "dim_vqvae_decode: bad argument");
   const VqModel& m = *h->vq[model];
@@ -658,6 +661,7 @@ extern "C" int dim_vqvae_decode(dim_handle_t h, int model, const int64_t* codes,
 
 extern "C" int dim_slmft_build(dim_handle_t h, const dim_s2s_config* cfg, int precision, int* model) {
   DIM_REQUIRE(h && cfg && model, "dim_slmft_build: null argument");
+  DIM_CHECK_CUDA(cudaSetDevice(h->device));            // the handle's device, whatever the caller's current device is
   DIM_REQUIRE(precision == DIM_PREC_FP32 || precision == DIM_PREC_FP32_TC || precision == DIM_PREC_BF16,
               "dim_slmft_build: unknown precision");
   const dim_s2s_config& c = *cfg;
@@ -771,6 +775,7 @@ extern "C" int dim_slmft_context(dim_handle_t h, int model, const float* v_speak
                                  const uint8_t* mask, int B, int T, float* ctx, float* x_s, void* ws, size_t ws_bytes,
                                  void* stream) {
   DIM_REQUIRE(h && model >= 0 && model < (int)h->s2s.size(), "dim_slmft_context: bad model");
+  DIM_CHECK_CUDA(cudaSetDevice(h->device));            // the handle's device, whatever the caller's current device is
   DIM_REQUIRE(v_speaker && (ctx || x_s) && (v_audio || !ctx) && B > 0 && T > 0, "dim_slmft_context: bad argument");
   const S2SModel& m = *h->s2s[model];
   const dim_s2s_config& c = m.cfg;
@@ -1164,6 +1169,7 @@ extern "C" int dim_slmft_generate(dim_handle_t h, int model, const float* ctx, c
                                   int B, int T, int steps, float temperature, int top_k, const float* uniforms,
                                   int64_t* out_codes, float* logits_out, void* ws, size_t ws_bytes, void* stream) {
   DIM_REQUIRE(h && model >= 0 && model < (int)h->s2s.size(), "dim_slmft_generate: bad model");
+  DIM_CHECK_CUDA(cudaSetDevice(h->device));            // the handle's device, whatever the caller's current device is
   DIM_REQUIRE(ctx && prompt && out_codes && B > 0 && T > 0 && steps > 0, "dim_slmft_generate: bad argument");
   DIM_REQUIRE(temperature >= 0.f, "temperature must be >= 0");
   DIM_REQUIRE(temperature == 0.f || (uniforms && top_k > 0), "sampling needs uniforms and top_k");
@@ -1232,6 +1238,7 @@ extern "C" int dim_slmft_generate_samples(dim_handle_t h, int model, const float
                                           const float* uniforms, int64_t* out_codes, float* logits_out, void* ws,
                                           size_t ws_bytes, void* stream) {
   DIM_REQUIRE(h && model >= 0 && model < (int)h->s2s.size(), "dim_slmft_generate_samples: bad model");
+  DIM_CHECK_CUDA(cudaSetDevice(h->device));            // the handle's device, whatever the caller's current device is
   DIM_REQUIRE(ctx && prompt && out_codes && B > 0 && T > 0 && steps > 0 && samples > 0, "dim_slmft_generate_samples: bad argument");
   DIM_REQUIRE(temperature >= 0.f, "temperature must be >= 0");
   DIM_REQUIRE(temperature == 0.f || (uniforms && top_k > 0), "sampling needs uniforms and top_k");
@@ -1280,6 +1287,7 @@ extern "C" int dim_slmft_teacher_forced(dim_handle_t h, int model, const float* 
                                         const uint8_t* kv_mask, int B, int T, int L, float* logits, void* ws, size_t ws_bytes,
                                         void* stream) {
   DIM_REQUIRE(h && model >= 0 && model < (int)h->s2s.size(), "dim_slmft_teacher_forced: bad model");
+  DIM_CHECK_CUDA(cudaSetDevice(h->device));            // the handle's device, whatever the caller's current device is
   DIM_REQUIRE(ctx && tokens && logits && B > 0 && T > 0 && L > 0, "dim_slmft_teacher_forced: bad argument");
   const S2SModel& m = *h->s2s[model];
   const dim_s2s_config& c = m.cfg;

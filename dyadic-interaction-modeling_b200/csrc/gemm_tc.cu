@@ -365,11 +365,8 @@ int make_map(const __nv_bfloat16* ptr, int rows, int cols, int ld, int box_rows,
 template <int BN, int STAGES, int ACT>
 int launch_tc_act(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcParams& p, cudaStream_t s) {
   constexpr size_t smem = (size_t)STAGES * (BM * BKE * 2 + BN * BKE * 2) + 1024;
-  static bool once = false;
-  if (!once) {
-    DIM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, STAGES, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    once = true;
-  }
+  static PerDeviceOnce once;
+  if (once.first()) DIM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, STAGES, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(cdiv(p.e.N, BN), cdiv(p.e.M, BM), p.splits);
   cfg.blockDim = dim3(192);

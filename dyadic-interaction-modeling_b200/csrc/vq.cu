@@ -288,11 +288,10 @@ int launch_vq_argmin(const float* z, const float* E, int64_t* idx, int N, int D,
   ProfScope ps(CAT_VQ_ARGMIN, s, (double)N * (4.0 * D + 8.0), 2.0 * N * (double)D * K);     // 520 B / token
 #define DIM_ARGMIN_CASE(DD)                                                                                      \
   {                                                                                                              \
-    static bool once = false;                                                                                    \
-    if (!once) {                                                                                                 \
+    static PerDeviceOnce once;                                                                                   \
+    if (once.first())                                                                                            \
       DIM_CHECK_CUDA(cudaFuncSetAttribute(vq_argmin_f32<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      once = true;                                                                                               \
-    }                                                                                                            \
+                                                                                                                 \
     vq_argmin_f32<DD><<<grid, 256, smem, s>>>(z, E, idx, N, K);                                                  \
   }
   if (D == 64) DIM_ARGMIN_CASE(64) else if (D == 128) DIM_ARGMIN_CASE(128) else DIM_ARGMIN_CASE(256)
