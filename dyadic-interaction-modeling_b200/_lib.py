@@ -89,7 +89,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 class VQConfigC(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("in_dim", "hidden", "layers", "heads", "ffn", "n_embed", "zdim", "pe_max_len")] \
-        + [("neg_slope", C.c_float)]
+        + [("neg_slope", C.c_float), ("fqn", C.c_int32), ("out_dim", C.c_int32)]
 
 
 class S2SConfigC(C.Structure):
@@ -127,6 +127,7 @@ SIGNATURES = {
     "dim_destroy": (I, [P]),
     "dim_set_tensor": (I, [P, C.c_char_p, P, I, I, C.POINTER(I64)]),
     "dim_vqvae_build": (I, [P, C.c_char_p, C.POINTER(VQConfigC), I, C.POINTER(I)]),
+    "dim_vqvae_build_parts": (I, [P, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(VQConfigC), I, C.POINTER(I)]),
     "dim_vqvae_workspace_bytes": (SZ, [P, I, I, I]),
     "dim_vqvae_encode": (I, [P, I, P, P, P, I, I, P, P, P, P, SZ, P]),
     "dim_vqvae_decode": (I, [P, I, P, P, P, I, I, P, P, SZ, P]),

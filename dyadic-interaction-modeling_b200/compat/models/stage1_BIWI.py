@@ -11,7 +11,7 @@ from base import BaseModel
 from dim_b200 import ops
 from dim_b200.engine import PREC_FP32_TC, Handle, VQEngine
 from dim_b200.paramtree import ParamTree, fingerprint, strip_prefix
-from dim_b200.schema import VQConfig, vqvae_schema
+from dim_b200.schema import SPEAKER_OUT_DIMS, VQConfig, vqspeaker_schema, vqvae_schema
 from models.lib.quantizer import VectorQuantizer
 
 
@@ -98,3 +98,61 @@ class VQAutoEncoder(BaseModel):
         else:
             ix = torch.topk(probs, k=1, dim=-1)[1]
         return ix, probs
+
+
+class VQSpeakerAutoEncoder(VQAutoEncoder):
+    """models.stage1_BIWI.VQSpeakerAutoEncoder (reference: code/models/stage1_BIWI.py:140-251; arch `stage1_BIWI_speaker`,
+    code/config_speaker_old.yaml): one TransformerEncoder over the 824-d speaker frame (56 motion | 768 audio), 8 codes per
+    frame from one 512 x 128 codebook, and TWO TransformerDecoders whose outputs are concatenated (decoder_v -> 56, decoder_a ->
+    768).  On the B200 kernels this is three engines over the same handle (dim_vqvae_build_parts): the encoder half and one
+    decoder-only model per output head; every other method is inherited (their bodies only call encode / decode)."""
+
+    def __init__(self, args):
+        BaseModel.__init__(self)
+        self.args = args
+        self._cfg = VQConfig.from_cfg(args)
+        schema = vqspeaker_schema(self._cfg)
+        self.encoder = ParamTree(strip_prefix(schema, "encoder."))
+        self.decoder_v = ParamTree(strip_prefix(schema, "decoder_v."))
+        self.decoder_a = ParamTree(strip_prefix(schema, "decoder_a."))
+        self.quantize = VectorQuantizer(args.n_embed, args.zquant_dim, beta=0.25)
+        self._engine = None
+        self._fp = None
+
+    def engine(self):
+        fp = fingerprint(self)
+        if self._engine is None or fp != self._fp:
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("VQSpeakerAutoEncoder runs on CUDA only (sm_100a kernels, no CPU fallback): call .cuda() first")
+            h = Handle(dev.index)
+            h.register(self.state_dict())
+            enc = VQEngine(h, self._cfg, precision=self.precision, encoder="encoder", decoder=None)
+            decs = [VQEngine(h, self._cfg, precision=self.precision, encoder=None, decoder=name, out_dim=od)
+                    for name, od in SPEAKER_OUT_DIMS]
+            self._engine = (enc, decs)
+            self._fp = fp
+        return self._engine
+
+    @torch.no_grad()
+    def encode(self, x, x_a=None, lens=None, batch_index=None):
+        idx, z, _ = self.engine()[0].encode(x.float(), lens=lens, batch_index=batch_index, want_z=True)
+        z = z.view(z.shape[0], -1, self._cfg.zquant_dim)                    # h.view(B, -1, zquant_dim): 8 tokens per frame
+        rows = ops.vq_gather(idx.reshape(-1), self.quantize.embedding.weight.detach().contiguous()).view(z.shape)
+        return self.quantize._package(z, rows, idx.reshape(-1))
+
+    @torch.no_grad()
+    def decode(self, quant, batch_index=None):
+        q = quant.float()
+        return torch.cat([d.decode(quant=q, batch_index=batch_index) for d in self.engine()[1]], dim=-1)
+
+    @torch.no_grad()
+    def get_distances(self, x):
+        _, z, _ = self.engine()[0].encode(x.float(), want_z=True)
+        return self.quantize.get_distance(z)
+
+    @torch.no_grad()
+    def decode_to_img(self, index, zshape, batch_index=None):
+        B, L = zshape[0], zshape[1]                                         # L counts codes: frames * face_quan_num
+        codes = index.long().reshape(B, L)
+        return torch.cat([d.decode(codes=codes, batch_index=batch_index) for d in self.engine()[1]], dim=-1)

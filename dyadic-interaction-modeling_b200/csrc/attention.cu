@@ -737,7 +737,7 @@ int launch_kv_head_major(const void* src, void* dst, int B, int T, int H, int bf
 }
 
 int launch_attention_prefill(const AttnArgs& a, cudaStream_t s) {
-  DIM_REQUIRE(a.Dh == 48 || a.Dh == 64, "attention: head dim must be 48 or 64");
+  DIM_REQUIRE(a.Dh == 48 || a.Dh == 64 || a.Dh == 96, "attention: head dim must be 48, 64 or 96");
   DIM_REQUIRE(a.B > 0 && a.H > 0 && a.Tq > 0 && a.Tk > 0, "attention: empty");
   DIM_REQUIRE(a.ldq % 4 == 0 && a.ldk % 4 == 0 && a.ldv % 4 == 0, "attention: leading dims must be multiples of 4");
   dim3 grid(cdiv(a.Tq, TQ), a.H, a.B);
@@ -750,11 +750,13 @@ int launch_attention_prefill(const AttnArgs& a, cudaStream_t s) {
   if (a.out_p != nullptr && (a.planes == 1 || a.planes == 3) && !force_ffma) {
     typedef void (*Kern)(const AttnArgs);
     const int np = a.planes;
+    // 48: VQAutoEncoder (384 / 8 heads), 64: x-transformers, 96: VQSpeakerAutoEncoder (768 / 8 heads, stage1_BIWI.py:140)
     Kern kern = a.Dh == 48 ? (np == 1 ? (Kern)attn_prefill_mma<48, 1> : (Kern)attn_prefill_mma<48, 3>)
-                           : (np == 1 ? (Kern)attn_prefill_mma<64, 1> : (Kern)attn_prefill_mma<64, 3>);
+              : a.Dh == 64 ? (np == 1 ? (Kern)attn_prefill_mma<64, 1> : (Kern)attn_prefill_mma<64, 3>)
+                           : (np == 1 ? (Kern)attn_prefill_mma<96, 1> : (Kern)attn_prefill_mma<96, 3>);
     const size_t smem = (size_t)3 * np * 64 * (a.Dh + 8) * sizeof(__nv_bfloat16);
-    static PerDeviceOnce configured[4];
-    const int slot = (a.Dh == 48 ? 0 : 2) + (np == 1 ? 0 : 1);
+    static PerDeviceOnce configured[6];
+    const int slot = (a.Dh == 48 ? 0 : a.Dh == 64 ? 2 : 4) + (np == 1 ? 0 : 1);
     if (configured[slot].first()) DIM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3(cdiv(a.Tq, 64), a.H, a.B), 128, smem, s>>>(a);
     DIM_LAUNCHED();
@@ -765,11 +767,16 @@ int launch_attention_prefill(const AttnArgs& a, cudaStream_t s) {
     static PerDeviceOnce once;
     if (once.first()) DIM_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_f32<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attn_prefill_f32<48><<<grid, 256, smem, s>>>(a);
-  } else {
+  } else if (a.Dh == 64) {
     constexpr size_t smem = (TQ * 68 + TKV * 68 + TKV * 64 + TQ * (TKV + 4)) * sizeof(float);
     static PerDeviceOnce once;
     if (once.first()) DIM_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_f32<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attn_prefill_f32<64><<<grid, 256, smem, s>>>(a);
+  } else {
+    constexpr size_t smem = (TQ * 100 + TKV * 100 + TKV * 96 + TQ * (TKV + 4)) * sizeof(float);
+    static PerDeviceOnce once;
+    if (once.first()) DIM_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_f32<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_prefill_f32<96><<<grid, 256, smem, s>>>(a);
   }
   DIM_LAUNCHED();
   return DIM_OK;

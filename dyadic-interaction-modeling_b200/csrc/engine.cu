@@ -56,6 +56,8 @@ struct VqModel {
   float* dconv_wr = nullptr;
   std::vector<VqLayer> dec;
   const float* codebook;
+  bool has_enc = true, has_dec = true;
+  int fqn = 1, out_dim = 0;            // codes per frame; decoder output channels
 };
 
 struct XtAttn {
@@ -220,8 +222,10 @@ VqWs carve_vq(const dim_vq_config& c, int planes, int B, int T, void* base) {
     return r;
   };
   w.h0 = take(R * c.hidden); w.h1 = take(R * c.hidden); w.x = take(R * c.hidden); w.ln = take(R * c.hidden);
-  w.qkv = take(R * 3 * c.hidden); w.att = take(R * c.hidden); w.ff = take(R * c.ffn); w.z = take(R * c.zdim);
-  w.idx = reinterpret_cast<int64_t*>(take(R * 2));
+  w.qkv = take(R * 3 * c.hidden); w.att = take(R * c.hidden); w.ff = take(R * c.ffn);
+  const size_t fq = (size_t)std::max(1, c.fqn);
+  w.z = take(R * fq * c.zdim);
+  w.idx = reinterpret_cast<int64_t*>(take(R * fq * 2));
   const size_t kmax = (size_t)tc_round_k(std::max(5 * c.hidden, c.ffn));        // widest A operand: the conv's im2col rows
   w.ap = planes ? reinterpret_cast<__nv_bfloat16*>(take(R * planes * kmax / 2 + 64)) : nullptr;
   w.ap2 = planes ? reinterpret_cast<__nv_bfloat16*>(take(R * planes * (size_t)tc_round_k(c.ffn) / 2 + 64)) : nullptr;
@@ -520,58 +524,76 @@ extern "C" int dim_set_tensor(dim_handle_t h, const char* name, const void* ptr,
   return DIM_OK;
 }
 
-extern "C" int dim_vqvae_build(dim_handle_t h, const char* prefix_c, const dim_vq_config* cfg, int precision, int* model) {
+extern "C" int dim_vqvae_build_parts(dim_handle_t h, const char* prefix_c, const char* enc_c, const char* dec_c, const dim_vq_config* cfg,
+                                     int precision, int* model) {
   DIM_REQUIRE(h && cfg && model, "dim_vqvae_build: null argument");
   DIM_CHECK_CUDA(cudaSetDevice(h->device));            // the handle's device, whatever the caller's current device is
   DIM_REQUIRE(precision == DIM_PREC_FP32 || precision == DIM_PREC_FP32_TC || precision == DIM_PREC_BF16,
               "dim_vqvae_build: unknown precision");
-  const dim_vq_config& c = *cfg;
+  DIM_REQUIRE(enc_c || dec_c, "dim_vqvae_build: a model needs an encoder or a decoder");
+  dim_vq_config c = *cfg;
+  if (c.fqn <= 0) c.fqn = 1;
+  if (c.out_dim <= 0) c.out_dim = c.in_dim;
   DIM_REQUIRE(c.hidden % 16 == 0 && c.hidden % c.heads == 0, "hidden must be a multiple of 16 and of heads");
-  DIM_REQUIRE(c.hidden / c.heads == 48 || c.hidden / c.heads == 64, "head dim must be 48 or 64");
-  DIM_REQUIRE(c.in_dim % 4 == 0 && c.zdim % 4 == 0 && c.ffn % 4 == 0, "dims must be multiples of 4");
+  DIM_REQUIRE(c.hidden / c.heads == 48 || c.hidden / c.heads == 64 || c.hidden / c.heads == 96, "head dim must be 48, 64 or 96");
+  DIM_REQUIRE(c.in_dim % 4 == 0 && c.out_dim % 4 == 0 && c.zdim % 4 == 0 && c.ffn % 4 == 0, "dims must be multiples of 4");
   std::string p = prefix_c ? prefix_c : "";
   auto m = std::make_unique<VqModel>();
   m->cfg = c;
   m->precision = precision;
   m->tc.planes = planes_of(precision);
-  const int64_t H = c.hidden, Z = c.zdim;
-  const float *conv_w, *dconv_w;
-  LOOKUP(m->map_w, p + "encoder.vertice_mapping.0.weight", true, H, c.in_dim);
-  LOOKUP(m->map_b, p + "encoder.vertice_mapping.0.bias", true, H);
-  LOOKUP(conv_w, p + "encoder.squasher.0.0.weight", true, H, H, 5);
-  LOOKUP(m->conv_b, p + "encoder.squasher.0.0.bias", true, H);
-  LOOKUP(m->emb_w, p + "encoder.encoder_linear_embedding.net.weight", true, H, H);
-  LOOKUP(m->emb_b, p + "encoder.encoder_linear_embedding.net.bias", true, H);
-  LOOKUP(m->pe, p + "encoder.encoder_pos_embedding.pe", true, c.pe_max_len, 1, H);
-  LOOKUP(m->post_w, p + "encoder.encoder_linear_embedding_post.net.weight", true, Z, H);
-  LOOKUP(m->post_b, p + "encoder.encoder_linear_embedding_post.net.bias", true, Z);
-  if (int e = build_vq_stack(h, p + "encoder.encoder_transformer", c, m->enc)) return e;
-  LOOKUP(m->pre_w, p + "decoder.decoder_linear_embedding_pre.net.weight", true, H, Z);
-  LOOKUP(m->pre_b, p + "decoder.decoder_linear_embedding_pre.net.bias", true, H);
-  LOOKUP(dconv_w, p + "decoder.expander.0.0.weight", true, H, H, 5);
-  LOOKUP(m->dconv_b, p + "decoder.expander.0.0.bias", true, H);
-  LOOKUP(m->demb_w, p + "decoder.decoder_linear_embedding.net.weight", true, H, H);
-  LOOKUP(m->demb_b, p + "decoder.decoder_linear_embedding.net.bias", true, H);
-  LOOKUP(m->dpe, p + "decoder.decoder_pos_embedding.pe", true, c.pe_max_len, 1, H);
-  LOOKUP(m->rev_w, p + "decoder.vertice_map_reverse.weight", true, c.in_dim, H);
-  if (int e = build_vq_stack(h, p + "decoder.decoder_transformer", c, m->dec)) return e;
+  m->has_enc = enc_c != nullptr;
+  m->has_dec = dec_c != nullptr;
+  m->fqn = c.fqn;
+  m->out_dim = c.out_dim;
+  const int64_t H = c.hidden, Z = c.zdim, ZT = (int64_t)c.fqn * c.zdim;
+  const float *conv_w = nullptr, *dconv_w = nullptr;
+  const size_t cb = (size_t)H * H * 5 * sizeof(float);
+  if (m->has_enc) {
+    const std::string e = p + enc_c + ".";
+    LOOKUP(m->map_w, e + "vertice_mapping.0.weight", true, H, c.in_dim);
+    LOOKUP(m->map_b, e + "vertice_mapping.0.bias", true, H);
+    LOOKUP(conv_w, e + "squasher.0.0.weight", true, H, H, 5);
+    LOOKUP(m->conv_b, e + "squasher.0.0.bias", true, H);
+    LOOKUP(m->emb_w, e + "encoder_linear_embedding.net.weight", true, H, H);
+    LOOKUP(m->emb_b, e + "encoder_linear_embedding.net.bias", true, H);
+    LOOKUP(m->pe, e + "encoder_pos_embedding.pe", true, c.pe_max_len, 1, H);
+    LOOKUP(m->post_w, e + "encoder_linear_embedding_post.net.weight", true, ZT, H);
+    LOOKUP(m->post_b, e + "encoder_linear_embedding_post.net.bias", true, ZT);
+    if (int err = build_vq_stack(h, e + "encoder_transformer", c, m->enc)) return err;
+    if (int err = owned_alloc(h, cb, &m->conv_wr)) return err;
+    if (int err = dim_repack_conv_weight(conv_w, m->conv_wr, c.hidden, c.hidden, nullptr)) return err;
+  }
+  if (m->has_dec) {
+    const std::string d = p + dec_c + ".";
+    LOOKUP(m->pre_w, d + "decoder_linear_embedding_pre.net.weight", true, H, ZT);
+    LOOKUP(m->pre_b, d + "decoder_linear_embedding_pre.net.bias", true, H);
+    LOOKUP(dconv_w, d + "expander.0.0.weight", true, H, H, 5);
+    LOOKUP(m->dconv_b, d + "expander.0.0.bias", true, H);
+    LOOKUP(m->demb_w, d + "decoder_linear_embedding.net.weight", true, H, H);
+    LOOKUP(m->demb_b, d + "decoder_linear_embedding.net.bias", true, H);
+    LOOKUP(m->dpe, d + "decoder_pos_embedding.pe", true, c.pe_max_len, 1, H);
+    LOOKUP(m->rev_w, d + "vertice_map_reverse.weight", true, c.out_dim, H);
+    if (int err = build_vq_stack(h, d + "decoder_transformer", c, m->dec)) return err;
+    if (int err = owned_alloc(h, cb, &m->dconv_wr)) return err;
+    if (int err = dim_repack_conv_weight(dconv_w, m->dconv_wr, c.hidden, c.hidden, nullptr)) return err;
+  }
   LOOKUP(m->codebook, p + "quantize.embedding.weight", true, c.n_embed, Z);
-  size_t cb = (size_t)H * H * 5 * sizeof(float);
-  if (int e = owned_alloc(h, cb, &m->conv_wr)) return e;
-  if (int e = owned_alloc(h, cb, &m->dconv_wr)) return e;
-  if (int e = dim_repack_conv_weight(conv_w, m->conv_wr, c.hidden, c.hidden, nullptr)) return e;
-  if (int e = dim_repack_conv_weight(dconv_w, m->dconv_wr, c.hidden, c.hidden, nullptr)) return e;
   {
     TcCtx& tc = m->tc;
     const int Hh = c.hidden;
-    if (int e = tc_add_weight(h, tc, m->map_w, Hh, c.in_dim)) return e;
-    if (int e = tc_add_weight(h, tc, m->conv_wr, Hh, 5 * Hh)) return e;
-    if (int e = tc_add_weight(h, tc, m->emb_w, Hh, Hh)) return e;
-    if (int e = tc_add_weight(h, tc, m->post_w, c.zdim, Hh)) return e;
-    if (int e = tc_add_weight(h, tc, m->pre_w, Hh, c.zdim)) return e;
-    if (int e = tc_add_weight(h, tc, m->dconv_wr, Hh, 5 * Hh)) return e;
-    if (int e = tc_add_weight(h, tc, m->demb_w, Hh, Hh)) return e;
-    if (int e = tc_add_weight(h, tc, m->rev_w, c.in_dim, Hh)) return e;
+    if (m->has_enc) {
+      if (int e = tc_add_weight(h, tc, m->map_w, Hh, c.in_dim)) return e;
+      if (int e = tc_add_weight(h, tc, m->conv_wr, Hh, 5 * Hh)) return e;
+      if (int e = tc_add_weight(h, tc, m->emb_w, Hh, Hh)) return e;
+      if (int e = tc_add_weight(h, tc, m->post_w, (int)ZT, Hh)) return e;
+    }
+    if (m->has_dec) {
+      if (int e = tc_add_weight(h, tc, m->pre_w, Hh, (int)ZT)) return e;
+      if (int e = tc_add_weight(h, tc, m->dconv_wr, Hh, 5 * Hh)) return e;
+      if (int e = tc_add_weight(h, tc, m->demb_w, Hh, Hh)) return e;
+      if (int e = tc_add_weight(h, tc, m->rev_w, c.out_dim, Hh)) return e;
+    }
     for (auto* stack : {&m->enc, &m->dec})
       for (const VqLayer& L : *stack) {
         if (int e = tc_add_weight(h, tc, L.wqkv, 3 * Hh, Hh)) return e;
@@ -586,6 +608,10 @@ extern "C" int dim_vqvae_build(dim_handle_t h, const char* prefix_c, const dim_v
   return DIM_OK;
 }
 
+extern "C" int dim_vqvae_build(dim_handle_t h, const char* prefix_c, const dim_vq_config* cfg, int precision, int* model) {
+  return dim_vqvae_build_parts(h, prefix_c, "encoder", "decoder", cfg, precision, model);
+}
+
 extern "C" size_t dim_vqvae_workspace_bytes(dim_handle_t h, int model, int B, int T) {
   if (!h || model < 0 || model >= (int)h->vq.size() || B <= 0 || T <= 0) return 0;
   return carve_vq(h->vq[model]->cfg, h->vq[model]->tc.planes, B, T, nullptr).bytes;
@@ -598,7 +624,9 @@ extern "C" int dim_vqvae_encode(dim_handle_t h, int model, const float* x, const
   DIM_CHECK_CUDA(cudaSetDevice(h->device));            // the handle's device, whatever the caller's current device is
   DIM_REQUIRE(x && B > 0 && T > 0 && (idx || z), "dim_vqvae_encode: bad argument");
   const VqModel& m = *h->vq[model];
+  DIM_REQUIRE(m.has_enc, "dim_vqvae_encode: this model was built without an encoder");
   const dim_vq_config& c = m.cfg;
+  const int ZT = m.fqn * c.zdim;
   DIM_REQUIRE(batch_index != nullptr || B <= c.pe_max_len, "batch larger than the positional table (SURVEY F4/H3)");
   VqWs w = carve_vq(c, m.tc.planes, B, T, ws);
   if (ws == nullptr || ws_bytes < w.bytes) return fail(DIM_EWORKSPACE, "dim_vqvae_encode: workspace too small");
@@ -614,14 +642,15 @@ extern "C" int dim_vqvae_encode(dim_handle_t h, int model, const float* x, const
   float* zbuf = z ? z : w.z;
   {
     GemmArgs a;
-    a.A = w.x; a.lda = H; a.W = m.post_w; a.bias = m.post_b; a.C = zbuf; a.ldc = c.zdim; a.M = R; a.N = c.zdim; a.K = H;
+    a.A = w.x; a.lda = H; a.W = m.post_w; a.bias = m.post_b; a.C = zbuf; a.ldc = ZT; a.M = R; a.N = ZT; a.K = H;
     if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
   }
+  // h.view(B, -1, zquant_dim) (stage1_BIWI.py:24-25,152-153): a frame's fqn*zdim channels are fqn consecutive tokens
   int64_t* ibuf = idx ? idx : w.idx;
   if (idx || quant_bcl)
-    if (int e = launch_vq_argmin(zbuf, m.codebook, ibuf, R, c.zdim, c.n_embed, s)) return e;
+    if (int e = launch_vq_argmin(zbuf, m.codebook, ibuf, R * m.fqn, c.zdim, c.n_embed, s)) return e;
   if (quant_bcl)
-    if (int e = launch_vq_gather_bcl(ibuf, m.codebook, quant_bcl, B, T, c.zdim, c.n_embed, s)) return e;
+    if (int e = launch_vq_gather_bcl(ibuf, m.codebook, quant_bcl, B, T * m.fqn, c.zdim, c.n_embed, s)) return e;
   return DIM_OK;
 }
 
@@ -633,27 +662,29 @@ extern "C" int dim_vqvae_decode(dim_handle_t h, int model, const int64_t* codes,
   DIM_REQUIRE((codes != nullptr) != (quant_bcl != nullptr), "dim_vqvae_decode: pass exactly one of codes / quant");
   DIM_REQUIRE(out && B > 0 && L > 0, "dim_vqvae_decode: bad argument");
   const VqModel& m = *h->vq[model];
+  DIM_REQUIRE(m.has_dec, "dim_vqvae_decode: this model was built without a decoder");
   const dim_vq_config& c = m.cfg;
+  const int ZT = m.fqn * c.zdim;
   DIM_REQUIRE(batch_index != nullptr || B <= c.pe_max_len, "batch larger than the positional table (SURVEY F4/H3)");
   VqWs w = carve_vq(c, m.tc.planes, B, L, ws);
   if (ws == nullptr || ws_bytes < w.bytes) return fail(DIM_EWORKSPACE, "dim_vqvae_decode: workspace too small");
   cudaStream_t s = as_stream(stream);
   const int R = B * L, H = c.hidden;
   if (codes) {
-    if (int e = launch_vq_gather(codes, m.codebook, w.z, R, c.zdim, c.n_embed, nullptr, s)) return e;
+    if (int e = launch_vq_gather(codes, m.codebook, w.z, R * m.fqn, c.zdim, c.n_embed, nullptr, s)) return e;
   } else {
-    if (int e = launch_rows_from_bcl(quant_bcl, w.z, B, L, c.zdim, s)) return e;
+    if (int e = launch_rows_from_bcl(quant_bcl, w.z, B, L * m.fqn, c.zdim, s)) return e;
   }
   {
     GemmArgs a;
-    a.A = w.z; a.lda = c.zdim; a.W = m.pre_w; a.bias = m.pre_b; a.C = w.h0; a.ldc = H; a.M = R; a.N = H; a.K = c.zdim;
+    a.A = w.z; a.lda = ZT; a.W = m.pre_w; a.bias = m.pre_b; a.C = w.h0; a.ldc = H; a.M = R; a.N = H; a.K = ZT;
     if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
   }
   if (int e = vq_trunk(m, m.dec, m.dconv_wr, m.dconv_b, m.demb_w, m.demb_b, m.dpe, w, nullptr, batch_index, B, L, s))
     return e;
   {
     GemmArgs a;
-    a.A = w.x; a.lda = H; a.W = m.rev_w; a.C = out; a.ldc = c.in_dim; a.M = R; a.N = c.in_dim; a.K = H;
+    a.A = w.x; a.lda = H; a.W = m.rev_w; a.C = out; a.ldc = m.out_dim; a.M = R; a.N = m.out_dim; a.K = H;
     if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
   }
   return DIM_OK;

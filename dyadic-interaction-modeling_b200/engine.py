@@ -97,14 +97,22 @@ class _Workspace:
 
 
 class VQEngine:
-    def __init__(self, handle: Handle, cfg: VQConfig = VQConfig(), prefix: str = "", precision: int = PREC_FP32):
+    """One VQ-VAE built from the tensors registered under `prefix`.  `encoder` / `decoder` name the two halves (None: absent);
+    `out_dim` is the decoder's output width (default in_dim).  VQSpeakerAutoEncoder (stage1_BIWI.py:140-173) is three engines over
+    one codebook: ("encoder", None), (None, "decoder_v", out_dim=56), (None, "decoder_a", out_dim=768)."""
+
+    def __init__(self, handle: Handle, cfg: VQConfig = VQConfig(), prefix: str = "", precision: int = PREC_FP32,
+                 encoder: str | None = "encoder", decoder: str | None = "decoder", out_dim: int | None = None):
         self.handle, self.cfg, self.prefix, self.precision = handle, cfg, prefix, precision
+        self.fqn = max(1, cfg.face_quan_num)
+        self.out_dim = out_dim or cfg.in_dim
         cc = _lib.VQConfigC(cfg.in_dim, cfg.hidden_size, cfg.num_hidden_layers, cfg.num_attention_heads,
-                            cfg.intermediate_size, cfg.n_embed, cfg.zquant_dim * cfg.face_quan_num, cfg.pe_max_len, cfg.neg)
+                            cfg.intermediate_size, cfg.n_embed, cfg.zquant_dim, cfg.pe_max_len, cfg.neg, self.fqn, self.out_dim)
         torch.cuda.synchronize(handle.device)
         m = C.c_int(-1)
-        _lib.check(handle.lib.dim_vqvae_build(handle.h, prefix.encode(), C.byref(cc), precision, C.byref(m)),
-                   "dim_vqvae_build")
+        _lib.check(handle.lib.dim_vqvae_build_parts(handle.h, prefix.encode(), encoder.encode() if encoder else None,
+                                                    decoder.encode() if decoder else None, C.byref(cc), precision, C.byref(m)),
+                   "dim_vqvae_build_parts")
         self.model = m.value
         self.ws = _Workspace(handle.device)
 
@@ -113,16 +121,16 @@ class VQEngine:
         return self.ws.get(n), n
 
     def encode(self, x, lens=None, batch_index=None, want_z=False, want_quant=False):
-        """x (B,T,in_dim) fp32 cuda -> idx (B,T) int64 [, z (B,T,zdim), quant (B,zdim,T)]."""
+        """x (B,T,in_dim) fp32 cuda -> idx (B,T*fqn) int64 [, z (B,T,fqn*zdim), quant (B,zdim,T*fqn)]."""
         assert x.is_cuda and x.dtype == torch.float32
         x = x.contiguous()
         B, T, _ = x.shape
         dev = x.device
         lens = _index_arg(lens, B, dev, "lens", 1, T + 1)            # an empty clip has no replicate-padding source (reference raises too)
         batch_index = _index_arg(batch_index, B, dev, "batch_index", 0, self.cfg.pe_max_len)
-        idx = torch.empty(B, T, dtype=torch.int64, device=dev)
-        z = torch.empty(B, T, self.cfg.zquant_dim, dtype=torch.float32, device=dev) if want_z else None
-        q = torch.empty(B, self.cfg.zquant_dim, T, dtype=torch.float32, device=dev) if want_quant else None
+        idx = torch.empty(B, T * self.fqn, dtype=torch.int64, device=dev)
+        z = torch.empty(B, T, self.fqn * self.cfg.zquant_dim, dtype=torch.float32, device=dev) if want_z else None
+        q = torch.empty(B, self.cfg.zquant_dim, T * self.fqn, dtype=torch.float32, device=dev) if want_quant else None
         ws, n = self._workspace(B, T)
         _lib.check(self.handle.lib.dim_vqvae_encode(self.handle.h, self.model, x.data_ptr(), _ptr(lens), _ptr(batch_index),
                                                     B, T, idx.data_ptr(), _ptr(z), _ptr(q), ws.data_ptr(), n, _stream()),
@@ -130,7 +138,7 @@ class VQEngine:
         return idx, z, q
 
     def decode(self, codes=None, quant=None, batch_index=None):
-        """codes (B,L) int64 or quant (B,zdim,L) fp32 -> frames (B,L,in_dim)."""
+        """codes (B,L*fqn) int64 or quant (B,zdim,L*fqn) fp32 -> frames (B,L,out_dim)."""
         src = codes if codes is not None else quant
         assert src.is_cuda
         if codes is not None:
@@ -139,8 +147,10 @@ class VQEngine:
         else:
             quant = quant.contiguous()
             B, _, L = quant.shape
+        assert L % self.fqn == 0, "the code sequence must hold face_quan_num codes per frame"
+        L //= self.fqn
         batch_index = _index_arg(batch_index, B, src.device, "batch_index", 0, self.cfg.pe_max_len)
-        out = torch.empty(B, L, self.cfg.in_dim, dtype=torch.float32, device=src.device)
+        out = torch.empty(B, L, self.out_dim, dtype=torch.float32, device=src.device)
         ws, n = self._workspace(B, L)
         _lib.check(self.handle.lib.dim_vqvae_decode(self.handle.h, self.model, _ptr(codes), _ptr(quant), _ptr(batch_index),
                                                     B, L, out.data_ptr(), ws.data_ptr(), n, _stream()), "dim_vqvae_decode")

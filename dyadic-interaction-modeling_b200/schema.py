@@ -111,6 +111,37 @@ def vqvae_schema(c: VQConfig = VQConfig()) -> "OrderedDict[str, tuple]":
     return d
 
 
+def _vq_decoder_keys(name: str, c: VQConfig, out_dim: int) -> "OrderedDict[str, tuple]":
+    H, Z = c.hidden_size, c.face_quan_num * c.zquant_dim
+    d = OrderedDict()
+    d[f"{name}.expander.0.0.weight"] = (H, H, 5)
+    d[f"{name}.expander.0.0.bias"] = (H,)
+    d.update(vq_transformer_keys(f"{name}.decoder_transformer", c))
+    d[f"{name}.decoder_pos_embedding.pe"] = (c.pe_max_len, 1, H)
+    d[f"{name}.decoder_linear_embedding.net.weight"] = (H, H)
+    d[f"{name}.decoder_linear_embedding.net.bias"] = (H,)
+    d[f"{name}.decoder_linear_embedding_pre.net.weight"] = (H, Z)
+    d[f"{name}.decoder_linear_embedding_pre.net.bias"] = (H,)
+    d[f"{name}.vertice_map_reverse.weight"] = (out_dim, H)
+    return d
+
+
+# code/config_speaker_old.yaml:15-30 (arch stage1_BIWI_speaker): motion (56) + audio (768) frames, 8 codes per frame
+SPEAKER_VQ = VQConfig(in_dim=824, hidden_size=768, face_quan_num=8)
+SPEAKER_OUT_DIMS = (("decoder_v", 56), ("decoder_a", 768))           # stage1_BIWI.py:146-147
+
+
+def vqspeaker_schema(c: VQConfig = SPEAKER_VQ) -> "OrderedDict[str, tuple]":
+    """Keys of VQSpeakerAutoEncoder.state_dict() (stage1_BIWI.py:140-151): one encoder, two decoders, one codebook."""
+    assert c.quant_factor == 0
+    full = vqvae_schema(c)
+    d = OrderedDict((k, v) for k, v in full.items() if k.startswith("encoder."))
+    for name, out_dim in SPEAKER_OUT_DIMS:
+        d.update(_vq_decoder_keys(name, c, out_dim))
+    d["quantize.embedding.weight"] = full["quantize.embedding.weight"]
+    return d
+
+
 def xt_layers_schema(prefix: str, dim: int, depth: int, inner: int, cross: bool, ff_mult: int = 4):
     """x-transformers AttentionLayers keys. Layer order ('a','f')*depth or ('a','c','f')*depth."""
     d = OrderedDict()

@@ -71,6 +71,12 @@ def make_vqvae_state_dict(seed: int = 131, cfg: VQConfig = VQConfig()) -> "Order
     return OrderedDict((k, _draw(k, s, seed)) for k, s in vqvae_schema(cfg).items())
 
 
+def make_vqspeaker_state_dict(seed: int = 131, cfg: VQConfig = None) -> "OrderedDict[str, torch.Tensor]":
+    """VQSpeakerAutoEncoder (stage1_BIWI.py:140-151) with synthetic weights, reference key names."""
+    from .schema import SPEAKER_VQ, vqspeaker_schema
+    return OrderedDict((k, _draw(k, s, seed)) for k, s in vqspeaker_schema(cfg or SPEAKER_VQ).items())
+
+
 def make_slmft_state_dict(seed: int = 131, cfg: S2SConfig = S2SConfig(), vq: VQConfig = VQConfig()):
     sd = OrderedDict()
     for pre, off in (("speaker_vq", 1), ("listener_vq", 2)):

@@ -137,19 +137,28 @@ int dim_set_tensor(dim_handle_t h, const char* name, const void* ptr, int dtype,
 typedef struct {
   int32_t in_dim, hidden, layers, heads, ffn, n_embed, zdim, pe_max_len;
   float neg_slope;
-} dim_vq_config;        /* code/config.yaml:15-30 */
+  int32_t fqn;          /* face_quan_num: codes per frame (the encoder emits fqn*zdim channels); 0 means 1 */
+  int32_t out_dim;      /* decoder output channels; 0 means in_dim */
+} dim_vq_config;        /* code/config.yaml:15-30, code/config_speaker_old.yaml:15-30 */
 
 /* Build a VQ-VAE from the tensors registered under `prefix` ("" or "listener_vq.").  Returns a model id >= 0 in *model. */
 int dim_vqvae_build(dim_handle_t h, const char* prefix, const dim_vq_config* cfg, int precision, int* model);
+/* The same with named halves: `encoder` / `decoder` are the module names under `prefix` (NULL: that half is absent and the
+ * matching call fails with DIM_EINVAL).  VQSpeakerAutoEncoder (stage1_BIWI.py:140-173: one encoder, decoder_v -> 56 channels,
+ * decoder_a -> 768 channels, 8 codes per frame) is three such models over one codebook: ("encoder", NULL), (NULL, "decoder_v")
+ * with out_dim 56 and (NULL, "decoder_a") with out_dim 768. */
+int dim_vqvae_build_parts(dim_handle_t h, const char* prefix, const char* encoder, const char* decoder, const dim_vq_config* cfg,
+                          int precision, int* model);
 size_t dim_vqvae_workspace_bytes(dim_handle_t h, int model, int B, int T);
 
-/* VQAutoEncoder.encode (stage1_BIWI.py:22-27): x (B,T,in_dim) -> idx (B*T) int64 [, z (B,T,zdim) pre-quantisation
- * latents, quant (B,zdim,T) = E[idx] channel-major like the reference's return].  lens/batch_index (B) int32 nullable:
+/* VQAutoEncoder.encode (stage1_BIWI.py:22-27): x (B,T,in_dim) -> idx (B*T*fqn) int64 [, z (B,T,fqn*zdim) pre-quantisation
+ * latents, quant (B,zdim,T*fqn) = E[idx] channel-major like the reference's return].  lens/batch_index (B) int32 nullable:
  * batch_index[b] selects the positional-encoding row (base_models.py:271-273); default b. */
 int dim_vqvae_encode(dim_handle_t h, int model, const float* x, const int32_t* lens, const int32_t* batch_index, int B,
                      int T, int64_t* idx, float* z, float* quant_bcl, void* ws, size_t ws_bytes, void* stream);
 /* VQAutoEncoder.decode (stage1_BIWI.py:29-37) of either codes (B*L) int64 -- the gather of seq2seq_pretrain.py:454-463
- * fused in front -- or a (B,zdim,L) fp32 `quant` tensor (exactly one of codes/quant_bcl non-NULL) -> out (B,L,in_dim). */
+ * fused in front -- or a (B,zdim,L*fqn) fp32 `quant` tensor (exactly one of codes/quant_bcl non-NULL; codes: (B*L*fqn))
+ * -> out (B,L,out_dim). */
 int dim_vqvae_decode(dim_handle_t h, int model, const int64_t* codes, const float* quant_bcl, const int32_t* batch_index,
                      int B, int L, float* out, void* ws, size_t ws_bytes, void* stream);
 

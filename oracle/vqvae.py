@@ -110,9 +110,9 @@ def encode(sd, x, cfg, batch_index=None, prefix=""):
     return quantize(sd, h, prefix)
 
 
-def decode(sd, quant_bcl, cfg, batch_index=None, prefix=""):
-    """quant (B,C,L) -> (B,L,in_dim)."""
-    p = prefix + "decoder"
+def decode(sd, quant_bcl, cfg, batch_index=None, prefix="", name="decoder"):
+    """quant (B,C,L*fqn) -> (B,L,out_dim) through the TransformerDecoder registered as `name`."""
+    p = prefix + name
     q = quant_bcl.permute(0, 2, 1)
     q = q.reshape(q.shape[0], -1, cfg.face_quan_num, cfg.zquant_dim)
     q = q.reshape(q.shape[0], -1, cfg.face_quan_num * cfg.zquant_dim)
@@ -132,6 +132,12 @@ def decode_indices(sd, indices_bl, cfg, batch_index=None, prefix=""):
     B, L = indices_bl.shape
     zq = codebook_entry(sd, indices_bl.reshape(-1), prefix).view(B, L, -1).permute(0, 2, 1)
     return decode(sd, zq, cfg, batch_index, prefix)
+
+
+def speaker_decode(sd, quant_bcl, cfg, batch_index=None, prefix=""):
+    """VQSpeakerAutoEncoder.decode (stage1_BIWI.py:156-165): cat([decoder_v(q) (..,56), decoder_a(q) (..,768)], -1)."""
+    return torch.cat([decode(sd, quant_bcl, cfg, batch_index, prefix, "decoder_v"),
+                      decode(sd, quant_bcl, cfg, batch_index, prefix, "decoder_a")], dim=-1)
 
 
 def roundtrip(sd, x, cfg, batch_index=None, prefix=""):

@@ -139,3 +139,7 @@ if has mkab; then
   echo "== 2-stage ring"; DIM_MK_ATTN_STAGES=2 timeout 300 python scripts/decode_trace.py 256 300 bf16 2>&1 | grep -v "  phase"
   echo "== no gelu fuse"; DIM_MK_NO_GELU_FUSE=1 timeout 300 python scripts/decode_trace.py 256 300 bf16 2>&1 | grep -v "  phase"
 fi
+if has speaker; then
+  timeout 900 python -m pytest tests/test_vqspeaker_gpu.py -x -q > $OUT/${TAG}_speaker.log 2>&1; echo "exit $?" >> $OUT/${TAG}_speaker.log
+  tail -15 $OUT/${TAG}_speaker.log
+fi

@@ -131,3 +131,19 @@ def test_feature_resamplers_match_reference_golden():
         assert np.array_equal(OF.window_mean(x), x[: int(len(x) * 0.6)].astype(np.float64))        # the window-of-1 quirk
         for n, ref in c["linear_new_t"].items():
             assert np.array_equal(OF.linear(x, n), ref.numpy()), (name, n)
+
+
+def test_speaker_oracle_matches_reference_golden():
+    """VQSpeakerAutoEncoder (stage1_BIWI.py:140-251): oracle/vqvae.py against the goldens minted from the real reference class
+    (tests/golden/make_speaker_golden.py): 8 codes per frame, two decoders concatenated."""
+    import os
+    from dim_b200.schema import SPEAKER_VQ
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vq_speaker_reference.pt"), weights_only=False)
+    sd = dim_b200.synth.make_vqspeaker_state_dict(g["weights_seed"])
+    case = g["cases"]["sp_T24_B3"]
+    x = torch.randn(case["B"], case["T"], 824, generator=torch.Generator().manual_seed(case["x_seed"])) * case["x_scale"]
+    with torch.no_grad():
+        quant, loss, (_, _, idx) = OV.encode(sd, x, SPEAKER_VQ)
+        dec = OV.speaker_decode(sd, quant, SPEAKER_VQ)
+    assert torch.equal(idx.view(case["B"], -1), case["idx"])
+    assert float((dec - case["dec"]).abs().max()) < 1e-5 and abs(float(loss) - float(case["loss"])) < 1e-6
