@@ -134,6 +134,7 @@ SIGNATURES = {
     "dim_slmft_build": (I, [P, C.POINTER(S2SConfigC), I, C.POINTER(I)]),
     "dim_slmft_workspace_bytes": (SZ, [P, I, I, I, I]),
     "dim_slmft_context": (I, [P, I, P, P, P, I, I, P, P, P, SZ, P]),
+    "dim_slmft_encode": (I, [P, I, I, P, P, P, I, I, I, I, P, P, SZ, P]),
     "dim_slmft_generate": (I, [P, I, P, P, P, I, I, I, F, I, P, P, P, P, SZ, P]),
     "dim_slmft_samples_workspace_bytes": (SZ, [P, I, I, I, I, I]),
     "dim_slmft_generate_samples": (I, [P, I, P, P, P, I, I, I, I, F, I, P, P, P, P, SZ, P]),

@@ -163,6 +163,61 @@ class SLMFT(nn.Module):
         return loss, d, pred
 
 
+class SLM(SLMFT):
+    """seq2seq_pretrain.SLM, the DIM PRE-TRAINING model (reference: code/seq2seq_pretrain.py:72-323), forward only: three
+    encoders (speaker, listener, joint -- no causal mask here), 15 % random masking of both streams, the speaker<->listener
+    contrastive NCE, and two teacher-forced passes of decoder_joint (which keeps its absolute positional table in this model,
+    :137) predicting each side's masked VQ codes from the OTHER side's joint representation + audio.  Runs on the same kernels as
+    SLMFT: dim_slmft_encode (libdimb200) per encoder call, dim_slmft_teacher_forced per decoder pass, the two VQ-VAEs.
+    `self.mask_speaker` / `self.mask_listener` (B,T) bool pin the random masks (None: drawn with torch.randperm like :171-183).
+    Returns (total_loss, dict, None) like :323.  No autograd graph is built (pre-training itself is out of scope)."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        dim, dim_a = 384, 768
+        dec_kwargs = {"depth": 4, "heads": 12, "max_seq_len": 2048, "num_tokens": 512}
+        kw = pick_and_pop(["num_tokens", "max_seq_len"], dec_kwargs)  # noqa: F405
+        kw.update(emb_dropout=0, scaled_sinu_pos_emb=False, use_abs_pos_emb=True)                      # :135-137
+        self.decoder_joint = AutoregressiveWrapper(TransformerWrapper(**kw, attn_layers=Decoder(dim=dim + dim_a, cross_attend=True, **dec_kwargs)),
+                                                   ignore_index=-100, pad_value=0)                     # :163-165 (mask_prob default 0)
+        self.mask_speaker = self.mask_listener = None
+        self.last_parts = None
+
+    def engines(self):
+        fp = fingerprint(self)
+        if self._engines is None or fp != self._fp:
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("SLM runs on CUDA only (sm_100a kernels, no CPU fallback): call .to('cuda') first")
+            h = Handle(dev.index)
+            h.register(self.state_dict())
+            vq_prec = PREC_FP32 if self.precision == PREC_FP32 else PREC_FP32_TC
+            self._engines = (SLMFTEngine(h, self._cfg, precision=self.precision),
+                             VQEngine(h, self._vq_cfg, prefix="listener_vq.", precision=vq_prec),
+                             VQEngine(h, self._vq_cfg, prefix="speaker_vq.", precision=vq_prec))
+            self._fp = fp
+        return self._engines
+
+    def random_masking_unstructured(self, x, mask, mask_ratio):
+        return compat_api.random_masking_unstructured(mask, mask_ratio)
+
+    def forward_contrastive(self, s_rep, l_rep, mask, bidirect_contrast=False):
+        nce, acc = compat_api.contrastive(s_rep, l_rep, mask)
+        if bidirect_contrast:
+            nce2, acc2 = compat_api.contrastive(l_rep, s_rep, mask)
+            return (nce + nce2) / 2, (acc + acc2) / 2
+        return nce, acc
+
+    def forward(self, v_speaker, v_listener, v_audio, mask, speaker_ids=None, listener_ids=None, mode="train"):
+        s2s, vq_l, vq_s = self.engines()
+        total, d, parts = compat_api.slm_forward(s2s, vq_s, vq_l, v_speaker.float(), v_listener.float(), v_audio.float(), mask,
+                                                 self.patch_embed_s.detach(), self.patch_embed_l.detach(),
+                                                 self.patch_embed_dec_s.detach(), self.patch_embed_dec_l.detach(),
+                                                 mask_speaker=self.mask_speaker, mask_listener=self.mask_listener, return_parts=True)
+        self.last_parts = parts
+        return total, d, None
+
+
 class SpeakerSLMFT(nn.Module):
     """Name kept so that `from seq2seq_pretrain import SLMFT, SpeakerSLMFT` (test_s2s_pretrain.py:7) resolves.  The BIWI speaker
     model (seq2seq_pretrain.py:516-757, 70110-d vertex head) is a sibling model outside the listener hot path."""

@@ -190,3 +190,89 @@ def slmft_forward_train(s2s_engine, vq_engine, v_speaker, v_listener, v_audio, m
     d = {"l_ce_s": 0, "l_ce_l": l_ce, "l_cont_s": 0, "l_cont_l": l_cont, "nce": 0, "c_acc": 0}
     out = (l_ce + l_cont, d, pred)
     return out + (logits,) if return_logits else out
+
+
+# ---- SLM pre-training forward (seq2seq_pretrain.py:72-323) -----------------------------------------------------------------------
+def random_masking_unstructured(mask, mask_ratio):
+    """SLM.random_masking_unstructured (seq2seq_pretrain.py:171-183): per clip, int(len * ratio) positions of its valid prefix drawn
+    with torch.randperm (host RNG, like the reference).  True = masked."""
+    N, L = mask.shape
+    lens = mask.sum(dim=1).to(torch.int32).tolist()
+    final = torch.zeros(N, L, dtype=torch.bool)
+    for i, n in enumerate(lens):
+        final[i, :n][torch.randperm(n)[: int(n * mask_ratio)]] = True
+    return final.to(mask.device)
+
+
+def contrastive(s_rep, l_rep, mask, temperature=0.05):
+    """SLM.forward_contrastive (seq2seq_pretrain.py:270-298), single direction: mean over each clip's valid frames, L2 normalise,
+    NCE over the batch.  Returns (nce, c_acc)."""
+    m = mask.unsqueeze(-1).to(s_rep.dtype)
+    n = m.sum(dim=1)
+    s = F.normalize((s_rep * m).sum(dim=1) / n, dim=-1)
+    l = F.normalize((l_rep * m).sum(dim=1) / n, dim=-1)
+    total = torch.mm(s, l.t()) / temperature
+    nce = -torch.mean(torch.diag(F.log_softmax(total, dim=0)))
+    c_acc = torch.sum(torch.eq(torch.argmax(F.softmax(total, dim=0), dim=0), torch.arange(total.shape[0], device=s.device))) / total.shape[0]
+    return nce, c_acc
+
+
+def _masked_cont_loss(pred, target, sel):
+    """SLM.forward_continuous_loss (seq2seq_pretrain.py:253-268) with the RANDOM-masking selection `sel` (B,T) in place of the
+    padding mask (the reference passes mask_speaker / mask_listener here, :311-312)."""
+    return continuous_loss(pred, target, sel)
+
+
+@torch.no_grad()
+def slm_forward(s2s_engine, speaker_vq_engine, listener_vq_engine, v_speaker, v_listener, v_audio, mask, patch_s, patch_l,
+                patch_dec_s, patch_dec_l, mask_speaker=None, mask_listener=None, mask_ratio=0.15, return_parts=False):
+    """SLM.forward (pre-training model, seq2seq_pretrain.py:300-323), forward only:
+      forward_vq (:185-200)  both VQ encoders on each clip's valid prefix, speaker codes padded with 0, listener with -100;
+      forward_encoder (:203-226)  random masking, encoder_s / encoder_l, encoder_joint on cat([x_s, x_l]) and on each alone,
+                                  norm / norm_l / norm_s;
+      forward_contrastive (:270-298), forward_decoder (:228-243: two teacher-forced decoder passes over the other side's joint
+      representation + audio), forward_vq_decoder (:245-251), forward_continuous_loss on the masked positions.
+    mask_speaker / mask_listener: the random masks (None: drawn like the reference does).  Returns (total_loss, dict, None)."""
+    B, T, _ = v_speaker.shape
+    z_s = listener_codes(speaker_vq_engine, v_speaker, mask)             # same per-clip prefix encode; padding rewritten below
+    z_s = torch.where(mask, z_s, torch.zeros_like(z_s))                  # speaker: pad value 0 (:194)
+    z_l = listener_codes(listener_vq_engine, v_listener, mask)           # listener: pad value -100 (:197)
+    if mask_speaker is None:
+        mask_speaker = random_masking_unstructured(mask, mask_ratio)
+    if mask_listener is None:
+        mask_listener = random_masking_unstructured(mask, mask_ratio)
+    vs = v_speaker + patch_s.reshape(1, 1, -1)
+    vl = v_listener + patch_l.reshape(1, 1, -1)
+    vs[mask_speaker] = 0
+    vl[mask_listener] = 0
+    e = s2s_engine.encode
+    x_s = e("encoder_s", vs, mask)
+    x_l = e("encoder_l", vl, mask)
+    x_joint = e("encoder_joint", torch.cat([x_s, x_l], dim=1), torch.cat([mask, mask], dim=-1), norm="norm")
+    x_l = e("encoder_joint", x_l, mask, norm="norm_l")
+    x_s = e("encoder_joint", x_s, mask, norm="norm_s")
+    nce, c_acc = contrastive(x_s, x_l, mask)
+    xj_s, xj_l = x_joint[:, :T], x_joint[:, T:]
+    z_s = torch.where(mask_speaker, z_s, torch.full_like(z_s, -100))     # only the masked positions enter the CE (:307-308)
+    z_l = torch.where(mask_listener, z_l, torch.full_like(z_l, -100))
+    ctx_s = torch.cat([xj_s + patch_dec_s.reshape(1, 1, -1), v_audio], dim=-1)
+    ctx_l = torch.cat([xj_l + patch_dec_l.reshape(1, 1, -1), v_audio], dim=-1)
+
+    def tf(tokens, ctx):
+        inp, target = tokens[:, :-1].clone(), tokens[:, 1:]
+        inp[inp == -100] = 0
+        logits = s2s_engine.teacher_forced(ctx, mask, inp, None)          # AutoregressiveWrapper default mask_prob = 0 in SLM (:165)
+        ce = F.cross_entropy(logits.transpose(1, 2), target, ignore_index=-100)
+        return ce, logits
+
+    l_ce_s, px_s = tf(z_s, ctx_l)
+    l_ce_l, px_l = tf(z_l, ctx_s)
+    pred_s = speaker_vq_engine.decode(codes=torch.argmax(px_s, dim=-1))
+    pred_l = listener_vq_engine.decode(codes=torch.argmax(px_l, dim=-1))
+    l_cont_s = _masked_cont_loss(pred_s, v_speaker, mask_speaker)
+    l_cont_l = _masked_cont_loss(pred_l, v_listener, mask_listener)
+    total = l_ce_s + l_ce_l + l_cont_s + l_cont_l + nce
+    d = {"l_ce_s": l_ce_s, "l_ce_l": l_ce_l, "l_cont_s": l_cont_s, "l_cont_l": l_cont_l, "nce": nce, "c_acc": c_acc}
+    if return_parts:
+        return total, d, dict(x_s=x_s, x_l=x_l, x_joint=x_joint, px_s=px_s, px_l=px_l, pred_s=pred_s, pred_l=pred_l, z_s=z_s, z_l=z_l)
+    return total, d, None

@@ -78,8 +78,11 @@ struct S2SModel {
   dim_s2s_config cfg{};
   int precision = DIM_PREC_FP32;
   TcCtx tc;
-  XtEncoder enc_s, enc_joint;
+  XtEncoder enc_s, enc_joint, enc_l;           // enc_l: SLM pre-training only (optional)
+  bool has_enc_l = false;
   const float *patch_s = nullptr, *patch_dec_s = nullptr, *norm_s_g = nullptr, *norm_s_b = nullptr;
+  const float *norm_l_g = nullptr, *norm_l_b = nullptr, *norm_j_g = nullptr, *norm_j_b = nullptr;     // SLM: norm_l, norm
+  const float* dec_pos_emb = nullptr;          // decoder_joint.net.pos_emb (SLM keeps use_abs_pos_emb=True; SLMFT has none)
   const float* token_emb = nullptr;
   std::vector<XtAttn> self_attn, cross_attn;
   std::vector<XtFF> ff;
@@ -372,7 +375,7 @@ CtxWs carve_ctx(const dim_s2s_config& c, int planes, int B, int T, void* base) {
 
 // ContinuousTransformerWrapper(x, mask, attn_mask=causal, return_embeddings=True); result left in w.x
 int xt_encoder_forward(const S2SModel& m, const XtEncoder& E, const float* in, const float* a_add, const uint8_t* mask,
-                       CtxWs& w, int B, int T, cudaStream_t s) {
+                       CtxWs& w, int B, int T, cudaStream_t s, int causal = 1) {
   const dim_s2s_config& c = m.cfg;
   const int R = B * T, D = c.dim, inner = c.heads * c.dim_head, F = c.ff_mult * c.dim;
   {  // x = project_in(in + a_add) + pos_emb[t] * dim^-0.5
@@ -399,7 +402,7 @@ int xt_encoder_forward(const S2SModel& m, const XtEncoder& E, const float* in, c
       a.q = w.qkv; a.k = w.qkv + inner; a.v = w.qkv + 2 * inner; a.ldq = a.ldk = a.ldv = 3 * inner;
       a.out = tcp ? nullptr : w.att; a.ldo = inner; a.out_p = tcp ? w.ap : nullptr; a.planes = P; a.kp = inner;
       a.key_mask = mask; a.B = B; a.H = c.heads; a.Tq = T; a.Tk = T; a.Dh = c.dim_head;
-      a.scale = 1.0f / sqrtf((float)c.dim_head); a.causal = 1;
+      a.scale = 1.0f / sqrtf((float)c.dim_head); a.causal = causal;
       if (int e = launch_attention_prefill(a, s)) return e;
     }
     {
@@ -710,8 +713,21 @@ extern "C" int dim_slmft_build(dim_handle_t h, const dim_s2s_config* cfg, int pr
   LOOKUP(m->patch_dec_s, "patch_embed_dec_s", true, 1, 1, c.dim);
   LOOKUP(m->norm_s_g, "norm_s.weight", true, c.dim);
   LOOKUP(m->norm_s_b, "norm_s.bias", true, c.dim);
+  LOOKUP(m->norm_l_g, "norm_l.weight", false, c.dim);
+  LOOKUP(m->norm_l_b, "norm_l.bias", false, c.dim);
+  LOOKUP(m->norm_j_g, "norm.weight", false, c.dim);
+  LOOKUP(m->norm_j_b, "norm.bias", false, c.dim);
+  {  // the listener encoder exists in every checkpoint but only the SLM pre-training forward runs it (seq2seq_pretrain.py:218)
+    const float* probe = nullptr;
+    LOOKUP(probe, "encoder_l.project_in.weight", false, c.dim, c.dim_in);
+    if (probe) {
+      if (int e = build_xt_encoder(h, "encoder_l", c.dim_in, c, m->enc_l)) return e;
+      m->has_enc_l = true;
+    }
+  }
   const std::string dn = "decoder_joint.net";
   LOOKUP(m->token_emb, dn + ".token_emb.emb.weight", true, c.num_tokens, D);
+  LOOKUP(m->dec_pos_emb, dn + ".pos_emb.emb.weight", false, c.max_seq_len, D);
   m->self_attn.resize(c.depth);
   m->cross_attn.resize(c.depth);
   m->ff.resize(c.depth);
@@ -727,7 +743,8 @@ extern "C" int dim_slmft_build(dim_handle_t h, const dim_s2s_config* cfg, int pr
   LOOKUP(m->logits_b, dn + ".to_logits.bias", false, c.num_tokens);
   {
     TcCtx& tc = m->tc;
-    for (XtEncoder* E : {&m->enc_s, &m->enc_joint}) {
+    for (XtEncoder* E : {&m->enc_s, &m->enc_joint, &m->enc_l}) {
+      if (E == &m->enc_l && !m->has_enc_l) continue;
       if (int e = tc_add_weight(h, tc, E->proj_w, c.dim, E->dim_in)) return e;
       for (int l = 0; l < c.depth; ++l) {
         if (int e = tc_add_weight(h, tc, E->attn[l].wqkv, 3 * inner, c.dim)) return e;
@@ -823,6 +840,33 @@ extern "C" int dim_slmft_context(dim_handle_t h, int model, const float* v_speak
   if (x_s) DIM_CHECK_CUDA(cudaMemcpyAsync(x_s, w.ln, (size_t)B * T * c.dim * sizeof(float), cudaMemcpyDeviceToDevice, s));
   if (!ctx) return DIM_OK;
   return launch_build_context(w.ln, m.patch_dec_s, v_audio, ctx, nullptr, (size_t)B * T, c.dim, c.dim_audio, s);
+}
+
+// One ContinuousTransformerWrapper call of the SLM pre-training forward (seq2seq_pretrain.py:216-224): encoder `which`
+// (0 encoder_s, 1 encoder_l, 2 encoder_joint) over x (B,T,dim_in of that encoder) with the key-padding mask, optional causal
+// attn_mask, then an optional LayerNorm head (0 none, 1 norm_s, 2 norm_l, 3 norm).  out (B,T,dim).
+extern "C" int dim_slmft_encode(dim_handle_t h, int model, int which, const float* x, const float* add, const uint8_t* mask, int causal,
+                                int norm, int B, int T, float* out, void* ws, size_t ws_bytes, void* stream) {
+  DIM_REQUIRE(h && model >= 0 && model < (int)h->s2s.size(), "dim_slmft_encode: bad model");
+  DIM_CHECK_CUDA(cudaSetDevice(h->device));
+  DIM_REQUIRE(x && out && B > 0 && T > 0 && which >= 0 && which <= 2 && norm >= 0 && norm <= 3, "dim_slmft_encode: bad argument");
+  const S2SModel& m = *h->s2s[model];
+  const dim_s2s_config& c = m.cfg;
+  DIM_REQUIRE(T <= c.max_seq_len, "sequence longer than the positional table");
+  DIM_REQUIRE(which != 1 || m.has_enc_l, "dim_slmft_encode: encoder_l is not registered");
+  const float *g = nullptr, *b = nullptr;
+  if (norm == 1) { g = m.norm_s_g; b = m.norm_s_b; }
+  if (norm == 2) { g = m.norm_l_g; b = m.norm_l_b; }
+  if (norm == 3) { g = m.norm_j_g; b = m.norm_j_b; }
+  DIM_REQUIRE(norm == 0 || (g && b), "dim_slmft_encode: that LayerNorm is not registered");
+  CtxWs w = carve_ctx(c, m.tc.planes, B, T, ws);
+  if (ws == nullptr || ws_bytes < w.bytes) return fail(DIM_EWORKSPACE, "dim_slmft_encode: workspace too small");
+  cudaStream_t s = as_stream(stream);
+  const XtEncoder& E = which == 0 ? m.enc_s : (which == 1 ? m.enc_l : m.enc_joint);
+  if (int e = xt_encoder_forward(m, E, x, add, mask, w, B, T, s, causal ? 1 : 0)) return e;
+  if (norm) return launch_layer_norm(w.x, g, b, out, nullptr, B * T, c.dim, 1e-5f, s);
+  DIM_CHECK_CUDA(cudaMemcpyAsync(out, w.x, (size_t)B * T * c.dim * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return DIM_OK;
 }
 
 namespace {
@@ -1205,6 +1249,7 @@ extern "C" int dim_slmft_generate(dim_handle_t h, int model, const float* ctx, c
   DIM_REQUIRE(temperature >= 0.f, "temperature must be >= 0");
   DIM_REQUIRE(temperature == 0.f || (uniforms && top_k > 0), "sampling needs uniforms and top_k");
   const S2SModel& m = *h->s2s[model];
+  DIM_REQUIRE(h->s2s[model]->dec_pos_emb == nullptr, "generate: a decoder with an absolute positional table (SLM) is teacher-forced only");
   const dim_s2s_config& c = m.cfg;
   const int D = c.dim + c.dim_audio, V = c.num_tokens;
   cudaStream_t s = as_stream(stream);
@@ -1274,6 +1319,7 @@ extern "C" int dim_slmft_generate_samples(dim_handle_t h, int model, const float
   DIM_REQUIRE(temperature >= 0.f, "temperature must be >= 0");
   DIM_REQUIRE(temperature == 0.f || (uniforms && top_k > 0), "sampling needs uniforms and top_k");
   const S2SModel& m = *h->s2s[model];
+  DIM_REQUIRE(h->s2s[model]->dec_pos_emb == nullptr, "generate: a decoder with an absolute positional table (SLM) is teacher-forced only");
   if ((int)m.graphs.size() < kMaxGroups + 1) m.graphs.resize(kMaxGroups + 1);
   return generate_group(m, m.graphs[kMaxGroups], ctx, mask, prompt, B, T, steps, temperature, top_k, uniforms, out_codes, logits_out,
                         ws, ws_bytes, as_stream(stream), samples);
@@ -1332,6 +1378,10 @@ extern "C" int dim_slmft_teacher_forced(dim_handle_t h, int model, const float* 
   const float scale = 1.0f / sqrtf((float)c.dim_head);
   // token embedding (TransformerWrapper; SLMFT has no positional embedding in the decoder, seq2seq_pretrain.py:386)
   if (int e = launch_vq_gather(tokens, m.token_emb, w.x, R, D, V, nullptr, s)) return e;
+  if (m.dec_pos_emb) {                                  // SLM flavour: + pos_emb[t] * D^-0.5 (x-transformers AbsolutePositionalEmbedding)
+    DIM_REQUIRE(L <= c.max_seq_len, "sequence longer than the decoder's positional table");
+    if (int e = launch_add_pos_table(w.x, m.dec_pos_emb, 1.0f / sqrtf((float)D), B, L, D, s)) return e;
+  }
   for (int l = 0; l < c.depth; ++l) {
     const XtAttn& SA = m.self_attn[l];
     const XtAttn& CA = m.cross_attn[l];

@@ -451,6 +451,27 @@ int launch_build_context(const float* xs, const float* pe_dec, const float* audi
   return DIM_OK;
 }
 
+__global__ void __launch_bounds__(256) add_pos_table_kernel(float* __restrict__ x, const float* __restrict__ tab, float scale, int L, int D4,
+                                                            size_t total4) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / D4;
+    const int c = (int)(i - row * D4), t = (int)(row % L);
+    float4 v = reinterpret_cast<float4*>(x)[i];
+    const float4 p = __ldg(reinterpret_cast<const float4*>(tab) + (size_t)t * D4 + c);
+    v.x = fmaf(p.x, scale, v.x); v.y = fmaf(p.y, scale, v.y); v.z = fmaf(p.z, scale, v.z); v.w = fmaf(p.w, scale, v.w);
+    reinterpret_cast<float4*>(x)[i] = v;
+  }
+}
+int launch_add_pos_table(float* x, const float* tab, float scale, int B, int L, int D, cudaStream_t s) {
+  DIM_REQUIRE(D % 4 == 0 && B > 0 && L > 0, "add_pos_table: bad sizes");
+  const size_t total4 = (size_t)B * L * (D / 4);
+  const int blocks = (int)std::min<size_t>((total4 + 255) / 256, (size_t)148 * 16);
+  ProfScope ps(CAT_MISC, s, (double)total4 * 32.0, 0);
+  add_pos_table_kernel<<<blocks, 256, 0, s>>>(x, tab, scale, L, D / 4, total4);
+  DIM_LAUNCHED();
+  return DIM_OK;
+}
+
 int launch_embed_tokens(const int64_t* tok, int tok_stride, const int* step, const float* emb, float* x, int B, int D, int V,
                         cudaStream_t s) {
   ProfScope ps(CAT_MISC, s, 8.0 * B * D, 0);

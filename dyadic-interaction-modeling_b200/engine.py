@@ -191,6 +191,24 @@ class SLMFTEngine:
                    "dim_slmft_context")
         return ctx if want == "ctx" else xs
 
+    ENCODERS = {"encoder_s": 0, "encoder_l": 1, "encoder_joint": 2}
+    NORMS = {None: 0, "norm_s": 1, "norm_l": 2, "norm": 3}
+
+    def encode(self, which, x, mask, causal=False, norm=None, add=None):
+        """One ContinuousTransformerWrapper call (return_embeddings=True) of the SLM forward (seq2seq_pretrain.py:216-224):
+        encoder `which` over x (B,T,dim_in of that encoder) under the key-padding mask [and the causal attn_mask], then the
+        LayerNorm head `norm` (None, "norm_s", "norm_l", "norm").  add: (dim_in,) row added to every frame (a patch embedding)."""
+        x = x.float().contiguous()
+        B, T, _ = x.shape
+        m8 = mask.to(torch.uint8).contiguous()
+        a = None if add is None else add.detach().float().reshape(-1).contiguous()
+        out = torch.empty(B, T, self.cfg.dim, dtype=torch.float32, device=x.device)
+        ws, n = self._workspace(B, T, 0)
+        _lib.check(self.handle.lib.dim_slmft_encode(self.handle.h, self.model, self.ENCODERS[which], x.data_ptr(), _ptr(a), m8.data_ptr(),
+                                                    int(bool(causal)), self.NORMS[norm], B, T, out.data_ptr(), ws.data_ptr(), n, _stream()),
+                   "dim_slmft_encode")
+        return out
+
     def teacher_forced(self, ctx, mask, tokens, kv_mask=None):
         """Teacher-forced decoder forward (seq2seq_pretrain.py:447-448): tokens (B,L) int64 decoder inputs (pad already substituted
         for ignore_index), kv_mask (B,L) bool/uint8 or None -> logits (B,L,num_tokens) fp32.  Forward only."""

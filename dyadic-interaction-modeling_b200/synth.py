@@ -87,6 +87,14 @@ def make_slmft_state_dict(seed: int = 131, cfg: S2SConfig = S2SConfig(), vq: VQC
     return sd
 
 
+def make_slm_state_dict(seed: int = 131, cfg: S2SConfig = S2SConfig(), vq: VQConfig = VQConfig()):
+    """SLM (pre-training model, seq2seq_pretrain.py:72-169): SLMFT's keys + the decoder's absolute positional table (:137)."""
+    sd = make_slmft_state_dict(seed, cfg, vq)
+    key = "decoder_joint.net.pos_emb.emb.weight"
+    sd[key] = _draw(key, (cfg.max_seq_len, cfg.dec_dim), seed)
+    return sd
+
+
 def make_clips(batch: int, frames: int, seed: int = 0, speaker: str = "randn", ragged: bool = False):
     """Synthetic dyadic clips.  Returns dict(v_speaker (B,T,56), v_listener (B,T,56), v_audio (B,T,768),
     lengths (B,) int64, mask (B,T) bool) on CPU in fp32.

@@ -176,6 +176,13 @@ size_t dim_slmft_workspace_bytes(dim_handle_t h, int model, int B, int T, int st
 int dim_slmft_context(dim_handle_t h, int model, const float* v_speaker, const float* v_audio, const uint8_t* mask, int B,
                       int T, float* ctx, float* x_s, void* ws, size_t ws_bytes, void* stream);
 
+/* One encoder call of the SLM pre-training forward (seq2seq_pretrain.py:205-226, x-transformers ContinuousTransformerWrapper with
+ * return_embeddings=True): which = 0 encoder_s, 1 encoder_l, 2 encoder_joint; x (B,T,dim_in of that encoder) [+ add (dim_in) on every
+ * frame, nullable]; mask (B,T) uint8 key padding; causal != 0 adds the causal attn_mask SLMFT passes; norm = 0 none, 1 norm_s,
+ * 2 norm_l, 3 norm (the nn.LayerNorm heads of :224).  out (B,T,dim).  Workspace: dim_slmft_workspace_bytes(B, T, 1). */
+int dim_slmft_encode(dim_handle_t h, int model, int which, const float* x, const float* add, const uint8_t* mask, int causal,
+                     int norm, int B, int T, float* out, void* ws, size_t ws_bytes, void* stream);
+
 /* decoder_joint.generate (seq2seq_pretrain.py:450; x-transformers AutoregressiveWrapper.generate): KV-cached
  * autoregressive decoding of `steps` tokens from prompt (B) int64, cross-attending ctx (B,T,D) under mask (B,T).
  * temperature == 0 -> argmax.  temperature > 0 -> top-k filter (top_k logits kept), softmax(logits/temperature) and an

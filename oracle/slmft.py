@@ -87,3 +87,47 @@ def forward_val(sd, v_speaker, v_listener, v_audio, mask, s2s_cfg, vq_cfg, tempe
     if return_intermediates:
         return l_cont, d, pred, dict(z_l=z_l, x_s=x_s, ctx=ctx, codes=codes)
     return l_cont, d, pred
+
+
+@torch.no_grad()
+def slm_forward(sd, v_speaker, v_listener, v_audio, mask, mask_speaker, mask_listener, s2s_cfg, vq_cfg):
+    """SLM.forward, the pre-training model (seq2seq_pretrain.py:300-323), restated line by line with the two random masks given
+    (the reference draws them with torch.randperm, :171-183).  `sd` must hold decoder_joint.net.pos_emb (SLM keeps
+    use_abs_pos_emb=True, :137).  x-transformers half: oracle/xt.py (unpinned, see its header)."""
+    B, T, _ = v_speaker.shape
+    z_s = forward_vq_speaker(sd, v_speaker, mask, vq_cfg)                                   # :185-200
+    z_l = forward_vq_listener(sd, v_listener, mask, vq_cfg)
+    vs = v_speaker.clone() + sd["patch_embed_s"]                                            # :203-226
+    vl = v_listener.clone() + sd["patch_embed_l"]
+    vs[mask_speaker] = 0
+    vl[mask_listener] = 0
+    x_s = X.continuous_wrapper(sd, "encoder_s", vs, s2s_cfg.depth, mask)
+    x_l = X.continuous_wrapper(sd, "encoder_l", vl, s2s_cfg.depth, mask)
+    x_joint = X.continuous_wrapper(sd, "encoder_joint", torch.cat([x_s, x_l], dim=1), s2s_cfg.depth, torch.cat([mask, mask], dim=-1))
+    x_l = X.continuous_wrapper(sd, "encoder_joint", x_l, s2s_cfg.depth, mask)
+    x_s = X.continuous_wrapper(sd, "encoder_joint", x_s, s2s_cfg.depth, mask)
+    ln = lambda x, n: F.layer_norm(x, (x.shape[-1],), sd[n + ".weight"], sd[n + ".bias"], 1e-5)
+    x_joint, x_l, x_s = ln(x_joint, "norm"), ln(x_l, "norm_l"), ln(x_s, "norm_s")
+    len_keep = torch.sum(mask, dim=1, dtype=torch.int32)                                    # :270-286
+    s_rep = torch.stack([torch.mean(x_s[i, :len_keep[i]], dim=0) for i in range(B)], dim=0)
+    l_rep = torch.stack([torch.mean(x_l[i, :len_keep[i]], dim=0) for i in range(B)], dim=0)
+    s_rep, l_rep = F.normalize(s_rep, dim=-1), F.normalize(l_rep, dim=-1)
+    total = torch.mm(s_rep, l_rep.t()) / 0.05
+    nce = -torch.mean(torch.diag(F.log_softmax(total, dim=0)))
+    c_acc = torch.sum(torch.eq(torch.argmax(F.softmax(total, dim=0), dim=0), torch.arange(0, B))) / B
+    xj_s, xj_l = x_joint[:, :T], x_joint[:, T:]
+    z_s = z_s.clone()
+    z_l = z_l.clone()
+    z_s[~mask_speaker] = -100                                                               # :307-308
+    z_l[~mask_listener] = -100
+    ctx_s = torch.cat([xj_s + sd["patch_embed_dec_s"], v_audio], dim=-1)                    # :228-233
+    ctx_l = torch.cat([xj_l + sd["patch_embed_dec_l"], v_audio], dim=-1)
+    l_ce_s, px_s = X.teacher_forced(sd, "decoder_joint.net", z_s, s2s_cfg.depth, ctx_l, mask)
+    l_ce_l, px_l = X.teacher_forced(sd, "decoder_joint.net", z_l, s2s_cfg.depth, ctx_s, mask)
+    pred_s = V.decode_indices(sd, torch.argmax(px_s, dim=-1), vq_cfg, prefix="speaker_vq.")  # :245-251
+    pred_l = V.decode_indices(sd, torch.argmax(px_l, dim=-1), vq_cfg, prefix="listener_vq.")
+    l_cont_s = continuous_loss(pred_s, v_speaker, mask_speaker)
+    l_cont_l = continuous_loss(pred_l, v_listener, mask_listener)
+    d = {"l_ce_s": l_ce_s, "l_ce_l": l_ce_l, "l_cont_s": l_cont_s, "l_cont_l": l_cont_l, "nce": nce, "c_acc": c_acc}
+    parts = dict(x_s=x_s, x_l=x_l, x_joint=x_joint, px_s=px_s, px_l=px_l, pred_s=pred_s, pred_l=pred_l, z_s=z_s, z_l=z_l)
+    return l_ce_s + l_ce_l + l_cont_s + l_cont_l + nce, d, parts

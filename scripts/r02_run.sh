@@ -143,3 +143,7 @@ if has speaker; then
   timeout 900 python -m pytest tests/test_vqspeaker_gpu.py -x -q > $OUT/${TAG}_speaker.log 2>&1; echo "exit $?" >> $OUT/${TAG}_speaker.log
   tail -15 $OUT/${TAG}_speaker.log
 fi
+if has slm; then
+  timeout 900 python -m pytest tests/test_slm_gpu.py tests/test_compat_gpu.py -x -q > $OUT/${TAG}_slm.log 2>&1; echo "exit $?" >> $OUT/${TAG}_slm.log
+  tail -25 $OUT/${TAG}_slm.log
+fi

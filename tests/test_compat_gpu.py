@@ -94,3 +94,33 @@ def test_reference_eval_script_flow(compat, slmft_sd, tmp_path):
     for j in range(B):
         n = int(c["lengths"][j]) - 1
         assert y_true[j].shape == (n, 56) and y_pred[j].shape == (n, 56) and x_all[j].shape == (n, 56)
+
+
+def test_slm_pretraining_class_forward(compat, tmp_path):
+    """seq2seq_pretrain.SLM (the pre-training model, reference seq2seq_pretrain.py:72-323; what train_s2s_pretrain.py builds):
+    zero-arg-style constructor from files, load_state_dict of an SLM checkpoint (SLMFT's keys + the decoder's positional table),
+    forward() -> (total_loss, dict, None), equal to the restated oracle with the same random masks."""
+    from dim_b200 import compat_api
+    sd = dim_b200.synth.make_slm_state_dict(131)
+    import shutil
+    shutil.copy(os.path.join(COMPAT, "config.yaml"), tmp_path / "config.yaml")
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        model = compat["s2s"].SLM(load_vq_checkpoints=False).to("cuda:0")
+    finally:
+        os.chdir(cwd)
+    assert set(model.state_dict().keys()) == set(sd.keys())
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    c = dim_b200.synth.make_clips(3, 22, seed=21, ragged=True)
+    torch.manual_seed(3)
+    model.mask_speaker = compat_api.random_masking_unstructured(c["mask"], 0.15).cuda()
+    model.mask_listener = compat_api.random_masking_unstructured(c["mask"], 0.15).cuda()
+    total, d, none = model(c["v_speaker"].cuda(), c["v_listener"].cuda(), c["v_audio"].cuda(), c["mask"].cuda())
+    assert none is None and set(d) == {"l_ce_s", "l_ce_l", "l_cont_s", "l_cont_l", "nce", "c_acc"}
+    ref_total, ref_d, _ = OS.slm_forward(sd, c["v_speaker"], c["v_listener"], c["v_audio"], c["mask"], model.mask_speaker.cpu(),
+                                         model.mask_listener.cpu(), S2SConfig(), VQConfig())
+    for k in ("l_ce_s", "l_ce_l", "nce"):
+        assert abs(float(d[k]) - float(ref_d[k])) < 1e-4, k
+    assert torch.isfinite(total)
