@@ -122,6 +122,7 @@ SIGNATURES = {
     "dim_instance_norm_f32": (I, [P, P, I, I, I, F, P]),
     "dim_layer_norm_f32": (I, [P, P, P, P, I, I, F, P]),
     "dim_resample_features": (I, [P, I, I, I, I, I, P, P]),
+    "dim_assemble_batch": (I, [P, P, P, P, I, I, I, I, P, P, P, P]),
     "dim_attention_f32": (I, [P, I, P, I, P, I, P, I, P, P, I, I, I, I, I, F, I, P]),
     "dim_create": (I, [C.POINTER(P), I]),
     "dim_destroy": (I, [P]),

@@ -451,6 +451,49 @@ int launch_build_context(const float* xs, const float* pe_dec, const float* audi
   return DIM_OK;
 }
 
+// Collate on the device: clip b owns rows [offsets[b], offsets[b+1]) of the packed (sum_len, D) arrays.  One thread per float4 of an
+// output row: src[b,t] = speaker[row] (or 1.0 when speaker == nullptr: ViCoDataset replaces the speaker motion by ones,
+// data_loader.py:147) | audio[row] (or 0.0: LmListenerDataset's audio, data_loader.py:242); tgt[b,t] = listener[row]; rows past the
+// clip's length are zero (pad_sequence padding_value 0, data_loader.py:432-433); mask[b,t] = t < len (x_engine_pt.py:246-249).
+__global__ void __launch_bounds__(256) assemble_batch_kernel(const float* __restrict__ speaker, const float* __restrict__ audio,
+                                                             const float* __restrict__ listener, const int64_t* __restrict__ offsets,
+                                                             int B, int T, int Dm4, int Da4, float* __restrict__ src,
+                                                             float* __restrict__ tgt, uint8_t* __restrict__ mask) {
+  const int W4 = Dm4 + Da4 + Dm4;                       // float4 per (b, t): src motion | src audio | tgt
+  const size_t total = (size_t)B * T * W4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t bt = i / W4;
+    const int c = (int)(i - bt * W4), b = (int)(bt / T), t = (int)(bt - (size_t)b * T);
+    const int64_t r0 = offsets[b];
+    const int len = (int)(offsets[b + 1] - r0);
+    const bool on = t < len;
+    const size_t row = (size_t)(r0 + t);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < Dm4) {
+      if (on) v = speaker ? __ldcs(reinterpret_cast<const float4*>(speaker) + row * Dm4 + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+      __stcs(reinterpret_cast<float4*>(src) + bt * (Dm4 + Da4) + c, v);
+      if (c == 0 && mask) mask[bt] = on ? 1 : 0;
+    } else if (c < Dm4 + Da4) {
+      if (on && audio) v = __ldcs(reinterpret_cast<const float4*>(audio) + row * Da4 + (c - Dm4));
+      __stcs(reinterpret_cast<float4*>(src) + bt * (Dm4 + Da4) + c, v);
+    } else {
+      if (on) v = __ldcs(reinterpret_cast<const float4*>(listener) + row * Dm4 + (c - Dm4 - Da4));
+      __stcs(reinterpret_cast<float4*>(tgt) + bt * Dm4 + (c - Dm4 - Da4), v);
+    }
+  }
+}
+int launch_assemble_batch(const float* speaker, const float* audio, const float* listener, const int64_t* offsets, int B, int T, int Dm,
+                          int Da, float* src, float* tgt, uint8_t* mask, cudaStream_t s) {
+  DIM_REQUIRE(B > 0 && T > 0 && Dm % 4 == 0 && Da % 4 == 0 && Dm > 0 && Da > 0, "assemble_batch: bad sizes");
+  DIM_REQUIRE(listener && offsets && src && tgt, "assemble_batch: null argument");
+  const size_t total = (size_t)B * T * (2 * Dm + Da) / 4;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 32);
+  ProfScope ps(CAT_MISC, s, (double)total * 32.0, 0);
+  assemble_batch_kernel<<<blocks, 256, 0, s>>>(speaker, audio, listener, offsets, B, T, Dm / 4, Da / 4, src, tgt, mask);
+  DIM_LAUNCHED();
+  return DIM_OK;
+}
+
 __global__ void __launch_bounds__(256) add_pos_table_kernel(float* __restrict__ x, const float* __restrict__ tab, float scale, int L, int D4,
                                                             size_t total4) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
@@ -549,6 +592,12 @@ using namespace dimb;
 extern "C" int dim_resample_features(const float* in, int t, int d, int new_t, int window, int mode, float* out, void* stream) {
   if (int e = ensure_device()) return e;
   return launch_resample(in, out, t, d, new_t, window, mode, as_stream(stream));
+}
+
+extern "C" int dim_assemble_batch(const float* speaker, const float* audio, const float* listener, const int64_t* offsets, int B, int T,
+                                  int motion_dim, int audio_dim, float* src, float* tgt, uint8_t* mask, void* stream) {
+  if (int e = ensure_device()) return e;
+  return launch_assemble_batch(speaker, audio, listener, offsets, B, T, motion_dim, audio_dim, src, tgt, mask, as_stream(stream));
 }
 
 extern "C" int dim_layer_norm_f32(const float* x, const float* gain, const float* bias, float* y, int rows, int dim,

@@ -10,6 +10,9 @@ int launch_layer_norm(const float* x, const float* gain, const float* bias, floa
 int launch_instance_norm(float* x, const int32_t* lens, int B, int T, int C, float eps, cudaStream_t s);
 int launch_build_context(const float* xs, const float* pe_dec, const float* audio, float* ctx, __nv_bfloat16* ctxb,
                          size_t rows, int d1, int d2, cudaStream_t s);
+// padded batch tensors from packed ragged clips (the loader's collate step, on the device)
+int launch_assemble_batch(const float* speaker, const float* audio, const float* listener, const int64_t* offsets, int B, int T, int Dm,
+                          int Da, float* src, float* tgt, uint8_t* mask, cudaStream_t s);
 // x[b,t,:] += tab[t,:] * scale   (absolute positional embedding of a teacher-forced sequence)
 int launch_add_pos_table(float* x, const float* tab, float scale, int B, int L, int D, cudaStream_t s);
 int launch_embed_tokens(const int64_t* tok, int tok_stride, const int* step, const float* emb, float* x, int B, int D, int V,

@@ -81,3 +81,27 @@ def write_vico_fixtures(data_root, clips, ids=None, split="test"):
     pd.DataFrame(rows, columns=["sentiment", "uuid", "listener", "speaker", "listener_id", "speaker_id", "split"]).to_csv(
         os.path.join(data_root, "RLD_data.csv"), index=False)
     return ids
+
+
+def make_lm_listener_segments(seed=0, lengths=(30, 10, 1100, 64), hubert=True):
+    """Synthetic `segments_<mode>.pth` content for the LM-Listener loaders (dataset/data_loader.py:210-227, dataset/l2l.py:31-60): a list
+    of dicts with p0/p1 expression (n,50) and pose (n,6) arrays, `fname`, split times and (hubert) a (t,768) feature array at ~50 fps
+    for n frames at 30 fps.  Lengths < 24 are dropped by the loaders, >= 1024 are cut into 1024-frame chunks."""
+    g = np.random.default_rng(seed)
+    segs = []
+    for i, n in enumerate(lengths):
+        d = {"p0_exp": g.standard_normal((n, 50)).astype(np.float32) * 0.3, "p1_exp": g.standard_normal((n, 50)).astype(np.float32) * 0.3,
+             "p0_pose": g.standard_normal((n, 6)).astype(np.float32) * 0.1, "p1_pose": g.standard_normal((n, 6)).astype(np.float32) * 0.1,
+             "fname": f"seg_{i:03d}", "split_start_time": float(i), "split_end_time": float(i) + n / 30.0}
+        if hubert:
+            d["hubert_feat"] = g.standard_normal((max(2, int(n * 50 / 30)), 768)).astype(np.float32)
+        segs.append(d)
+    return segs
+
+
+def write_lm_listener_fixtures(data_path, mode="test", **kw):
+    import torch
+    os.makedirs(data_path, exist_ok=True)
+    segs = make_lm_listener_segments(**kw)
+    torch.save(segs, os.path.join(data_path, f"segments_{mode}.pth"))
+    return segs

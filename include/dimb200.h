@@ -108,6 +108,14 @@ int dim_instance_norm_f32(float* x, const int32_t* lens, int B, int T, int C, fl
  * mode 1: linear interpolation with align_corners=True -- dataset/l2l.downsample_mean (code/dataset/l2l.py:23-29). */
 int dim_resample_features(const float* in, int t, int d, int new_t, int window, int mode, float* out, void* stream);
 
+/* The loaders' collate step on the device (dataset/data_loader.py:138-152 ViCoDataset.__getitem__, :229-245
+ * LmListenerDataset.__getitem__, :429-439 pad_collate, x_engine_pt.py:246-249 mask): clip b owns rows [offsets[b], offsets[b+1]) of the
+ * packed (sum_len, .) device arrays; src (B,T,motion_dim+audio_dim) = speaker | audio, tgt (B,T,motion_dim) = listener, zero past
+ * each clip's length, mask (B,T) uint8 = t < len (nullable).  speaker == NULL writes ones (the ViCo loader's torch.ones_like),
+ * audio == NULL writes zeros (the LM-Listener loader's torch.zeros).  offsets: (B+1) int64 on the device. */
+int dim_assemble_batch(const float* speaker, const float* audio, const float* listener, const int64_t* offsets, int B, int T,
+                       int motion_dim, int audio_dim, float* src, float* tgt, uint8_t* mask, void* stream);
+
 /* LayerNorm over the last dim (eps), gain, optional bias.  base_models.py:14 ; x-transformers bias-free LayerNorm. */
 int dim_layer_norm_f32(const float* x, const float* gain, const float* bias, float* y, int rows, int dim, float eps,
                        void* stream);

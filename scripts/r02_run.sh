@@ -147,3 +147,7 @@ if has slm; then
   timeout 900 python -m pytest tests/test_slm_gpu.py tests/test_compat_gpu.py -x -q > $OUT/${TAG}_slm.log 2>&1; echo "exit $?" >> $OUT/${TAG}_slm.log
   tail -25 $OUT/${TAG}_slm.log
 fi
+if has loader; then
+  timeout 900 python -m pytest tests/test_loader_gpu.py -x -q > $OUT/${TAG}_loader.log 2>&1; echo "exit $?" >> $OUT/${TAG}_loader.log
+  tail -25 $OUT/${TAG}_loader.log
+fi
