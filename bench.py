@@ -344,7 +344,7 @@ def run_native(args):
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             roof["traffic"] = tj.get("decode_megakernel_" + leg.precision)
-            roof["traffic_note"] = tj.get("_note")
+            roof["traffic_note"] = tj.get("_note_r02") if roof["traffic"] else "no ncu capture of this mode"
         else:
             roof["traffic"] = None
         return roof

@@ -151,3 +151,11 @@ if has loader; then
   timeout 900 python -m pytest tests/test_loader_gpu.py -x -q > $OUT/${TAG}_loader.log 2>&1; echo "exit $?" >> $OUT/${TAG}_loader.log
   tail -25 $OUT/${TAG}_loader.log
 fi
+if has launchlist; then
+  # launch list of the bench command (ncu replays every launch: serialised, cold-cache times -- shares, not absolutes)
+  timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file $OUT/${TAG}_launches.csv \
+      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity-leg --no-other-workloads > $OUT/${TAG}_launches_bench.log 2>&1
+  python scripts/launch_list_summary.py $OUT/${TAG}_launches.csv > $OUT/${TAG}_launches_summary.txt 2>&1 || true
+  tail -25 $OUT/${TAG}_launches_summary.txt
+  gzip -f $OUT/${TAG}_launches.csv
+fi
