@@ -367,8 +367,10 @@ def run_native(args):
     prof, trace = profiled_step(leg) if (rank == 0 or world > 1) else ([], [])
     barrier()
 
-    # multi-GPU correctness on hardware (outside the timed region): rank 0 recomputes the first 4 clips of a FOREIGN shard (the
-    # last rank's) from their seeds, with the global batch positions, and compares with that shard's rows of the all-gathered codes
+    # multi-GPU correctness on hardware (outside the timed region): rank 0 recomputes the first 16 clips of a FOREIGN shard (the
+    # last rank's) from their seeds, with the global batch positions, and compares with that shard's rows of the all-gathered codes.
+    # 16 rows, not 4: <= 8 rows run the GEMV kernel family, whose bf16-mode bits differ from the tensor-core family's; within one
+    # family a row's bits do not depend on its batch (tests/test_decode_mk_gpu.py::test_rows_do_not_depend_on_the_batch)
     sharded_ok = None
     if world > 1:
         _, all_codes = leg.step_resident()
@@ -376,12 +378,13 @@ def run_native(args):
             from dim_b200.compat_api import slmft_forward_val
             fr = world - 1
             fc = dim_b200.synth.make_clips(B, T, seed=1000 + fr, speaker="ones" if args.speaker_ones else "randn")
-            fu = torch.rand(B, steps_ar, generator=torch.Generator().manual_seed(7 + fr))[:4].to(dev)
-            sub = {k: fc[k][:4].to(dev) for k in ("v_speaker", "v_listener", "v_audio", "mask")}
-            bi = torch.arange(fr * B, fr * B + 4, dtype=torch.int32, device=dev)
+            nchk = min(16, B)
+            fu = torch.rand(B, steps_ar, generator=torch.Generator().manual_seed(7 + fr))[:nchk].to(dev)
+            sub = {k: fc[k][:nchk].to(dev) for k in ("v_speaker", "v_listener", "v_audio", "mask")}
+            bi = torch.arange(fr * B, fr * B + nchk, dtype=torch.int32, device=dev)
             _, _, _, codes4 = slmft_forward_val(leg.s2s, leg.vq, sub["v_speaker"], sub["v_listener"], sub["v_audio"], sub["mask"],
                                                 temperature=1.0, uniforms=fu, batch_index=bi, return_codes=True, vq_decode_engine=leg.vq_dec)
-            sharded_ok = bool(torch.equal(codes4, all_codes[fr * B: fr * B + 4]))
+            sharded_ok = bool(torch.equal(codes4, all_codes[fr * B: fr * B + nchk]))
         barrier()
 
     if rank != 0:
