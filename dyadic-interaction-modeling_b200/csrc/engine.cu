@@ -179,6 +179,11 @@ int run_gemm(const TcCtx& tc, const GemmArgs& a_in, __nv_bfloat16* scratch, cuda
   const bool tc_ok = tc_on(tc, a.M) && it != tc.wmap.end() && (scratch != nullptr || a.Ap != nullptr);
   if (!tc_ok) {
     if (a.Ap != nullptr || a.Cp != nullptr) return fail(DIM_EINVAL, "run_gemm: plane operands without a tensor-core path");
+    // <= 8 rows in bf16 mode: the GEMV reads the bf16 weight image (half the bytes of the stream that bounds a small-batch decode
+    // step; VERDICT r01: "B <= 8 ignores the precision mode").  DIM_GEMV_FP32=1 keeps the fp32 weights (A/B hook).
+    static const bool gemv_fp32 = getenv("DIM_GEMV_FP32") != nullptr;
+    if (tc.planes == 1 && a.M <= 8 && a.conv_T == 0 && a.K % 8 == 0 && it != tc.wmap.end() && !gemv_fp32)
+      return launch_gemv_bf16w(a, it->second, tc_round_k(a.K), s);
     return launch_gemm_f32(a, s);
   }
   const int kp = tc_round_k(a.K);

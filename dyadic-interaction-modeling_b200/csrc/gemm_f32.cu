@@ -221,6 +221,67 @@ __global__ void __launch_bounds__(128) gemm_f32_skinny(const GemmArgs p) {
   }
 }
 
+// The same GEMV with the weight row read as bf16 (plane 0 of the tensor-core weight image, [N, kp] zero-padded): half the bytes of
+// the stream that bounds a <= 8-row decode step.  Used in DIM_PREC_BF16 only (the mode's GEMM operands are bf16 by definition);
+// activations stay fp32 here, accumulation fp32.
+template <int MT>
+__global__ void __launch_bounds__(128) gemm_bf16w_skinny(const GemmArgs p, const __nv_bfloat16* __restrict__ Wb, int kp) {
+  __shared__ float part[4][MT];
+  pdl_prologue();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int n = blockIdx.x;
+  const int k8n = p.K >> 3;                              // whole 8-element vectors; K % 8 == 0 is checked by the launcher
+  const uint4* w = reinterpret_cast<const uint4*>(Wb + (size_t)n * kp);
+  float acc[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) acc[m] = 0.f;
+  constexpr int U = 4;
+  for (int k8 = tid; k8 < k8n; k8 += 128 * U) {
+    uint4 wv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int kk = k8 + u * 128;
+      wv[u] = kk < k8n ? __ldcs(w + kk) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int kk = k8 + u * 128;
+      if (kk < k8n) {
+        const uint32_t ww[4] = {wv[u].x, wv[u].y, wv[u].z, wv[u].w};
+        float wf[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { wf[2 * i] = __uint_as_float(ww[i] << 16); wf[2 * i + 1] = __uint_as_float(ww[i] & 0xffff0000u); }
+        float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0;
+        if (p.a_add) { e0 = __ldg(reinterpret_cast<const float4*>(p.a_add) + 2 * kk); e1 = __ldg(reinterpret_cast<const float4*>(p.a_add) + 2 * kk + 1); }
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          if (m < p.M) {
+            const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.A + (size_t)m * p.lda) + 2 * kk);
+            const float4 a1 = __ldg(reinterpret_cast<const float4*>(p.A + (size_t)m * p.lda) + 2 * kk + 1);
+            acc[m] = fmaf(a0.x + e0.x, wf[0], acc[m]); acc[m] = fmaf(a0.y + e0.y, wf[1], acc[m]);
+            acc[m] = fmaf(a0.z + e0.z, wf[2], acc[m]); acc[m] = fmaf(a0.w + e0.w, wf[3], acc[m]);
+            acc[m] = fmaf(a1.x + e1.x, wf[4], acc[m]); acc[m] = fmaf(a1.y + e1.y, wf[5], acc[m]);
+            acc[m] = fmaf(a1.z + e1.z, wf[6], acc[m]); acc[m] = fmaf(a1.w + e1.w, wf[7], acc[m]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    acc[m] = warp_sum(acc[m]);
+    if (lane == 0) part[warp][m] = acc[m];
+  }
+  __syncthreads();
+  if (tid < MT && tid < p.M) {
+    const int m = tid;
+    const float tot = (part[0][m] + part[1][m]) + (part[2][m] + part[3][m]);
+    float o = epilogue_elem(p, tot, m, n);
+    if (p.C) p.C[(size_t)m * p.ldc + n] = o;
+    if (p.Cb) p.Cb[(size_t)m * p.ldcb + n] = __float2bfloat16_rn(o);
+  }
+}
+
 __global__ void repack_conv_kernel(const float* __restrict__ w, float* __restrict__ o, int Cout, int Cin) {
   size_t n = (size_t)Cout * Cin * 5;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -242,6 +303,20 @@ int launch_tiled(const GemmArgs& a, cudaStream_t s) {
 }
 
 }  // namespace
+
+// <= 8 rows with bf16 weights (plane 0 of the tensor-core weight image)
+int launch_gemv_bf16w(const GemmArgs& a, const __nv_bfloat16* Wb, int kp, cudaStream_t s) {
+  DIM_REQUIRE(a.M > 0 && a.M <= 8 && a.N > 0 && a.K > 0 && a.K % 8 == 0 && a.conv_T == 0, "gemv_bf16w: bad problem");
+  DIM_REQUIRE(a.lda % 4 == 0 && (a.C != nullptr || a.Cb != nullptr), "gemv_bf16w: bad operands");
+  dim3 grid(a.N);
+  ProfScope ps(CAT_GEMM_SKINNY, s, 4.0 * ((double)a.M * a.K + (double)a.M * a.N) + 2.0 * (double)a.N * a.K, 2.0 * a.M * (double)a.N * a.K);
+  if (a.M == 1) DIM_CHECK_CUDA(launch_k(gemm_bf16w_skinny<1>, grid, dim3(128), 0, s, a, Wb, kp));
+  else if (a.M == 2) DIM_CHECK_CUDA(launch_k(gemm_bf16w_skinny<2>, grid, dim3(128), 0, s, a, Wb, kp));
+  else if (a.M <= 4) DIM_CHECK_CUDA(launch_k(gemm_bf16w_skinny<4>, grid, dim3(128), 0, s, a, Wb, kp));
+  else DIM_CHECK_CUDA(launch_k(gemm_bf16w_skinny<8>, grid, dim3(128), 0, s, a, Wb, kp));
+  DIM_LAUNCHED();
+  return DIM_OK;
+}
 
 int launch_gemm_f32(const GemmArgs& a, cudaStream_t s) {
   DIM_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem");

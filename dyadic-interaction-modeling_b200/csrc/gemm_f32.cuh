@@ -31,5 +31,7 @@ struct GemmArgs {
 };
 
 int launch_gemm_f32(const GemmArgs& a, cudaStream_t s);
+// M <= 8 rows, weight row read as bf16 from plane 0 of the tensor-core weight image [N, kp] (DIM_PREC_BF16)
+int launch_gemv_bf16w(const GemmArgs& a, const __nv_bfloat16* Wb, int kp, cudaStream_t s);
 
 }  // namespace dimb
