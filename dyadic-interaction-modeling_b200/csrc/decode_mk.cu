@@ -226,6 +226,106 @@ __device__ __forceinline__ void mk_gemm(const MkPlan& P, const MkPhase& ph, uint
   }
 }
 
+// ---- MK_GEMM for <= 8 decode rows: GEMV ------------------------------------------------------------------------------------
+// A decode step of a single clip is one weight stream (144 MB in bf16 mode) against a handful of activation rows: tiles and tensor
+// cores have nothing to offer.  Every warp of the grid owns whole output columns n = gw, gw + #warps, ...; the M activation rows are
+// staged once per CTA in shared memory as fp32 (the sum of their bf16 planes, which is exact), the weight row streams through
+// registers with 128-bit loads -- the first batch is requested BEFORE the staging, so the HBM round trip and the L2 round trip
+// overlap -- and a warp reduction yields part[0][m][n] (or, epi == 1, gelu(acc + bias) as the next GEMV's bf16 planes).
+// bf16 mode reads the bf16 weight image; the fp32-grade mode reads the original fp32 weights (fewer bytes than three planes).
+template <bool W16>
+__device__ __forceinline__ void mk_gemv(const MkPlan& P, const MkPhase& ph, uint8_t* smem) {
+  constexpr int NB = 9;                                 // 128-bit weight vectors in flight per lane and batch
+  constexpr int EPV = W16 ? 8 : 4;                      // weights per vector
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int M = ph.M, N = ph.N, kp = ph.kp;
+  const int kw = W16 ? kp : ph.K;                       // weights per row actually streamed
+  const int nvec = kw / EPV;
+  float* a_s = reinterpret_cast<float*>(smem);          // [M][kp]
+  const int gw = (int)blockIdx.x * MK_WARPS + warp, nw = (int)gridDim.x * MK_WARPS;
+  const uint4* wrow0 = W16 ? reinterpret_cast<const uint4*>(ph.wb) : reinterpret_cast<const uint4*>(ph.w32);
+  const size_t row_vecs = (size_t)(W16 ? kp : ph.K) / EPV;
+  uint4 wv[NB];
+  auto load_batch = [&](int n, int b0) {
+    const uint4* wr = wrow0 + (size_t)n * row_vecs;
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      const int j = b0 + u * 32 + lane;
+      wv[u] = j < nvec ? __ldcs(wr + j) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  int n = gw;
+  if (n < N) load_batch(n, 0);
+  {  // stage A: fp32 = sum of the planes in plane order (h + m, then + l: both sums exact)
+    const int v8 = kp / 8;
+    for (int i = threadIdx.x; i < M * v8; i += MK_THREADS) {
+      const int m = i / v8, j = i - m * v8;
+      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int pl = 0; pl < P.planes; ++pl) {
+        const uint4 q = *reinterpret_cast<const uint4*>(ph.a_planes + ((size_t)m * P.planes + pl) * kp + j * 8);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { f[2 * t] += __uint_as_float(w[t] << 16); f[2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u); }
+      }
+      float4* d = reinterpret_cast<float4*>(a_s + (size_t)m * kp + j * 8);
+      d[0] = make_float4(f[0], f[1], f[2], f[3]);
+      d[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+  }
+  __syncthreads();
+  for (bool first = true; n < N; n += nw, first = false) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int b0 = 0; b0 < nvec; b0 += NB * 32) {
+      if (!(first && b0 == 0)) load_batch(n, b0);
+#pragma unroll
+      for (int u = 0; u < NB; ++u) {
+        const int j = b0 + u * 32 + lane;
+        if (j < nvec) {
+          float wf[EPV];
+          const uint32_t w[4] = {wv[u].x, wv[u].y, wv[u].z, wv[u].w};
+          if (W16) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { wf[2 * t] = __uint_as_float(w[t] << 16); wf[(2 * t + 1) % EPV] = __uint_as_float(w[t] & 0xffff0000u); }
+          } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) wf[t % EPV] = __uint_as_float(w[t]);
+          }
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            if (m < M) {
+              const float4* ar = reinterpret_cast<const float4*>(a_s + (size_t)m * kp + (size_t)j * EPV);
+              const float4 a0 = ar[0];
+              acc[m] = fmaf(a0.x, wf[0], acc[m]); acc[m] = fmaf(a0.y, wf[1], acc[m]);
+              acc[m] = fmaf(a0.z, wf[2], acc[m]); acc[m] = fmaf(a0.w, wf[3], acc[m]);
+              if (W16) {
+                const float4 a1 = ar[1];
+                acc[m] = fmaf(a1.x, wf[4 % EPV], acc[m]); acc[m] = fmaf(a1.y, wf[5 % EPV], acc[m]);
+                acc[m] = fmaf(a1.z, wf[6 % EPV], acc[m]); acc[m] = fmaf(a1.w, wf[7 % EPV], acc[m]);
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 8; ++m)
+      if (m < M) acc[m] = warp_sum(acc[m]);
+    if (lane == 0) {
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        if (m >= M) continue;
+        if (ph.epi == 1) {
+          const float v = act_apply(acc[m] + (ph.bias ? __ldg(ph.bias + n) : 0.f), DIM_ACT_GELU_ERF, 0.f);
+          store_planes1(ph.outp + (size_t)m * P.planes * ph.out_kp + n, v, P.planes, ph.out_kp);
+        } else {
+          ph.part[(size_t)m * N + n] = acc[m];
+        }
+      }
+    }
+  }
+  __syncthreads();                                       // a_s is the next phase's scratch
+}
+
 // ---- MK_ATTN ------------------------------------------------------------------------------------------------------------
 template <bool BF16>
 __device__ __forceinline__ void mk_attn_item(const MkPhase& ph, int Brows, int H, int planes, int sc_floats, uint8_t* reg, int sub,
@@ -1003,19 +1103,23 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const __grid_
     for (int i = 0; i < nph; ++i) {
       const MkPhase& ph = P.phases[i];                 // kernel-parameter space: uniform constant-bank reads
       const int nxt = i + 1 < nph ? i + 1 : 0;
-      if (threadIdx.x == 32 && P.phases[nxt].type == MK_GEMM) {     // descriptors of the next GEMM phase
+      if (threadIdx.x == 32 && P.phases[nxt].type == MK_GEMM && !P.phases[nxt].gemv) {     // descriptors of the next GEMM phase
         asm volatile("prefetch.tensormap [%0];" ::"l"(&P.maps[P.phases[nxt].mapA]) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&P.maps[P.phases[nxt].mapW]) : "memory");
       }
       switch (ph.type) {
-        case MK_GEMM: mk_gemm(P, ph, smem, smem_base, ctl, pipe, tmem_base); break;
+        case MK_GEMM:
+          if (!ph.gemv) mk_gemm(P, ph, smem, smem_base, ctl, pipe, tmem_base);
+          else if (P.planes == 1) mk_gemv<true>(P, ph, smem);
+          else mk_gemv<false>(P, ph, smem);
+          break;
         case MK_ATTN: mk_attn(P, ph, smem, ctl, st); break;
         case MK_ROW_RESLN: mk_row_resln(P, ph, ctl); break;
         case MK_ROW_GELU: mk_row_gelu(P, ph); break;
         case MK_ROW_SAMPLE: mk_row_sample(P, ph, reinterpret_cast<float*>(smem), ctl, st); break;
         default: break;
       }
-      grid_sync(P.bar, bar_target, P.phases[nxt].type == MK_GEMM);
+      grid_sync(P.bar, bar_target, P.phases[nxt].type == MK_GEMM && !P.phases[nxt].gemv);
       if (tracing) {
         const unsigned long long t = gtime_ns();
         P.trace[i] += t - t_prev;

@@ -23,6 +23,11 @@ struct MkPhase {
   int pa[6], pw[6];
   float w_keep;                              // > 0: fraction of the weight tiles loaded with L2 evict_last
   int epi;                                   // 0: fp32 partials -> part; 1 (splits == 1 only): gelu_erf(acc + bias) -> planes outp
+  // <= 8 decode rows: the phase runs as a GEMV (every warp streams whole weight rows; A staged in shared memory), splits == 1
+  int gemv, K;
+  const __nv_bfloat16* a_planes;             // the A operand behind mapA: [M, planes * kp] bf16
+  const __nv_bfloat16* wb;                   // planes == 1: bf16 weight image [N, kp]
+  const float* w32;                          // planes == 3: the fp32 weight [N, K] (A is reconstructed exactly from its planes)
   float* part;
   // ---- MK_ATTN: one query row per (decode row, head) over a head-major K/V cache
   int q_splits, q_ld, q_col, k_col, v_col;   // the producing GEMM's partials: pitch and column offsets of q / new k / new v

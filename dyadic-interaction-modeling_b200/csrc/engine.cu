@@ -784,7 +784,8 @@ int plan_groups(const S2SModel& m, int B, int max_keys, int* begin /*[kMaxGroups
   {  // the persistent decode kernel owns every SM: one chain
     const dim_s2s_config& c = m.cfg;
     const int D = c.dim + c.dim_audio;
-    if (g_decode_impl == 0 && tc_on(m.tc, B) &&
+    static const bool small_mk = getenv("DIM_SMALL_BATCH_MK") != nullptr;
+    if (g_decode_impl == 0 && m.tc.planes > 0 && (B > 8 || small_mk) &&
         mk_supported(D, c.heads * c.dim_head, c.ff_mult * D, c.num_tokens, c.heads, m.tc.planes, max_keys)) {
       begin[0] = 0;
       begin[1] = B;
@@ -900,6 +901,7 @@ struct MkBuilder {
   int add_map(const __nv_bfloat16* ptr, int nrows, int cols, int box_rows, int* idx) {
     if (nmaps >= MK_MAX_MAPS) return fail(DIM_EINVAL, "decode plan: too many tensor maps");
     if (int e = tc_make_map(ptr, nrows, cols, cols, box_rows, &P.maps[nmaps])) return e;
+    map_ptr[nmaps] = ptr;
     *idx = nmaps++;
     return DIM_OK;
   }
@@ -911,6 +913,7 @@ struct MkBuilder {
     return ph;
   }
   // part[z][rows][N] = A_planes . W^T ; returns the split factor
+  const __nv_bfloat16* map_ptr[MK_MAX_MAPS] = {};       // the operand behind an A map (the GEMV phases read it directly)
   int gemm(int mapA, const float* W, int N, int K, float* part, float w_keep, int* splits_out) {
     auto it = m.tc.wmap.find(W);
     if (it == m.tc.wmap.end()) return fail(DIM_EINVAL, "decode plan: weight without bf16 planes");
@@ -924,6 +927,9 @@ struct MkBuilder {
     if (int e = add_map(it->second, N, planes * kp, ph->bn, &ph->mapW)) return e;
     ph->part = part;
     ph->w_keep = w_keep;
+    if (rows <= 8) {                                    // small batches: the phase streams weights as a GEMV (decode_mk.cu: mk_gemv)
+      ph->gemv = 1; ph->splits = 1; ph->K = K; ph->a_planes = map_ptr[mapA]; ph->wb = it->second; ph->w32 = W;
+    }
     *splits_out = ph->splits;
     return DIM_OK;
   }
@@ -992,6 +998,7 @@ int build_mk_plan(const S2SModel& m, const GenWs& w, int B, int Bc, int T, int s
       // rounding of FF2's A operand run in the GEMM's own epilogue and the GELU row phase (and its grid barrier) disappears
       MkPhase* ph = &P.phases[P.nphases - 1];
       ph->bn = 64; ph->splits = 1; ph->epi = 1; ph->bias = FF.b1; ph->outp = w.ap2; ph->out_kp = F;
+      sp = 1;
       if (int e = tc_make_map(m.tc.wmap.find(FF.w1)->second, F, planes * tc_round_k(D), planes * tc_round_k(D), 64, &P.maps[ph->mapW])) return e;
     } else {
       MkPhase* ph = b.next(MK_ROW_GELU);
@@ -1066,7 +1073,11 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
   if (int e = launch_set_step(w.step, 0, s)) return e;
 
   const int max_keys = std::max(T, steps + 1);
-  if (g_decode_impl == 0 && tc_on(m.tc, B) && mk_supported(D, inner, F, V, c.heads, m.tc.planes, max_keys)) {
+  // <= 8 rows: the persistent kernel has a GEMV flavour of its GEMM phases (decode_mk.cu: mk_gemv), but measured SLOWER than the
+  // per-kernel chain there (B = 1, bf16: 311 vs 249 us per step: 8 single-item attention phases at 10 us and 12 row phases at 3.5 us
+  // pay a grid barrier each for work one CTA does) -- opt-in with DIM_SMALL_BATCH_MK=1 until its attention items split their keys
+  static const bool small_mk = getenv("DIM_SMALL_BATCH_MK") != nullptr;
+  if (g_decode_impl == 0 && m.tc.planes > 0 && (B > 8 || small_mk) && mk_supported(D, inner, F, V, c.heads, m.tc.planes, max_keys)) {
     // persistent decode kernel (more than 8 decode rows; fewer stay on the weight-streaming GEMV chain, which is faster there:
     // 77.9 vs 94 ms per single 300-frame clip, profiles/r02_notes.md): prompt embedding + layer 0's LayerNorm here, then every step inside ONE cooperative launch
     const XtAttn& SA0 = m.self_attn[0];

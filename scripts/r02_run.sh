@@ -159,3 +159,12 @@ if has launchlist; then
   tail -25 $OUT/${TAG}_launches_summary.txt
   gzip -f $OUT/${TAG}_launches.csv
 fi
+if has b1ab; then
+  for prec in bf16 fp32_tc; do
+    for env in "X=1" "DIM_SMALL_BATCH_GRAPH=1"; do
+      echo "== vico_b1 $prec $env"
+      env $env timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-parity-leg --no-other-workloads --workload vico_b1 --precision $prec 2>/dev/null | python -c "
+import json,sys; d=json.loads([l for l in sys.stdin if l.startswith(chr(123))][-1]); print(round(d['value']), 'frames/s', round(d['ms_per_step'],2), 'ms'); [print('   ',k) for k in d['kernels'][:4]]"
+    done
+  done
+fi

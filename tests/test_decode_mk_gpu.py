@@ -168,3 +168,42 @@ def test_phase_trace(engine_tc):
     assert kinds.count("gemm") == 6 * S2S.depth + 1 and kinds.count("attention") == 2 * S2S.depth
     assert all(ms > 0 for _, ms in tr)
 
+
+
+def test_small_batch_gemv_phases_match_graph_path(slmft_sd):
+    """<= 8 decode rows through the persistent kernel's GEMV phases (opt-in, DIM_SMALL_BATCH_MK=1: slower than the per-kernel chain
+    today) against the per-kernel chain: same codes (or a near-tie at the first difference), logits within 2e-4.  Runs in a
+    subprocess because the switch is read once per process."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+import dim_b200
+from dim_b200.engine import PREC_FP32_TC, Handle, SLMFTEngine
+from dim_b200.schema import S2SConfig
+sd = dim_b200.synth.make_slmft_state_dict(131)
+h = Handle(); h.register(sd)
+e = SLMFTEngine(h, S2SConfig(), precision=PREC_FP32_TC)
+c = dim_b200.synth.make_clips(3, 40, seed=9, ragged=True)
+ctx = e.context(c["v_speaker"].cuda(), c["v_audio"].cuda(), c["mask"].cuda())
+codes, logits = e.generate(ctx, c["mask"].cuda(), torch.tensor([3, 5, 7]).cuda(), 39, return_logits=True)
+torch.save((codes.cpu(), logits.cpu()), sys.argv[1])
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import tempfile
+    outs = []
+    for env in ({}, {"DIM_SMALL_BATCH_MK": "1"}):
+        with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+            r = subprocess.run([sys.executable, "-c", code, f.name], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs.append(torch.load(f.name))
+    (c0, l0), (c1, l1) = outs
+    for b in range(3):
+        neq = (c0[b] != c1[b]).nonzero()
+        n = len(c0[b]) if len(neq) == 0 else int(neq[0])
+        upto = min(n + 1, len(c0[b]))
+        assert float((l0[b, :upto] - l1[b, :upto]).abs().max()) < 2e-4
+        if n < len(c0[b]):
+            top2 = torch.topk(l0[b, n].double(), 2).values
+            assert float(top2[0] - top2[1]) < 4e-4
