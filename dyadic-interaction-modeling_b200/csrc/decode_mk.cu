@@ -1067,6 +1067,9 @@ __device__ __forceinline__ void mk_row_sample(const MkPlan& P, const MkPhase& ph
   }
 }
 
+// SMALL: the <= 8-row flavour (GEMV phases, no tile GEMM): a separate instantiation so that the GEMV's registers (9 weight vectors in
+// flight per lane) do not spill the tile kernel's hot loops.
+template <bool SMALL>
 __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const __grid_constant__ MkPlan P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) Ctl ctl;
@@ -1109,7 +1112,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const __grid_
       }
       switch (ph.type) {
         case MK_GEMM:
-          if (!ph.gemv) mk_gemm(P, ph, smem, smem_base, ctl, pipe, tmem_base);
+          if (!SMALL) mk_gemm(P, ph, smem, smem_base, ctl, pipe, tmem_base);
           else if (P.planes == 1) mk_gemv<true>(P, ph, smem);
           else mk_gemv<false>(P, ph, smem);
           break;
@@ -1154,9 +1157,12 @@ int launch_decode_megakernel(const MkPlan& plan, cudaStream_t s) {
   int dev = 0, sms = 0;
   DIM_CHECK_CUDA(cudaGetDevice(&dev));
   DIM_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  DIM_CHECK_CUDA(cudaFuncSetAttribute(decode_megakernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  bool small = false;
+  for (int i = 0; i < plan.nphases; ++i) small = small || (plan.phases[i].type == MK_GEMM && plan.phases[i].gemv);
+  auto kern = small ? decode_megakernel<true> : decode_megakernel<false>;
+  DIM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  DIM_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_megakernel, MK_THREADS, smem));
+  DIM_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MK_THREADS, smem));
   DIM_REQUIRE(per_sm >= 1, "decode megakernel: one CTA does not fit an SM");
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(sms);
@@ -1169,7 +1175,7 @@ int launch_decode_megakernel(const MkPlan& plan, cudaStream_t s) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   ProfScope ps(CAT_DECODE_MK, s, 0, 0);
-  DIM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_megakernel, plan));
+  DIM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, plan));
   DIM_LAUNCHED();
   return DIM_OK;
 }
