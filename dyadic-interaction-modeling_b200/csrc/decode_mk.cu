@@ -815,6 +815,13 @@ __device__ __forceinline__ float4 sum_slices(const float* p, size_t slice_stride
 __device__ __forceinline__ void ln_pair(const float4 (&v)[2], const bool (&on)[2], int c, int n4, int dim, const float* gain,
                                         const float* beta, __nv_bfloat16* const (&out)[2], int planes, int kp, float* red) {
   const bool mine = c < n4;
+  // gain / bias are requested before the two block reductions (loads do not move across __syncthreads on their own): their L2
+  // round trip overlaps the reductions instead of following them
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f), bb = g;
+  if (mine) {
+    g = __ldg(reinterpret_cast<const float4*>(gain) + c);
+    if (beta) bb = __ldg(reinterpret_cast<const float4*>(beta) + c);
+  }
   float s0 = (mine && on[0]) ? (v[0].x + v[0].y) + (v[0].z + v[0].w) : 0.f;
   float s1 = (mine && on[1]) ? (v[1].x + v[1].y) + (v[1].z + v[1].w) : 0.f;
   block_sum2(s0, s1, red);
@@ -828,9 +835,6 @@ __device__ __forceinline__ void ln_pair(const float4 (&v)[2], const bool (&on)[2
     }
   block_sum2(q[0], q[1], red);
   if (!mine) return;
-  const float4 g = __ldg(reinterpret_cast<const float4*>(gain) + c);
-  float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (beta) bb = __ldg(reinterpret_cast<const float4*>(beta) + c);
 #pragma unroll
   for (int k = 0; k < 2; ++k)
     if (on[k]) {
