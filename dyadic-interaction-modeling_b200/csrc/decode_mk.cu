@@ -1063,6 +1063,11 @@ __device__ __forceinline__ void mk_row_sample(const MkPlan& P, const MkPhase& ph
       for (int k = 0; k < 2; ++k)
         if (on[k]) {
           v[k] = __ldg(reinterpret_cast<const float4*>(ph.emb + (size_t)ctl.tok[k] * D) + c);
+          if (ph.pos) {                                   // absolute positional table: the token enters at position st + 1
+            const float4 q = __ldg(reinterpret_cast<const float4*>(ph.pos + (size_t)(st + 1) * D) + c);
+            v[k].x = fmaf(q.x, ph.pos_scale, v[k].x); v[k].y = fmaf(q.y, ph.pos_scale, v[k].y);
+            v[k].z = fmaf(q.z, ph.pos_scale, v[k].z); v[k].w = fmaf(q.w, ph.pos_scale, v[k].w);
+          }
           *reinterpret_cast<float4*>(ph.x + (size_t)row[k] * D + c * 4) = v[k];
         }
     }

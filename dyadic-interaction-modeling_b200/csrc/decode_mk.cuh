@@ -44,6 +44,8 @@ struct MkPhase {
   float* x;                                  // residual stream [M, N]
   const float *gain, *beta;                  // LayerNorm (beta nullable)
   const float* emb;                          // MK_ROW_SAMPLE: token embedding [V, D]
+  const float* pos;                          // MK_ROW_SAMPLE: nullable absolute positional table [max_seq_len, D] (+ pos[st + 1] * pos_scale)
+  float pos_scale;
   int D;                                     // MK_ROW_SAMPLE: model width (N = vocabulary)
 };
 

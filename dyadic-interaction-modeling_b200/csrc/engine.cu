@@ -78,8 +78,8 @@ struct S2SModel {
   dim_s2s_config cfg{};
   int precision = DIM_PREC_FP32;
   TcCtx tc;
-  XtEncoder enc_s, enc_joint, enc_l;           // enc_l: SLM pre-training only (optional)
-  bool has_enc_l = false;
+  XtEncoder enc_s, enc_joint, enc_l;           // enc_l: SLM pre-training only (optional); enc_joint absent in single-encoder models
+  bool has_enc_l = false, has_enc_joint = false;
   const float *patch_s = nullptr, *patch_dec_s = nullptr, *norm_s_g = nullptr, *norm_s_b = nullptr;
   const float *norm_l_g = nullptr, *norm_l_b = nullptr, *norm_j_g = nullptr, *norm_j_b = nullptr;     // SLM: norm_l, norm
   const float* dec_pos_emb = nullptr;          // decoder_joint.net.pos_emb (SLM keeps use_abs_pos_emb=True; SLMFT has none)
@@ -713,11 +713,19 @@ extern "C" int dim_slmft_build(dim_handle_t h, const dim_s2s_config* cfg, int pr
   m->tc.planes = planes_of(precision);
   const int inner = c.heads * c.dim_head, D = c.dim + c.dim_audio;
   if (int e = build_xt_encoder(h, "encoder_s", c.dim_in, c, m->enc_s)) return e;
-  if (int e = build_xt_encoder(h, "encoder_joint", c.dim, c, m->enc_joint)) return e;
-  LOOKUP(m->patch_s, "patch_embed_s", true, 1, 1, c.dim_in);
-  LOOKUP(m->patch_dec_s, "patch_embed_dec_s", true, 1, 1, c.dim);
-  LOOKUP(m->norm_s_g, "norm_s.weight", true, c.dim);
-  LOOKUP(m->norm_s_b, "norm_s.bias", true, c.dim);
+  {  // single-encoder models (the older ListenerGenerator, seq2seq.py:172-182, registered as encoder_s + decoder_joint) have no joint
+     // encoder, patch embeddings or norm_s: dim_slmft_context needs them, dim_slmft_encode / generate / teacher_forced do not
+    const float* probe = nullptr;
+    LOOKUP(probe, "encoder_joint.project_in.weight", false, c.dim, c.dim);
+    if (probe) {
+      if (int e = build_xt_encoder(h, "encoder_joint", c.dim, c, m->enc_joint)) return e;
+      m->has_enc_joint = true;
+    }
+  }
+  LOOKUP(m->patch_s, "patch_embed_s", false, 1, 1, c.dim_in);
+  LOOKUP(m->patch_dec_s, "patch_embed_dec_s", false, 1, 1, c.dim);
+  LOOKUP(m->norm_s_g, "norm_s.weight", false, c.dim);
+  LOOKUP(m->norm_s_b, "norm_s.bias", false, c.dim);
   LOOKUP(m->norm_l_g, "norm_l.weight", false, c.dim);
   LOOKUP(m->norm_l_b, "norm_l.bias", false, c.dim);
   LOOKUP(m->norm_j_g, "norm.weight", false, c.dim);
@@ -750,6 +758,7 @@ extern "C" int dim_slmft_build(dim_handle_t h, const dim_s2s_config* cfg, int pr
     TcCtx& tc = m->tc;
     for (XtEncoder* E : {&m->enc_s, &m->enc_joint, &m->enc_l}) {
       if (E == &m->enc_l && !m->has_enc_l) continue;
+      if (E == &m->enc_joint && !m->has_enc_joint) continue;
       if (int e = tc_add_weight(h, tc, E->proj_w, c.dim, E->dim_in)) return e;
       for (int l = 0; l < c.depth; ++l) {
         if (int e = tc_add_weight(h, tc, E->attn[l].wqkv, 3 * inner, c.dim)) return e;
@@ -834,6 +843,8 @@ extern "C" int dim_slmft_context(dim_handle_t h, int model, const float* v_speak
   const S2SModel& m = *h->s2s[model];
   const dim_s2s_config& c = m.cfg;
   DIM_REQUIRE(T <= c.max_seq_len, "sequence longer than the positional table");
+  DIM_REQUIRE(m.has_enc_joint && m.patch_s && m.patch_dec_s && m.norm_s_g && m.norm_s_b,
+              "dim_slmft_context: the model has no encoder_joint / patch embeddings / norm_s (single-encoder model: use dim_slmft_encode)");
   CtxWs w = carve_ctx(c, m.tc.planes, B, T, ws);
   if (ws == nullptr || ws_bytes < w.bytes) return fail(DIM_EWORKSPACE, "dim_slmft_context: workspace too small");
   cudaStream_t s = as_stream(stream);
@@ -860,6 +871,7 @@ extern "C" int dim_slmft_encode(dim_handle_t h, int model, int which, const floa
   const dim_s2s_config& c = m.cfg;
   DIM_REQUIRE(T <= c.max_seq_len, "sequence longer than the positional table");
   DIM_REQUIRE(which != 1 || m.has_enc_l, "dim_slmft_encode: encoder_l is not registered");
+  DIM_REQUIRE(which != 2 || m.has_enc_joint, "dim_slmft_encode: encoder_joint is not registered");
   const float *g = nullptr, *b = nullptr;
   if (norm == 1) { g = m.norm_s_g; b = m.norm_s_b; }
   if (norm == 2) { g = m.norm_l_g; b = m.norm_l_b; }
@@ -1015,6 +1027,7 @@ int build_mk_plan(const S2SModel& m, const GenWs& w, int B, int Bc, int T, int s
     MkPhase* ph = b.next(MK_ROW_SAMPLE);
     if (!ph) return fail(DIM_EINVAL, "decode plan: too many phases");
     ph->N = V; ph->D = D; ph->part = w.mk_part; ph->in_splits = sp; ph->bias = m.logits_b; ph->emb = m.token_emb; ph->x = w.x;
+    ph->pos = m.dec_pos_emb; ph->pos_scale = 1.0f / sqrtf((float)D);
     ph->gain = m.self_attn[0].norm_g; ph->beta = m.self_attn[0].norm_b; ph->outp = w.ap; ph->out_kp = D;
   }
   P.nmaps = b.nmaps;
@@ -1081,7 +1094,7 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
     // persistent decode kernel (more than 8 decode rows; fewer stay on the weight-streaming GEMV chain, which is faster there:
     // 77.9 vs 94 ms per single 300-frame clip, profiles/r02_notes.md): prompt embedding + layer 0's LayerNorm here, then every step inside ONE cooperative launch
     const XtAttn& SA0 = m.self_attn[0];
-    if (int e = launch_embed_tokens(w.tokens, steps + 1, w.step, m.token_emb, w.x, B, D, V, s)) return e;
+    if (int e = launch_embed_tokens(w.tokens, steps + 1, w.step, m.token_emb, w.x, B, D, V, s, m.dec_pos_emb, 1.0f / sqrtf((float)D))) return e;
     if (int e = launch_layer_norm(w.x, SA0.norm_g, SA0.norm_b, nullptr, nullptr, B, D, 1e-5f, s, w.ap, m.tc.planes, D)) return e;
     DIM_CHECK_CUDA(cudaMemsetAsync(w.mk_bar, 0, 256, s));
     if (g_mk_trace_on) DIM_CHECK_CUDA(cudaMemsetAsync(w.mk_trace, 0, MK_MAX_PHASES * sizeof(unsigned long long), s));
@@ -1104,7 +1117,7 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
   // Head of the very first step: embedding of the prompt token and layer 0's self-attention LayerNorm.  Every later step gets
   // both from the tail kernel of the step before it (sample_next_kernel).
   auto enqueue_prologue = [&](cudaStream_t s) -> int {
-    if (int e = launch_embed_tokens(w.tokens, steps + 1, w.step, m.token_emb, w.x, B, D, V, s)) return e;
+    if (int e = launch_embed_tokens(w.tokens, steps + 1, w.step, m.token_emb, w.x, B, D, V, s, m.dec_pos_emb, 1.0f / sqrtf((float)D))) return e;
     const XtAttn& SA0 = m.self_attn[0];
     return launch_layer_norm(w.x, SA0.norm_g, SA0.norm_b, tcp ? nullptr : w.ln, nullptr, B, D, 1e-5f, s, tcp ? w.ap : nullptr, P, D);
   };
@@ -1192,7 +1205,8 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
     const XtAttn& SA0 = m.self_attn[0];
     if (int e = launch_sample_next(w.logits, B, V, temperature, top_k, uniforms_g, steps, w.step,
                                    reinterpret_cast<unsigned int*>(w.step + 16), w.tokens, steps + 1, 1, logits_out, steps * V,
-                                   m.token_emb, w.x, D, SA0.norm_g, SA0.norm_b, tcp ? nullptr : w.ln, tcp ? w.ap : nullptr, P, 1e-5f, s))
+                                   m.token_emb, w.x, D, SA0.norm_g, SA0.norm_b, tcp ? nullptr : w.ln, tcp ? w.ap : nullptr, P, 1e-5f, s, m.dec_pos_emb,
+                                   1.0f / sqrtf((float)D)))
       return e;
     return DIM_OK;
   };
@@ -1265,7 +1279,7 @@ extern "C" int dim_slmft_generate(dim_handle_t h, int model, const float* ctx, c
   DIM_REQUIRE(temperature >= 0.f, "temperature must be >= 0");
   DIM_REQUIRE(temperature == 0.f || (uniforms && top_k > 0), "sampling needs uniforms and top_k");
   const S2SModel& m = *h->s2s[model];
-  DIM_REQUIRE(h->s2s[model]->dec_pos_emb == nullptr, "generate: a decoder with an absolute positional table (SLM) is teacher-forced only");
+  DIM_REQUIRE(h->s2s[model]->dec_pos_emb == nullptr || steps + 1 <= h->s2s[model]->cfg.max_seq_len, "generate: longer than the decoder's positional table");
   const dim_s2s_config& c = m.cfg;
   const int D = c.dim + c.dim_audio, V = c.num_tokens;
   cudaStream_t s = as_stream(stream);
@@ -1335,7 +1349,7 @@ extern "C" int dim_slmft_generate_samples(dim_handle_t h, int model, const float
   DIM_REQUIRE(temperature >= 0.f, "temperature must be >= 0");
   DIM_REQUIRE(temperature == 0.f || (uniforms && top_k > 0), "sampling needs uniforms and top_k");
   const S2SModel& m = *h->s2s[model];
-  DIM_REQUIRE(h->s2s[model]->dec_pos_emb == nullptr, "generate: a decoder with an absolute positional table (SLM) is teacher-forced only");
+  DIM_REQUIRE(h->s2s[model]->dec_pos_emb == nullptr || steps + 1 <= h->s2s[model]->cfg.max_seq_len, "generate: longer than the decoder's positional table");
   if ((int)m.graphs.size() < kMaxGroups + 1) m.graphs.resize(kMaxGroups + 1);
   return generate_group(m, m.graphs[kMaxGroups], ctx, mask, prompt, B, T, steps, temperature, top_k, uniforms, out_codes, logits_out,
                         ws, ws_bytes, as_stream(stream), samples);

@@ -137,16 +137,27 @@ __global__ void build_context_kernel(const float* __restrict__ xs, const float* 
 }
 
 // x[b,:] = token_emb[tok[b],:]   (TransformerWrapper token embedding; no positional term for SLMFT)
+// pos != nullptr: + pos[position,:] * pos_scale (x-transformers AbsolutePositionalEmbedding; position = the step index)
 __global__ void embed_tokens_kernel(const int64_t* __restrict__ tok, int tok_stride, const int* __restrict__ step,
-                                    const float* __restrict__ emb, float* __restrict__ x, int B, int D, int V) {
+                                    const float* __restrict__ emb, float* __restrict__ x, int B, int D, int V,
+                                    const float* __restrict__ pos, float pos_scale) {
   pdl_prologue();
   const int b = blockIdx.x;
-  const int64_t* tp = tok + (size_t)b * tok_stride + (step ? *step : 0);
+  const int st = step ? *step : 0;
+  const int64_t* tp = tok + (size_t)b * tok_stride + st;
   int64_t t = *tp;
   t = t < 0 ? 0 : (t >= V ? V - 1 : t);
   const float4* src = reinterpret_cast<const float4*>(emb + (size_t)t * D);
+  const float4* ps = pos ? reinterpret_cast<const float4*>(pos + (size_t)st * D) : nullptr;
   float4* dst = reinterpret_cast<float4*>(x + (size_t)b * D);
-  for (int i = threadIdx.x; i < (D >> 2); i += blockDim.x) dst[i] = __ldg(src + i);
+  for (int i = threadIdx.x; i < (D >> 2); i += blockDim.x) {
+    float4 v = __ldg(src + i);
+    if (ps) {
+      const float4 q = __ldg(ps + i);
+      v.x = fmaf(q.x, pos_scale, v.x); v.y = fmaf(q.y, pos_scale, v.y); v.z = fmaf(q.z, pos_scale, v.z); v.w = fmaf(q.w, pos_scale, v.w);
+    }
+    dst[i] = v;
+  }
 }
 
 // One block (256 threads) per row of logits [V <= 1024].  Greedy: first maximal index (torch.argmax on CPU returns the
@@ -297,7 +308,8 @@ __global__ void __launch_bounds__(256) sample_next_kernel(const float* __restric
                                                           int out_offset, float* __restrict__ logits_out, int lo_stride,
                                                           const float* __restrict__ emb, float* __restrict__ x, int D,
                                                           const float* __restrict__ gain, const float* __restrict__ bias,
-                                                          float* __restrict__ y, __nv_bfloat16* __restrict__ yp, int planes, float eps) {
+                                                          float* __restrict__ y, __nv_bfloat16* __restrict__ yp, int planes, float eps,
+                                                          const float* __restrict__ pos, float pos_scale) {
   __shared__ float redn[8];
   pdl_prologue();
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -306,6 +318,7 @@ __global__ void __launch_bounds__(256) sample_next_kernel(const float* __restric
   tok = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
   const int n4 = D >> 2;
   const float4* src = reinterpret_cast<const float4*>(emb + (size_t)tok * D);
+  const float4* ps = pos ? reinterpret_cast<const float4*>(pos + (size_t)(st + 1) * D) : nullptr;     // the token enters at position st + 1
   float4 v[MAXV];
   float sum = 0.f;
 #pragma unroll
@@ -313,6 +326,11 @@ __global__ void __launch_bounds__(256) sample_next_kernel(const float* __restric
     const int c = tid + 256 * i;
     if (c < n4) {
       v[i] = __ldg(src + c);
+      if (ps) {
+        const float4 q = __ldg(ps + c);
+        v[i].x = fmaf(q.x, pos_scale, v[i].x); v[i].y = fmaf(q.y, pos_scale, v[i].y);
+        v[i].z = fmaf(q.z, pos_scale, v[i].z); v[i].w = fmaf(q.w, pos_scale, v[i].w);
+      }
       reinterpret_cast<float4*>(x + (size_t)b * D)[c] = v[i];
       sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
@@ -516,9 +534,9 @@ int launch_add_pos_table(float* x, const float* tab, float scale, int B, int L, 
 }
 
 int launch_embed_tokens(const int64_t* tok, int tok_stride, const int* step, const float* emb, float* x, int B, int D, int V,
-                        cudaStream_t s) {
+                        cudaStream_t s, const float* pos, float pos_scale) {
   ProfScope ps(CAT_MISC, s, 8.0 * B * D, 0);
-  DIM_CHECK_CUDA(launch_k(embed_tokens_kernel, dim3(B), dim3(128), 0, s, tok, tok_stride, step, emb, x, B, D, V));
+  DIM_CHECK_CUDA(launch_k(embed_tokens_kernel, dim3(B), dim3(128), 0, s, tok, tok_stride, step, emb, x, B, D, V, pos, pos_scale));
   DIM_LAUNCHED();
   return DIM_OK;
 }
@@ -538,17 +556,17 @@ int launch_sample(const float* logits, int B, int V, float temperature, int top_
 int launch_sample_next(const float* logits, int B, int V, float temperature, int top_k, const float* uniforms, int u_stride,
                        int* step, unsigned int* ticket, int64_t* out, int out_stride, int out_offset, float* logits_out,
                        int lo_stride, const float* emb, float* x, int D, const float* gain, const float* bias, float* y,
-                       __nv_bfloat16* yp, int planes, float eps, cudaStream_t s) {
+                       __nv_bfloat16* yp, int planes, float eps, cudaStream_t s, const float* pos, float pos_scale) {
   DIM_REQUIRE(V > 0 && V <= 1024, "sample: vocabulary must be <= 1024");
   DIM_REQUIRE(temperature == 0.f || (uniforms != nullptr && top_k > 0), "sample: sampling needs uniforms and top_k");
   DIM_REQUIRE(D % 4 == 0 && D <= 256 * 4 * 4, "sample_next: model dim must be a multiple of 4, <= 4096");
   ProfScope ps(CAT_SAMPLE, s, 4.0 * B * V + 8.0 * B + 12.0 * B * D, 8.0 * B * D);
   if (D <= 256 * 4 * 2)
     DIM_CHECK_CUDA(launch_k(sample_next_kernel<2>, dim3(B), dim3(256), 0, s, logits, V, temperature, top_k, uniforms, u_stride, step,
-                            ticket, out, out_stride, out_offset, logits_out, lo_stride, emb, x, D, gain, bias, y, yp, planes, eps));
+                            ticket, out, out_stride, out_offset, logits_out, lo_stride, emb, x, D, gain, bias, y, yp, planes, eps, pos, pos_scale));
   else
     DIM_CHECK_CUDA(launch_k(sample_next_kernel<4>, dim3(B), dim3(256), 0, s, logits, V, temperature, top_k, uniforms, u_stride, step,
-                            ticket, out, out_stride, out_offset, logits_out, lo_stride, emb, x, D, gain, bias, y, yp, planes, eps));
+                            ticket, out, out_stride, out_offset, logits_out, lo_stride, emb, x, D, gain, bias, y, yp, planes, eps, pos, pos_scale));
   DIM_LAUNCHED();
   return DIM_OK;
 }

@@ -16,7 +16,7 @@ int launch_assemble_batch(const float* speaker, const float* audio, const float*
 // x[b,t,:] += tab[t,:] * scale   (absolute positional embedding of a teacher-forced sequence)
 int launch_add_pos_table(float* x, const float* tab, float scale, int B, int L, int D, cudaStream_t s);
 int launch_embed_tokens(const int64_t* tok, int tok_stride, const int* step, const float* emb, float* x, int B, int D, int V,
-                        cudaStream_t s);
+                        cudaStream_t s, const float* pos = nullptr, float pos_scale = 0.f);
 int launch_sample(const float* logits, int B, int V, float temperature, int top_k, const float* uniforms, int u_stride,
                   const int* step, int64_t* out, int out_stride, int out_offset, float* logits_out, int lo_stride,
                   cudaStream_t s);
@@ -24,7 +24,7 @@ int launch_sample(const float* logits, int B, int V, float temperature, int top_
 int launch_sample_next(const float* logits, int B, int V, float temperature, int top_k, const float* uniforms, int u_stride,
                        int* step, unsigned int* ticket, int64_t* out, int out_stride, int out_offset, float* logits_out,
                        int lo_stride, const float* emb, float* x, int D, const float* gain, const float* bias, float* y,
-                       __nv_bfloat16* yp, int planes, float eps, cudaStream_t s);
+                       __nv_bfloat16* yp, int planes, float eps, cudaStream_t s, const float* pos = nullptr, float pos_scale = 0.f);
 int launch_resample(const float* in, float* out, int t, int d, int new_t, int window, int mode, cudaStream_t s);
 int launch_init_tokens(int64_t* tokens, int stride, const int64_t* prompt, int rows, int samples, cudaStream_t s);
 int launch_advance_step(int* step, cudaStream_t s);

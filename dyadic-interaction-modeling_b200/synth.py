@@ -87,6 +87,35 @@ def make_slmft_state_dict(seed: int = 131, cfg: S2SConfig = S2SConfig(), vq: VQC
     return sd
 
 
+def make_listener_generator_state_dict(seed: int = 131):
+    """ListenerGenerator (seq2seq.py:138-199): speaker_vq (VQSpeakerAutoEncoder) + listener_vq + generator (encoder / decoder of dim 512,
+    depth 6, 8 heads, dim_in 1024, decoder with a positional table) + the identity-embedding heads, reference key names."""
+    from .schema import SPEAKER_VQ, vqspeaker_schema, xt_encoder_wrapper_schema, xt_layers_schema
+    cfg = S2SConfig(dim_in=1024, dim=512, dim_audio=0, depth=6, heads=8, dim_head=64, max_seq_len=1024, num_tokens=512, ff_mult=4)
+    sd = OrderedDict()
+    for k, sh in vqspeaker_schema(SPEAKER_VQ).items():
+        sd["speaker_vq." + k] = _draw("speaker_vq." + k, sh, seed + 1)
+    for k, v in make_vqvae_state_dict(seed + 2).items():
+        sd["listener_vq." + k] = v
+    for k, sh in xt_encoder_wrapper_schema("generator.encoder", cfg.dim_in, cfg).items():
+        sd[k] = _draw(k, sh, seed)
+    d = OrderedDict()
+    d["generator.decoder.net.token_emb.emb.weight"] = (cfg.num_tokens, cfg.dim)
+    d["generator.decoder.net.pos_emb.emb.weight"] = (cfg.max_seq_len, cfg.dim)
+    d.update(xt_layers_schema("generator.decoder.net.attn_layers", cfg.dim, cfg.depth, cfg.inner, True, cfg.ff_mult))
+    d["generator.decoder.net.to_logits.weight"] = (cfg.num_tokens, cfg.dim)
+    for k, sh in d.items():
+        sd[k] = _draw(k, sh, seed)
+    g = _gen(seed, "identity_heads")
+    sd["speaker_embeddings.weight"] = torch.randn(100, 256, generator=g)
+    sd["listener_embeddings.weight"] = torch.randn(100, 256, generator=g)
+    sd["fc_speaker.weight"] = torch.randn(1024, 256, generator=g) * 0.05
+    sd["fc_speaker.bias"] = torch.zeros(1024)
+    sd["fc_listener.weight"] = torch.randn(512, 256, generator=g) * 0.05
+    sd["fc_listener.bias"] = torch.zeros(512)
+    return sd
+
+
 def make_slm_state_dict(seed: int = 131, cfg: S2SConfig = S2SConfig(), vq: VQConfig = VQConfig()):
     """SLM (pre-training model, seq2seq_pretrain.py:72-169): SLMFT's keys + the decoder's absolute positional table (:137)."""
     sd = make_slmft_state_dict(seed, cfg, vq)

@@ -131,3 +131,30 @@ def slm_forward(sd, v_speaker, v_listener, v_audio, mask, mask_speaker, mask_lis
     d = {"l_ce_s": l_ce_s, "l_ce_l": l_ce_l, "l_cont_s": l_cont_s, "l_cont_l": l_cont_l, "nce": nce, "c_acc": c_acc}
     parts = dict(x_s=x_s, x_l=x_l, x_joint=x_joint, px_s=px_s, px_l=px_l, pred_s=pred_s, pred_l=pred_l, z_s=z_s, z_l=z_l)
     return l_ce_s + l_ce_l + l_cont_s + l_cont_l + nce, d, parts
+
+
+@torch.no_grad()
+def listener_generator(sd, v_speaker, v_listener, mask, speaker_cfg, listener_cfg, depth=6, generate_steps=None):
+    """ListenerGenerator.forward / .generate (seq2seq.py:223-290) restated, identity tokens absent.  Returns
+    (loss, pred_cont_seq, logits, x_speaker, z_listener[, generated codes (B, generate_steps), greedy])."""
+    B, T, _ = v_speaker.shape
+    fqn, zd = speaker_cfg.face_quan_num, speaker_cfg.zquant_dim
+    xs, zl = [], []
+    for i in range(B):
+        q = V.encode(sd, v_speaker[i][mask[i]].unsqueeze(0), speaker_cfg, prefix="speaker_vq.")[0]          # (1, 128, len*8)
+        xs.append(F.pad(q, (0, T * fqn - q.shape[-1]), value=0))
+        idx = V.encode(sd, v_listener[i][mask[i]].unsqueeze(0), listener_cfg, prefix="listener_vq.")[2][2].reshape(-1)
+        zl.append(F.pad(idx, (0, T - idx.shape[-1]), value=-100))
+    x = torch.cat(xs, dim=0)
+    # the reference views the (B, 128, T*8) tensor as (B, -1, 8, 128) WITHOUT permuting first (seq2seq.py:238-239): kept as is
+    x = x.view(B, -1, fqn, zd).contiguous().view(B, -1, fqn * zd).contiguous()
+    z = torch.stack(zl, dim=0)
+    enc = X.continuous_wrapper(sd, "generator.encoder", x, depth, mask)
+    loss, logits = X.teacher_forced(sd, "generator.decoder.net", z, depth, enc, mask)
+    pred = V.decode_indices(sd, torch.argmax(logits, dim=-1), listener_cfg, prefix="listener_vq.")
+    total = loss + continuous_loss(pred, v_listener, mask)
+    out = (total, pred, logits, x, z)
+    if generate_steps:
+        gen = X.generate(sd, "generator.decoder.net", z[:, 0:1], generate_steps, depth, enc, mask, use_cache=False)
+        out = out + (gen,)
+    return out

@@ -65,9 +65,11 @@ def attend(q, k, v, key_mask=None, attn_mask=None, causal=False):
     return out.permute(0, 2, 1, 3).reshape(b, n, h * d)
 
 
-def attention_block(sd, p, x, context=None, key_mask=None, attn_mask=None, causal=False, cache=None, heads=HEADS):
+def attention_block(sd, p, x, context=None, key_mask=None, attn_mask=None, causal=False, cache=None, heads=None):
     """One Attention module.  `cache` = (k,v) of earlier positions for cached causal self-attention;
-    returns (out, (k,v))."""
+    returns (out, (k,v)).  heads: inner dim / 64 (x-transformers' dim_head default) unless given: 12 for DIM's SLM / SLMFT,
+    8 for the older ListenerGenerator (seq2seq.py:172-182)."""
+    heads = heads or sd[f"{p}.to_q.weight"].shape[0] // DIM_HEAD
     kv_in = x if context is None else context
     q = _split_heads(F.linear(x, sd[f"{p}.to_q.weight"]), heads)
     k = _split_heads(F.linear(kv_in, sd[f"{p}.to_k.weight"]), heads)
@@ -127,7 +129,7 @@ def decoder_layers(sd, p, x, depth, context, context_mask, caches=None, cross_kv
             ai += 1
         elif kind == "c":
             if cross_kv is not None:
-                q = _split_heads(F.linear(h, sd[f"{lp}.1.to_q.weight"]), HEADS)
+                q = _split_heads(F.linear(h, sd[f"{lp}.1.to_q.weight"]), sd[f"{lp}.1.to_q.weight"].shape[0] // DIM_HEAD)
                 k, v = cross_kv[ci]
                 out = F.linear(attend(q, k, v, key_mask=context_mask), sd[f"{lp}.1.to_out.weight"])
                 used_cross.append((k, v))

@@ -168,3 +168,14 @@ import json,sys; d=json.loads([l for l in sys.stdin if l.startswith(chr(123))][-
     done
   done
 fi
+if has gpab; then
+  for e in "X=1" "DIM_TC_NO_GROUPED_PLANES=1"; do
+    echo "== $e"
+    env $e timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-other-workloads 2>/dev/null | python -c "
+import json,sys; d=json.loads([l for l in sys.stdin if l.startswith(chr(123))][-1]); print('bf16', round(d['value']), round(d['ms_per_step'],1), 'parity', round(d['fp32_parity_mode']['value']), round(d['fp32_parity_mode']['ms_per_step'],1)); [print('   ',k) for k in d['kernels'][:4]]"
+  done
+fi
+if has lgen; then
+  timeout 900 python -m pytest tests/test_listener_generator_gpu.py tests/test_slm_gpu.py tests/test_slmft_gpu.py tests/test_compat_gpu.py -x -q > $OUT/${TAG}_lgen.log 2>&1; echo "exit $?" >> $OUT/${TAG}_lgen.log
+  tail -25 $OUT/${TAG}_lgen.log
+fi

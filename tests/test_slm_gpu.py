@@ -80,10 +80,3 @@ def test_slm_forward_matches_oracle(engines, slm_sd):
         assert float((p[k].cpu()[same] - ref_p[k][same]).abs().max()) < 1e-4
     if bool(((p["px_s"].cpu().argmax(-1) == ref_p["px_s"].argmax(-1)).all()) and ((p["px_l"].cpu().argmax(-1) == ref_p["px_l"].argmax(-1)).all())):
         assert abs(float(total) - float(ref_total)) < 5e-4
-
-
-def test_generate_refuses_a_positional_decoder(engines):
-    s2s, _, _ = engines
-    ctx = torch.zeros(9, 8, S2S.dec_dim, device="cuda")
-    with pytest.raises(RuntimeError, match="teacher-forced only"):
-        s2s.generate(ctx, torch.ones(9, 8, dtype=torch.bool, device="cuda"), torch.zeros(9, dtype=torch.int64, device="cuda"), 4)
