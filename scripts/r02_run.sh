@@ -179,3 +179,11 @@ if has lgen; then
   timeout 900 python -m pytest tests/test_listener_generator_gpu.py tests/test_slm_gpu.py tests/test_slmft_gpu.py tests/test_compat_gpu.py -x -q > $OUT/${TAG}_lgen.log 2>&1; echo "exit $?" >> $OUT/${TAG}_lgen.log
   tail -25 $OUT/${TAG}_lgen.log
 fi
+if has sanitize; then
+  # memcheck over the round-2 kernels on small shapes (the 2^20-token argmin cases and the long tests are deselected: memcheck is ~30x slower)
+  timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 20 python -m pytest -x -q \
+      tests/test_decode_mk_gpu.py tests/test_loader_gpu.py tests/test_vqspeaker_gpu.py tests/test_slm_gpu.py tests/test_listener_generator_gpu.py \
+      "tests/test_vq_argmin_tc_gpu.py" -k "not 1048576 and not 76800 and not small_batch_gemv" > $OUT/${TAG}_memcheck.log 2>&1
+  echo "exit $?" >> $OUT/${TAG}_memcheck.log
+  grep -E "ERROR SUMMARY|passed|failed|exit|Invalid|out of bounds" $OUT/${TAG}_memcheck.log | head -20
+fi
