@@ -72,7 +72,7 @@ class SLMFT(nn.Module):
         self.decoder_joint = TransformerWrapper(**dec_transformer_kwargs,
                                                 attn_layers=Decoder(dim=dim + dim_a, cross_attend=True, **dec_kwargs))
         self.decoder_joint = AutoregressiveWrapper(self.decoder_joint, ignore_index=-100, pad_value=0, mask_prob=0.15)
-        self.decoder_joint.bind(self._generate)
+        self.decoder_joint.bind(self._generate, self._teacher_forced)
 
         self._cfg, self._vq_cfg = S2SConfig(), VQConfig.from_cfg(config_listener)
         self._engines, self._fp = None, None
@@ -95,6 +95,9 @@ class SLMFT(nn.Module):
                              VQEngine(h, self._vq_cfg, prefix="listener_vq.", precision=vq_prec))
             self._fp = fp
         return self._engines
+
+    def _teacher_forced(self, context, context_mask, inp, kv_mask):
+        return self.engines()[0].teacher_forced(context.contiguous(), context_mask, inp, kv_mask)
 
     def _generate(self, prompts, seq_len, temperature=1.0, context=None, context_mask=None, uniforms=None):
         s2s, _ = self.engines()
@@ -180,6 +183,7 @@ class SLM(SLMFT):
         kw.update(emb_dropout=0, scaled_sinu_pos_emb=False, use_abs_pos_emb=True)                      # :135-137
         self.decoder_joint = AutoregressiveWrapper(TransformerWrapper(**kw, attn_layers=Decoder(dim=dim + dim_a, cross_attend=True, **dec_kwargs)),
                                                    ignore_index=-100, pad_value=0)                     # :163-165 (mask_prob default 0)
+        self.decoder_joint.bind(self._generate, self._teacher_forced)
         self.mask_speaker = self.mask_listener = None
         self.last_parts = None
 

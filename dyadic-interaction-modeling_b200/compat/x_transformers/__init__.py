@@ -91,9 +91,12 @@ class AutoregressiveWrapper(nn.Module):
         self.net, self.ignore_index, self.pad_value, self.mask_prob = net, ignore_index, pad_value, mask_prob
         self.max_seq_len = net.max_seq_len
         self._generate_impl = None
+        self._forward_impl = None
 
-    def bind(self, fn):
+    def bind(self, fn, forward_fn=None):
         self._generate_impl = fn
+        if forward_fn is not None:
+            self._forward_impl = forward_fn
 
     @torch.no_grad()
     def generate(self, prompts, seq_len, eos_token=None, temperature=1.0, filter_logits_fn=None, filter_thres=0.9,
@@ -103,8 +106,23 @@ class AutoregressiveWrapper(nn.Module):
         return self._generate_impl(prompts, seq_len, temperature=temperature, context=context, context_mask=context_mask,
                                    uniforms=uniforms)
 
-    def forward(self, x, return_outputs=False, **kwargs):
-        raise NotImplementedError("teacher-forced forward (training) is outside the inference hot path (SURVEY.md 8(f).2)")
+    @torch.no_grad()
+    def forward(self, x, return_outputs=False, context=None, context_mask=None, self_attn_kv_mask=None, **kwargs):
+        """AutoregressiveWrapper.forward(x, context=, context_mask=, return_outputs=) -> loss [, (logits, cache=None)]: teacher forcing
+        through the owning model's engine (dim_slmft_teacher_forced).  inp = x[:, :-1] with ignore_index -> pad_value, target =
+        x[:, 1:], cross-entropy with ignore_index; the random key mask of mask_prob > 0 is drawn like upstream unless
+        `self_attn_kv_mask` (B, L-1) is given.  Forward only: the loss carries no autograd graph."""
+        if self._forward_impl is None:
+            raise RuntimeError("AutoregressiveWrapper.forward needs the owning model (engine binding)")
+        inp, target = x[:, :-1].clone(), x[:, 1:]
+        inp[inp == self.ignore_index] = self.pad_value
+        kv = self_attn_kv_mask
+        if kv is None and self.mask_prob > 0:
+            from dim_b200.compat_api import draw_kv_mask
+            kv = draw_kv_mask(inp.shape, self.mask_prob, inp.device)
+        logits = self._forward_impl(context, context_mask, inp, kv)
+        loss = torch.nn.functional.cross_entropy(logits.transpose(1, 2), target, ignore_index=self.ignore_index)
+        return (loss, (logits, None)) if return_outputs else loss
 
 
 class ContinuousAutoregressiveWrapper(nn.Module):      # imported by the reference, never instantiated by SLMFT

@@ -209,27 +209,50 @@ __device__ __forceinline__ void split_store4(__nv_bfloat16* base, int r, int c, 
     *reinterpret_cast<uint2*>(base + ((size_t)pl * 64 + r) * PITCH + c) = make_uint2(lo[pl], hi[pl]);
 }
 
-template <int DH, int NP>
+__device__ __forceinline__ void cp_async_16_zf(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+
+// IN16 (NP == 1 only): q/k/v are the bf16 output of the QKV GEMM.  The tiles go global -> shared memory with cp.async (no register
+// staging, no conversion), K/V double-buffered: half the bytes of the fp32 round trip, ~64 registers fewer.  The values are the same
+// bf16 roundings the fp32 path produces on the fly, so the result is bit-identical.
+template <int DH, int NP, bool IN16>
 __global__ void __launch_bounds__(128) attn_prefill_mma(const AttnArgs p) {
+  static_assert(!IN16 || NP == 1, "bf16 inputs are the plain-bf16 mode");
   constexpr int PITCH = DH + 8;                       // bf16 elements per smem row: 16-byte aligned, conflict-free ldmatrix
   constexpr int KC = DH / 16;                         // k-chunks of the QK^T product
   constexpr int ONT = DH / 8;                         // 8-column n-tiles of the output
-  constexpr int F4 = 64 * DH / 4 / 128;               // float4 per thread per 64-row tile
+  constexpr int F4 = IN16 ? 1 : 64 * DH / 4 / 128;    // float4 per thread per 64-row tile (fp32 inputs)
+  constexpr int NBUF = IN16 ? 2 : 1;
+  constexpr int TILE = NP * 64 * PITCH;               // elements of one staged tile
   extern __shared__ __align__(16) uint8_t smem_mma[];
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_mma);      // [NP][64][PITCH]
-  __nv_bfloat16* Ks = Qs + NP * 64 * PITCH;
-  __nv_bfloat16* Vs = Ks + NP * 64 * PITCH;
+  __nv_bfloat16* Ks = Qs + TILE;                                       // [NBUF][NP][64][PITCH]
+  __nv_bfloat16* Vs = Ks + NBUF * TILE;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 64;
   const float* qb = p.q + (size_t)b * p.Tq * p.ldq + h * DH;
   const float* kb = p.k + (size_t)b * p.Tk * p.ldk + h * DH;
   const float* vb = p.v + (size_t)b * p.Tk * p.ldv + h * DH;
+  const __nv_bfloat16* qh = reinterpret_cast<const __nv_bfloat16*>(p.q) + (size_t)b * p.Tq * p.ldq + h * DH;     // IN16 views
+  const __nv_bfloat16* kh = reinterpret_cast<const __nv_bfloat16*>(p.k) + (size_t)b * p.Tk * p.ldk + h * DH;
+  const __nv_bfloat16* vh = reinterpret_cast<const __nv_bfloat16*>(p.v) + (size_t)b * p.Tk * p.ldv + h * DH;
   const int klen = p.lens ? min(__ldg(p.lens + b), p.Tk) : p.Tk;
   const uint8_t* km = p.key_mask ? p.key_mask + (size_t)b * p.Tk : nullptr;
 
   int nkt = (klen + 63) / 64;
   if (p.causal) nkt = min(nkt, (min(q0 + 64, p.Tq) - 1) / 64 + 1);
+
+  // IN16: 64 rows x DH bf16 of a row-major matrix -> a staged tile, rows >= limit zero-filled
+  auto fill16 = [&](const __nv_bfloat16* src, int ld, int row0, int limit, __nv_bfloat16* dst) {
+    constexpr int CPR = DH / 8;                       // 16-byte chunks per row
+    for (int i = tid; i < 64 * CPR; i += 128) {
+      const int r = i / CPR, c = (i - r * CPR) * 8;
+      const bool ok = row0 + r < limit;
+      cp_async_16_zf((uint32_t)__cvta_generic_to_shared(dst + r * PITCH + c), ok ? src + (size_t)(row0 + r) * ld + c : src, ok ? 16u : 0u);
+    }
+  };
 
   float4 kreg[F4], vreg[F4];
   auto load_kv = [&](int kt) {
@@ -244,13 +267,19 @@ __global__ void __launch_bounds__(128) attn_prefill_mma(const AttnArgs p) {
       }
     }
   };
-  if (nkt > 0) load_kv(0);
+  if constexpr (IN16) {
+    fill16(qh, p.ldq, q0, p.Tq, Qs);
+    if (nkt > 0) { fill16(kh, p.ldk, 0, klen, Ks); fill16(vh, p.ldv, 0, klen, Vs); }
+    cp_async_commit();
+  } else {
+    if (nkt > 0) load_kv(0);
 #pragma unroll
-  for (int u = 0; u < F4; ++u) {
-    const int i = tid + 128 * u, r = i / (DH / 4), c = (i % (DH / 4)) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q0 + r < p.Tq) v = *reinterpret_cast<const float4*>(qb + (size_t)(q0 + r) * p.ldq + c);
-    split_store4<NP, PITCH>(Qs, r, c, v);
+    for (int u = 0; u < F4; ++u) {
+      const int i = tid + 128 * u, r = i / (DH / 4), c = (i % (DH / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q0 + r < p.Tq) v = *reinterpret_cast<const float4*>(qb + (size_t)(q0 + r) * p.ldq + c);
+      split_store4<NP, PITCH>(Qs, r, c, v);
+    }
   }
 
   float o[ONT][4];
@@ -265,17 +294,29 @@ __global__ void __launch_bounds__(128) attn_prefill_mma(const AttnArgs p) {
   const int bk_row = (lane & 7) + (lane >> 4) * 8, bk_col = ((lane >> 3) & 1) * 8;               // B of S (K rows = keys): two n-tiles per x4
   const int bv_row = (lane & 7) + ((lane >> 3) & 1) * 8, bv_col = (lane >> 4) * 8;               // B of PV (V rows = keys, transposed): two n-tiles per x4
 
+  const uint32_t ks_base = ks_u, vs_base = vs_u;
   for (int kt = 0; kt < nkt; ++kt) {
     const int k0 = kt * 64;
-    __syncthreads();                                  // previous tile fully consumed (first pass: nothing to wait for)
+    if constexpr (IN16) {
+      cp_async_wait<0>();                             // tile kt (and Q) have landed
+      __syncthreads();                                // ... for every thread; buffer (kt + 1) & 1 is no longer being read
+      if (kt + 1 < nkt) {
+        fill16(kh, p.ldk, (kt + 1) * 64, klen, Ks + ((kt + 1) & 1) * TILE);
+        fill16(vh, p.ldv, (kt + 1) * 64, klen, Vs + ((kt + 1) & 1) * TILE);
+        cp_async_commit();
+      }
+    } else {
+      __syncthreads();                                // previous tile fully consumed (first pass: nothing to wait for)
 #pragma unroll
-    for (int u = 0; u < F4; ++u) {
-      const int i = tid + 128 * u, r = i / (DH / 4), c = (i % (DH / 4)) * 4;
-      split_store4<NP, PITCH>(Ks, r, c, kreg[u]);
-      split_store4<NP, PITCH>(Vs, r, c, vreg[u]);
+      for (int u = 0; u < F4; ++u) {
+        const int i = tid + 128 * u, r = i / (DH / 4), c = (i % (DH / 4)) * 4;
+        split_store4<NP, PITCH>(Ks, r, c, kreg[u]);
+        split_store4<NP, PITCH>(Vs, r, c, vreg[u]);
+      }
+      __syncthreads();
+      if (kt + 1 < nkt) load_kv(kt + 1);              // in flight during the MMAs below
     }
-    __syncthreads();
-    if (kt + 1 < nkt) load_kv(kt + 1);                // in flight during the MMAs below
+    const uint32_t ks_u = ks_base + (IN16 ? (uint32_t)((kt & 1) * TILE * 2) : 0u), vs_u = vs_base + (IN16 ? (uint32_t)((kt & 1) * TILE * 2) : 0u);
 
     // ---- S = Q K^T : 16 rows x 64 keys per warp
     float s[8][4];
@@ -740,6 +781,7 @@ int launch_attention_prefill(const AttnArgs& a, cudaStream_t s) {
   DIM_REQUIRE(a.Dh == 48 || a.Dh == 64 || a.Dh == 96, "attention: head dim must be 48, 64 or 96");
   DIM_REQUIRE(a.B > 0 && a.H > 0 && a.Tq > 0 && a.Tk > 0, "attention: empty");
   DIM_REQUIRE(a.ldq % 4 == 0 && a.ldk % 4 == 0 && a.ldv % 4 == 0, "attention: leading dims must be multiples of 4");
+  DIM_REQUIRE(!a.in_bf16 || (a.out_p != nullptr && a.planes == 1), "attention: bf16 inputs are served by the tensor-core kernel only");
   dim3 grid(cdiv(a.Tq, TQ), a.H, a.B);
   // algorithmic: read q,k,v once, write out once; QK^T and PV (causal: half)
   ProfScope ps(CAT_ATTN_PREFILL, s, 4.0 * a.B * a.H * a.Dh * (2.0 * a.Tq + 2.0 * a.Tk),
@@ -751,12 +793,15 @@ int launch_attention_prefill(const AttnArgs& a, cudaStream_t s) {
     typedef void (*Kern)(const AttnArgs);
     const int np = a.planes;
     // 48: VQAutoEncoder (384 / 8 heads), 64: x-transformers, 96: VQSpeakerAutoEncoder (768 / 8 heads, stage1_BIWI.py:140)
-    Kern kern = a.Dh == 48 ? (np == 1 ? (Kern)attn_prefill_mma<48, 1> : (Kern)attn_prefill_mma<48, 3>)
-              : a.Dh == 64 ? (np == 1 ? (Kern)attn_prefill_mma<64, 1> : (Kern)attn_prefill_mma<64, 3>)
-                           : (np == 1 ? (Kern)attn_prefill_mma<96, 1> : (Kern)attn_prefill_mma<96, 3>);
-    const size_t smem = (size_t)3 * np * 64 * (a.Dh + 8) * sizeof(__nv_bfloat16);
-    static PerDeviceOnce configured[6];
-    const int slot = (a.Dh == 48 ? 0 : a.Dh == 64 ? 2 : 4) + (np == 1 ? 0 : 1);
+    const bool in16 = a.in_bf16 != 0;
+    DIM_REQUIRE(!in16 || np == 1, "attention: bf16 inputs need the plain-bf16 mode (planes == 1)");
+    DIM_REQUIRE(!in16 || (a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0), "attention: bf16 rows must be 16-byte aligned");
+    Kern kern = a.Dh == 48 ? (np == 1 ? (in16 ? (Kern)attn_prefill_mma<48, 1, true> : (Kern)attn_prefill_mma<48, 1, false>) : (Kern)attn_prefill_mma<48, 3, false>)
+              : a.Dh == 64 ? (np == 1 ? (in16 ? (Kern)attn_prefill_mma<64, 1, true> : (Kern)attn_prefill_mma<64, 1, false>) : (Kern)attn_prefill_mma<64, 3, false>)
+                           : (np == 1 ? (in16 ? (Kern)attn_prefill_mma<96, 1, true> : (Kern)attn_prefill_mma<96, 1, false>) : (Kern)attn_prefill_mma<96, 3, false>);
+    const size_t smem = (size_t)(in16 ? 5 : 3) * np * 64 * (a.Dh + 8) * sizeof(__nv_bfloat16);
+    static PerDeviceOnce configured[9];
+    const int slot = (a.Dh == 48 ? 0 : a.Dh == 64 ? 3 : 6) + (np == 1 ? (in16 ? 2 : 0) : 1);
     if (configured[slot].first()) DIM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3(cdiv(a.Tq, 64), a.H, a.B), 128, smem, s>>>(a);
     DIM_LAUNCHED();

@@ -7,6 +7,8 @@ namespace dimb {
 struct AttnArgs {
   const float *q = nullptr, *k = nullptr, *v = nullptr;   // element (b=0,t=0,h=0,d=0); rows ld* apart; head h at h*Dh
   int ldq = 0, ldk = 0, ldv = 0;
+  int in_bf16 = 0;                                        // 1: q/k/v point to bf16 data (ld* in bf16 elements): the QKV GEMM's bf16 output,
+                                                          //    plain-bf16 mode only (planes == 1, tensor-core kernel)
   float* out = nullptr; int ldo = 0;                      // (B,Tq,H*Dh)  (nullable when out_p is given)
   __nv_bfloat16* out_p = nullptr; int planes = 0, kp = 0; // optional bf16-plane copy [B*Tq, planes*kp] for the next GEMM
   const uint8_t* key_mask = nullptr;                      // (B,Tk) 1 = keep  (masked -> -FLT_MAX)

@@ -266,14 +266,23 @@ int vq_trunk(const VqModel& m, const std::vector<VqLayer>& layers, const float* 
   for (const VqLayer& L : layers) {
     if (int e = launch_layer_norm(w.x, L.ln1_g, L.ln1_b, tcp ? nullptr : w.ln, nullptr, R, H, 1e-5f, s, tcp ? w.ap : nullptr, P, H))
       return e;
+    static const bool qkv_fp32 = getenv("DIM_ATTN_QKV_FP32") != nullptr;
+    const bool q16 = tcp && P == 1 && !qkv_fp32;        // plain-bf16 mode: bf16 QKV straight into the attention kernel (see xt_encoder_forward)
+    __nv_bfloat16* qkv16 = reinterpret_cast<__nv_bfloat16*>(w.qkv);
     {
       GemmArgs a;
-      a.A = w.ln; a.lda = H; a.Ap = tcp ? w.ap : nullptr; a.W = L.wqkv; a.C = w.qkv; a.ldc = 3 * H; a.M = R; a.N = 3 * H; a.K = H;
+      a.A = w.ln; a.lda = H; a.Ap = tcp ? w.ap : nullptr; a.W = L.wqkv; a.M = R; a.N = 3 * H; a.K = H;
+      if (q16) { a.Cb = qkv16; a.ldcb = 3 * H; } else { a.C = w.qkv; a.ldc = 3 * H; }
       if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
     }
     {
       AttnArgs a;                      // 'b n (qkv h d)': q at col 0, k at H, v at 2H
       a.q = w.qkv; a.k = w.qkv + H; a.v = w.qkv + 2 * H; a.ldq = a.ldk = a.ldv = 3 * H;
+      if (q16) {
+        a.in_bf16 = 1;
+        a.q = reinterpret_cast<const float*>(qkv16); a.k = reinterpret_cast<const float*>(qkv16 + H);
+        a.v = reinterpret_cast<const float*>(qkv16 + 2 * H);
+      }
       a.out = tcp ? nullptr : w.att; a.ldo = H; a.out_p = tcp ? w.ap : nullptr; a.planes = P; a.kp = H;
       a.lens = lens; a.B = B; a.H = c.heads; a.Tq = T; a.Tk = T; a.Dh = Dh;
       a.scale = 1.0f / sqrtf((float)H);          // hidden_size**-0.5, not head_dim
@@ -396,15 +405,26 @@ int xt_encoder_forward(const S2SModel& m, const XtEncoder& E, const float* in, c
     const XtFF& FF = E.ff[l];
     if (int e = launch_layer_norm(w.x, A.norm_g, A.norm_b, tcp ? nullptr : w.ln, nullptr, R, D, 1e-5f, s, tcp ? w.ap : nullptr, P, D))
       return e;
+    // plain-bf16 mode: the QKV GEMM writes bf16 and the attention kernel stages it with cp.async -- the same roundings the fp32
+    // round trip produced inside the attention kernel, at half the bytes (DIM_ATTN_QKV_FP32=1: A/B hook)
+    static const bool qkv_fp32 = getenv("DIM_ATTN_QKV_FP32") != nullptr;
+    const bool q16 = tcp && P == 1 && !qkv_fp32;
+    __nv_bfloat16* qkv16 = reinterpret_cast<__nv_bfloat16*>(w.qkv);
     {
       GemmArgs a;
-      a.A = w.ln; a.lda = D; a.Ap = tcp ? w.ap : nullptr; a.W = A.wqkv; a.C = w.qkv; a.ldc = 3 * inner; a.M = R; a.N = 3 * inner;
+      a.A = w.ln; a.lda = D; a.Ap = tcp ? w.ap : nullptr; a.W = A.wqkv; a.M = R; a.N = 3 * inner;
       a.K = D;
+      if (q16) { a.Cb = qkv16; a.ldcb = 3 * inner; } else { a.C = w.qkv; a.ldc = 3 * inner; }
       if (int e = run_gemm(m.tc, a, w.ap, s)) return e;
     }
     {
       AttnArgs a;
       a.q = w.qkv; a.k = w.qkv + inner; a.v = w.qkv + 2 * inner; a.ldq = a.ldk = a.ldv = 3 * inner;
+      if (q16) {
+        a.in_bf16 = 1;
+        a.q = reinterpret_cast<const float*>(qkv16); a.k = reinterpret_cast<const float*>(qkv16 + inner);
+        a.v = reinterpret_cast<const float*>(qkv16 + 2 * inner);
+      }
       a.out = tcp ? nullptr : w.att; a.ldo = inner; a.out_p = tcp ? w.ap : nullptr; a.planes = P; a.kp = inner;
       a.key_mask = mask; a.B = B; a.H = c.heads; a.Tq = T; a.Tk = T; a.Dh = c.dim_head;
       a.scale = 1.0f / sqrtf((float)c.dim_head); a.causal = causal;

@@ -69,14 +69,16 @@ __device__ __noinline__ float4 tc_tab_add(const GemmArgs& e, float4 o, int row, 
   o.z = __fadd_rn(o.z, __fmul_rn(t.z, sc)); o.w = __fadd_rn(o.w, __fmul_rn(t.w, sc));
   return o;
 }
+// plain bf16 copy of the result (cross-attention K/V rows; the bf16 QKV rows of the plain-bf16 prefill attention): inline -- six
+// instructions; the plane split below stays out of line (instruction-cache footprint of the epilogue, see the header)
+__device__ __forceinline__ void tc_emit_bf16(const GemmArgs& e, float4 o, int row, int col) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&lo);
+  pk.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(e.Cb + (size_t)row * e.ldcb + col) = pk;
+}
 __device__ __noinline__ void tc_emit_narrow(const GemmArgs& e, float4 o, int row, int col) {
-  if (e.Cb) {
-    __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&lo);
-    pk.y = *reinterpret_cast<uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(e.Cb + (size_t)row * e.ldcb + col) = pk;
-  }
   if (e.Cp) {
     __nv_bfloat16* dst = e.Cp + (size_t)row * e.cp_planes * e.cp_kp + col;
     float v[4] = {o.x, o.y, o.z, o.w};
@@ -243,7 +245,6 @@ __global__ void __launch_bounds__(192) gemm_bf16_tcgen05(const __grid_constant__
       float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
       const int stride = 6 * RPI;
-      const bool narrow = e.Cb != nullptr || e.Cp != nullptr;
 #pragma unroll 1
       for (int r0 = row_begin + warp * RPI + lane / LPR; r0 < row_end; r0 += stride * RB) {
         float4 acc[RB], res[RB];
@@ -301,7 +302,8 @@ __global__ void __launch_bounds__(192) gemm_bf16_tcgen05(const __grid_constant__
           o.x = __fadd_rn(o.x, res[u].x); o.y = __fadd_rn(o.y, res[u].y);
           o.z = __fadd_rn(o.z, res[u].z); o.w = __fadd_rn(o.w, res[u].w);
           if (e.C) *reinterpret_cast<float4*>(e.C + (size_t)row * e.ldc + col) = o;
-          if (narrow) tc_emit_narrow(e, o, row, col);
+          if (e.Cb) tc_emit_bf16(e, o, row, col);
+          if (e.Cp) tc_emit_narrow(e, o, row, col);
         }
       }
     }

@@ -187,3 +187,10 @@ if has sanitize; then
   echo "exit $?" >> $OUT/${TAG}_memcheck.log
   grep -E "ERROR SUMMARY|passed|failed|exit|Invalid|out of bounds" $OUT/${TAG}_memcheck.log | head -20
 fi
+if has q16ab; then
+  for e in "X=1" "DIM_ATTN_QKV_FP32=1"; do
+    echo "== $e"
+    env $e timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-other-workloads --no-parity-leg 2>/dev/null | python -c "
+import json,sys; d=json.loads([l for l in sys.stdin if l.startswith(chr(123))][-1]); print('bf16', round(d['value']), round(d['ms_per_step'],1)); [print('   ',k) for k in d['kernels'][:5]]"
+  done
+fi

@@ -124,3 +124,28 @@ def test_slm_pretraining_class_forward(compat, tmp_path):
     for k in ("l_ce_s", "l_ce_l", "nce"):
         assert abs(float(d[k]) - float(ref_d[k])) < 1e-4, k
     assert torch.isfinite(total)
+
+
+def test_autoregressive_wrapper_forward_delegates(compat, slmft_sd, tmp_path):
+    """decoder_joint(z, context=, context_mask=, return_outputs=True) (seq2seq_pretrain.py:448) on the stand-in wrapper: the teacher-
+    forced loss / logits of the owning model's engine, equal to forward_decoder(mode='train') with the same key mask."""
+    import shutil
+    shutil.copy(os.path.join(COMPAT, "config.yaml"), tmp_path / "config.yaml")
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        model = compat["s2s"].SLMFT(load_vq_checkpoints=False).to("cuda:0")
+    finally:
+        os.chdir(cwd)
+    model.load_state_dict(slmft_sd)
+    model.eval()
+    c = dim_b200.synth.make_clips(2, 20, seed=3, ragged=True)
+    m = c["mask"].cuda()
+    x_s = model.forward_encoder(c["v_speaker"].cuda(), m)
+    ctx = torch.cat([x_s + model.patch_embed_dec_s, c["v_audio"].cuda()], dim=-1)
+    _, z_l = model.forward_vq(c["v_speaker"].cuda(), c["v_listener"].cuda(), m)
+    kv = torch.ones(2, 19, dtype=torch.bool, device="cuda")
+    loss, (logits, cache) = model.decoder_joint(z_l, context=ctx, context_mask=m, return_outputs=True, self_attn_kv_mask=kv)
+    model.train_kv_mask = kv
+    ref_loss, ref_logits = model.forward_decoder(x_s, z_l, c["v_audio"].cuda(), m, "train")
+    assert cache is None and torch.equal(logits, ref_logits) and float(loss) == float(ref_loss)
