@@ -303,7 +303,17 @@ __global__ void __launch_bounds__(192) gemm_bf16_tcgen05(const __grid_constant__
           o.z = __fadd_rn(o.z, res[u].z); o.w = __fadd_rn(o.w, res[u].w);
           if (e.C) *reinterpret_cast<float4*>(e.C + (size_t)row * e.ldc + col) = o;
           if (e.Cb) tc_emit_bf16(e, o, row, col);
-          if (e.Cp) tc_emit_narrow(e, o, row, col);
+          if (e.Cp) {
+            if (e.cp_planes == 1) {                     // one plane = a plain bf16 row: the inline store (plain-bf16 FF1 -> FF2 operand)
+              __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+              uint2 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&lo);
+              pk.y = *reinterpret_cast<uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(e.Cp + (size_t)row * e.cp_kp + col) = pk;
+            } else {
+              tc_emit_narrow(e, o, row, col);
+            }
+          }
         }
       }
     }
