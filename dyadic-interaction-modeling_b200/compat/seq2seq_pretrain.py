@@ -222,10 +222,148 @@ class SLM(SLMFT):
         return total, d, None
 
 
-class SpeakerSLMFT(nn.Module):
-    """Name kept so that `from seq2seq_pretrain import SLMFT, SpeakerSLMFT` (test_s2s_pretrain.py:7) resolves.  The BIWI speaker
-    model (seq2seq_pretrain.py:516-757, 70110-d vertex head) is a sibling model outside the listener hot path."""
+def _mesh_modules(owner, size, dim=56):
+    """The converter's modules with the reference's names (seq2seq_pretrain.py:777-813); parameter containers only."""
+    owner.vertice_mapping = nn.Sequential(nn.Linear(size, dim), nn.LeakyReLU(0.2, True))
+    owner.squasher = nn.Sequential(nn.Sequential(nn.Conv1d(dim, dim, 5, stride=1, padding=2, padding_mode="replicate"),
+                                                 nn.LeakyReLU(0.2, True), nn.InstanceNorm1d(dim, affine=False)))
+    lstm = lambda: nn.LSTM(input_size=dim, hidden_size=384, num_layers=2, batch_first=True, bidirectional=True)
+    head = lambda: nn.Sequential(nn.Linear(768, 768), nn.LeakyReLU(0.2, True), nn.Linear(768, size))
+    owner.vertice_map_reverse_lstm, owner.vertice_map_reverse_lstm_2 = lstm(), lstm()
+    owner.vertice_map_reverse, owner.vertice_map_reverse2 = head(), head()
 
-    def __init__(self, *a, **k):
+
+def _mesh_head(owner, which="emoca"):
+    lstm, head = (owner.vertice_map_reverse_lstm, owner.vertice_map_reverse) if which == "emoca" else \
+        (owner.vertice_map_reverse_lstm_2, owner.vertice_map_reverse2)
+    return dict(lstm.named_parameters()), head[0].weight, head[0].bias, head[2].weight, head[2].bias
+
+
+class EmocaConverter(nn.Module):
+    """seq2seq_pretrain.EmocaConverter (reference: code/seq2seq_pretrain.py:759-825) on the B200 kernels: the frozen 56-d speaker
+    VQ-VAE followed by the 2-layer bidirectional LSTM(384) and the 768 -> 768 -> 70110 vertex head.  Same module names and
+    state_dict keys; forward(inputs, template, v_speaker) -> (outputs (B,T,size), None) like :815-832 (`inputs` is unused there too).
+    `size` exposes the hard-coded 70110 (:775) for small tests."""
+    precision = PREC_FP32_TC
+
+    def __init__(self, config_path="./config.yaml", model_speaker_pth="./runs_speaker_new/_RANK0/model/model.pth.tar",
+                 load_vq_checkpoints=True, size=70110):
         super().__init__()
-        raise NotImplementedError("SpeakerSLMFT (BIWI speaker mesh model) is outside the hot path built here (SURVEY 8(f).4)")
+        config_speaker = config.load_cfg_from_cfg_file(config_path)
+        model_speaker = get_model(config_speaker)
+        if load_vq_checkpoints:
+            ckpt = torch.load(model_speaker_pth, map_location=lambda storage, loc: storage.cpu())
+            load_state_dict(model_speaker, ckpt["state_dict"])
+            print("Load models successfully")
+        self.speaker_face_quan_num, self.speaker_zquant_dim = config_speaker.face_quan_num, config_speaker.zquant_dim
+        self.speaker_vq = model_speaker.eval()
+        for p in self.speaker_vq.parameters():
+            p.requires_grad = False
+        _mesh_modules(self, size)
+        self.criterion = nn.MSELoss()
+
+    def forward_motion(self, inputs, template):
+        """vertice_mapping + squasher on (inputs - template) (the lines commented out at :817-819; live in SpeakerSLMFT :710-713)."""
+        return compat_api.mesh_to_motion(inputs.float(), template.float(), self.vertice_mapping[0].weight, self.vertice_mapping[0].bias,
+                                         self.squasher[0][0].weight, self.squasher[0][0].bias)
+
+    @torch.no_grad()
+    def forward(self, inputs, template, v_speaker):
+        self.speaker_vq.precision = PREC_FP32 if self.precision == PREC_FP32 else PREC_FP32_TC
+        dec, _, _ = self.speaker_vq(v_speaker)                                           # :820
+        return compat_api.motion_to_mesh(dec, *_mesh_head(self), template=template.float()), None
+
+
+class SpeakerSLMFT(nn.Module):
+    """seq2seq_pretrain.SpeakerSLMFT (reference: code/seq2seq_pretrain.py:516-757), forward only, on the B200 kernels: listener-VQ
+    codes of the speaker's EMOCA coefficients -> decoder_joint (teacher forced in mode='train', generate otherwise) over
+    cat(speaker embedding | zeros, audio) -> speaker-VQ decode -> LSTM + vertex head -> losses.  Same module names / state_dict
+    keys as the reference (its three encoders and patch embeddings exist and are never called in forward, like there).
+    Paths the reference hard-codes are constructor arguments with its values as defaults; `mouth_map` (list of vertex ids) replaces
+    reading ../data/CodeTalker/BIWI/regions/lve.txt when given.  NOTE (:738-739): the mouth loss drops one row of the FLATTENED
+    batch, so like the reference the call only works for B == 1 (or when torch can broadcast the two row counts)."""
+    precision = PREC_FP32_TC
+
+    def __init__(self, config_path="./config.yaml", model_speaker_pth="./runs_speaker_new/_RANK0/model/model.pth.tar",
+                 model_listener_pth="./runs/listener_exp/model/model.pth.tar", model_converter_path="./best_converter.pt",
+                 mouth_map_path="../data/CodeTalker/BIWI/regions/lve.txt", load_checkpoints=True, size=70110, mouth_map=None):
+        super().__init__()
+        cfg_s, cfg_l = config.load_cfg_from_cfg_file(config_path), config.load_cfg_from_cfg_file(config_path)
+        model_speaker, model_listener = get_model(cfg_s), get_model(cfg_l)
+        _mesh_modules(self, size)
+        if load_checkpoints:
+            to_cpu = lambda storage, loc: storage.cpu()
+            load_state_dict(model_speaker, torch.load(model_speaker_pth, map_location=to_cpu)["state_dict"])
+            load_state_dict(model_listener, torch.load(model_listener_pth, map_location=to_cpu)["state_dict"])
+            print("Load models successfully")
+            conv = torch.load(model_converter_path, map_location=to_cpu)                  # EmocaConverter state_dict (:549-552)
+            own = {k: v for k, v in conv.items() if not k.startswith("speaker_vq.")}
+            self.load_state_dict(own, strict=False)
+        self.speaker_face_quan_num, self.speaker_zquant_dim = cfg_s.face_quan_num, cfg_s.zquant_dim
+        self.listener_vq, self.speaker_vq = model_listener.eval(), model_speaker.eval()
+        for p in list(self.listener_vq.parameters()) + list(self.speaker_vq.parameters()):
+            p.requires_grad = False
+
+        dim_in, dim, enc_max_seq_len, dim_a = 56, 384, 2048, 768
+        enc_kwargs = {"depth": 4, "heads": 12, "max_seq_len": 2048}
+        dec_kwargs = {"depth": 4, "heads": 12, "max_seq_len": 2048, "num_tokens": 512}
+        kw = pick_and_pop(["num_tokens", "max_seq_len"], dec_kwargs)  # noqa: F405
+        kw.update(emb_dropout=0, scaled_sinu_pos_emb=False, use_abs_pos_emb=True)          # :587-589
+        mk_enc = lambda d_in: ContinuousTransformerWrapper(dim_in=d_in, dim_out=dim, max_seq_len=enc_max_seq_len,
+                                                           attn_layers=Encoder(dim=dim, **enc_kwargs))
+        self.encoder_s, self.encoder_l, self.encoder_joint = mk_enc(dim_in), mk_enc(dim_in), mk_enc(dim)
+        self.patch_embed_s = nn.Parameter(torch.zeros(1, 1, dim_in))
+        self.patch_embed_l = nn.Parameter(torch.zeros(1, 1, dim_in))
+        self.patch_embed_dec_s = nn.Parameter(torch.zeros(1, 1, dim))
+        self.patch_embed_dec_l = nn.Parameter(torch.zeros(1, 1, dim))
+        self.norm_s, self.norm_l, self.norm = nn.LayerNorm(dim), nn.LayerNorm(dim), nn.LayerNorm(dim)
+        self.decoder_joint = AutoregressiveWrapper(TransformerWrapper(**kw, attn_layers=Decoder(dim=dim + dim_a, cross_attend=True, **dec_kwargs)),
+                                                   ignore_index=-100, pad_value=0)
+        self.mse_loss = nn.MSELoss()
+        if mouth_map is None:
+            with open(mouth_map_path) as f:
+                mouth_map = [int(i) for i in f.read().split(", ")]
+        self.mouth_map = list(mouth_map)
+        self.W = nn.Parameter(torch.randn(2))
+        self.speaker_embed = nn.Embedding(15, 384)
+
+        self._cfg, self._vq_cfg = S2SConfig(), VQConfig.from_cfg(cfg_l)
+        self._engines, self._fp = None, None
+        self.greedy, self.decode_uniforms, self.last_parts = False, None, None
+
+    def engines(self):
+        fp = fingerprint(self)
+        if self._engines is None or fp != self._fp:
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("SpeakerSLMFT runs on CUDA only (sm_100a kernels, no CPU fallback): call .to('cuda') first")
+            h = Handle(dev.index)
+            h.register(self.state_dict())
+            vq_prec = PREC_FP32 if self.precision == PREC_FP32 else PREC_FP32_TC
+            self._engines = (SLMFTEngine(h, self._cfg, precision=self.precision),
+                             VQEngine(h, self._vq_cfg, prefix="speaker_vq.", precision=vq_prec),
+                             VQEngine(h, self._vq_cfg, prefix="listener_vq.", precision=vq_prec))
+            self._mouth = torch.as_tensor(self.mouth_map, dtype=torch.long, device=dev)
+            self._fp = fp
+        return self._engines
+
+    def forward_motion(self, v_speaker, template):
+        """:710-713: vertice_mapping + squasher (their result only feeds the dead z_s in forward)."""
+        return compat_api.mesh_to_motion(v_speaker.float(), template.float(), self.vertice_mapping[0].weight, self.vertice_mapping[0].bias,
+                                         self.squasher[0][0].weight, self.squasher[0][0].bias)
+
+    def forward_vq_decoder(self, logits_s, type="emoca", mode="train"):
+        _, vq_s, _ = self.engines()
+        codes = torch.argmax(logits_s, dim=-1) if mode == "train" else logits_s
+        pred_emoca = vq_s.decode(codes=codes.contiguous())
+        return compat_api.motion_to_mesh(pred_emoca, *_mesh_head(self, type)), pred_emoca
+
+    def forward(self, v_speaker, v_speaker_emoca, v_audio, mask, template, mode="train", speaker_ids=None):
+        s2s, vq_s, vq_l = self.engines()
+        rows = None if speaker_ids is None else self.speaker_embed.weight.detach()[speaker_ids]
+        uniforms = None if self.greedy else self.decode_uniforms
+        total, d, pred_emoca, parts = compat_api.speaker_slmft_forward(
+            s2s, vq_s, vq_l, _mesh_head(self), v_speaker.float(), v_speaker_emoca.float(), v_audio.float(), mask, template.float(),
+            self.patch_embed_dec_l.detach(), self._mouth, mode=mode, speaker_rows=rows, uniforms=uniforms, greedy=self.greedy)
+        self.last_parts = parts
+        return total, d, pred_emoca

@@ -276,3 +276,75 @@ def slm_forward(s2s_engine, speaker_vq_engine, listener_vq_engine, v_speaker, v_
     if return_parts:
         return total, d, dict(x_s=x_s, x_l=x_l, x_joint=x_joint, px_s=px_s, px_l=px_l, pred_s=pred_s, pred_l=pred_l, z_s=z_s, z_l=z_l)
     return total, d, None
+
+
+# ---- EmocaConverter / SpeakerSLMFT mesh modules (seq2seq_pretrain.py:516-842) -------------------------------------------------
+ACT_LEAKY = 1
+
+
+@torch.no_grad()
+def mesh_to_motion(v, template, map_w, map_b, conv_w, conv_b):
+    """vertice_mapping + squasher (seq2seq_pretrain.py:710-713; modules :777-785): (B,T,size) vertices - template -> Linear(size,56)
+    + LeakyReLU(0.2) -> Conv1d(k=5, replicate) + LeakyReLU(0.2) + InstanceNorm1d over time -> (B,T,56).
+    Kernels: dim_linear_ragged_f32 (split over the 70110-wide K), dim_conv5_leaky_f32, dim_instance_norm_f32."""
+    from . import ops
+    B, T, size = v.shape
+    x = (v - template.reshape(B, 1, size)).reshape(B * T, size).contiguous()
+    y = ops.linear_ragged(x, map_w.detach().contiguous(), map_b.detach(), act=ACT_LEAKY, slope=0.2).view(B, T, -1)
+    y = ops.conv5_leaky(y, ops.repack_conv_weight(conv_w.detach().contiguous()), conv_b.detach(), 0.2)
+    return ops.instance_norm_(y)
+
+
+@torch.no_grad()
+def motion_to_mesh(dec, lstm_params, lin0_w, lin0_b, lin2_w, lin2_b, template=None):
+    """vertice_map_reverse_lstm + vertice_map_reverse (seq2seq_pretrain.py:657-658, :823-825; modules :789-807): (B,L,56) ->
+    2-layer bidirectional LSTM(384) -> Linear(768,768) + LeakyReLU(0.2) -> Linear(768,size) (+ template).
+    Kernels: dim_lstm_layer_f32 per layer, dim_linear_f32, dim_linear_ragged_f32."""
+    from . import ops
+    B, L, _ = dec.shape
+    h = ops.lstm(dec.contiguous(), lstm_params, hidden=lstm_params["weight_hh_l0"].shape[1])
+    h = ops.linear(h.view(B * L, -1), lin0_w.detach().contiguous(), lin0_b.detach(), act=ACT_LEAKY, slope=0.2)
+    out = ops.linear_ragged(h, lin2_w.detach().contiguous(), lin2_b.detach()).view(B, L, -1)
+    return out if template is None else out + template.reshape(B, 1, -1)
+
+
+@torch.no_grad()
+def speaker_slmft_forward(s2s_engine, speaker_vq_engine, listener_vq_engine, mesh, v_speaker, v_speaker_emoca, v_audio, mask,
+                          template, patch_dec_l, mouth_map, mode="train", speaker_rows=None, temperature=1.0, uniforms=None,
+                          greedy=False):
+    """SpeakerSLMFT.forward (seq2seq_pretrain.py:707-757), forward only.  `mesh` = (lstm_params, lin0_w, lin0_b, lin2_w, lin2_b) of
+    the 'emoca' head.  The reference also runs vertice_mapping + squasher + a speaker-VQ encode of the result (:710-715) and never
+    reads them (z_s is dead: :725 is commented out) -- skipped here like SURVEY F10; mesh_to_motion() is that path on its own.
+    Returns (total_loss, dict, pred_cont_seq_s_emoca, parts)."""
+    B, T, size = v_speaker.shape
+    z = listener_codes(listener_vq_engine, v_speaker_emoca, mask)                       # forward_vq :701-703 (pad -100)
+    x_l = torch.zeros(B, T, patch_dec_l.numel(), device=v_audio.device) if speaker_rows is None \
+        else speaker_rows.unsqueeze(1).repeat(1, T, 1)                                   # :718-722
+    ctx = torch.cat([x_l + patch_dec_l.reshape(1, 1, -1), v_audio], dim=-1).contiguous()  # forward_decoder :640-642
+    if mode == "train":
+        inp, target = z[:, :-1].clone(), z[:, 1:]
+        inp[inp == -100] = 0
+        logits = s2s_engine.teacher_forced(ctx, mask, inp, None)
+        l_ce = F.cross_entropy(logits.transpose(1, 2), target, ignore_index=-100)
+        codes = torch.argmax(logits, dim=-1)                                             # forward_vq_decoder :650-651
+    else:
+        if greedy or temperature == 0.0:
+            codes = s2s_engine.generate(ctx, mask, z[:, 0:1].contiguous(), T - 1, temperature=0.0)
+        else:
+            if uniforms is None:
+                uniforms = torch.rand(B, T - 1, device=ctx.device)
+            codes = s2s_engine.generate(ctx, mask, z[:, 0:1].contiguous(), T - 1, temperature=temperature, uniforms=uniforms)
+        l_ce, logits = 0.0, None
+    pred_emoca = speaker_vq_engine.decode(codes=codes.contiguous())                      # :652-656: SPEAKER codebook rows, speaker decoder
+    pred_mesh = motion_to_mesh(pred_emoca, *mesh, template=template)                     # :657-658, :731
+    mse = F.mse_loss
+    l_cont_mesh = mse(pred_mesh, v_speaker[:, 1:, :])                                    # :734 (overwritten at :749)
+    nv = size // 3
+    orig_mouth = v_speaker.reshape(-1, nv, 3)[:, mouth_map, :].reshape(-1, len(mouth_map) * 3)
+    pred_mouth = pred_mesh.reshape(-1, nv, 3)[:, mouth_map, :].reshape(-1, len(mouth_map) * 3)
+    l_mouth = mse(pred_mouth, orig_mouth[1:, :])                                         # :739: drops ONE row of the flattened batch
+    l_emoca = mse(pred_emoca, v_speaker_emoca[:, 1:, :])
+    total = l_ce + l_emoca
+    d = {"l_ce_s": 0, "l_ce_l": l_ce, "l_cont_s": 1.0 * l_mouth, "l_cont_l": l_emoca, "nce": 0, "c_acc": 0}
+    parts = dict(z=z, codes=codes, logits=logits, pred_mesh=pred_mesh, l_cont_mesh=l_cont_mesh)
+    return total, d, pred_emoca, parts

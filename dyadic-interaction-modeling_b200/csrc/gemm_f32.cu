@@ -1,4 +1,6 @@
 // fp32 FFMA GEMMs with fused prologue/epilogue (see gemm_f32.cuh).  sm_100a.
+#include <algorithm>
+
 #include "gemm_f32.cuh"
 
 namespace dimb {
@@ -292,6 +294,113 @@ __global__ void repack_conv_kernel(const float* __restrict__ w, float* __restric
   }
 }
 
+// Linear with no alignment requirement on K, N or the leading dimensions (the 70110-wide mesh layers of EmocaConverter,
+// /root/reference/code/seq2seq_pretrain.py:777, :803-812): 64 x 64 tiles, scalar guarded loads and stores, ascending-k fmaf
+// chains.  gridDim.z > 1 splits K: slice z writes its partial tile to part[z][M][N]; ragged_reduce_kernel adds the slices in
+// ascending z, then bias and activation (deterministic).
+template <int V>   // V consecutive k per load: 4 when every row of A and W is 16-byte aligned, 2 when 8-byte aligned, else 1
+__global__ void __launch_bounds__(256) gemm_f32_ragged(const GemmArgs p, int ldw, int kslice, float* part) {
+  constexpr int BM = 64, BN = 64, NL = 4 / V, KV = BK / V;
+  __shared__ float As[BK][BM + 1];
+  __shared__ float Ws[BK][BN + 1];
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kb = blockIdx.z * kslice, ke = min(p.K, kb + kslice);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float ra[NL][V], rw[NL][V];
+  auto ldv = [&](const float* src, int k, float* dst) {       // V elements at src[k..k+V), zero beyond ke
+    if (k + V <= ke) {
+      if constexpr (V == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + k));
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+      } else if constexpr (V == 2) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(src + k));
+        dst[0] = v.x; dst[1] = v.y;
+      } else {
+        dst[0] = __ldg(src + k);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < V; ++e) dst[e] = k + e < ke ? __ldg(src + k + e) : 0.f;
+    }
+  };
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      const int idx = tid + i * 256, r = idx / KV, k = k0 + (idx % KV) * V;
+#pragma unroll
+      for (int e = 0; e < V; ++e) { ra[i][e] = 0.f; rw[i][e] = 0.f; }
+      if (m0 + r < p.M) ldv(p.A + (size_t)(m0 + r) * p.lda, k, ra[i]);
+      if (n0 + r < p.N) ldv(p.W + (size_t)(n0 + r) * ldw, k, rw[i]);
+    }
+  };
+  auto store_tiles = [&]() {
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      const int idx = tid + i * 256, r = idx / KV, k = (idx % KV) * V;
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        As[k + e][r] = ra[i][e];
+        Ws[k + e][r] = rw[i][e];
+      }
+    }
+  };
+  load_tiles(kb);
+  store_tiles();
+  __syncthreads();
+  for (int k0 = kb; k0 < ke; k0 += BK) {
+    if (k0 + BK < ke) load_tiles(k0 + BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; w[i] = Ws[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+    if (k0 + BK < ke) {
+      store_tiles();
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = m0 + ty * 4 + i;
+    if (row >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + tx * 4 + j;
+      if (col >= p.N) continue;
+      if (part) part[((size_t)blockIdx.z * p.M + row) * p.N + col] = acc[i][j];
+      else p.C[(size_t)row * p.ldc + col] = epilogue_elem(p, acc[i][j], row, col);
+    }
+  }
+}
+
+__global__ void ragged_reduce_kernel(const GemmArgs p, const float* part, int splits) {
+  const size_t n = (size_t)p.M * p.N;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float v = 0.f;
+    for (int z = 0; z < splits; ++z) v += part[(size_t)z * n + i];
+    const int row = (int)(i / p.N), col = (int)(i - (size_t)row * p.N);
+    p.C[(size_t)row * p.ldc + col] = epilogue_elem(p, v, row, col);
+  }
+}
+
+int ragged_splits(int M, int N, int K) {
+  const long tiles = (long)cdiv(M, 64) * cdiv(N, 64);
+  if (tiles >= 148 || K < 2048) return 1;
+  long s = (2 * 148 + tiles - 1) / tiles;
+  return (int)std::min<long>(s, K / 512);
+}
+
 template <int BM, int BN, int TM, int TN>
 int launch_tiled(const GemmArgs& a, cudaStream_t s) {
   dim3 grid(cdiv(a.N, BN), cdiv(a.M, BM));
@@ -323,7 +432,7 @@ int launch_gemm_f32(const GemmArgs& a, cudaStream_t s) {
   DIM_REQUIRE(a.K % 4 == 0 && a.N % 4 == 0, "gemm: K and N must be multiples of 4");
   DIM_REQUIRE(a.lda % 4 == 0 && (a.C == nullptr || a.ldc % 4 == 0), "gemm: leading dims must be multiples of 4");
   DIM_REQUIRE(a.C != nullptr || a.Cb != nullptr, "gemm: no output");
-  if (a.conv_T > 0) DIM_REQUIRE(a.conv_C % BK == 0 && a.K == 5 * a.conv_C, "gemm: conv mode needs Cin % 16 == 0");
+  if (a.conv_T > 0) DIM_REQUIRE(a.conv_C % 4 == 0 && a.K == 5 * a.conv_C, "gemm: conv mode needs Cin % 4 == 0");
   if (a.M <= 8 && a.conv_T == 0) {
     dim3 grid(a.N);                                    // one CTA per output column
     ProfScope ps(CAT_GEMM_SKINNY, s, 4.0 * ((double)a.M * a.K + (double)a.N * a.K + (double)a.M * a.N),
@@ -374,5 +483,40 @@ extern "C" int dim_repack_conv_weight(const float* w_oik, float* w_oki, int Cout
   ProfScope ps(CAT_MISC, as_stream(stream), 8.0 * Cout * Cin * 5, 0);
   repack_conv_kernel<<<148 * 4, 256, 0, as_stream(stream)>>>(w_oik, w_oki, Cout, Cin);
   DIM_LAUNCHED();
+  return DIM_OK;
+}
+
+extern "C" size_t dim_linear_ragged_workspace_bytes(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  const int sp = ragged_splits(M, N, K);
+  return sp > 1 ? (size_t)sp * M * N * sizeof(float) : 0;
+}
+
+extern "C" int dim_linear_ragged_f32(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
+                                     int M, int N, int K, int act, float slope, void* ws, size_t ws_bytes, void* stream) {
+  if (int e = ensure_device()) return e;
+  DIM_REQUIRE(A && W && C && M > 0 && N > 0 && K > 0 && lda >= K && ldw >= K && ldc >= N, "linear_ragged: bad operands");
+  GemmArgs a;
+  a.A = A; a.lda = lda; a.W = W; a.bias = bias; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K; a.act = act; a.slope = slope;
+  cudaStream_t s = as_stream(stream);
+  const int sp = ragged_splits(M, N, K);
+  float* part = nullptr;
+  int kslice = K;
+  if (sp > 1) {
+    DIM_REQUIRE(ws != nullptr && ws_bytes >= (size_t)sp * M * N * sizeof(float), "linear_ragged: workspace too small");
+    part = static_cast<float*>(ws);
+    kslice = cdiv(cdiv(K, sp), BK) * BK;
+  }
+  ProfScope ps(CAT_GEMM_TILED, s, 4.0 * ((double)M * K + (double)N * K + (double)M * N), 2.0 * M * (double)N * K);
+  const dim3 grid(cdiv(N, 64), cdiv(M, 64), cdiv(K, kslice));
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | (uintptr_t)lda * 4 | (uintptr_t)ldw * 4;
+  if (bits % 16 == 0) gemm_f32_ragged<4><<<grid, 256, 0, s>>>(a, ldw, kslice, part);        // kslice % 16 == 0: slices stay aligned
+  else if (bits % 8 == 0) gemm_f32_ragged<2><<<grid, 256, 0, s>>>(a, ldw, kslice, part);
+  else gemm_f32_ragged<1><<<grid, 256, 0, s>>>(a, ldw, kslice, part);
+  DIM_LAUNCHED();
+  if (part) {
+    ragged_reduce_kernel<<<std::min(148 * 4, cdiv(M * N, 256)), 256, 0, s>>>(a, part, cdiv(K, kslice));
+    DIM_LAUNCHED();
+  }
   return DIM_OK;
 }

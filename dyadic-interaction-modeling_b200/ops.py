@@ -59,6 +59,41 @@ def linear(a, w, bias=None, residual=None, act=0, slope=0.0):
     return out
 
 
+def linear_ragged(a, w, bias=None, act=0, slope=0.0):
+    """act(a @ w.T + bias) with no alignment requirement (K or N = 70110: seq2seq_pretrain.py:777, :803-807).  a (M,K), w (N,K)."""
+    _req(a, torch.float32, "a"); _req(w, torch.float32, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    lib = _lib.load()
+    out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    nws = lib.dim_linear_ragged_workspace_bytes(M, N, K)
+    ws = torch.empty(max(nws, 1), dtype=torch.uint8, device=a.device)
+    _lib.check(lib.dim_linear_ragged_f32(_ptr(a), K, _ptr(w), K, _ptr(bias), _ptr(out), N, M, N, K, act, float(slope),
+                                         _ptr(ws), nws, _stream()), "dim_linear_ragged_f32")
+    return out
+
+
+def lstm(x, params, hidden, layers=2, bidirectional=True, prefix=""):
+    """nn.LSTM(batch_first=True) forward with zero initial state (seq2seq_pretrain.py:789-802): x (B,T,in) -> (B,T,ndir*hidden).
+    `params`: mapping with torch's parameter names (weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0, *_reverse, ...)."""
+    _req(x, torch.float32, "x")
+    B, T, _ = x.shape
+    lib = _lib.load()
+    ndir = 2 if bidirectional else 1
+    nws = lib.dim_lstm_layer_workspace_bytes(B, T, hidden, ndir)
+    ws = torch.empty(nws, dtype=torch.uint8, device=x.device)
+    cur = x
+    for k in range(layers):
+        names = [f"{prefix}{n}_l{k}{sfx}" for sfx in ("", "_reverse") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+        w = [_req(params[n].detach(), torch.float32, n) for n in names[:4]]
+        w += [_req(params[n].detach(), torch.float32, n) for n in names[4:]] if bidirectional else [None] * 4
+        out = torch.empty(B, T, ndir * hidden, dtype=torch.float32, device=x.device)
+        _lib.check(lib.dim_lstm_layer_f32(_ptr(cur), cur.shape[-1], *[_ptr(t) for t in w], B, T, hidden, _ptr(out), _ptr(ws), nws,
+                                          _stream()), "dim_lstm_layer_f32")
+        cur = out
+    return cur
+
+
 def split_planes(x, planes):
     """fp32 (rows,K) -> bf16 plane matrix (rows, planes*Kp), Kp = K rounded up to 64 (zero padded)."""
     _req(x, torch.float32, "x")

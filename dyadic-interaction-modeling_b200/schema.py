@@ -199,3 +199,49 @@ def slmft_schema(c: S2SConfig = S2SConfig(), vq: VQConfig = VQConfig()):
             d[f"{pre}.{k}"] = s
     d.update(slmft_own_schema(c))
     return d
+
+
+MESH_SIZE = 70110       # BIWI vertex vector (23370 vertices x 3), hard-coded at seq2seq_pretrain.py:775
+LSTM_HIDDEN = 384
+
+
+def lstm_schema(name: str, in_dim: int, hidden: int, layers: int = 2, bidirectional: bool = True):
+    """torch.nn.LSTM parameter names and shapes."""
+    d = OrderedDict()
+    nd = 2 if bidirectional else 1
+    for k in range(layers):
+        for sfx in ("", "_reverse")[:nd]:
+            d[f"{name}.weight_ih_l{k}{sfx}"] = (4 * hidden, in_dim if k == 0 else nd * hidden)
+            d[f"{name}.weight_hh_l{k}{sfx}"] = (4 * hidden, hidden)
+            d[f"{name}.bias_ih_l{k}{sfx}"] = (4 * hidden,)
+            d[f"{name}.bias_hh_l{k}{sfx}"] = (4 * hidden,)
+    return d
+
+
+def emoca_converter_own_schema(size: int = MESH_SIZE, dim: int = 56):
+    """EmocaConverter's own modules (seq2seq_pretrain.py:775-813), i.e. without speaker_vq."""
+    d = OrderedDict()
+    d["vertice_mapping.0.weight"] = (dim, size)
+    d["vertice_mapping.0.bias"] = (dim,)
+    d["squasher.0.0.weight"] = (dim, dim, 5)
+    d["squasher.0.0.bias"] = (dim,)
+    d.update(lstm_schema("vertice_map_reverse_lstm", dim, LSTM_HIDDEN))
+    d.update(lstm_schema("vertice_map_reverse_lstm_2", dim, LSTM_HIDDEN))
+    for n in ("vertice_map_reverse", "vertice_map_reverse2"):
+        d[f"{n}.0.weight"] = (2 * LSTM_HIDDEN, 2 * LSTM_HIDDEN)
+        d[f"{n}.0.bias"] = (2 * LSTM_HIDDEN,)
+        d[f"{n}.2.weight"] = (size, 2 * LSTM_HIDDEN)
+        d[f"{n}.2.bias"] = (size,)
+    return d
+
+
+def speaker_slmft_own_schema(c: S2SConfig = S2SConfig(), size: int = MESH_SIZE):
+    """SpeakerSLMFT keys excluding the two VQ-VAEs (seq2seq_pretrain.py:516-637): SLMFT's transformer stack with the decoder's
+    absolute positional table, the converter's mesh modules (squasher and both LSTM heads are attributes of the model, :563-568),
+    W (2,) and speaker_embed (15, 384)."""
+    d = slmft_own_schema(c)
+    d["decoder_joint.net.pos_emb.emb.weight"] = (c.max_seq_len, c.dec_dim)
+    d.update(emoca_converter_own_schema(size, c.dim_in))
+    d["W"] = (2,)
+    d["speaker_embed.weight"] = (15, c.dim)
+    return d

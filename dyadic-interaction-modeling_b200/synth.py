@@ -64,6 +64,10 @@ def _draw(key: str, shape, seed: int) -> torch.Tensor:
         return (torch.rand(shape, generator=g) * 2 - 1) * b
     if leaf == "bias":
         return (torch.rand(shape, generator=g) * 2 - 1) * 0.05
+    if leaf.startswith(("weight_ih_l", "weight_hh_l", "bias_ih_l", "bias_hh_l")):       # nn.LSTM: U(+-1/sqrt(hidden)) everywhere
+        return (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(shape[0] // 4)
+    if key == "W":
+        return torch.randn(shape, generator=g)
     raise KeyError(key)
 
 
@@ -149,3 +153,26 @@ CLIP_SHAPES = {          # name -> (frames, note)
     "lm_listener_64": 64,
     "lm_listener_1024": 1024,
 }
+
+
+def make_emoca_converter_state_dict(seed: int = 131, size: int = None, vq: VQConfig = VQConfig()):
+    """EmocaConverter (seq2seq_pretrain.py:759-813): speaker_vq (a 56-d VQAutoEncoder, ./config.yaml) + the mesh modules."""
+    from .schema import MESH_SIZE, emoca_converter_own_schema
+    sd = OrderedDict()
+    for k, v in make_vqvae_state_dict(seed + 1, vq).items():
+        sd["speaker_vq." + k] = v
+    for k, sh in emoca_converter_own_schema(size or MESH_SIZE, vq.in_dim).items():
+        sd[k] = _draw(k, sh, seed)
+    return sd
+
+
+def make_speaker_slmft_state_dict(seed: int = 131, size: int = None, cfg: S2SConfig = S2SConfig(), vq: VQConfig = VQConfig()):
+    """SpeakerSLMFT (seq2seq_pretrain.py:516-637) with synthetic weights, reference key names."""
+    from .schema import MESH_SIZE, speaker_slmft_own_schema
+    sd = OrderedDict()
+    for pre, off in (("speaker_vq", 1), ("listener_vq", 2)):
+        for k, v in make_vqvae_state_dict(seed + off, vq).items():
+            sd[f"{pre}.{k}"] = v
+    for k, sh in speaker_slmft_own_schema(cfg, size or MESH_SIZE).items():
+        sd[k] = torch.randn(sh, generator=_gen(seed, k)) if k == "speaker_embed.weight" else _draw(k, sh, seed)   # nn.Embedding: N(0,1)
+    return sd

@@ -102,6 +102,23 @@ int dim_repack_conv_weight(const float* w_oik /*[Cout][Cin][5]*/, float* w_oki /
  * t < lens[b] (or T).  Replaces stage1_BIWI.py:268 / :334. */
 int dim_instance_norm_f32(float* x, const int32_t* lens, int B, int T, int C, float eps, void* stream);
 
+/* Linear with NO alignment requirement on K, N, lda, ldw or ldc: C[M,N] = act(A[M,K] @ W[N,K]^T + bias).  For the 70110-wide
+ * mesh layers of EmocaConverter / SpeakerSLMFT (nn.Linear(70110, 56) + LeakyReLU: seq2seq_pretrain.py:777, applied at :712;
+ * nn.Linear(768, 70110): :803-807, applied at :658).  A wide-K, narrow-N problem is split over K into a workspace
+ * (dim_linear_ragged_workspace_bytes; 0 = none needed) and reduced in a fixed order. */
+size_t dim_linear_ragged_workspace_bytes(int M, int N, int K);
+int dim_linear_ragged_f32(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N,
+                          int K, int act, float slope, void* ws, size_t ws_bytes, void* stream);
+
+/* One nn.LSTM layer, batch_first, zero initial state, fp32: x (B,T,in_dim) -> out (B,T,ndir*H), forward direction in columns
+ * [0,H), reverse (when w_ih_r != NULL) in [H,2H).  Weights in torch's layout: w_ih [4H,in_dim], w_hh [4H,H], b_* [4H], gate
+ * order i,f,g,o.  Replaces EmocaConverter.vertice_map_reverse_lstm (seq2seq_pretrain.py:789-802; calls :657, :823): call once
+ * per layer, feeding layer k's out to layer k+1.  in_dim % 4 == 0, H % 64 == 0.  ws: dim_lstm_layer_workspace_bytes. */
+size_t dim_lstm_layer_workspace_bytes(int B, int T, int H, int ndir);
+int dim_lstm_layer_f32(const float* x, int in_dim, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                       const float* w_ih_r, const float* w_hh_r, const float* b_ih_r, const float* b_hh_r, int B, int T, int H,
+                       float* out, void* ws, size_t ws_bytes, void* stream);
+
 /* Audio-feature resampling to the motion frame rate, (t,d) fp32 -> (new_t,d) fp32, d % 4 == 0.
  * mode 0: window mean, out[i] = mean(in[i*window : (i+1)*window])  -- vico_preprocessing.downsample_mean
  *         (code/vico_preprocessing.py:7-19: new_t = int(t*0.6), window = int(t/new_t), i.e. 1 for the 50->30 fps case);

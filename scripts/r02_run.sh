@@ -194,3 +194,8 @@ if has q16ab; then
 import json,sys; d=json.loads([l for l in sys.stdin if l.startswith(chr(123))][-1]); print('bf16', round(d['value']), round(d['ms_per_step'],1)); [print('   ',k) for k in d['kernels'][:5]]"
   done
 fi
+if has mesh; then
+  timeout 900 python -m pytest tests/test_speaker_mesh_gpu.py -q > $OUT/${TAG}_mesh.log 2>&1; echo "exit $?" >> $OUT/${TAG}_mesh.log
+  tail -40 $OUT/${TAG}_mesh.log
+  timeout 300 python scripts/lstm_timing.py > $OUT/${TAG}_lstm_timing.txt 2>&1; tail -12 $OUT/${TAG}_lstm_timing.txt
+fi

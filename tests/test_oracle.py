@@ -147,3 +147,20 @@ def test_speaker_oracle_matches_reference_golden():
         dec = OV.speaker_decode(sd, quant, SPEAKER_VQ)
     assert torch.equal(idx.view(case["B"], -1), case["idx"])
     assert float((dec - case["dec"]).abs().max()) < 1e-5 and abs(float(loss) - float(case["loss"])) < 1e-6
+
+
+def test_emoca_converter_oracle_matches_reference_golden():
+    """EmocaConverter (seq2seq_pretrain.py:759-832): oracle/speaker_mesh.py against the golden minted from the real reference class
+    (tests/golden/make_emoca_golden.py) at the real 70110-d mesh size; the state_dict key set is the reference's."""
+    import os
+    from oracle import speaker_mesh as OM
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "emoca_reference.pt"), weights_only=False)
+    sd = dim_b200.synth.make_emoca_converter_state_dict(g["weights_seed"])
+    gen = torch.Generator().manual_seed(g["x_seed"])
+    v = torch.randn(g["B"], g["T"], 56, generator=gen) * 0.3
+    tpl = torch.randn(g["B"], 70110, generator=gen) * 0.1
+    out, dec = OM.emoca_converter_forward(sd, tpl, v, VQConfig())
+    assert float((dec - g["dec"]).abs().max()) <= 1e-5
+    assert float((out[..., ::g["stride"]] - g["out_strided"]).abs().max()) <= 1e-5
+    assert abs(float(out.double().sum()) - g["out_sum"]) <= 1e-5 * g["out_abs_sum"]
+    assert float((OM.mesh_to_motion(sd, out, tpl) - g["motion"]).abs().max()) <= 1e-4
