@@ -188,8 +188,17 @@ int run_gemm(const TcCtx& tc, const GemmArgs& a_in, __nv_bfloat16* scratch, cuda
   }
   const int kp = tc_round_k(a.K);
   if (a.Ap != nullptr) return launch_gemm_tc(a, a.Ap, it->second, kp, tc.planes, s);
+  // 5-tap conv: implicit GEMM over the padded frame planes (five row-shifted TMA boxes per k-range) when the channel count allows;
+  // DIM_CONV_IM2COL=1 keeps the explicit im2col plane rows (A/B hook; bit-identical results: same products, same order)
+  static const bool im2col = getenv("DIM_CONV_IM2COL") != nullptr;
+  if (a.conv_T > 0 && a.conv_C % 64 == 0 && a.M % a.conv_T == 0 && !im2col) {
+    if (int e = launch_split_conv_pad(a, scratch, tc.planes, s)) return e;
+    return launch_gemm_tc(a, scratch, it->second, kp, tc.planes, s);
+  }
+  GemmArgs flat = a;                                    // explicit path: the GEMM sees a plain [M, 5C] operand
+  flat.conv_T = 0;
   if (int e = launch_split_planes(a, scratch, kp, tc.planes, s)) return e;
-  return launch_gemm_tc(a, scratch, it->second, kp, tc.planes, s);
+  return launch_gemm_tc(flat, scratch, it->second, kp, tc.planes, s);
 }
 
 int build_vq_stack(dim_handle_s* h, const std::string& p, const dim_vq_config& c, std::vector<VqLayer>& out) {

@@ -44,7 +44,11 @@ struct TcParams {
   int splits;                 // split-K factor = cluster size along z (1, 2, 4 or 8)
   long long* dbg;             // optional timeline of CTA (0,0,0): clock64 stamps (debug / tuning only)
   float w_keep;               // > 0: fraction of the weight tiles loaded with an L2 evict_last policy (decode-step GEMMs:
-                              //      keep part of the per-step weight stream L2-resident across steps), rest evict_first
+                              //      keep part of the per-step weight stream L2-resident across steps), rest evict_first  // implicit 5-tap Conv1d (conv_cb > 0): A is the PADDED frame matrix [B*(T+4), planes*a_kp] (row b*(T+4)+t' = frame
+  // clamp(t'-2, 0, L_b-1) of clip b), k-block kb = tap*conv_cb + c reads A rows m0+tap.. at columns c*64: the five taps are five
+  // row-shifted TMA boxes of the same matrix, no im2col copy.  Tile rows live in the padded row space; the epilogue maps
+  // m' = b*(T+4)+t back to output row b*T+t and drops t >= T.
+  int conv_cb = 0, a_kp = 0, conv_T = 0, conv_Mp = 0;
 };
 
 template <int ACT>
@@ -173,7 +177,12 @@ __global__ void __launch_bounds__(192) gemm_bf16_tcgen05(const __grid_constant__
         const uint32_t fb = smem_u32(&full_bar[stage]);
         mbar_expect_tx(fb, STAGE_BYTES);
         const uint32_t sa = smem_base + stage * STAGE_BYTES;
-        tma_load_2d(sa, &tmA, p.pa[pair] * p.kp + kb * BKE, m0, fb);
+        if (p.conv_cb > 0) {
+          const int tap = kb / p.conv_cb, cb = kb - tap * p.conv_cb;
+          tma_load_2d(sa, &tmA, p.pa[pair] * p.a_kp + cb * BKE, m0 + tap, fb);
+        } else {
+          tma_load_2d(sa, &tmA, p.pa[pair] * p.kp + kb * BKE, m0, fb);
+        }
         if (p.w_keep > 0.f) tma_load_2d_hint(sa + A_BYTES, &tmW, p.pw[pair] * p.kp + kb * BKE, n0, fb, wpol);
         else tma_load_2d(sa + A_BYTES, &tmW, p.pw[pair] * p.kp + kb * BKE, n0, fb);
         if (dbg && it - it_begin < 16) p.dbg[8 + (it - it_begin)] = clock64();
@@ -249,17 +258,24 @@ __global__ void __launch_bounds__(192) gemm_bf16_tcgen05(const __grid_constant__
       for (int r0 = row_begin + warp * RPI + lane / LPR; r0 < row_end; r0 += stride * RB) {
         float4 acc[RB], res[RB];
         bool ok[RB];
+        int orow[RB];                                  // output row of tile row r
 #pragma unroll
         for (int u = 0; u < RB; ++u) {
           const int r = r0 + u * stride;
-          ok[u] = r < row_end && (m0 + r) < e.M;
+          orow[u] = m0 + r;
+          ok[u] = r < row_end && orow[u] < e.M;
+          if (p.conv_cb > 0) {                         // padded row space -> frame row (uniform branch)
+            const int tp = p.conv_T + 4, b = orow[u] / tp, t = orow[u] - b * tp;
+            ok[u] = r < row_end && orow[u] < p.conv_Mp && t < p.conv_T;
+            orow[u] = b * p.conv_T + t;
+          }
           acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
           res[u] = acc[u];
         }
         if (e.residual) {                              // independent of the tile data: in flight under the DSMEM reads below
 #pragma unroll
           for (int u = 0; u < RB; ++u)
-            if (ok[u]) res[u] = *reinterpret_cast<const float4*>(e.residual + (size_t)(m0 + r0 + u * stride) * e.ldr + col);
+            if (ok[u]) res[u] = *reinterpret_cast<const float4*>(e.residual + (size_t)orow[u] * e.ldr + col);
         }
         if (S == 1) {
 #pragma unroll
@@ -293,7 +309,7 @@ __global__ void __launch_bounds__(192) gemm_bf16_tcgen05(const __grid_constant__
 #pragma unroll
         for (int u = 0; u < RB; ++u) {
           if (!ok[u]) continue;
-          const int row = m0 + r0 + u * stride;
+          const int row = orow[u];
           float4 o = acc[u];
           o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w;
           if (e.tab_mode != 0) o = tc_tab_add(e, o, row, col);
@@ -380,7 +396,7 @@ int launch_tc_act(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcParams
   static PerDeviceOnce once;
   if (once.first()) DIM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, STAGES, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(cdiv(p.e.N, BN), cdiv(p.e.M, BM), p.splits);
+  cfg.gridDim = dim3(cdiv(p.e.N, BN), cdiv(p.conv_cb > 0 ? p.conv_Mp : p.e.M, BM), p.splits);
   cfg.blockDim = dim3(192);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
@@ -464,7 +480,37 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const GemmArgs a, __n
   }
 }
 
+// Conv operand: fp32 frames (B,T,C) -> padded bf16 plane matrix [B*(T+4), planes*cp]: row b*(T+4)+t' holds frame
+// clamp(t'-2, 0, L_b-1) of clip b (replicate padding; lens as in the explicit gather), columns C..cp zero.
+__global__ void __launch_bounds__(256) split_conv_pad_kernel(const GemmArgs a, __nv_bfloat16* __restrict__ out, int cp, int planes) {
+  const int c4n = cp >> 2, T = a.conv_T, Tp = T + 4;
+  const size_t total = (size_t)(a.M / T) * Tp * c4n;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / c4n), c0 = (int)(i - (size_t)row * c4n) * 4;
+    const int b = row / Tp, tq = row - b * Tp;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c0 < a.conv_C) {
+      const int L = a.lens ? __ldg(a.lens + b) : T;
+      const int ts = min(max(tq - 2, 0), L - 1);
+      x = *reinterpret_cast<const float4*>(a.A + ((size_t)b * T + ts) * a.lda + c0);
+    }
+    store_planes4(out + (size_t)row * planes * cp + c0, x, planes, cp);
+  }
+}
+
 }  // namespace
+
+int launch_split_conv_pad(const GemmArgs& a, __nv_bfloat16* out, int planes, cudaStream_t s) {
+  DIM_REQUIRE(a.conv_T > 0 && a.conv_C % 64 == 0 && a.M % a.conv_T == 0 && a.K == 5 * a.conv_C && a.a_add == nullptr,
+              "split_conv_pad: needs C % 64 == 0 and whole clips");
+  DIM_REQUIRE(planes >= 1 && planes <= 3, "split: planes must be 1..3");
+  const size_t total = (size_t)(a.M / a.conv_T) * (a.conv_T + 4) * (a.conv_C / 4);
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 32);
+  ProfScope ps(CAT_MISC, s, (double)a.M * a.conv_C * 4.0 + (double)total * 4 * planes * 2.0, 0);
+  split_conv_pad_kernel<<<blocks, 256, 0, s>>>(a, out, a.conv_C, planes);
+  DIM_LAUNCHED();
+  return DIM_OK;
+}
 
 int tc_make_map(const __nv_bfloat16* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
   return make_map(ptr, rows, cols, ld, box_rows, out);
@@ -513,6 +559,14 @@ int launch_gemm_tc(const GemmArgs& e, const __nv_bfloat16* Ap, const __nv_bfloat
   p.npairs = tc_pairs(planes, p.pa, p.pw);
   p.splits = 1;
   p.dbg = g_tc_dbg;
+  const bool conv = e.conv_T > 0;                       // Ap = padded frame planes (launch_split_conv_pad), kp = 5 * C
+  if (conv) {
+    DIM_REQUIRE(e.conv_C % BKE == 0 && kp == 5 * e.conv_C && e.M % e.conv_T == 0, "gemm_tc: conv mode needs C % 64 == 0, Kp = 5*C");
+    p.conv_cb = e.conv_C / BKE;
+    p.a_kp = e.conv_C;
+    p.conv_T = e.conv_T;
+    p.conv_Mp = e.M / e.conv_T * (e.conv_T + 4);
+  }
   // Decode-step GEMMs re-read the same weights every step (144 MB of bf16 planes per step, more than the 126 MB L2): load 70 % of
   // the weight tiles with an L2 evict_last policy and the rest evict_first, so that most of the stream is served from L2 on the
   // next step instead of thrashing (measured: 261.9 -> 251.8 ms per bench step; 0.4: 254.5, 1.0: 256.4; profiles/r01_notes.md).
@@ -549,7 +603,9 @@ int launch_gemm_tc(const GemmArgs& e, const __nv_bfloat16* Ap, const __nv_bfloat
   if (g_tc_force_splits > 0) p.splits = g_tc_force_splits;
   while (p.splits > 1 && p.splits > total_kb) p.splits >>= 1;
   CUtensorMap tmA, tmW;
-  if (int err = make_map(Ap, e.M, planes * kp, planes * kp, BM, &tmA)) return err;
+  if (conv) {
+    if (int err = make_map(Ap, p.conv_Mp, planes * p.a_kp, planes * p.a_kp, BM, &tmA)) return err;
+  } else if (int err = make_map(Ap, e.M, planes * kp, planes * kp, BM, &tmA)) return err;
   if (int err = make_map(Wp, e.N, planes * kp, planes * kp, bn, &tmW)) return err;
   if (bn == 128) return launch_tc<128, 3>(tmA, tmW, p, s);
   if (bn == 64) return launch_tc<64, 4>(tmA, tmW, p, s);

@@ -13,7 +13,12 @@ inline int tc_round_k(int K) { return (K + 63) / 64 * 64; }
 // prologue applied (a_add, conv-mode gather with replicate clamp / lens).  Uses a.A, a.lda, a.M, a.K, a.a_add, a.conv_*.
 int launch_split_planes(const GemmArgs& a, __nv_bfloat16* out, int kp, int planes, cudaStream_t s);
 
+// Conv operand for the implicit 5-tap conv GEMM: frames (B,T,C) fp32 -> padded plane matrix [B*(T+4), planes*C] (C % 64 == 0):
+// row b*(T+4)+t' = frame clamp(t'-2, 0, lens[b]-1).  1.01x the activation bytes instead of the 5x im2col rows.
+int launch_split_conv_pad(const GemmArgs& a, __nv_bfloat16* out, int planes, cudaStream_t s);
+
 // C = epilogue(sum over plane pairs of Ap_i @ Wp_j^T); epilogue fields, M and N are taken from `e`.
+// e.conv_T > 0: implicit conv -- Ap is the padded matrix of launch_split_conv_pad, kp = 5*C, e.M = B*T output rows.
 int launch_gemm_tc(const GemmArgs& e, const __nv_bfloat16* Ap, const __nv_bfloat16* Wp, int kp, int planes, cudaStream_t s);
 
 int tc_pairs(int planes, int* pa, int* pw);
