@@ -199,3 +199,23 @@ if has mesh; then
   tail -40 $OUT/${TAG}_mesh.log
   timeout 300 python scripts/lstm_timing.py > $OUT/${TAG}_lstm_timing.txt 2>&1; tail -12 $OUT/${TAG}_lstm_timing.txt
 fi
+if has pdlb1; then
+  for env in "X=1" "DIM_PDL=1"; do
+    echo "== vico_b1 bf16 $env"
+    env $env timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-parity-leg --no-other-workloads --workload vico_b1 2>/dev/null | python -c "
+import json,sys; d=json.loads([l for l in sys.stdin if l.startswith(chr(123))][-1]); print(round(d['value']), 'frames/s', round(d['ms_per_step'],2), 'ms'); [print('   ',k) for k in d['kernels'][:4]]"
+  done
+  DIM_PDL=1 timeout 900 python -m pytest tests/test_slmft_gpu.py -x -q > $OUT/${TAG}_slmft_pdl.log 2>&1; echo "exit $?" >> $OUT/${TAG}_slmft_pdl.log
+  tail -5 $OUT/${TAG}_slmft_pdl.log
+fi
+if has sanitize2; then
+  # memcheck + racecheck over the last kernels of the round: LSTM recurrence, alignment-free Linear, implicit-conv GEMM (small shapes)
+  timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 20 --target-processes all python -m pytest -x -q \
+      tests/test_speaker_mesh_gpu.py tests/test_conv_implicit_gpu.py tests/test_vqvae_gpu.py -k "not 256-12 and not 300-6 and not 8-138 and not full_size and not 70110" > $OUT/${TAG}_memcheck2.log 2>&1
+  echo "exit $?" >> $OUT/${TAG}_memcheck2.log
+  grep -E "ERROR SUMMARY|passed|failed|exit|Invalid|out of bounds" $OUT/${TAG}_memcheck2.log | sort | uniq -c | head -20
+  timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 --print-limit 20 python -m pytest -x -q \
+      tests/test_speaker_mesh_gpu.py -k "lstm and (1-27 or 33-50 or 5-40 or 3-1)" > $OUT/${TAG}_racecheck_lstm.log 2>&1
+  echo "exit $?" >> $OUT/${TAG}_racecheck_lstm.log
+  grep -E "RACECHECK SUMMARY|passed|failed|exit|hazard" $OUT/${TAG}_racecheck_lstm.log | sort | uniq -c | head -20
+fi
