@@ -2,7 +2,11 @@
 after evaluate_test_epoch.  Same printed lines in the same order, same return value (fid_pose, fid_exp); the arithmetic runs as
 device tensor ops (dim_b200.metrics) instead of numpy / scipy loops -- note that the reference's own
 `calculate_frechet_distance` no longer runs on current scipy (`sqrtm(..., disp=False)`, eval_utils.py:28).
-BIWI vertex metrics (print_biwi_metrics) belong to the SpeakerSLMFT path, which is out of scope."""
+print_biwi_metrics (mymetrics.py:122-182: lip vertex error and upper-face dynamics deviation of the SpeakerSLMFT / BIWI path) likewise;
+the two data paths it hard-codes are keyword arguments with the reference's values as defaults."""
+import os
+import pickle
+
 import numpy as np
 import torch
 
@@ -45,3 +49,17 @@ def print_metrics_full(y_true, y_pred, x):
     print('pfid: ', float(pfid))
     print('mse: ', float(mse))
     print('var: ', float(G.var(unbiased=False)), float(P.var(unbiased=False)))
+
+
+def print_biwi_metrics(y_true, y_pred, file_names, templates_path="../data/BIWI_data/templates.pkl",
+                       region_path="../data/CodeTalker/BIWI/regions/"):
+    with open(templates_path, 'rb') as fin:
+        templates = pickle.load(fin, encoding='latin1')
+    read_map = lambda name: [int(i) for i in open(os.path.join(region_path, name)).read().split(", ")]
+    mouth_map, upper_map = read_map("lve.txt"), read_map("fdd.txt")
+    gt, pred = _dev(y_true), _dev(y_pred)
+    tpl = _dev([templates[f.split("_")[0]] for f in file_names])
+    lve, fdd = M.biwi_metrics(gt, pred, tpl, mouth_map, upper_map)
+    print('Lip Vertex Error: {:.4e}'.format(lve))
+    print('FDD: {:.4e}'.format(fdd))
+    return lve, fdd

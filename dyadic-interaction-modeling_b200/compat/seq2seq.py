@@ -7,7 +7,7 @@ Same constructor files, sub-module names and state_dict keys as the reference.  
 entry points as SLMFT: the generator's tensors are registered as `encoder_s.*` / `decoder_joint.net.*` of a single-encoder model
 (dim_slmft_build accepts a model without encoder_joint / patch embeddings / norm_s), one dim_slmft_encode call gives the context,
 dim_slmft_teacher_forced the logits of `forward`, dim_slmft_generate (persistent decode kernel, positional table added per step)
-the codes of `generate`.  speaker_ids / listener_ids (identity tokens prepended to the context) are not supported.  Forward only.
+the codes of `generate`.  speaker_ids / listener_ids (identity tokens: :240-250) are supported in forward, like the reference (its generate takes none).  Forward only.
 """
 import torch
 import torch.nn as nn
@@ -116,19 +116,39 @@ class ListenerGenerator(nn.Module):
         z_listener = compat_api.listener_codes(vq_l, v_listener.float(), mask)
         return x_speaker, z_listener
 
+    def _identity_row(self, emb, fc, ids):
+        """fc(relu(embedding(ids))) (:242, :248) -> (B, fc.out_features); the Linear runs in libdimb200 (dim_linear_f32)."""
+        from dim_b200 import ops
+        rows = torch.relu(emb.weight.detach()[ids]).contiguous()
+        return ops.linear(rows, fc.weight.detach().contiguous(), fc.bias.detach())
+
     @torch.no_grad()
     def forward(self, v_speaker, v_listener, mask, speaker_ids=None, listener_ids=None):
-        if speaker_ids is not None or listener_ids is not None:
-            raise NotImplementedError("identity tokens (speaker_ids / listener_ids, seq2seq.py:240-250) are not built")
+        """:223-261.  Identity tokens (:240-250, Transformer.forward :47-67): the speaker token is prepended to the ENCODER INPUT (mask
+        grows by one True), the listener token to the ENCODER OUTPUT (the decoder's context; mask grows again, the target gets a leading
+        -100 and the first logit row is dropped)."""
         s2s, _, vq_l = self.engines()
         x_speaker, z_listener = self._inputs(v_speaker, v_listener, mask)
-        enc = s2s.encode("encoder_s", x_speaker, mask)                                              # generator.encoder(..., mask=mask)
-        inp, target = z_listener[:, :-1].clone(), z_listener[:, 1:]
+        B = mask.shape[0]
+        one = torch.ones(B, 1, dtype=torch.bool, device=mask.device)
+        mask_u, tgt = mask, z_listener
+        if speaker_ids is not None:
+            x_speaker = torch.cat([self._identity_row(self.speaker_embeddings, self.fc_speaker, speaker_ids).unsqueeze(1), x_speaker], dim=1)
+            mask_u = torch.cat([one, mask_u], dim=1)
+        enc = s2s.encode("encoder_s", x_speaker.contiguous(), mask_u)                               # generator.encoder(..., mask=mask)
+        if listener_ids is not None:
+            enc = torch.cat([self._identity_row(self.listener_embeddings, self.fc_listener, listener_ids).unsqueeze(1), enc], dim=1)
+            mask_u = torch.cat([one, mask_u], dim=1)
+            tgt = torch.cat([torch.full((B, 1), -100, dtype=tgt.dtype, device=tgt.device), tgt], dim=1)
+        inp, target = tgt[:, :-1].clone(), tgt[:, 1:]
         inp[inp == -100] = 0
-        logits = s2s.teacher_forced(enc, mask, inp, None)
+        logits = s2s.teacher_forced(enc.contiguous(), mask_u, inp.contiguous(), None)
         loss = F.cross_entropy(logits.transpose(1, 2), target, ignore_index=-100)
-        pred_cont_seq = vq_l.decode(codes=torch.argmax(logits, dim=-1))
+        if listener_ids is not None:
+            logits = logits[:, 1:, :]
+        pred_cont_seq = vq_l.decode(codes=torch.argmax(logits, dim=-1).contiguous())
         loss_cont = compat_api.continuous_loss(pred_cont_seq, v_listener.float(), mask)
+        self.last_logits = logits
         return loss + loss_cont, pred_cont_seq
 
     @torch.no_grad()

@@ -101,3 +101,21 @@ def metrics_suite(y_true, y_pred, x, with_sid=True):
         out["sid_exp"] = (sid(y_true, y_pred, "exp"), sid(y_true, y_true, "exp"))
     f = lambda v: tuple(float(t) for t in v) if isinstance(v, tuple) else float(v)
     return {k: f(v) for k, v in out.items()}
+
+
+def biwi_metrics(y_true, y_pred, templates, mouth_map, upper_map):
+    """mymetrics.print_biwi_metrics (code/mymetrics.py:122-182) on the device: lip vertex error (LVE) = mean over ALL frames of the
+    max over the mouth vertices of the squared distance between ground-truth and predicted vertex, and the upper-face dynamics
+    deviation (FDD) = mean over clips of (mean over upper-face vertices of the temporal std of the squared motion norm, ground truth
+    minus prediction).  y_true[i] (n_i, V*3), y_pred[i] (>= n_i, V*3: cut to n_i frames, :145), templates[i] (V*3).  -> (lve, fdd)."""
+    mouth = torch.as_tensor(mouth_map, dtype=torch.long, device=y_true[0].device)
+    upper = torch.as_tensor(upper_map, dtype=torch.long, device=y_true[0].device)
+    err, fdd = [], []
+    for g, p, tpl in zip(y_true, y_pred, templates):
+        g = g.double().reshape(g.shape[0], -1, 3)
+        p = p.double().reshape(p.shape[0], -1, 3)[: g.shape[0]]
+        t = tpl.double().reshape(1, -1, 3)
+        err.append(((g[:, mouth] - p[:, mouth]) ** 2).sum(dim=2).max(dim=1).values)
+        std = lambda m: (m[:, upper] ** 2).sum(dim=2).std(dim=0, unbiased=False).mean()      # np.std: population std over time
+        fdd.append(std(g - t) - std(p - t))
+    return float(torch.cat(err).mean()), float(torch.stack(fdd).mean())

@@ -134,8 +134,9 @@ def slm_forward(sd, v_speaker, v_listener, v_audio, mask, mask_speaker, mask_lis
 
 
 @torch.no_grad()
-def listener_generator(sd, v_speaker, v_listener, mask, speaker_cfg, listener_cfg, depth=6, generate_steps=None):
-    """ListenerGenerator.forward / .generate (seq2seq.py:223-290) restated, identity tokens absent.  Returns
+def listener_generator(sd, v_speaker, v_listener, mask, speaker_cfg, listener_cfg, depth=6, generate_steps=None, speaker_ids=None,
+                       listener_ids=None):
+    """ListenerGenerator.forward / .generate (seq2seq.py:223-290) restated, identity tokens (:240-250, :47-67) included.  Returns
     (loss, pred_cont_seq, logits, x_speaker, z_listener[, generated codes (B, generate_steps), greedy])."""
     B, T, _ = v_speaker.shape
     fqn, zd = speaker_cfg.face_quan_num, speaker_cfg.zquant_dim
@@ -149,8 +150,21 @@ def listener_generator(sd, v_speaker, v_listener, mask, speaker_cfg, listener_cf
     # the reference views the (B, 128, T*8) tensor as (B, -1, 8, 128) WITHOUT permuting first (seq2seq.py:238-239): kept as is
     x = x.view(B, -1, fqn, zd).contiguous().view(B, -1, fqn * zd).contiguous()
     z = torch.stack(zl, dim=0)
-    enc = X.continuous_wrapper(sd, "generator.encoder", x, depth, mask)
-    loss, logits = X.teacher_forced(sd, "generator.decoder.net", z, depth, enc, mask)
+    x_in, mask_u, tgt = x, mask, z
+    one = torch.ones(B, 1, dtype=torch.bool)
+    if speaker_ids is not None:                                                              # :240-244
+        tok = F.linear(F.relu(sd["speaker_embeddings.weight"][speaker_ids]), sd["fc_speaker.weight"], sd["fc_speaker.bias"])
+        x_in = torch.cat([tok.unsqueeze(1), x_in], dim=1)
+        mask_u = torch.cat([one, mask_u], dim=1)
+    enc = X.continuous_wrapper(sd, "generator.encoder", x_in, depth, mask_u)
+    if listener_ids is not None:                                                             # :247-248, Transformer.forward :49-57
+        tok = F.linear(F.relu(sd["listener_embeddings.weight"][listener_ids]), sd["fc_listener.weight"], sd["fc_listener.bias"])
+        enc = torch.cat([tok.unsqueeze(1), enc], dim=1)
+        mask_u = torch.cat([one, mask_u], dim=1)
+        tgt = torch.cat([torch.full((B, 1), -100, dtype=torch.long), tgt], dim=1)
+    loss, logits = X.teacher_forced(sd, "generator.decoder.net", tgt, depth, enc, mask_u)
+    if listener_ids is not None:
+        logits = logits[:, 1:, :]                                                            # :66-67
     pred = V.decode_indices(sd, torch.argmax(logits, dim=-1), listener_cfg, prefix="listener_vq.")
     total = loss + continuous_loss(pred, v_listener, mask)
     out = (total, pred, logits, x, z)

@@ -91,3 +91,25 @@ def test_generate_matches_oracle(lg):
             enc_ref = OX.continuous_wrapper(sd, "generator.encoder", out[3], 6, mask)
             _, ref_logits = OX.generate(sd, "generator.decoder.net", out[4][:, 0:1], 12, 6, enc_ref, mask, use_cache=False, return_logits=True)
             explain_first_difference(c2.cpu()[b], logits[b].cpu(), ref_gen[b], ref_logits[b])
+
+
+@pytest.mark.parametrize("sp,li", [(True, False), (False, True), (True, True)])
+def test_identity_tokens_match_oracle(lg, sp, li):
+    """speaker_ids / listener_ids (seq2seq.py:240-250; Transformer.forward :47-67): the speaker token enters the encoder input, the
+    listener token the decoder context; the first logit row is dropped when the listener token is present."""
+    model, sd = lg
+    v_s, v_l, mask = _clips(3, 14, 11)
+    sid = torch.tensor([5, 0, 99]) if sp else None
+    lid = torch.tensor([7, 42, 1]) if li else None
+    ref_loss, ref_pred, ref_logits, _, ref_z = OS.listener_generator(sd, v_s, v_l, mask, SPEAKER_VQ, VQConfig(), speaker_ids=sid, listener_ids=lid)
+    loss, pred = model(v_s.cuda(), v_l.cuda(), mask.cuda(), speaker_ids=None if sid is None else sid.cuda(),
+                       listener_ids=None if lid is None else lid.cuda())
+    logits = model.last_logits.cpu()
+    assert logits.shape == ref_logits.shape == (3, 13, 512)
+    sel = ref_z[:, 1:] != -100
+    assert float((logits - ref_logits)[sel].abs().max()) < 5e-4
+    same = (logits.argmax(-1) == ref_logits.argmax(-1)).all(dim=1)
+    assert int(same.sum()) >= 2
+    assert float((pred.cpu()[same] - ref_pred[same]).abs().max()) < 1e-4
+    if bool(same.all()):
+        assert abs(float(loss) - float(ref_loss)) < 5e-4

@@ -44,3 +44,39 @@ def test_metric_suite_on_the_gpu():
     g = torch.load(GOLD, weights_only=False)
     dev = lambda seq: [t.cuda() for t in seq]
     _check(M.metrics_suite(dev(g["gt"]), dev(g["pred"]), dev(g["x"])), g["ref"])
+
+
+def _biwi_case():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_biwi_metrics_golden", os.path.join(os.path.dirname(GOLD), "make_biwi_metrics_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)           # only its seeded input generator is used: nothing under /root/reference is read
+    return mod.biwi_case(11)
+
+
+def test_biwi_vertex_metrics_match_reference_golden(tmp_path, capsys):
+    """mymetrics.print_biwi_metrics (code/mymetrics.py:122-182; the SpeakerSLMFT / BIWI eval): lip vertex error and FDD against the
+    values the REAL reference function printed for the same seeded vertices (tests/golden/make_biwi_metrics_golden.py); the compat
+    function reads the same two data files and prints the same two lines.  Tolerance 1e-5 relative (the reference works in fp32)."""
+    import pickle
+    import sys
+    g = torch.load(os.path.join(os.path.dirname(GOLD), "biwi_metrics_reference.pt"), weights_only=False)
+    names, templates, gt, pred, mouth, upper = _biwi_case()
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    t = lambda a: torch.from_numpy(a).to(dev)
+    lve, fdd = M.biwi_metrics([t(a) for a in gt], [t(a) for a in pred], [t(templates[n.split("_")[0]]) for n in names], mouth, upper)
+    assert abs(lve - g["lve"]) <= 1e-5 * abs(g["lve"]) and abs(fdd - g["fdd"]) <= 1e-5 * abs(g["fdd"]) + 1e-9
+    (tmp_path / "regions").mkdir()
+    pickle.dump(templates, open(tmp_path / "templates.pkl", "wb"))
+    (tmp_path / "regions" / "lve.txt").write_text(", ".join(map(str, mouth)))
+    (tmp_path / "regions" / "fdd.txt").write_text(", ".join(map(str, upper)))
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dyadic-interaction-modeling_b200", "compat")
+    sys.path.insert(0, compat)
+    try:
+        import mymetrics
+        lve2, fdd2 = mymetrics.print_biwi_metrics(gt, pred, names, templates_path=str(tmp_path / "templates.pkl"), region_path=str(tmp_path / "regions"))
+    finally:
+        sys.path.remove(compat)
+    out = capsys.readouterr().out
+    assert (lve2, fdd2) == (lve, fdd)
+    assert "Lip Vertex Error: {:.4e}".format(g["lve"]) in out and "FDD: {:.4e}".format(g["fdd"]) in out
