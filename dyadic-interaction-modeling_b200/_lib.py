@@ -123,7 +123,7 @@ SIGNATURES = {
     "dim_layer_norm_f32": (I, [P, P, P, P, I, I, F, P]),
     "dim_linear_ragged_workspace_bytes": (SZ, [I, I, I]),
     "dim_linear_ragged_f32": (I, [P, I, P, I, P, P, I, I, I, I, I, F, P, SZ, P]),
-    "dim_lstm_layer_workspace_bytes": (SZ, [I, I, I, I]),
+    "dim_lstm_layer_workspace_bytes": (SZ, [I, I, I, I, I]),
     "dim_lstm_layer_f32": (I, [P, I, P, P, P, P, P, P, P, P, I, I, I, P, P, SZ, P]),
     "dim_resample_features": (I, [P, I, I, I, I, I, P, P]),
     "dim_assemble_batch": (I, [P, P, P, P, I, I, I, I, P, P, P, P]),

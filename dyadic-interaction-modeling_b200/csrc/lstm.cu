@@ -3,7 +3,8 @@
 //   (/root/reference/code/seq2seq_pretrain.py:789-802 construction, :657 and :823 call sites; nn.LSTM gate order i, f, g, o).
 //
 // Two stages per layer:
-//   1. gx[d] = x @ W_ih[d]^T + b_ih[d] for every (b, t) at once: the tiled fp32 GEMM (gemm_f32.cu), one launch per direction.
+//   1. gx[d] = x @ W_ih[d]^T + b_ih[d] for every (b, t) at once, one GEMM per direction: the tiled FFMA GEMM (gemm_f32.cu) below
+//      2048 rows, the tcgen05 GEMM on 3-plane bf16 splits of x and W_ih (fp32-grade products, gemm_tc.cu) from there on.
 //   2. the recurrence: ONE cooperative launch for all T steps and both directions.  The hidden units are sliced across CTAs
 //      (UPC units = 4*UPC gate rows of W_hh per CTA, resident in shared memory for the whole sequence); per step a CTA reads
 //      h_{t-1} of every batch row from the layer output itself (L2), adds its slice of h W_hh^T to gx, applies the gates, keeps
@@ -13,6 +14,7 @@
 // ascending in k, then a butterfly: deterministic, and independent of the batch size within each of the three layouts.
 #include "common.cuh"
 #include "gemm_f32.cuh"
+#include "gemm_tc.cuh"
 
 namespace dimb {
 namespace {
@@ -208,15 +210,23 @@ void* rec_kernel(int kpn) {
   return kpn == 16 ? (void*)lstm_recurrence<UPC, 16> : kpn == 4 ? (void*)lstm_recurrence<UPC, 4> : (void*)lstm_recurrence<UPC, 1>;
 }
 
+constexpr int LSTM_TC_ROWS = 2048;     // from this many (clip, frame) rows on, the input GEMMs run on the tensor cores (3 bf16 planes:
+                                       // fp32-grade products, gemm_tc.cu); below it the FFMA GEMM is launch-latency bound anyway
 struct WsLayout {
-  size_t gx[2], c, bar, total;
+  size_t gx[2], c, bar, ap, wp[2], total;
+  int kp;                              // 0: FFMA input GEMMs
 };
-WsLayout ws_layout(int B, int T, int H, int ndir) {
+WsLayout ws_layout(int B, int T, int in_dim, int H, int ndir) {
   WsLayout w{};
   size_t off = 0;
   for (int d = 0; d < ndir; ++d) { w.gx[d] = off; off += align_up((size_t)B * T * 4 * H * sizeof(float), 256); }
   w.c = off; off += align_up((size_t)ndir * B * H * sizeof(float), 256);
   w.bar = off; off += 256;
+  if ((long)B * T >= LSTM_TC_ROWS) {
+    w.kp = tc_round_k(in_dim);
+    w.ap = off; off += align_up((size_t)B * T * 3 * w.kp * sizeof(__nv_bfloat16), 256);
+    for (int d = 0; d < ndir; ++d) { w.wp[d] = off; off += align_up((size_t)4 * H * 3 * w.kp * sizeof(__nv_bfloat16), 256); }
+  }
   w.total = off;
   return w;
 }
@@ -226,9 +236,9 @@ WsLayout ws_layout(int B, int T, int H, int ndir) {
 
 using namespace dimb;
 
-extern "C" size_t dim_lstm_layer_workspace_bytes(int B, int T, int H, int ndir) {
-  if (B <= 0 || T <= 0 || H <= 0 || ndir < 1 || ndir > 2) return 0;
-  return ws_layout(B, T, H, ndir).total;
+extern "C" size_t dim_lstm_layer_workspace_bytes(int B, int T, int in_dim, int H, int ndir) {
+  if (B <= 0 || T <= 0 || in_dim <= 0 || H <= 0 || ndir < 1 || ndir > 2) return 0;
+  return ws_layout(B, T, in_dim, H, ndir).total;
 }
 
 extern "C" int dim_lstm_layer_f32(const float* x, int in_dim, const float* w_ih, const float* w_hh, const float* b_ih,
@@ -240,7 +250,7 @@ extern "C" int dim_lstm_layer_f32(const float* x, int in_dim, const float* w_ih,
   DIM_REQUIRE(x && w_ih && w_hh && b_ih && b_hh && out && ws, "lstm: null operand");
   DIM_REQUIRE(ndir == 1 || (w_hh_r && b_ih_r && b_hh_r), "lstm: incomplete reverse direction");
   DIM_REQUIRE(B > 0 && T > 0 && in_dim > 0 && in_dim % 4 == 0 && H > 0 && H % LSTM_KC == 0, "lstm: bad shape (in_dim % 4, H % 64)");
-  const WsLayout L = ws_layout(B, T, H, ndir);
+  const WsLayout L = ws_layout(B, T, in_dim, H, ndir);
   DIM_REQUIRE(ws_bytes >= L.total, "lstm: workspace too small");
   cudaStream_t s = as_stream(stream);
   int dev = 0, sms = 0;
@@ -253,12 +263,27 @@ extern "C" int dim_lstm_layer_f32(const float* x, int in_dim, const float* w_ih,
   const float* wi[2] = {w_ih, w_ih_r};
   const float* bi[2] = {b_ih, b_ih_r};
   LstmArgs a{};
+  __nv_bfloat16* ap = L.kp ? reinterpret_cast<__nv_bfloat16*>(base + L.ap) : nullptr;
+  if (ap) {                                            // x -> bf16 planes once, shared by both directions
+    GemmArgs sp;
+    sp.A = x; sp.lda = in_dim; sp.M = B * T; sp.K = in_dim;
+    if (int e = launch_split_planes(sp, ap, L.kp, 3, s)) return e;
+  }
   for (int d = 0; d < ndir; ++d) {
     GemmArgs g;
     g.A = x; g.lda = in_dim; g.W = wi[d]; g.bias = bi[d];
     g.C = reinterpret_cast<float*>(base + L.gx[d]); g.ldc = 4 * H;
     g.M = B * T; g.N = 4 * H; g.K = in_dim;
-    if (int e = launch_gemm_f32(g, s)) return e;
+    if (ap) {
+      __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(base + L.wp[d]);
+      GemmArgs sw;
+      sw.A = wi[d]; sw.lda = in_dim; sw.M = 4 * H; sw.K = in_dim;
+      if (int e = launch_split_planes(sw, wp, L.kp, 3, s)) return e;
+      g.split_hint = DIM_SPLIT_NEVER;
+      if (int e = launch_gemm_tc(g, ap, wp, L.kp, 3, s)) return e;
+    } else if (int e = launch_gemm_f32(g, s)) {
+      return e;
+    }
     a.gx[d] = g.C;
   }
   a.whh[0] = w_hh; a.whh[1] = w_hh_r;

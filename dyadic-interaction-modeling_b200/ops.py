@@ -80,10 +80,10 @@ def lstm(x, params, hidden, layers=2, bidirectional=True, prefix=""):
     B, T, _ = x.shape
     lib = _lib.load()
     ndir = 2 if bidirectional else 1
-    nws = lib.dim_lstm_layer_workspace_bytes(B, T, hidden, ndir)
-    ws = torch.empty(nws, dtype=torch.uint8, device=x.device)
     cur = x
     for k in range(layers):
+        nws = lib.dim_lstm_layer_workspace_bytes(B, T, cur.shape[-1], hidden, ndir)
+        ws = torch.empty(nws, dtype=torch.uint8, device=x.device)
         names = [f"{prefix}{n}_l{k}{sfx}" for sfx in ("", "_reverse") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
         w = [_req(params[n].detach(), torch.float32, n) for n in names[:4]]
         w += [_req(params[n].detach(), torch.float32, n) for n in names[4:]] if bidirectional else [None] * 4

@@ -114,7 +114,7 @@ int dim_linear_ragged_f32(const float* A, int lda, const float* W, int ldw, cons
  * [0,H), reverse (when w_ih_r != NULL) in [H,2H).  Weights in torch's layout: w_ih [4H,in_dim], w_hh [4H,H], b_* [4H], gate
  * order i,f,g,o.  Replaces EmocaConverter.vertice_map_reverse_lstm (seq2seq_pretrain.py:789-802; calls :657, :823): call once
  * per layer, feeding layer k's out to layer k+1.  in_dim % 4 == 0, H % 64 == 0.  ws: dim_lstm_layer_workspace_bytes. */
-size_t dim_lstm_layer_workspace_bytes(int B, int T, int H, int ndir);
+size_t dim_lstm_layer_workspace_bytes(int B, int T, int in_dim, int H, int ndir);
 int dim_lstm_layer_f32(const float* x, int in_dim, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
                        const float* w_ih_r, const float* w_hh_r, const float* b_ih_r, const float* b_hh_r, int B, int T, int H,
                        float* out, void* ws, size_t ws_bytes, void* stream);

@@ -219,3 +219,13 @@ if has sanitize2; then
   echo "exit $?" >> $OUT/${TAG}_racecheck_lstm.log
   grep -E "RACECHECK SUMMARY|passed|failed|exit|hazard" $OUT/${TAG}_racecheck_lstm.log | sort | uniq -c | head -20
 fi
+if has ncuprefill; then
+  # --set full captures of the prefill attention (bf16 operands, Dh = 64: the SLMFT encoders) and of one tcgen05 prefill GEMM
+  timeout 900 ncu --set full --import-source on --clock-control none -k regex:attn_prefill_mma --launch-skip 8 -c 2 -o $OUT/${TAG}_ncu_attn -f \
+      python scripts/prefill_once.py > $OUT/${TAG}_ncu_attn.log 2>&1
+  ncu -i $OUT/${TAG}_ncu_attn.ncu-rep --page raw --csv > $OUT/${TAG}_ncu_attn.raw.csv 2>/dev/null
+  ncu -i $OUT/${TAG}_ncu_attn.ncu-rep --page details > $OUT/${TAG}_ncu_attn.details.txt 2>/dev/null
+  ncu -i $OUT/${TAG}_ncu_attn.ncu-rep --page source --csv --print-source sass > $OUT/${TAG}_ncu_attn.source.csv 2>/dev/null
+  gzip -f $OUT/${TAG}_ncu_attn.source.csv
+  ls -la $OUT/${TAG}_ncu_attn*; tail -3 $OUT/${TAG}_ncu_attn.log
+fi
