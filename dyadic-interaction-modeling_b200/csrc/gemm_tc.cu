@@ -345,6 +345,226 @@ __global__ void __launch_bounds__(192) gemm_bf16_tcgen05(const __grid_constant__
   }
 }
 
+// ---- persistent flavour for the large-M (prefill) GEMMs ---------------------------------------------------------------------
+// The one-tile-per-CTA kernel above pays barrier init + TMEM allocation + a cold pipeline per 128 x 128 tile and its epilogue
+// only overlaps the OTHER resident CTA's main loop through the shared smem port: ncu put its tensor pipe at 28-66 %
+// (profiles/r01z_ncu/summary.md).  Here one CTA per SM stays resident and walks the tile list (n fastest, so the CTAs of a wave
+// share their A panel through L2 and W stays L2-resident):
+//   * 128 x bn tiles, bn in {128, 192, 256} picked on the host so that N is covered without padding waste (1152 = 6 x 192):
+//     a 256-wide tile moves 1.5x fewer operand bytes per flop from L2 than a 128-wide one;
+//   * TWO accumulators in TMEM (2 x 256 of the 512 columns): the MMA warp starts tile i+1 while 8 epilogue warps drain tile i;
+//     tmem_full / tmem_empty mbarriers hand the halves back and forth;
+//   * the 4-slot TMA ring (16 KB A + up to 32 KB W per slot) never drains between tiles;
+//   * every epilogue warp owns 32 TMEM lanes x bn/2 columns and transposes them through a PRIVATE 32 x 16 staging block
+//     (__syncwarp only, no CTA-wide barrier anywhere in the steady state), then applies the same fused epilogue code, in the
+//     same order, as the kernel above -- the accumulation order over K is unchanged too, so results are bit-identical.
+constexpr int PG_THREADS = 320, PG_STAGES = 4, PG_EPI_WARPS = 8, PG_ACC_COLS = 256;
+constexpr uint32_t PG_A_BYTES = BM * BKE * 2;                       // 16 KB
+constexpr uint32_t PG_STAGE_BYTES = PG_A_BYTES + 256 * BKE * 2;     // + 32 KB W slot (a bn-row tile uses bn * 128 B of it)
+constexpr int PG_SP = 20;                                           // staging pitch in floats: conflict-free float4 rows
+constexpr uint32_t PG_STAGING = PG_EPI_WARPS * 32 * PG_SP * 4;
+constexpr size_t PG_SMEM = (size_t)PG_STAGES * PG_STAGE_BYTES + PG_STAGING + 1024;
+
+// bounded mbarrier wait: a protocol error traps after ~2 s instead of wedging the GPU
+__device__ __forceinline__ void pg_wait(uint32_t bar, uint32_t parity) {
+  unsigned long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((it & 1023) == 1023) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 2000000000ull) __trap();
+    }
+  }
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(PG_THREADS, 1) gemm_bf16_tcgen05_persist(const __grid_constant__ CUtensorMap tmA,
+                                                                           const __grid_constant__ CUtensorMap tmW, const TcParams p,
+                                                                           const int bn) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[PG_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[PG_STAGES];
+  __shared__ __align__(8) uint64_t tfull_bar[2];       // accumulator half complete (MMA -> epilogue)
+  __shared__ __align__(8) uint64_t tempty_bar[2];      // accumulator half drained (8 epilogue warps -> MMA)
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_kb = p.kblocks * p.npairs;
+  const int nt = (p.e.N + bn - 1) / bn, mt = (p.e.M + BM - 1) / BM, ntiles = mt * nt;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+#pragma unroll
+    for (int s = 0; s < PG_STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tfull_bar[a]), 1);
+      mbar_init(smem_u32(&tempty_bar[a]), PG_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {                                     // the whole TMEM: two 256-column accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(2 * PG_ACC_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_slot;
+  pdl_prologue();
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t stage_tx = PG_A_BYTES + (uint32_t)bn * (BKE * 2);
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int m_i = t / nt, n_i = t - m_i * nt;
+        const int m0 = m_i * BM, n0 = n_i * bn;
+        for (int it = 0; it < total_kb; ++it) {
+          const int pair = it / p.kblocks, kb = it - pair * p.kblocks;
+          pg_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, stage_tx);
+          const uint32_t sa = smem_base + stage * PG_STAGE_BYTES;
+          tma_load_2d(sa, &tmA, p.pa[pair] * p.kp + kb * BKE, m0, fb);
+          tma_load_2d(sa + PG_A_BYTES, &tmW, p.pw[pair] * p.kp + kb * BKE, n0, fb);
+          if (++stage == PG_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int i = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
+        const int a = i & 1;
+        pg_wait(smem_u32(&tempty_bar[a]), (((uint32_t)i >> 1) & 1u) ^ 1u);      // the epilogue has drained this half (first use: free)
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc = tmem_base + (uint32_t)(a * PG_ACC_COLS);
+        for (int it = 0; it < total_kb; ++it) {
+          pg_wait(smem_u32(&full_bar[stage]), phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_base + stage * PG_STAGE_BYTES;
+          const uint64_t adesc = make_sdesc(sa), bdesc = make_sdesc(sa + PG_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BKE / 16; ++k)
+            umma_f16(acc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit(smem_u32(&empty_bar[stage]));
+          if (++stage == PG_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(smem_u32(&tfull_bar[a]));
+      }
+    }
+  } else {
+    // ===== epilogue: warp w drains TMEM lanes 32*(w%4) .. +31 (hardware rule), column half (w-2)/4 of every tile =====
+    const int ew = warp - 2, q = warp & 3, hf = ew >> 2;
+    float* st = reinterpret_cast<float*>(smem + (size_t)PG_STAGES * PG_STAGE_BYTES) + (size_t)ew * 32 * PG_SP;
+    const int half = bn >> 1, cb = hf * half, ce = cb + half;
+    const GemmArgs& e = p.e;
+    const int rr = lane >> 2, cc = (lane & 3) * 4;      // re-read: 4 lanes per staged row, 8 rows per instruction
+    int i = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
+      const int a = i & 1;
+      const int m_i = t / nt, n_i = t - m_i * nt;
+      const int m0 = m_i * BM + q * 32, n0 = n_i * bn;
+      pg_wait(smem_u32(&tfull_bar[a]), ((uint32_t)i >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * PG_ACC_COLS);
+#pragma unroll 1
+      for (int c0 = cb; c0 < ce; c0 += 16) {
+        {
+          float v[16];
+          tmem_ld16(tl + (uint32_t)c0, v);
+          float* w = st + lane * PG_SP;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<float4*>(w + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        }
+        __syncwarp();
+        const int col = n0 + c0 + cc;
+        if (col < e.N) {                                 // N % 4 == 0: a float4 is entirely inside or outside
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+          float4 acc[4], res[4];
+          bool ok[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            ok[u] = m0 + u * 8 + rr < e.M;
+            res[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          if (e.residual) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (ok[u]) res[u] = *reinterpret_cast<const float4*>(e.residual + (size_t)(m0 + u * 8 + rr) * e.ldr + col);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] = *reinterpret_cast<const float4*>(st + (u * 8 + rr) * PG_SP + cc);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (!ok[u]) continue;
+            const int row = m0 + u * 8 + rr;
+            float4 o = acc[u];
+            o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w;
+            if (e.tab_mode != 0) o = tc_tab_add(e, o, row, col);
+            o.x = act_fixed<ACT>(o.x, e.slope); o.y = act_fixed<ACT>(o.y, e.slope);
+            o.z = act_fixed<ACT>(o.z, e.slope); o.w = act_fixed<ACT>(o.w, e.slope);
+            o.x = __fadd_rn(o.x, res[u].x); o.y = __fadd_rn(o.y, res[u].y);
+            o.z = __fadd_rn(o.z, res[u].z); o.w = __fadd_rn(o.w, res[u].w);
+            if (e.C) *reinterpret_cast<float4*>(e.C + (size_t)row * e.ldc + col) = o;
+            if (e.Cb) tc_emit_bf16(e, o, row, col);
+            if (e.Cp) {
+              if (e.cp_planes == 1) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(e.Cp + (size_t)row * e.cp_kp + col) = pk;
+              } else {
+                tc_emit_narrow(e, o, row, col);
+              }
+            }
+          }
+        }
+        __syncwarp();                                    // the staging block is rewritten by the next chunk
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty_bar[a])) : "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncwarp();                                          // re-converge the single-lane roles for the .aligned barrier
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * PG_ACC_COLS) : "memory");
+  }
+}
+
 // ---- host: tensor maps ----------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -426,6 +646,46 @@ int launch_tc_act(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcParams
   DIM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05<BN, STAGES, ACT>, tmA, tmW, p));
   DIM_LAUNCHED();
   return DIM_OK;
+}
+
+template <int ACT>
+int launch_tc_persist_act(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcParams& p, int bn, cudaStream_t s) {
+  static PerDeviceOnce once;
+  if (once.first())
+    DIM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_persist<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PG_SMEM));
+  int dev = 0, sms = 0;
+  DIM_CHECK_CUDA(cudaGetDevice(&dev));
+  DIM_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int ntiles = cdiv(p.e.M, BM) * cdiv(p.e.N, bn);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(std::min(sms, ntiles));
+  cfg.blockDim = dim3(PG_THREADS);
+  cfg.dynamicSmemBytes = PG_SMEM;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (g_pdl_on) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  const int planes_n = p.npairs == 1 ? 1 : (p.npairs == 3 ? 2 : 3);
+  ProfScope ps(CAT_GEMM_TC, s, 2.0 * ((double)p.e.M + p.e.N) * p.kp * planes_n + 4.0 * p.e.M * p.e.N,
+               2.0 * p.e.M * (double)p.e.N * p.kp * p.npairs);
+  DIM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_persist<ACT>, tmA, tmW, p, bn));
+  DIM_LAUNCHED();
+  return DIM_OK;
+}
+
+int launch_tc_persist(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcParams& p, int bn, cudaStream_t s) {
+  switch (p.e.act) {
+    case DIM_ACT_LEAKY: return launch_tc_persist_act<DIM_ACT_LEAKY>(tmA, tmW, p, bn, s);
+    case DIM_ACT_GELU_TANH: return launch_tc_persist_act<DIM_ACT_GELU_TANH>(tmA, tmW, p, bn, s);
+    case DIM_ACT_GELU_ERF: return launch_tc_persist_act<DIM_ACT_GELU_ERF>(tmA, tmW, p, bn, s);
+    default: return launch_tc_persist_act<DIM_ACT_NONE>(tmA, tmW, p, bn, s);
+  }
 }
 
 template <int BN, int STAGES>
@@ -603,6 +863,17 @@ int launch_gemm_tc(const GemmArgs& e, const __nv_bfloat16* Ap, const __nv_bfloat
   if (g_tc_force_splits > 0) p.splits = g_tc_force_splits;
   while (p.splits > 1 && p.splits > total_kb) p.splits >>= 1;
   CUtensorMap tmA, tmW;
+  // Large-M (prefill) GEMMs: the persistent kernel with a double-buffered TMEM accumulator.  Tile width = the widest of 256 / 192 /
+  // 128 that covers N without padding waste -- a function of N only.  DIM_GEMM_PERSIST=0 keeps the one-tile-per-CTA kernel (A/B).
+  static const bool persist_off = getenv("DIM_GEMM_PERSIST") != nullptr && atoi(getenv("DIM_GEMM_PERSIST")) == 0;
+  if (!persist_off && !conv && !skinny && p.splits == 1 && e.N >= 128 && g_tc_force_bn == 0 && p.dbg == nullptr) {
+    int pbn = 256, best = cdiv(e.N, 256) * 256;
+    if (cdiv(e.N, 192) * 192 < best) { pbn = 192; best = cdiv(e.N, 192) * 192; }
+    if (cdiv(e.N, 128) * 128 < best) { pbn = 128; best = cdiv(e.N, 128) * 128; }
+    if (int err = make_map(Ap, e.M, planes * kp, planes * kp, BM, &tmA)) return err;
+    if (int err = make_map(Wp, e.N, planes * kp, planes * kp, pbn, &tmW)) return err;
+    return launch_tc_persist(tmA, tmW, p, pbn, s);
+  }
   if (conv) {
     if (int err = make_map(Ap, p.conv_Mp, planes * p.a_kp, planes * p.a_kp, BM, &tmA)) return err;
   } else if (int err = make_map(Ap, e.M, planes * kp, planes * kp, BM, &tmA)) return err;

@@ -193,6 +193,39 @@ def test_linear_tcgen05(M, N, K, planes):
     assert err <= tol, err
 
 
+@pytest.mark.parametrize("M,N,K", [(4096, 1152, 768), (2500, 768, 1152), (2048, 1000, 384), (3000, 4608, 1152), (2048, 128, 384),
+                                    (5000, 2304, 1152), (2304, 192, 64), (19072, 1152, 1152)])
+@pytest.mark.parametrize("planes", [1, 3])
+@pytest.mark.parametrize("act", [0, 3])
+def test_linear_tcgen05_persistent(M, N, K, planes, act):
+    """Large-M GEMMs run on the persistent kernel (gemm_bf16_tcgen05_persist: 128 x 256/192/128 tiles, two TMEM accumulators).  It
+    must agree with the fp32 reference like the one-tile-per-CTA kernel does AND be bit-identical to it (same accumulation order
+    over K, same epilogue arithmetic): forcing a tile width through the tuning hook selects the old kernel."""
+    from dim_b200 import ops, _lib
+    g = _g(M + N + K + planes)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / math.sqrt(K)
+    b = torch.randn(N, generator=g) * 0.1
+    r = torch.randn(M, N, generator=g)
+    ac, wc, bc, rc = a.cuda(), w.cuda(), b.cuda(), r.cuda()
+    out = ops.linear_tc(ac, wc, bc, rc, act=act, planes=planes)
+    lib = _lib.load()
+    lib.dim_debug_tc_bn(128)
+    try:
+        old = ops.linear_tc(ac, wc, bc, rc, act=act, planes=planes)
+    finally:
+        lib.dim_debug_tc_bn(0)
+    assert torch.equal(out, old)
+    f = (lambda x: 0.5 * x * (1.0 + torch.erf(x * 0.7071067811865476))) if act == 3 else (lambda x: x)
+    if planes == 1:
+        ref = f(F.linear(a.bfloat16().float(), w.bfloat16().float(), b)) + r
+    else:
+        ref = f(F.linear(a, w, b)) + r
+    tol = 2e-5 * max(1.0, K / 1152)
+    err = float((out.cpu() - ref).abs().max())
+    assert err <= tol, err
+
+
 def test_split_planes_is_exact():
     from dim_b200 import ops
     x = torch.randn(37, 56, generator=_g(2)) * 3
