@@ -392,7 +392,7 @@ __device__ __forceinline__ void pg_wait(uint32_t bar, uint32_t parity) {
 template <int ACT>
 __global__ void __launch_bounds__(PG_THREADS, 1) gemm_bf16_tcgen05_persist(const __grid_constant__ CUtensorMap tmA,
                                                                            const __grid_constant__ CUtensorMap tmW, const TcParams p,
-                                                                           const int bn) {
+                                                                           const int bn, const int pf, const int rpf) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[PG_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[PG_STAGES];
@@ -438,11 +438,26 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_bf16_tcgen05_persist(const
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t stage_tx = PG_A_BYTES + (uint32_t)bn * (BKE * 2);
+      // Optional L2 prefetch cursor, `pf` k-blocks ahead of the loads (DIM_GEMM_PF, default 0 = off).  Measured (B200, M = 76800): a
+      // k-block costs ~600 + 1.3 bn cycles against 2 bn of MMA time, but an extra tensor prefetch per k-block made it WORSE
+      // (1262 -> 835 TFLOP/s at N = 1536, K = 1152, 6 plane pairs; profiles/r02_prefill_gemm_pf.txt): the cost is per TMA
+      // request, not HBM latency -- fewer operand rows per flop (wider tiles, CTA pairs) is what helps, not earlier requests.
+      int pt = blockIdx.x, pit = 0;
+      auto prefetch_next = [&]() {
+        if (pt >= ntiles) return;
+        const int pm = pt / nt, pn = pt - pm * nt;
+        const int pair = pit / p.kblocks, kb = pit - pair * p.kblocks;
+        tma_prefetch_2d(&tmA, p.pa[pair] * p.kp + kb * BKE, pm * BM);
+        if (pt == (int)blockIdx.x) tma_prefetch_2d(&tmW, p.pw[pair] * p.kp + kb * BKE, pn * bn);
+        if (++pit == total_kb) { pit = 0; pt += gridDim.x; }
+      };
+      for (int i = 0; i < pf; ++i) prefetch_next();
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int m_i = t / nt, n_i = t - m_i * nt;
         const int m0 = m_i * BM, n0 = n_i * bn;
         for (int it = 0; it < total_kb; ++it) {
           const int pair = it / p.kblocks, kb = it - pair * p.kblocks;
+          if (pf > 0) prefetch_next();
           pg_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_expect_tx(fb, stage_tx);
@@ -491,6 +506,15 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_bf16_tcgen05_persist(const
       const int a = i & 1;
       const int m_i = t / nt, n_i = t - m_i * nt;
       const int m0 = m_i * BM + q * 32, n0 = n_i * bn;
+      if (e.residual && rpf && t + (int)gridDim.x < ntiles) {
+        // residual rows of this CTA's NEXT tile -> L2 (one row segment per lane): the epilogue keeps only 4 float4 per lane in flight,
+        // far too few to stream a cold residual tile at HBM latency
+        const int t2 = t + (int)gridDim.x, m2 = t2 / nt, n2 = t2 - m2 * nt;
+        const int row = m2 * BM + q * 32 + lane, c2 = n2 * bn + cb;
+        const int cols = min(half, e.N - c2);
+        if (row < e.M && cols > 0)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(e.residual + (size_t)row * e.ldr + c2), "r"(cols * 4) : "memory");
+      }
       pg_wait(smem_u32(&tfull_bar[a]), ((uint32_t)i >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * PG_ACC_COLS);
@@ -674,7 +698,9 @@ int launch_tc_persist_act(const CUtensorMap& tmA, const CUtensorMap& tmW, const 
   const int planes_n = p.npairs == 1 ? 1 : (p.npairs == 3 ? 2 : 3);
   ProfScope ps(CAT_GEMM_TC, s, 2.0 * ((double)p.e.M + p.e.N) * p.kp * planes_n + 4.0 * p.e.M * p.e.N,
                2.0 * p.e.M * (double)p.e.N * p.kp * p.npairs);
-  DIM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_persist<ACT>, tmA, tmW, p, bn));
+  static const int pf = getenv("DIM_GEMM_PF") ? std::max(0, atoi(getenv("DIM_GEMM_PF"))) : 0;      // operand L2 prefetch distance in k-blocks
+  static const int rpf = getenv("DIM_GEMM_RPF") ? atoi(getenv("DIM_GEMM_RPF")) : 0;               // residual rows of the next tile -> L2 (measured: no gain)
+  DIM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_persist<ACT>, tmA, tmW, p, bn, pf, rpf));
   DIM_LAUNCHED();
   return DIM_OK;
 }
@@ -866,10 +892,14 @@ int launch_gemm_tc(const GemmArgs& e, const __nv_bfloat16* Ap, const __nv_bfloat
   // Large-M (prefill) GEMMs: the persistent kernel with a double-buffered TMEM accumulator.  Tile width = the widest of 256 / 192 /
   // 128 that covers N without padding waste -- a function of N only.  DIM_GEMM_PERSIST=0 keeps the one-tile-per-CTA kernel (A/B).
   static const bool persist_off = getenv("DIM_GEMM_PERSIST") != nullptr && atoi(getenv("DIM_GEMM_PERSIST")) == 0;
-  if (!persist_off && !conv && !skinny && p.splits == 1 && e.N >= 128 && g_tc_force_bn == 0 && p.dbg == nullptr) {
+  if (!persist_off && !conv && !skinny && p.splits == 1 && e.N >= 128 && g_tc_force_bn <= 0 && p.dbg == nullptr) {
     int pbn = 256, best = cdiv(e.N, 256) * 256;
     if (cdiv(e.N, 192) * 192 < best) { pbn = 192; best = cdiv(e.N, 192) * 192; }
     if (cdiv(e.N, 128) * 128 < best) { pbn = 128; best = cdiv(e.N, 128) * 128; }
+    // long main loops (>= 24 k-block iterations per tile) are bound by operand traffic, where the widest tile wins even with
+    // 10 % of padded columns (N = 1152, 6 pairs, K = 384: 390 us at 256 vs 418 at 192); short ones by the epilogue, where padding loses
+    if (total_kb >= 24 && e.N >= 1024 && cdiv(e.N, 256) * 256 * 8 <= e.N * 9) pbn = 256;
+    if (g_tc_force_bn < 0) pbn = -g_tc_force_bn;          // tuning hook: dim_debug_tc_bn(-bn), bn % 32 == 0, 32 <= bn <= 256
     if (int err = make_map(Ap, e.M, planes * kp, planes * kp, BM, &tmA)) return err;
     if (int err = make_map(Wp, e.N, planes * kp, planes * kp, pbn, &tmW)) return err;
     return launch_tc_persist(tmA, tmW, p, pbn, s);

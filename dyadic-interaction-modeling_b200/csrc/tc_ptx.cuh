@@ -39,6 +39,10 @@ __device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap
       "l"(map), "r"(x), "r"(y), "r"(bar), "l"(policy)
       : "memory");
 }
+// box of a tensor map -> L2 only (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, int y) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
+}
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
 //   start address >> 4 | LBO (=1, unused for swizzled K-major) << 16 | SBO (1024 B between 8-row groups) >> 4 << 32 |
 //   version 1 << 46 | layout SWIZZLE_128B (2) << 61
