@@ -36,14 +36,19 @@ namespace dimb {
 
 namespace {
 
-constexpr int MK_THREADS = 384;                     // 12 warps
-constexpr int MK_WARPS = MK_THREADS / 32;
-constexpr int MK_NSUB = MK_THREADS / 64;            // attention sub-groups per CTA
+// Threads per CTA: 384 (12 warps, 6 attention sub-groups of 64 threads) or, for bf16 caches with the mma.sync attention items, 512
+// (16 warps, 8 sub-groups: the attention phases are neither issue- nor HBM-bound with 6 -- 27 % of the issue slots, 64 % of the HBM
+// peak -- so two more items in flight per SM shorten them, and 3072 items make 3 rounds of 1184 instead of 4 of 888).  The wide
+// flavour is a separate instantiation limited to 128 registers; it leaves out the FFMA attention items (64 registers of q alone).
+constexpr int MK_THREADS = 384, MK_THREADS_WIDE = 512;
+constexpr int MK_MAX_WARPS = MK_THREADS_WIDE / 32;
+constexpr int MK_MAX_NSUB = MK_THREADS_WIDE / 64;
+#define MK_NTHREADS ((int)blockDim.x)
+#define MK_NWARPS ((int)(blockDim.x >> 5))
 constexpr int MK_STAGES = 6;
 constexpr uint32_t MK_A_BYTES = 128 * 64 * 2;       // one A tile: 128 rows x 64 bf16 (128-byte swizzle rows)
 constexpr uint32_t MK_SLOT = 2 * MK_A_BYTES;        // ring slot: A tile + W tile of up to 128 rows
 constexpr uint32_t MK_RING = MK_STAGES * MK_SLOT;   // 192 KB, also the attention / staging scratch
-constexpr uint32_t MK_SUB_BYTES = MK_RING / MK_NSUB;
 constexpr int MK_TMEM_COLS = 128;
 constexpr int MK_MAXS = 9;                          // largest split-K factor (engine.cu: mk_gemm_cfg)
 constexpr unsigned long long MK_TIMEOUT_NS = 4000000000ull;
@@ -114,8 +119,8 @@ struct Ctl {             // static shared memory
   uint64_t accum_bar;
   uint32_t tmem_slot;
   int attn_ctr;
-  int sub_item[MK_NSUB];
-  float red[2 * MK_WARPS];               // block reductions of the row phases
+  int sub_item[MK_MAX_NSUB];
+  float red[2 * MK_MAX_WARPS];           // block reductions of the row phases
   int tok[2];
 };
 
@@ -207,7 +212,7 @@ __device__ __forceinline__ void mk_gemm(const MkPlan& P, const MkPhase& ph, uint
         if (col < N) {
           float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
           if (ph.bias) bb = __ldg(reinterpret_cast<const float4*>(ph.bias + col));
-          for (int r = warp * RPI + lane / LPR; r < rows; r += MK_WARPS * RPI) {
+          for (int r = warp * RPI + lane / LPR; r < rows; r += MK_NWARPS * RPI) {
             float4 v = *reinterpret_cast<const float4*>(stage_tile + (size_t)r * CP + c);
             v.x = act_apply(v.x + bb.x, DIM_ACT_GELU_ERF, 0.f); v.y = act_apply(v.y + bb.y, DIM_ACT_GELU_ERF, 0.f);
             v.z = act_apply(v.z + bb.z, DIM_ACT_GELU_ERF, 0.f); v.w = act_apply(v.w + bb.w, DIM_ACT_GELU_ERF, 0.f);
@@ -217,7 +222,7 @@ __device__ __forceinline__ void mk_gemm(const MkPlan& P, const MkPhase& ph, uint
       } else {
         float* dst = ph.part + ((size_t)z * M + m0) * N + col;
         if (col < N)
-          for (int r = warp * RPI + lane / LPR; r < rows; r += MK_WARPS * RPI)
+          for (int r = warp * RPI + lane / LPR; r < rows; r += MK_NWARPS * RPI)
             *reinterpret_cast<float4*>(dst + (size_t)r * N) = *reinterpret_cast<const float4*>(stage_tile + (size_t)r * CP + c);
       }
     }
@@ -242,7 +247,7 @@ __device__ __forceinline__ void mk_gemv(const MkPlan& P, const MkPhase& ph, uint
   const int kw = W16 ? kp : ph.K;                       // weights per row actually streamed
   const int nvec = kw / EPV;
   float* a_s = reinterpret_cast<float*>(smem);          // [M][kp]
-  const int gw = (int)blockIdx.x * MK_WARPS + warp, nw = (int)gridDim.x * MK_WARPS;
+  const int gw = (int)blockIdx.x * MK_NWARPS + warp, nw = (int)gridDim.x * MK_NWARPS;
   const uint4* wrow0 = W16 ? reinterpret_cast<const uint4*>(ph.wb) : reinterpret_cast<const uint4*>(ph.w32);
   const size_t row_vecs = (size_t)(W16 ? kp : ph.K) / EPV;
   uint4 wv[NB];
@@ -258,7 +263,7 @@ __device__ __forceinline__ void mk_gemv(const MkPlan& P, const MkPhase& ph, uint
   if (n < N) load_batch(n, 0);
   {  // stage A: fp32 = sum of the planes in plane order (h + m, then + l: both sums exact)
     const int v8 = kp / 8;
-    for (int i = threadIdx.x; i < M * v8; i += MK_THREADS) {
+    for (int i = threadIdx.x; i < M * v8; i += MK_NTHREADS) {
       const int m = i / v8, j = i - m * v8;
       float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       for (int pl = 0; pl < P.planes; ++pl) {
@@ -512,6 +517,40 @@ __device__ __forceinline__ uint32_t pack_part(float x, float y, int sel) {
   return sel <= 1 ? w : 0u;
 }
 
+// rows [c*64, c*64+64) of a bf16 head block -> one ring slot (64 rows of 144 bytes); thread -> 8 fixed 16-byte pieces (rows tid/8 + 8i,
+// chunk tid%8); rows past the last cached key (>= nold) are zero-filled
+__device__ __forceinline__ void mk_issue_kv_tile(const __nv_bfloat16* head, int c, int nold, uint32_t slot_addr, int tid, uint64_t kvpol) {
+  const int row0 = c * 64, valid = nold - row0, row_t = tid >> 3;
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(head + (size_t)row0 * 64) + tid * 16;
+  const uint32_t dst = slot_addr + (uint32_t)(row_t * 144 + (tid & 7) * 16);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool ok = row_t + 8 * i < valid;
+    cp_async_16_zfill(dst + i * 8 * 144, ok ? src + i * 1024 : reinterpret_cast<const uint8_t*>(head), ok ? 16u : 0u, kvpol);
+  }
+}
+
+// The first tiles of every sub-group's FIRST item do not depend on the projection GEMM that precedes an attention phase (they are
+// cached keys of earlier steps / of the context): at the END of that GEMM phase one lane per sub-group asks for them with an L2
+// bulk prefetch, so they come from HBM during the grid barrier and the cp.async stream after it starts on L2 hits.  (Requesting the
+// tiles themselves with cp.async before the barrier was measured and lost: the barrier's gpu-scope release waits for the CTA's pending
+// cp.async, +2.5-3 us per projection phase against -2.6 us per attention phase; profiles/r02_notes.md.)  The first nsub entries of a
+// CTA's item list are therefore assigned statically (entry s to sub-group s); the rest are still handed out through the shared counter.
+__device__ __forceinline__ void mk_attn_prefetch(const MkPlan& P, const MkPhase& ph, int pos) {
+  const int sub = threadIdx.x >> 6, tid = threadIdx.x & 63;
+  if (sub >= P.attn_nsub || tid >= 2) return;          // lane 0: K block, lane 1: V block
+  const int items = P.B * P.H;
+  const int mine = (int)blockIdx.x < items ? (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int nold = ph.append ? pos : ph.Tk;
+  if (sub >= mine || nold <= 0) return;
+  const int item = (int)blockIdx.x + sub * (int)gridDim.x;
+  const int b = item / P.H, h = item - b * P.H, bkv = b / ph.kv_group;
+  const size_t off = (size_t)bkv * ph.kv_batch_stride + (size_t)h * ph.kv_head_stride;
+  const __nv_bfloat16* head = static_cast<const __nv_bfloat16*>(tid == 0 ? ph.kcache : ph.vcache) + off;
+  const int rows = min(nold, tid == 0 ? P.attn_pre : P.attn_pre / 2);       // rows of 128 bytes
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(head), "r"(rows * 128) : "memory");
+}
+
 // The K tiles then the V tiles of an item form one stream of 2*nch tiles through an NST-slot cp.async ring, and the stream runs on
 // into the NEXT item of the sub-group (every item of a phase has the same tile count): while an item finishes (softmax tail, output
 // reduction, store) and the next one sums its projection partials, the next item's first tiles are already in flight.  `issued`
@@ -522,8 +561,8 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
                                                  int tid, int item, int next_item, int pos, int& issued, int& g0) {
   constexpr int NT = 64, DH = 64, CHUNK = 64, PITCH = 144, STAGE = CHUNK * PITCH;
   float* sc = reinterpret_cast<float*>(reg + NST * STAGE);
-  float* part = sc + sc_floats;                        // [2][64] partial outputs of the two warps (sized [8][64] by the carve)
-  float* qs = part + 8 * DH;                           // [64]
+  float* part = sc + sc_floats;                        // [2][64] partial outputs of the two warps
+  float* qs = part + 2 * DH;                           // [64]
   float* red = qs + DH;                                // [4]
   float* knew = red + 4;                               // [64] this step's key row (append)
   float* vnew = knew + DH;                             // [64]
@@ -538,9 +577,6 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
   const int nch = (nold + CHUNK - 1) / CHUNK;
   uint64_t kvpol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(kvpol));
-  // thread -> 8 fixed 16-byte pieces of a tile: rows tid/8 + 8i, chunk tid%8
-  const uint32_t dst0 = (uint32_t)((tid >> 3) * PITCH + (tid & 7) * 16);
-  const int row_t = tid >> 3;
   const int n = 2 * nch;                                // tiles of one item's stream
   // head blocks of the next item (its first tiles are prefetched at the end of this one): computed once, not per tile
   const __nv_bfloat16 *knext = khead, *vnext = vhead;
@@ -551,14 +587,7 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
     vnext = static_cast<const __nv_bfloat16*>(ph.vcache) + off;
   }
   auto issue_tile = [&](const __nv_bfloat16* head, int c, int slot) {     // rows [c*64, c*64+64) of a head block -> ring[slot]
-    const int row0 = c * CHUNK, valid = nold - row0;                     // rows >= valid are zero-filled
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(head + (size_t)row0 * DH) + tid * 16;
-    const uint32_t dst = ring_u + slot * STAGE + dst0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const bool ok = row_t + 8 * i < valid;
-      cp_async_16_zfill(dst + i * 8 * PITCH, ok ? src + i * 1024 : reinterpret_cast<const uint8_t*>(head), ok ? 16u : 0u, kvpol);
-    }
+    mk_issue_kv_tile(head, c, nold, ring_u + slot * STAGE, tid, kvpol);
   };
   int slot_next = issued % NST;                         // ring slot of stream position `issued`
   auto issue_upto = [&](int limit) {                    // commit one group per stream position below `limit`
@@ -741,8 +770,10 @@ __device__ __forceinline__ void mk_attn_mma_loop(const MkPlan& P, const MkPhase&
     bar_sub(sub);
     return k;
   };
+  // entry `sub` of the list is this sub-group's first item (mk_attn starts the counter at nsub): mk_attn_prefetch has asked for its
+  // first tiles before the grid barrier
   int issued = 0, g0 = 0;
-  int k = fetch();
+  int k = sub;
   while (k < mine) {
     const int kn = fetch();
     const int item = (int)blockIdx.x + k * (int)gridDim.x;
@@ -754,27 +785,32 @@ __device__ __forceinline__ void mk_attn_mma_loop(const MkPlan& P, const MkPhase&
   cp_async_wait<0>();                                  // only empty groups can be pending here
 }
 
+template <bool WIDE>
 __device__ __forceinline__ void mk_attn(const MkPlan& P, const MkPhase& ph, uint8_t* smem, Ctl& ctl, int pos) {
   const int items = P.B * P.H;
   const int mine = (int)blockIdx.x < items ? (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  if (threadIdx.x == 0) ctl.attn_ctr = 0;
+  const bool mma = WIDE || (P.kv_bf16 && P.attn_mma);
+  if (threadIdx.x == 0) ctl.attn_ctr = mma ? P.attn_nsub : 0;      // mma items: the first nsub entries are assigned statically
   __syncthreads();
   const int sub = threadIdx.x >> 6, tid = threadIdx.x & 63;
-  uint8_t* reg = smem + (size_t)sub * MK_SUB_BYTES;
-  if (P.kv_bf16 && P.attn_mma) {
+  if (sub >= P.attn_nsub) return;                      // long key lists: fewer, larger scratch regions than 64-thread groups
+  uint8_t* reg = smem + (size_t)sub * (MK_RING / (uint32_t)P.attn_nsub);
+  if (mma) {
     if (P.attn_stages == 3) mk_attn_mma_loop<3>(P, ph, reg, ctl, sub, tid, mine, pos);
     else mk_attn_mma_loop<2>(P, ph, reg, ctl, sub, tid, mine, pos);
     return;
   }
-  for (;;) {
-    if (tid == 0) ctl.sub_item[sub] = atomicAdd(&ctl.attn_ctr, 1);
-    bar_sub(sub);
-    const int k = ctl.sub_item[sub];
-    if (k >= mine) break;
-    const int item = (int)blockIdx.x + k * (int)gridDim.x;
-    if (P.kv_bf16) mk_attn_item<true>(ph, P.B, P.H, P.planes, P.sc_floats, reg, sub, tid, item, pos);
-    else mk_attn_item<false>(ph, P.B, P.H, P.planes, P.sc_floats, reg, sub, tid, item, pos);
-    bar_sub(sub);
+  if constexpr (!WIDE) {
+    for (;;) {
+      if (tid == 0) ctl.sub_item[sub] = atomicAdd(&ctl.attn_ctr, 1);
+      bar_sub(sub);
+      const int k = ctl.sub_item[sub];
+      if (k >= mine) break;
+      const int item = (int)blockIdx.x + k * (int)gridDim.x;
+      if (P.kv_bf16) mk_attn_item<true>(ph, P.B, P.H, P.planes, P.sc_floats, reg, sub, tid, item, pos);
+      else mk_attn_item<false>(ph, P.B, P.H, P.planes, P.sc_floats, reg, sub, tid, item, pos);
+      bar_sub(sub);
+    }
   }
 }
 
@@ -788,11 +824,12 @@ __device__ __forceinline__ void block_sum2(float& a, float& b, float* red) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   a = warp_sum(a);
   b = warp_sum(b);
-  if (lane == 0) { red[warp] = a; red[MK_WARPS + warp] = b; }
+  if (lane == 0) { red[warp] = a; red[MK_MAX_WARPS + warp] = b; }
   __syncthreads();
   float sa = 0.f, sb = 0.f;
-#pragma unroll
-  for (int w = 0; w < MK_WARPS; ++w) { sa += red[w]; sb += red[MK_WARPS + w]; }
+  const int nwarps = MK_NWARPS;
+#pragma unroll 4
+  for (int w = 0; w < nwarps; ++w) { sa += red[w]; sb += red[MK_MAX_WARPS + w]; }
   __syncthreads();
   a = sa;
   b = sb;
@@ -884,8 +921,8 @@ __device__ __forceinline__ void mk_row_gelu(const MkPlan& P, const MkPhase& ph) 
   constexpr int U = 3;
   const int N = ph.N, n4 = N >> 2;
   const size_t mn = (size_t)ph.M * N;
-  const int total = ph.M * n4, stride = (int)gridDim.x * MK_THREADS;
-  for (int i0 = (int)blockIdx.x * MK_THREADS + (int)threadIdx.x; i0 < total; i0 += U * stride) {
+  const int total = ph.M * n4, stride = (int)gridDim.x * MK_NTHREADS;
+  for (int i0 = (int)blockIdx.x * MK_NTHREADS + (int)threadIdx.x; i0 < total; i0 += U * stride) {
     float4 a[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -1035,7 +1072,7 @@ __device__ __forceinline__ void mk_row_sample(const MkPlan& P, const MkPhase& ph
   for (int r0 = (int)blockIdx.x; r0 < ph.M; r0 += 2 * (int)gridDim.x) {
     const int row[2] = {r0, r0 + (int)gridDim.x};
     const bool on[2] = {true, row[1] < ph.M};
-    for (int f = c; f < 2 * v4; f += MK_THREADS) {
+    for (int f = c; f < 2 * v4; f += MK_NTHREADS) {
       const int k = f / v4, j = f - k * v4;
       if (!on[k]) continue;
       float4 a = sum_slices(ph.part + (size_t)row[k] * V + j * 4, mn, ph.in_splits);
@@ -1078,8 +1115,8 @@ __device__ __forceinline__ void mk_row_sample(const MkPlan& P, const MkPhase& ph
 
 // SMALL: the <= 8-row flavour (GEMV phases, no tile GEMM): a separate instantiation so that the GEMV's registers (9 weight vectors in
 // flight per lane) do not spill the tile kernel's hot loops.
-template <bool SMALL>
-__global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const __grid_constant__ MkPlan P) {
+template <bool SMALL, bool WIDE>
+__global__ void __launch_bounds__(WIDE ? MK_THREADS_WIDE : MK_THREADS, 1) decode_megakernel(const __grid_constant__ MkPlan P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) Ctl ctl;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B tiles need 1024-byte alignment
@@ -1125,11 +1162,14 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const __grid_
           else if (P.planes == 1) mk_gemv<true>(P, ph, smem);
           else mk_gemv<false>(P, ph, smem);
           break;
-        case MK_ATTN: mk_attn(P, ph, smem, ctl, st); break;
+        case MK_ATTN: mk_attn<WIDE>(P, ph, smem, ctl, st); break;
         case MK_ROW_RESLN: mk_row_resln(P, ph, ctl); break;
         case MK_ROW_GELU: mk_row_gelu(P, ph); break;
         case MK_ROW_SAMPLE: mk_row_sample(P, ph, reinterpret_cast<float*>(smem), ctl, st); break;
         default: break;
+      }
+      if (!SMALL && P.attn_pre && ph.type == MK_GEMM && P.phases[nxt].type == MK_ATTN && nxt > i) {
+        mk_attn_prefetch(P, P.phases[nxt], st);
       }
       grid_sync(P.bar, bar_target, P.phases[nxt].type == MK_GEMM && !P.phases[nxt].gemv);
       if (tracing) {
@@ -1155,8 +1195,17 @@ bool mk_supported(int D, int inner, int F, int V, int H, int planes, int max_key
   if (D % 64 || inner % 64 || F % 64 || D > 4 * MK_THREADS || inner != H * 64) return false;
   if (!(V == 256 || V == 512 || V == 1024)) return false;
   // per attention sub-group: 2-stage K/V ring + scores + partial outputs + q + reduction slots
-  const size_t need = 2 * 64 * 144 + (size_t)((max_keys + 3) / 4 * 4) * 4 + 8 * 64 * 4 + 3 * 64 * 4 + 16;
-  return need <= MK_SUB_BYTES;
+  return mk_attn_scratch(max_keys) <= MK_RING / 6;
+}
+
+size_t mk_attn_scratch(int max_keys) { return 2 * 64 * 144 + (size_t)((max_keys + 3) / 4 * 4) * 4 + 8 * 64 * 4 + 3 * 64 * 4 + 16; }
+
+int mk_attn_subgroups(int kv_bf16, int attn_mma, int small, int max_keys) {
+  static const bool wide_off = getenv("DIM_MK_WIDE") != nullptr && atoi(getenv("DIM_MK_WIDE")) == 0;      // A/B hook
+  if (wide_off || !kv_bf16 || !attn_mma || small) return 6;
+  // the mma items keep [2][64] partial outputs, not [8][64]
+  const size_t need = 2 * 64 * 144 + (size_t)((max_keys + 3) / 4 * 4) * 4 + 2 * 64 * 4 + 3 * 64 * 4 + 16;
+  return need <= MK_RING / 8 ? 8 : 6;
 }
 
 int launch_decode_megakernel(const MkPlan& plan, cudaStream_t s) {
@@ -1168,14 +1217,17 @@ int launch_decode_megakernel(const MkPlan& plan, cudaStream_t s) {
   DIM_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   bool small = false;
   for (int i = 0; i < plan.nphases; ++i) small = small || (plan.phases[i].type == MK_GEMM && plan.phases[i].gemv);
-  auto kern = small ? decode_megakernel<true> : decode_megakernel<false>;
+  DIM_REQUIRE(plan.attn_nsub == 6 || (plan.attn_nsub == 8 && !small && plan.kv_bf16 && plan.attn_mma), "decode megakernel: bad sub-group count");
+  const bool wide = plan.attn_nsub == 8;
+  const int threads = wide ? MK_THREADS_WIDE : MK_THREADS;
+  auto kern = small ? decode_megakernel<true, false> : (wide ? decode_megakernel<false, true> : decode_megakernel<false, false>);
   DIM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  DIM_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MK_THREADS, smem));
+  DIM_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   DIM_REQUIRE(per_sm >= 1, "decode megakernel: one CTA does not fit an SM");
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(sms);
-  cfg.blockDim = dim3(MK_THREADS);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];

@@ -61,6 +61,9 @@ struct alignas(128) MkPlan {
   int steps;
   int attn_stages;                           // cp.async ring slots of the mma attention items (3 when the scores fit beside them)
   int attn_mma;                              // bf16 caches: 1 = mma.sync attention items, 0 = FFMA items (A/B hook DIM_MK_ATTN_FFMA)
+  int attn_pre;                              // mma items: rows of the first item's K block (half as many of V) prefetched into L2 before the
+                                             // grid barrier that precedes an attention phase (DIM_MK_ATTN_PRE=rows, 0 = off)
+  int attn_nsub;                             // attention sub-groups per CTA: 6 (384 threads) or 8 (512-thread flavour, mk_attn_subgroups)
   int sc_floats;                             // score slots per attention work item (>= max keys, multiple of 4)
   unsigned int* bar;                         // grid barrier counter, zero at launch
   unsigned long long* trace;                 // nullable: [MK_MAX_PHASES] ns spent per phase (summed over steps), CTA 0's view
@@ -76,6 +79,9 @@ struct alignas(128) MkPlan {
 
 // True when the persistent kernel can decode this configuration (otherwise the caller keeps the per-kernel path).
 bool mk_supported(int D, int inner, int F, int V, int H, int planes, int max_keys);
+// Bytes of shared-memory scratch one attention sub-group needs for `max_keys` keys, and the sub-group count the launch will use.
+size_t mk_attn_scratch(int max_keys);
+int mk_attn_subgroups(int kv_bf16, int attn_mma, int small, int max_keys);
 // Cooperative launch of the persistent kernel; the plan travels as a __grid_constant__ kernel parameter (TMA descriptors
 // included).  The barrier counter (plan.bar) must have been zeroed on the same stream.
 int launch_decode_megakernel(const MkPlan& plan, cudaStream_t s);

@@ -1074,6 +1074,11 @@ int build_mk_plan(const S2SModel& m, const GenWs& w, int B, int Bc, int T, int s
     for (int i = 0; i < nops; ++i)
       if (!b.next(MK_NOP)) break;
   }
+  P.attn_nsub = P.attn_stages == 3 ? 6 : mk_attn_subgroups(P.kv_bf16, P.attn_mma, B <= 8 ? 1 : 0, std::max(T, steps + 1));
+  {
+    static const int pre_rows = getenv("DIM_MK_ATTN_PRE") != nullptr ? std::max(0, atoi(getenv("DIM_MK_ATTN_PRE"))) : 0;      // measured: what the attention phase gains the barrier before it loses
+    P.attn_pre = (P.kv_bf16 && P.attn_mma && B > 8) ? pre_rows : 0;
+  }
   P.bar = w.mk_bar; P.trace = g_mk_trace_on ? w.mk_trace : nullptr;
   P.tokens = w.tokens; P.tok_stride = steps + 1;
   P.uniforms = uniforms; P.u_stride = steps;
