@@ -517,16 +517,24 @@ __device__ __forceinline__ uint32_t pack_part(float x, float y, int sel) {
   return sel <= 1 ? w : 0u;
 }
 
-// rows [c*64, c*64+64) of a bf16 head block -> one ring slot (64 rows of 144 bytes); thread -> 8 fixed 16-byte pieces (rows tid/8 + 8i,
-// chunk tid%8); rows past the last cached key (>= nold) are zero-filled
+// rows [c*64, c*64+64) of a bf16 head block -> one ring slot (64 rows of 144 bytes).  WARP w of the sub-group copies rows 32w..32w+31
+// -- exactly the keys whose scores and PV products it computes -- so a tile needs no barrier between the two warps: a lane waits for
+// its own cp.async groups and a __syncwarp publishes them to the warp.  Lane -> 8 pieces of 16 bytes: rows 32w + lane/8 + 4i, chunk
+// lane%8 (a warp instruction covers 4 whole rows = 512 contiguous bytes).  Rows past the last cached key (>= nold) are zero-filled.
 __device__ __forceinline__ void mk_issue_kv_tile(const __nv_bfloat16* head, int c, int nold, uint32_t slot_addr, int tid, uint64_t kvpol) {
-  const int row0 = c * 64, valid = nold - row0, row_t = tid >> 3;
-  const uint8_t* src = reinterpret_cast<const uint8_t*>(head + (size_t)row0 * 64) + tid * 16;
-  const uint32_t dst = slot_addr + (uint32_t)(row_t * 144 + (tid & 7) * 16);
+  const int row0 = c * 64, valid = nold - row0;
+  const int r0 = (tid >> 5) * 32 + ((tid & 31) >> 3), ch = tid & 7;
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(head + (size_t)(row0 + r0) * 64) + ch * 16;
+  const uint32_t dst = slot_addr + (uint32_t)(r0 * 144 + ch * 16);
+  if (valid >= 64) {                                   // whole tile cached (all but the last tile of a block): no per-piece predicates
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cp_async_16_hint(dst + i * 4 * 144, src + i * 512, kvpol);
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const bool ok = row_t + 8 * i < valid;
-    cp_async_16_zfill(dst + i * 8 * 144, ok ? src + i * 1024 : reinterpret_cast<const uint8_t*>(head), ok ? 16u : 0u, kvpol);
+    const bool ok = r0 + 4 * i < valid;
+    cp_async_16_zfill(dst + i * 4 * 144, ok ? src + i * 512 : reinterpret_cast<const uint8_t*>(head), ok ? 16u : 0u, kvpol);
   }
 }
 
@@ -551,6 +559,35 @@ __device__ __forceinline__ void mk_attn_prefetch(const MkPlan& P, const MkPhase&
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(head), "r"(rows * 128) : "memory");
 }
 
+// K/V of the next attention phase -> L2 while a latency-bound phase runs.  The GEMM / row / sampling phases of a step take ~280 us
+// during which HBM carries only the 144 MB of weights; the attention phases are the HBM-bound part.  Every non-attention phase
+// therefore starts by asking (bulk L2 prefetch, no shared-memory destination, nothing to wait for) for the K and V blocks of the
+// first entries of this CTA's item list of the NEXT attention phase -- the entries its sub-groups take first -- so that the
+// attention phase begins on L2 hits and streams only the rest from HBM.  The byte budget per CTA (plan.pf_budget) is spread over
+// the phases of the window by the host (pf_f0 .. pf_f1).  Issued by the CTA's last two warps, which have no producer / MMA role.
+__device__ __forceinline__ void mk_kv_prefetch(const MkPlan& P, const MkPhase& ph, int phase_idx, int st) {
+  const int t = (int)threadIdx.x - ((int)blockDim.x - 64);
+  if (t < 0) return;
+  const MkPhase& at = P.phases[ph.pf_target];
+  const int pos = st + (ph.pf_target < phase_idx ? 1 : 0);       // a target earlier in the program belongs to the next step
+  if (pos >= P.steps) return;
+  const int nold = at.append ? pos : at.Tk;
+  if (nold <= 0) return;
+  const int items = P.B * P.H;
+  const int mine = (int)blockIdx.x < items ? (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const unsigned esize = P.kv_bf16 ? 2u : 4u, rowb = 64u * esize;
+  const unsigned long long per_item = 2ull * (unsigned)nold * rowb;
+  const int E = (int)min((unsigned long long)mine, P.pf_budget / per_item);
+  const int k0 = (int)(ph.pf_f0 * (float)E), k1 = (int)(ph.pf_f1 * (float)E);
+  for (int j = t; j < 2 * (k1 - k0); j += 64) {
+    const int item = (int)blockIdx.x + (k0 + (j >> 1)) * (int)gridDim.x;
+    const int b = item / P.H, h = item - b * P.H, bkv = b / at.kv_group;
+    const size_t off = ((size_t)bkv * at.kv_batch_stride + (size_t)h * at.kv_head_stride) * esize;
+    const uint8_t* src = static_cast<const uint8_t*>((j & 1) ? at.vcache : at.kcache) + off;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((unsigned)nold * rowb) : "memory");
+  }
+}
+
 // The K tiles then the V tiles of an item form one stream of 2*nch tiles through an NST-slot cp.async ring, and the stream runs on
 // into the NEXT item of the sub-group (every item of a phase has the same tile count): while an item finishes (softmax tail, output
 // reduction, store) and the next one sums its projection partials, the next item's first tiles are already in flight.  `issued`
@@ -558,7 +595,7 @@ __device__ __forceinline__ void mk_attn_prefetch(const MkPlan& P, const MkPhase&
 // the stream position of this item's first tile; slot = position % NST.
 template <int NST>
 __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, int H, int planes, int sc_floats, uint8_t* reg, int sub,
-                                                 int tid, int item, int next_item, int pos, int& issued, int& g0) {
+                                                 int tid, int item, int next_item, int pos, int& issued, int& g0, int dbg) {
   constexpr int NT = 64, DH = 64, CHUNK = 64, PITCH = 144, STAGE = CHUNK * PITCH;
   float* sc = reinterpret_cast<float*>(reg + NST * STAGE);
   float* part = sc + sc_floats;                        // [2][64] partial outputs of the two warps
@@ -587,7 +624,7 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
     vnext = static_cast<const __nv_bfloat16*>(ph.vcache) + off;
   }
   auto issue_tile = [&](const __nv_bfloat16* head, int c, int slot) {     // rows [c*64, c*64+64) of a head block -> ring[slot]
-    mk_issue_kv_tile(head, c, nold, ring_u + slot * STAGE, tid, kvpol);
+    if (!(dbg & 1)) mk_issue_kv_tile(head, c, nold, ring_u + slot * STAGE, tid, kvpol);      // dbg bit 0: timing ablation without the K/V loads
   };
   int slot_next = issued % NST;                         // ring slot of stream position `issued`
   auto issue_upto = [&](int limit) {                    // commit one group per stream position below `limit`
@@ -602,32 +639,33 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
       if (++slot_next == NST) slot_next = 0;
     }
   };
-  // key-padding mask bytes of this thread's keys (tid, tid + 64, ...), fetched now: the softmax below must not wait for them
+  // key-padding mask: prefix masks (the usual case, key_valid[clip] >= 0) need no bytes at all -- one int per clip, requested here and
+  // first looked at after the projection partials have been requested (so its round trip hides behind theirs)
   const uint8_t* km = ph.key_mask ? ph.key_mask + (size_t)bkv * ph.Tk : nullptr;
-  uint32_t kmbits = 0xffffffffu;                       // bit i: key tid + 64 i is kept
-  if (km) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (tid + 64 * i < nkeys && !km[tid + 64 * i]) kmbits &= ~(1u << i);
-  }
+  const int kval = (km && ph.key_valid && !(dbg & 8)) ? __ldg(ph.key_valid + bkv) : -1;
+  uint32_t kmbits = 0xffffffffu;                       // arbitrary masks: bit i = key tid + 64 i is kept
   int slot_cur = g0 % NST;                             // ring slot of this item's next tile to consume
   issue_upto(g0 + NST);                                // the first tiles travel while the projection partials are summed (a no-op
                                                        // when the previous item of this sub-group has already sent them)
   {  // q (and this step's k, v) = sum of the K slices of the projection, in slice order; thread t owns element t of the head row
     const size_t mn = (size_t)Brows * ph.q_ld;
     const float* base = reinterpret_cast<const float*>(ph.part) + (size_t)b * ph.q_ld + h * DH + tid;
+    const float *bq = base + ph.q_col, *bk = base + ph.k_col, *bv = base + ph.v_col;
+    const int S = ph.q_splits;
+    const bool app = ph.append != 0;
     float pq[MK_MAXS], pk[MK_MAXS], pv[MK_MAXS];
 #pragma unroll
-    for (int z = 0; z < MK_MAXS; ++z) {
-      const bool on = z < ph.q_splits;
-      pq[z] = on ? base[z * mn + ph.q_col] : 0.f;
-      pk[z] = (on && ph.append) ? base[z * mn + ph.k_col] : 0.f;
-      pv[z] = (on && ph.append) ? base[z * mn + ph.v_col] : 0.f;
+    for (int z = 0; z < MK_MAXS; ++z) {                 // all loads before the first add; one pointer step per slice
+      const bool on = z < S && !(dbg & 4);             // dbg bit 2: without the projection partials
+      pq[z] = on ? *bq : 0.f;
+      pk[z] = (on && app) ? *bk : 0.f;
+      pv[z] = (on && app) ? *bv : 0.f;
+      bq += mn; bk += mn; bv += mn;
     }
     float qv = pq[0], kv = pk[0], vv = pv[0];
 #pragma unroll
     for (int z = 1; z < MK_MAXS; ++z)
-      if (z < ph.q_splits) { qv += pq[z]; kv += pk[z]; vv += pv[z]; }
+      if (z < S) { qv += pq[z]; kv += pk[z]; vv += pv[z]; }
     qs[tid] = qv;
     if (ph.append) {
       const __nv_bfloat16 kb = __float2bfloat16_rn(kv), vb = __float2bfloat16_rn(vv);
@@ -636,6 +674,12 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
       knew[tid] = __bfloat162float(kb);
       vnew[tid] = __bfloat162float(vb);
     }
+  }
+  if (km && kval < 0 && !(dbg & 8)) {                  // not a prefix mask: bytes of this thread's keys (tid, tid + 64, ...); dbg bit 3: none
+    const int nw = min(32, (nkeys + 63) >> 6);
+#pragma unroll 4
+    for (int i = 0; i < nw; ++i)
+      if (tid + 64 * i < nkeys && !km[tid + 64 * i]) kmbits &= ~(1u << i);
   }
   bar_sub(sub);
   // A fragments of q: lanes g == 0 carry the high parts (row 0), lanes g == 1 the low parts (row 1), every other row is zero
@@ -661,12 +705,13 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
   // ---- pass 1: S = q K^T; warp w owns keys 32w .. 32w+31 of the tile
   for (int c = 0; c < nch; ++c) {
     cp_async_wait<NST - 1>();                          // the NST - 1 stream positions after this tile may still be in flight
-    bar_sub(sub);
+    __syncwarp();                                      // this warp's rows of the tile (its own copies) are complete: no sub-group barrier
     const uint32_t tile = ring_u + slot_cur * STAGE;
     if (++slot_cur == NST) slot_cur = 0;
     float s[4][4];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    if (!(dbg & 2))                                    // dbg bit 1: timing ablation without the tensor-core products
 #pragma unroll
     for (int n2 = 0; n2 < 2; ++n2) {
 #pragma unroll
@@ -687,7 +732,7 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
         if (j + 1 < nold) sc[j + 1] = s1 * ph.scale;
       }
     }
-    bar_sub(sub);
+    __syncwarp();                                      // every lane has read its rows: the slot may be refilled (by this warp only)
     issue_upto(g0 + c + 1 + NST);
   }
   bar_sub(sub);                                        // the own key's score is visible (covers the no-tile first step too)
@@ -695,7 +740,7 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
   float mx = -INFINITY;
   for (int j = tid, i = 0; j < nkeys; j += NT, ++i) {
     float v = sc[j];
-    const bool keep = i < 32 ? ((kmbits >> i) & 1u) != 0 : !(km && !km[j]);
+    const bool keep = kval >= 0 ? j < kval : (i < 32 ? ((kmbits >> i) & 1u) != 0 : !(km && !km[j]));
     if (!keep) { v = -FLT_MAX; sc[j] = v; }
     mx = fmaxf(mx, v);
   }
@@ -720,9 +765,10 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
   for (int nt = 0; nt < 8; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
   for (int c = 0; c < nch; ++c) {
     cp_async_wait<NST - 1>();
-    bar_sub(sub);
+    __syncwarp();
     const uint32_t tile = ring_u + slot_cur * STAGE;
     if (++slot_cur == NST) slot_cur = 0;
+    if (!(dbg & 2))
 #pragma unroll
     for (int k2 = 0; k2 < 2; ++k2) {
       const int kb = warp * 32 + k2 * 16, j0 = c * CHUNK + kb + 2 * t4;     // this lane's key columns: j0, j0+1, j0+8, j0+9
@@ -743,7 +789,7 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
         mma_bf16(o[2 * n2 + 1], ap, b2, b3);
       }
     }
-    bar_sub(sub);
+    __syncwarp();
     issue_upto(g0 + nch + c + 1 + NST);                // past this item's last tile: the next item's first tiles
   }
   g0 += n;
@@ -778,7 +824,7 @@ __device__ __forceinline__ void mk_attn_mma_loop(const MkPlan& P, const MkPhase&
     const int kn = fetch();
     const int item = (int)blockIdx.x + k * (int)gridDim.x;
     const int next = kn < mine ? (int)blockIdx.x + kn * (int)gridDim.x : -1;
-    mk_attn_item_mma<NST>(ph, P.B, P.H, P.planes, P.sc_floats, reg, sub, tid, item, next, pos, issued, g0);
+    mk_attn_item_mma<NST>(ph, P.B, P.H, P.planes, P.sc_floats, reg, sub, tid, item, next, pos, issued, g0, P.attn_dbg);
     bar_sub(sub);
     k = kn;
   }
@@ -1156,6 +1202,7 @@ __global__ void __launch_bounds__(WIDE ? MK_THREADS_WIDE : MK_THREADS, 1) decode
         asm volatile("prefetch.tensormap [%0];" ::"l"(&P.maps[P.phases[nxt].mapA]) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&P.maps[P.phases[nxt].mapW]) : "memory");
       }
+      if (ph.pf_f1 > ph.pf_f0 && P.pf_budget > 0) mk_kv_prefetch(P, ph, i, st);
       switch (ph.type) {
         case MK_GEMM:
           if (!SMALL) mk_gemm(P, ph, smem, smem_base, ctl, pipe, tmem_base);

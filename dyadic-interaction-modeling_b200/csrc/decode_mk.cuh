@@ -35,6 +35,7 @@ struct MkPhase {
   void *kcache, *vcache;
   unsigned long long kv_batch_stride, kv_head_stride;
   const uint8_t* key_mask;
+  const int32_t* key_valid;                  // nullable, per clip: >= 0 = key_mask[b] keeps exactly the first key_valid[b] keys (no byte loads)
   float scale;
   // ---- row phases (also the outputs of MK_ATTN): bf16 planes [M, planes * out_kp] = the next GEMM's A operand
   __nv_bfloat16* outp;
@@ -47,6 +48,11 @@ struct MkPhase {
   const float* pos;                          // MK_ROW_SAMPLE: nullable absolute positional table [max_seq_len, D] (+ pos[st + 1] * pos_scale)
   float pos_scale;
   int D;                                     // MK_ROW_SAMPLE: model width (N = vocabulary)
+  // ---- any non-attention phase: while it runs (HBM nearly idle) the CTA asks for a slice of the NEXT attention phase's K/V blocks
+  // to be brought into L2 (decode_mk.cu: mk_kv_prefetch).  pf_target = index of that attention phase (-1: none); the phase covers
+  // the fraction [pf_f0, pf_f1) of the entries the byte budget allows.
+  int pf_target;
+  float pf_f0, pf_f1;
 };
 
 struct alignas(128) MkPlan {
@@ -63,6 +69,8 @@ struct alignas(128) MkPlan {
   int attn_mma;                              // bf16 caches: 1 = mma.sync attention items, 0 = FFMA items (A/B hook DIM_MK_ATTN_FFMA)
   int attn_pre;                              // mma items: rows of the first item's K block (half as many of V) prefetched into L2 before the
                                              // grid barrier that precedes an attention phase (DIM_MK_ATTN_PRE=rows, 0 = off)
+  int attn_dbg;                              // timing ablations of the mma attention items (DIM_MK_ATTN_DBG bits: 1 no K/V loads, 2 no products, 4 no projection partials, 8 no mask bytes; results are wrong)
+  unsigned long long pf_budget;              // K/V bytes per CTA and attention phase to prefetch into L2 (0 = off)
   int attn_nsub;                             // attention sub-groups per CTA: 6 (384 threads) or 8 (512-thread flavour, mk_attn_subgroups)
   int sc_floats;                             // score slots per attention work item (>= max keys, multiple of 4)
   unsigned int* bar;                         // grid barrier counter, zero at launch

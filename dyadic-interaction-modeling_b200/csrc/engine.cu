@@ -471,6 +471,7 @@ struct GenWs {
   float *x, *ln, *qkv, *att, *ff, *logits;
   int64_t* tokens;                         // [B, steps+1]
   int* step;
+  int32_t* key_valid;                      // [B] prefix length of each clip's key-padding mask, -1 = not a prefix mask (persistent kernel)
   uint8_t* mask_stage;                     // [B,T] copy of the caller's key-padding mask   } what the captured step graph reads:
   float* u_stage;                          // [R,steps] copy of the caller's uniforms       } the graph never holds caller pointers
   __nv_bfloat16 *ap, *ap2;                 // A-operand plane scratch for the tensor-core GEMMs
@@ -503,6 +504,7 @@ GenWs carve_gen(const dim_s2s_config& c, int planes, bool kv_bf16, int B, int T,
   w.att = take(R * inner); w.ff = take(R * c.ff_mult * D); w.logits = take(R * c.num_tokens);
   w.tokens = reinterpret_cast<int64_t*>(take(R * (steps + 1) * 2));
   w.step = reinterpret_cast<int*>(take(64));
+  w.key_valid = reinterpret_cast<int32_t*>(take((size_t)B + 1));
   w.mask_stage = reinterpret_cast<uint8_t*>(take(((size_t)B * T + 3) / 4 + 1));
   w.u_stage = take(R * (size_t)steps + 1);
   {
@@ -1027,7 +1029,7 @@ int build_mk_plan(const S2SModel& m, const GenWs& w, int B, int Bc, int T, int s
       ph->vcache = kv16 ? static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(w.cross_kv[l]) + vplane)
                         : static_cast<void*>(w.cross_kv[l] + vplane);
       ph->kv_batch_stride = (size_t)T * inner; ph->kv_head_stride = (size_t)T * c.dim_head;
-      ph->key_mask = mask; ph->scale = scale; ph->outp = w.mk_attp; ph->out_kp = inner;
+      ph->key_mask = mask; ph->key_valid = mask ? w.key_valid : nullptr; ph->scale = scale; ph->outp = w.mk_attp; ph->out_kp = inner;
     }
     if (int e = b.gemm(mapAtt, CA.wo, D, inner, w.mk_part, w_keep, &sp)) return e;
     if (int e = resln(sp, nullptr, FF.norm_g, FF.norm_b)) return e;
@@ -1073,6 +1075,43 @@ int build_mk_plan(const S2SModel& m, const GenWs& w, int B, int Bc, int T, int s
     P.attn_mma = ffma ? 0 : 1;
     for (int i = 0; i < nops; ++i)
       if (!b.next(MK_NOP)) break;
+  }
+  {  // K/V prefetch windows: every non-attention phase serves the next attention phase of the program (cyclically), with a share of
+     // the budget proportional to a rough duration weight
+    static const double pf_mb = getenv("DIM_MK_PF_MB") ? atof(getenv("DIM_MK_PF_MB")) : 0.0;      // whole-GPU budget per attention phase
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    P.pf_budget = B > 8 ? (unsigned long long)(pf_mb * 1048576.0 / sms) : 0ull;
+    const int n = P.nphases;
+    auto weight = [&](const MkPhase& ph) -> float {
+      if (ph.type == MK_GEMM) return (float)ph.N * (float)ph.kp >= 4.0e6f ? 2.f : 1.f;
+      if (ph.type == MK_ROW_SAMPLE) return 3.f;
+      return ph.type == MK_NOP ? 0.f : 1.f;
+    };
+    for (int i = 0; i < n; ++i) P.phases[i].pf_target = -1;
+    for (int q = 0; q < n; ++q) {
+      if (P.phases[q].type != MK_ATTN) continue;
+      // window = the phases between the previous attention phase (cyclically) and q
+      int first = q;
+      float total = 0.f;
+      for (int back = 1; back < n; ++back) {
+        const int i = (q - back + n) % n;
+        if (P.phases[i].type == MK_ATTN) break;
+        first = i;
+        total += weight(P.phases[i]);
+      }
+      float acc = 0.f;
+      for (int i = first; i != q && total > 0.f; i = (i + 1) % n) {
+        P.phases[i].pf_target = q;
+        P.phases[i].pf_f0 = acc / total;
+        acc += weight(P.phases[i]);
+        P.phases[i].pf_f1 = acc / total;
+      }
+    }
+  }
+  {
+    static const int dbg = getenv("DIM_MK_ATTN_DBG") ? atoi(getenv("DIM_MK_ATTN_DBG")) : 0;
+    P.attn_dbg = dbg;
   }
   P.attn_nsub = P.attn_stages == 3 ? 6 : mk_attn_subgroups(P.kv_bf16, P.attn_mma, B <= 8 ? 1 : 0, std::max(T, steps + 1));
   {
@@ -1132,6 +1171,7 @@ int generate_group(const S2SModel& m, S2SModel::StepGraph& G, const float* ctx, 
     if (int e = launch_layer_norm(w.x, SA0.norm_g, SA0.norm_b, nullptr, nullptr, B, D, 1e-5f, s, w.ap, m.tc.planes, D)) return e;
     DIM_CHECK_CUDA(cudaMemsetAsync(w.mk_bar, 0, 256, s));
     if (g_mk_trace_on) DIM_CHECK_CUDA(cudaMemsetAsync(w.mk_trace, 0, MK_MAX_PHASES * sizeof(unsigned long long), s));
+    if (mask) { if (int e = launch_mask_prefix(mask, Bc, T, w.key_valid, s)) return e; }
     static thread_local MkPlan plan;
     if (int e = build_mk_plan(m, w, B, Bc, T, steps, samples, temperature, top_k, mask, uniforms, logits_out, plan)) return e;
     if (int e = launch_decode_megakernel(plan, s)) return e;

@@ -426,6 +426,22 @@ __global__ void init_tokens_kernel(int64_t* __restrict__ tokens, int stride, con
   if (r < rows) tokens[(size_t)r * stride] = prompt[r / samples];
 }
 
+// Key-padding masks are almost always prefix masks (keys 0 .. L_b-1 kept, seq2seq_pretrain.py:433-436 builds them from src_len):
+// out[b] = L_b when clip b's mask is one, -1 otherwise (arbitrary mask: the attention items read its bytes).  One warp per clip.
+__global__ void mask_prefix_kernel(const uint8_t* __restrict__ mask, int B, int T, int32_t* __restrict__ out) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const uint8_t* m = mask + (size_t)b * T;
+  int total = 0, first_zero = T;
+  for (int j = lane; j < T; j += 32) {
+    if (m[j]) ++total;
+    else first_zero = min(first_zero, j);
+  }
+  total = __reduce_add_sync(0xffffffffu, total);
+  first_zero = __reduce_min_sync(0xffffffffu, first_zero);
+  if (lane == 0) out[b] = total == first_zero ? first_zero : -1;
+}
+
 __global__ void advance_step_kernel(int* step) {
   pdl_prologue();
   *step += 1;
@@ -586,6 +602,14 @@ int launch_init_tokens(int64_t* tokens, int stride, const int64_t* prompt, int r
   DIM_REQUIRE(rows > 0 && samples >= 1, "init_tokens: bad sizes");
   ProfScope ps(CAT_MISC, s, 16.0 * rows, 0);
   init_tokens_kernel<<<cdiv(rows, 256), 256, 0, s>>>(tokens, stride, prompt, rows, samples);
+  DIM_LAUNCHED();
+  return DIM_OK;
+}
+
+int launch_mask_prefix(const uint8_t* mask, int B, int T, int32_t* out, cudaStream_t s) {
+  DIM_REQUIRE(mask && out && B > 0 && T > 0, "mask_prefix: bad arguments");
+  ProfScope ps(CAT_MISC, s, (double)B * T + 4.0 * B, 0);
+  mask_prefix_kernel<<<cdiv(B, 8), 256, 0, s>>>(mask, B, T, out);
   DIM_LAUNCHED();
   return DIM_OK;
 }

@@ -27,6 +27,8 @@ int launch_sample_next(const float* logits, int B, int V, float temperature, int
                        __nv_bfloat16* yp, int planes, float eps, cudaStream_t s, const float* pos = nullptr, float pos_scale = 0.f);
 int launch_resample(const float* in, float* out, int t, int d, int new_t, int window, int mode, cudaStream_t s);
 int launch_init_tokens(int64_t* tokens, int stride, const int64_t* prompt, int rows, int samples, cudaStream_t s);
+// out[b] = number of kept keys when mask[b, :] is a prefix mask, -1 otherwise
+int launch_mask_prefix(const uint8_t* mask, int B, int T, int32_t* out, cudaStream_t s);
 int launch_advance_step(int* step, cudaStream_t s);
 int launch_set_step(int* step, int v, cudaStream_t s);
 }  // namespace dimb

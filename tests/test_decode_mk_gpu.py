@@ -137,6 +137,31 @@ def test_bf16_mode_matches_graph_path(engine_bf16):
     assert float((codes == rcodes).float().mean()) > 0.8
 
 
+def test_bf16_mode_arbitrary_key_mask(engine_bf16):
+    """Key-padding masks that are NOT prefix masks (holes) take the byte-mask path of the mma attention items; prefix masks take the
+    per-clip length (mask_prefix_kernel).  Half of the clips get holes; both kinds must agree with the per-kernel graph path."""
+    s2s = engine_bf16
+    B, T = 48, 20
+    c = dim_b200.synth.make_clips(B, T, seed=77, ragged=True)
+    m = c["mask"].clone()
+    g = torch.Generator().manual_seed(5)
+    holes = torch.rand(B, T, generator=g) < 0.25
+    holes[:, 0] = False
+    holes[::2] = False                                   # even clips keep their prefix mask
+    m = (m.bool() & ~holes).to(c["mask"].dtype)
+    assert bool((m[1::2].bool() != c["mask"][1::2].bool()).any())
+    mc = m.cuda()
+    ctx = s2s.context(c["v_speaker"].cuda(), c["v_audio"].cuda(), mc)
+    prompt = torch.randint(0, 512, (B,), generator=torch.Generator().manual_seed(10)).cuda()
+    (codes, logits), (rcodes, rlogits) = _both(lambda: s2s.generate(ctx, mc, prompt, T - 1, return_logits=True))
+    assert float((logits[:, 0] - rlogits[:, 0]).abs().max()) < 5e-2
+    assert float((codes == rcodes).float().mean()) > 0.8
+    # the mask matters: dropping the holes changes the first-step logits of the clips that had them
+    (codes2, logits2) = s2s.generate(ctx, c["mask"].cuda(), prompt, T - 1, return_logits=True)
+    assert float((logits2[1::2, 0] - logits[1::2, 0]).abs().max()) > 1e-3
+    assert float((logits2[::2, 0] - logits[::2, 0]).abs().max()) == 0.0
+
+
 def test_samples_share_the_context(engine_tc):
     s2s = engine_tc
     B, S, T = 11, 3, 12
