@@ -356,6 +356,7 @@ __device__ __forceinline__ void mk_attn_item(const MkPhase& ph, int Brows, int H
   // written to the cache for the later steps and used here from shared memory (rounded to the cache's element type first)
   const int nold = ph.append ? pos : ph.Tk;
   const int nch = (nold + CHUNK - 1) / CHUNK;
+  const int kval = (ph.key_mask && ph.key_valid) ? __ldg(ph.key_valid + bkv) : -1;      // requested now, used in the softmax
   uint64_t kvpol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(kvpol));
   auto issue = [&](const KT* head, int c, int stage) {                   // rows [c*CHUNK, ..) of a head block -> ring[stage]
@@ -436,7 +437,8 @@ __device__ __forceinline__ void mk_attn_item(const MkPhase& ph, int Brows, int H
   float mx = -INFINITY;
   for (int j = tid; j < nkeys; j += NT) {
     float v = sc[j];
-    if (km && !km[j]) { v = -FLT_MAX; sc[j] = v; }
+    const bool drop = kval >= 0 ? j >= kval : (km && !km[j]);      // prefix mask: one length per clip, no bytes
+    if (drop) { v = -FLT_MAX; sc[j] = v; }
     mx = fmaxf(mx, v);
   }
   mx = warp_max(mx);
@@ -1247,9 +1249,12 @@ bool mk_supported(int D, int inner, int F, int V, int H, int planes, int max_key
 
 size_t mk_attn_scratch(int max_keys) { return 2 * 64 * 144 + (size_t)((max_keys + 3) / 4 * 4) * 4 + 8 * 64 * 4 + 3 * 64 * 4 + 16; }
 
-int mk_attn_subgroups(int kv_bf16, int attn_mma, int small, int max_keys) {
+int mk_attn_subgroups(int kv_bf16, int attn_mma, int small, int max_keys, int items) {
   static const bool wide_off = getenv("DIM_MK_WIDE") != nullptr && atoi(getenv("DIM_MK_WIDE")) == 0;      // A/B hook
   if (wide_off || !kv_bf16 || !attn_mma || small) return 6;
+  // fewer (row, head) items than 6 sub-groups per SM can hold at once: the extra warps only slow the GEMM / row phases down
+  // (32 LM-Listener chunks: 449.6 ms with 384 threads, 464.6 with 512).  Numerics do not depend on the choice.
+  if (items <= 6 * 148) return 6;
   // the mma items keep [2][64] partial outputs, not [8][64]
   const size_t need = 2 * 64 * 144 + (size_t)((max_keys + 3) / 4 * 4) * 4 + 2 * 64 * 4 + 3 * 64 * 4 + 16;
   return need <= MK_RING / 8 ? 8 : 6;

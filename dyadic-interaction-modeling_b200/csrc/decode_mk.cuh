@@ -89,7 +89,7 @@ struct alignas(128) MkPlan {
 bool mk_supported(int D, int inner, int F, int V, int H, int planes, int max_keys);
 // Bytes of shared-memory scratch one attention sub-group needs for `max_keys` keys, and the sub-group count the launch will use.
 size_t mk_attn_scratch(int max_keys);
-int mk_attn_subgroups(int kv_bf16, int attn_mma, int small, int max_keys);
+int mk_attn_subgroups(int kv_bf16, int attn_mma, int small, int max_keys, int items);
 // Cooperative launch of the persistent kernel; the plan travels as a __grid_constant__ kernel parameter (TMA descriptors
 // included).  The barrier counter (plan.bar) must have been zeroed on the same stream.
 int launch_decode_megakernel(const MkPlan& plan, cudaStream_t s);

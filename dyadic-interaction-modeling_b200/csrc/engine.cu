@@ -1113,7 +1113,7 @@ int build_mk_plan(const S2SModel& m, const GenWs& w, int B, int Bc, int T, int s
     static const int dbg = getenv("DIM_MK_ATTN_DBG") ? atoi(getenv("DIM_MK_ATTN_DBG")) : 0;
     P.attn_dbg = dbg;
   }
-  P.attn_nsub = P.attn_stages == 3 ? 6 : mk_attn_subgroups(P.kv_bf16, P.attn_mma, B <= 8 ? 1 : 0, std::max(T, steps + 1));
+  P.attn_nsub = P.attn_stages == 3 ? 6 : mk_attn_subgroups(P.kv_bf16, P.attn_mma, B <= 8 ? 1 : 0, std::max(T, steps + 1), B * c.heads);
   {
     static const int pre_rows = getenv("DIM_MK_ATTN_PRE") != nullptr ? std::max(0, atoi(getenv("DIM_MK_ATTN_PRE"))) : 0;      // measured: what the attention phase gains the barrier before it loses
     P.attn_pre = (P.kv_bf16 && P.attn_mma && B > 8) ? pre_rows : 0;
