@@ -927,6 +927,10 @@ void mk_gemm_cfg(int N, int K, int planes, int* bn, int* splits) {
   const int kp = tc_round_k(K), npairs = planes == 1 ? 1 : (planes == 2 ? 3 : 6);
   const int total_it = kp / 64 * npairs;
   *bn = (N >= 2048 || kp >= 2048) ? 128 : 64;
+  // fp32-grade planes: 6 products per k-block make the phase ingest-bound (A tile 16 KB + W tile per 128 x bn x 64 product), so the
+  // wider tile with a deeper K split wins from N = 1024 on (DIM_MK_BN128=0: A/B hook)
+  static const bool bn128 = !(getenv("DIM_MK_BN128") != nullptr && atoi(getenv("DIM_MK_BN128")) == 0);
+  if (planes >= 2 && N >= 1024 && bn128) *bn = 128;
   const int nt = cdiv(N, *bn);
   int sp = (72 + nt / 2) / nt;
   sp = std::max(1, std::min(sp, 9));

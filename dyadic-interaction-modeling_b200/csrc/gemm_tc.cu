@@ -518,21 +518,30 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_bf16_tcgen05_persist(const
       pg_wait(smem_u32(&tfull_bar[a]), ((uint32_t)i >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * PG_ACC_COLS);
+      // software pipeline over the 16-column chunks: the TMEM load and the bias of chunk c+1 are requested before chunk c is
+      // processed (ncu: 17 % of the epilogue's samples waited for tcgen05.ld, 22 % for the bias)
+      uint32_t tv[16];
+      tmem_ld16_issue(tl + (uint32_t)cb, tv);
+      float4 bias_nx = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e.bias && n0 + cb + cc < e.N) bias_nx = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + cb + cc));
 #pragma unroll 1
       for (int c0 = cb; c0 < ce; c0 += 16) {
         {
-          float v[16];
-          tmem_ld16(tl + (uint32_t)c0, v);
+          tmem_ld16_wait(tv);
           float* w = st + lane * PG_SP;
 #pragma unroll
           for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<float4*>(w + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+            *reinterpret_cast<float4*>(w + g * 4) = make_float4(__uint_as_float(tv[g * 4]), __uint_as_float(tv[g * 4 + 1]),
+                                                                __uint_as_float(tv[g * 4 + 2]), __uint_as_float(tv[g * 4 + 3]));
+        }
+        const float4 bias4 = bias_nx;
+        if (c0 + 16 < ce) {
+          tmem_ld16_issue(tl + (uint32_t)(c0 + 16), tv);
+          if (e.bias && n0 + c0 + 16 + cc < e.N) bias_nx = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + c0 + 16 + cc));
         }
         __syncwarp();
         const int col = n0 + c0 + cc;
         if (col < e.N) {                                 // N % 4 == 0: a float4 is entirely inside or outside
-          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
           float4 acc[4], res[4];
           bool ok[4];
 #pragma unroll
