@@ -217,7 +217,7 @@ __device__ __forceinline__ void cp_async_16_zf(uint32_t dst_smem, const void* sr
 // staging, no conversion), K/V double-buffered: half the bytes of the fp32 round trip, ~64 registers fewer.  The values are the same
 // bf16 roundings the fp32 path produces on the fly, so the result is bit-identical.
 template <int DH, int NP, bool IN16>
-__global__ void __launch_bounds__(128) attn_prefill_mma(const AttnArgs p) {
+__global__ void __launch_bounds__(128, (NP == 1 && IN16 && DH <= 64) ? 4 : 1) attn_prefill_mma(const AttnArgs p) {
   static_assert(!IN16 || NP == 1, "bf16 inputs are the plain-bf16 mode");
   constexpr int PITCH = DH + 8;                       // bf16 elements per smem row: 16-byte aligned, conflict-free ldmatrix
   constexpr int KC = DH / 16;                         // k-chunks of the QK^T product
