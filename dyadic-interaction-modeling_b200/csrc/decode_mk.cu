@@ -710,28 +710,28 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
     __syncwarp();                                      // this warp's rows of the tile (its own copies) are complete: no sub-group barrier
     const uint32_t tile = ring_u + slot_cur * STAGE;
     if (++slot_cur == NST) slot_cur = 0;
-    float s[4][4];
+    // keys as the M dimension: A = a 16-key x 16-dim block of the K tile (ldmatrix, no transpose), B = q with column 0 = bf16 high
+    // parts and column 1 = low parts (the other six columns are zero): 8 instead of 16 mma.sync per warp and tile, and the two parts
+    // of a score land in ONE lane (t4 == 0: c0 + c1 for key g, c2 + c3 for key g + 8) -- no shuffle
+    float s[2][4];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    for (int mt = 0; mt < 2; ++mt) s[mt][0] = s[mt][1] = s[mt][2] = s[mt][3] = 0.f;
     if (!(dbg & 2))                                    // dbg bit 1: timing ablation without the tensor-core products
 #pragma unroll
-    for (int n2 = 0; n2 < 2; ++n2) {
+    for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
       for (int kc = 0; kc < 4; ++kc) {
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4(tile + (uint32_t)((warp * 32 + n2 * 16) * PITCH + kc * 32) + bk_off, b0, b1, b2, b3);
-        mma_bf16(s[2 * n2], aq[kc], b0, b1);
-        mma_bf16(s[2 * n2 + 1], aq[kc], b2, b3);
+        uint32_t a[4];
+        ldsm_x4(tile + (uint32_t)((warp * 32 + mt * 16) * PITCH + kc * 32) + bv_off, a[0], a[1], a[2], a[3]);
+        mma_bf16(s[mt], a, aq[kc][0], aq[kc][2]);
       }
     }
+    if (t4 == 0) {
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const float s0 = s[nt][0] + __shfl_xor_sync(0xffffffffu, s[nt][0], 4);      // row 0 (high part of q) + row 1 (low part)
-      const float s1 = s[nt][1] + __shfl_xor_sync(0xffffffffu, s[nt][1], 4);
-      const int j = c * CHUNK + warp * 32 + nt * 8 + 2 * t4;
-      if (g == 0) {
-        if (j < nold) sc[j] = s0 * ph.scale;
-        if (j + 1 < nold) sc[j + 1] = s1 * ph.scale;
+      for (int mt = 0; mt < 2; ++mt) {
+        const int j = c * CHUNK + warp * 32 + mt * 16 + g;
+        if (j < nold) sc[j] = (s[mt][0] + s[mt][1]) * ph.scale;
+        if (j + 8 < nold) sc[j + 8] = (s[mt][2] + s[mt][3]) * ph.scale;
       }
     }
     __syncwarp();                                      // every lane has read its rows: the slot may be refilled (by this warp only)
@@ -762,9 +762,11 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
   bar_sub(sub);
   const float inv = 1.f / (red[0] + red[1]);
   // ---- pass 2: O = P V; warp w owns keys 32w .. 32w+31 of the tile (two 16-key k-steps), all 64 output columns
-  float o[8][4];
+  // dims as the M dimension: A = a 16-dim x 16-key block of V^T (ldmatrix.trans of the V rows), B = p with column 0 = high parts and
+  // column 1 = low parts: 8 instead of 16 mma.sync per warp and tile, 16 instead of 32 accumulator registers
+  float o[4][4];
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+  for (int mt = 0; mt < 4; ++mt) o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f;
   for (int c = 0; c < nch; ++c) {
     cp_async_wait<NST - 1>();
     __syncwarp();
@@ -773,33 +775,27 @@ __device__ __forceinline__ void mk_attn_item_mma(const MkPhase& ph, int Brows, i
     if (!(dbg & 2))
 #pragma unroll
     for (int k2 = 0; k2 < 2; ++k2) {
-      const int kb = warp * 32 + k2 * 16, j0 = c * CHUNK + kb + 2 * t4;     // this lane's key columns: j0, j0+1, j0+8, j0+9
-      uint32_t ap[4];
-      {
-        const float p0 = j0 < nold ? sc[j0] : 0.f, p1 = j0 + 1 < nold ? sc[j0 + 1] : 0.f;
-        const float p2 = j0 + 8 < nold ? sc[j0 + 8] : 0.f, p3 = j0 + 9 < nold ? sc[j0 + 9] : 0.f;
-        ap[0] = pack_part(p0, p1, g);
-        ap[1] = 0u;
-        ap[2] = pack_part(p2, p3, g);
-        ap[3] = 0u;
-      }
+      const int kb = warp * 32 + k2 * 16, j0 = c * CHUNK + kb + 2 * t4;     // this lane's keys of the B operand: j0, j0+1, j0+8, j0+9
+      const float p0 = j0 < nold ? sc[j0] : 0.f, p1 = j0 + 1 < nold ? sc[j0 + 1] : 0.f;
+      const float p2 = j0 + 8 < nold ? sc[j0 + 8] : 0.f, p3 = j0 + 9 < nold ? sc[j0 + 9] : 0.f;
+      const uint32_t bp0 = pack_part(p0, p1, g), bp1 = pack_part(p2, p3, g);
 #pragma unroll
-      for (int n2 = 0; n2 < 4; ++n2) {
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4_t(tile + (uint32_t)(kb * PITCH + n2 * 32) + bv_off, b0, b1, b2, b3);
-        mma_bf16(o[2 * n2], ap, b0, b1);
-        mma_bf16(o[2 * n2 + 1], ap, b2, b3);
+      for (int mt = 0; mt < 4; ++mt) {
+        uint32_t a[4];
+        ldsm_x4_t(tile + (uint32_t)(kb * PITCH + mt * 32) + bk_off, a[0], a[1], a[2], a[3]);
+        mma_bf16(o[mt], a, bp0, bp1);
       }
     }
     __syncwarp();
     issue_upto(g0 + nch + c + 1 + NST);                // past this item's last tile: the next item's first tiles
   }
   g0 += n;
+  if (t4 == 0) {
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    const float o0 = o[nt][0] + __shfl_xor_sync(0xffffffffu, o[nt][0], 4);
-    const float o1 = o[nt][1] + __shfl_xor_sync(0xffffffffu, o[nt][1], 4);
-    if (g == 0) *reinterpret_cast<float2*>(part + warp * DH + nt * 8 + 2 * t4) = make_float2(o0, o1);
+    for (int mt = 0; mt < 4; ++mt) {
+      part[warp * DH + mt * 16 + g] = o[mt][0] + o[mt][1];          // high part of p + low part
+      part[warp * DH + mt * 16 + g + 8] = o[mt][2] + o[mt][3];
+    }
   }
   bar_sub(sub);
   {
